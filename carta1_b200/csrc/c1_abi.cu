@@ -1,0 +1,772 @@
+// c1_abi.cu -- the extern "C" boundary declared in include/carta1_b200.h: context, tables,
+// workspaces, chunked host<->device staging and the stateful stream handles.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/carta1_b200.h"
+#include "c1_common.cuh"
+#include "c1_launch.h"
+
+using namespace c1;
+
+namespace {
+
+std::string g_create_error;
+
+// ---------------------------------------------------------------- host tables
+const int kSpecs[52] = {8, 8, 8, 8, 4, 4, 4, 4, 8, 8, 8, 8, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 7, 7,
+                        7, 7, 9, 9, 9, 9, 10, 10, 10, 10, 12, 12, 12, 12, 12, 12, 12, 12, 20, 20, 20,
+                        20, 20, 20, 20, 20};
+const int kStartLong[52] = {0, 8, 16, 24, 32, 36, 40, 44, 48, 56, 64, 72, 80, 86, 92, 98, 104, 110, 116,
+                            122, 128, 134, 140, 146, 152, 159, 166, 173, 180, 189, 198, 207, 216, 226,
+                            236, 246, 256, 268, 280, 292, 304, 316, 328, 340, 352, 372, 392, 412, 432,
+                            452, 472, 492};
+const int kStartShort[52] = {0, 32, 64, 96, 8, 40, 72, 104, 12, 44, 76, 108, 20, 52, 84, 116, 26, 58, 90,
+                             122, 128, 160, 192, 224, 134, 166, 198, 230, 141, 173, 205, 237, 150, 182,
+                             214, 246, 256, 288, 320, 352, 384, 416, 448, 480, 268, 300, 332, 364, 396,
+                             428, 460, 492};
+// QMF prototype, decimal literals of codec/core/constants.js:74-80 (stored as Float32Array)
+const double kQmfLiterals[24] = {
+    -0.00001461907, -0.00009205479, -0.000056157569, 0.00030117269, 0.0002422519,
+    -0.00085293897, -0.0005205574,  0.0020340169,    0.00078333891, -0.0042153862,
+    -0.00075614988, 0.0078402944,   -0.000061169922, -0.01344162,   0.0024626821,
+    0.021736089,    -0.007801671,   -0.034090221,    0.01880949,    0.054326009,
+    -0.043596379,   -0.099384367,   0.13207909,      0.46424159};
+
+void fill_mdct_table(double *tab, int size, double scale) {  // mdct.js:21-37
+  const double alpha = (2.0 * M_PI) / (8.0 * size);
+  const double omega = (2.0 * M_PI) / size;
+  const double root = sqrt(scale / size);
+  for (int i = 0; i < size / 4; i++) {
+    const double angle = omega * i + alpha;
+    tab[2 * i] = root * cos(angle);
+    tab[2 * i + 1] = root * sin(angle);
+  }
+}
+
+// fdlibm log1p(10): the k != 0 branch of s_log1p.c evaluated for x = 10 (host, no FMA).
+double fdlibm_log1p_10() {
+  const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+               Lp1 = 6.666666666666735130e-01, Lp2 = 3.999999999940941908e-01,
+               Lp3 = 2.857142874366239149e-01, Lp4 = 2.222219843214978396e-01,
+               Lp5 = 1.818357216161805012e-01, Lp6 = 1.531383769920937332e-01,
+               Lp7 = 1.479819860511658591e-01;
+  // u = 11 = 1.375 * 2^3, hu = 0x60000 < 0x6a09e -> k = 3, f = 0.375, c = 0
+  volatile double f = 0.375;
+  const int k = 3;
+  const double c = 0.0;
+  volatile double hfsq = 0.5 * f * f;
+  volatile double s = f / (2.0 + f);
+  volatile double z = s * s;
+  volatile double R = z * (Lp1 + z * (Lp2 + z * (Lp3 + z * (Lp4 + z * (Lp5 + z * (Lp6 + z * Lp7))))));
+  return k * ln2_hi - ((hfsq - (s * (hfsq + R) + (k * ln2_lo + c))) - f);
+}
+
+void build_dev_tables(const carta1_tables &t, DevTables *d) {
+  memset(d, 0, sizeof(*d));
+  float window[48];
+  for (int i = 0; i < 24; i++) {  // constants.js:83-90
+    const float c = (float)kQmfLiterals[i];
+    window[i] = (float)((double)c * 2.0);
+    window[47 - i] = window[i];
+  }
+  for (int i = 0; i < 24; i++) {  // constants.js:93-107
+    d->qmf_even[i] = (double)window[2 * i];
+    d->qmf_odd[i] = (double)window[2 * i + 1];
+  }
+  memcpy(d->win, t.window_short, sizeof d->win);
+  memcpy(d->sf, t.scale_factors, sizeof d->sf);
+  memcpy(d->mdct_fwd64, t.mdct_fwd64, sizeof d->mdct_fwd64);
+  memcpy(d->mdct_fwd256, t.mdct_fwd256, sizeof d->mdct_fwd256);
+  memcpy(d->mdct_fwd512, t.mdct_fwd512, sizeof d->mdct_fwd512);
+  memcpy(d->mdct_inv64, t.mdct_inv64, sizeof d->mdct_inv64);
+  memcpy(d->mdct_inv256, t.mdct_inv256, sizeof d->mdct_inv256);
+  memcpy(d->mdct_inv512, t.mdct_inv512, sizeof d->mdct_inv512);
+  // FFT twiddles by the recurrence of fft.js:42-65 (restarts for every group, so it is a
+  // pure per-stride table).  volatile keeps the host compiler from contracting.
+  for (int lv = 0; lv < 8; lv++) {
+    const int half = 1 << lv;
+    const double wr = t.fft_w[lv][0], wi = t.fft_w[lv][1];
+    volatile double tr = 1.0, ti = 0.0;
+    for (int k = 0; k < half; k++) {
+      d->fft_tw[half - 1 + k] = make_double2(tr, ti);
+      volatile double a = tr * wr, b = ti * wi, c = tr * wi, e = ti * wr;
+      const double nr = a - b;
+      ti = c + e;
+      tr = nr;
+    }
+  }
+  // Exact findScaleFactor thresholds: thr[k] = largest f32 <= 2^(k/3 - 21), derived with
+  // integer arithmetic (cube roots of 2 and 4 to 24 bits).
+  uint32_t root[3] = {1u << 23, 0, 0};
+  for (int r = 1; r <= 2; r++) {
+    uint32_t lo = 1u << 23, hi = (1u << 24) - 1;
+    const unsigned __int128 target = (unsigned __int128)(r == 1 ? 2 : 4) << 69;
+    while (lo < hi) {
+      const uint32_t mid = lo + (hi - lo + 1) / 2;
+      const unsigned __int128 cube = (unsigned __int128)mid * mid * mid;
+      if (cube <= target) lo = mid; else hi = mid - 1;
+    }
+    root[r] = lo;
+  }
+  for (int k = 0; k < 63; k++) d->sf_thr[k] = (float)ldexp((double)root[k % 3], k / 3 - 21 - 23);
+  d->sf_thr[63] = INFINITY;
+  d->log1p10 = fdlibm_log1p_10();
+  for (int b = 0; b < 52; b++) {
+    d->fmt.specs[b] = (uint8_t)kSpecs[b];
+    d->fmt.start_long[b] = (uint16_t)kStartLong[b];
+    d->fmt.start_short[b] = (uint16_t)kStartShort[b];
+    for (int j = 0; j < kSpecs[b]; j++) {
+      d->fmt.bfu_of_long[kStartLong[b] + j] = (uint8_t)b;
+      d->fmt.bfu_of_short[kStartShort[b] + j] = (uint8_t)b;
+    }
+  }
+}
+
+// DISTORTION_DELTA_FACTORS / WORD_LENGTH_DELTA_BITS (constants.js:162-179)
+double ddf(int i) { return i == 0 ? 2.0 - 0.25 : ldexp(1.0, -(i + 1)) - ldexp(1.0, -(i + 2)); }
+int delta_bits(int i) { return i == 0 ? 2 : 1; }
+
+void build_enc_params(const carta1_tables &t, const carta1_enc_opts &o, DevEncParams *p) {
+  memset(p, 0, sizeof(*p));
+  p->threshold = o.transient_threshold_low;
+  for (int i = 0; i < 64; i++) {  // bitallocation.js:46-61
+    if (o.biased_scale_factors) p->bsf[i] = o.biased_scale_factors[i];
+    else p->bsf[i] = (o.allocation_bias == 1.0) ? t.scale_factors[i] : pow(t.scale_factors[i], o.allocation_bias);
+  }
+  p->use_fixed = o.use_fixed_block_modes ? 1 : 0;
+  for (int i = 0; i < 3; i++) p->fixed[i] = o.fixed_block_modes[i];
+  // Heap priorities as the reference stores them: f32((bsf[sfi] * DDF[wl]) / deltaBits[wl])
+  // (bitallocation.js:226-230,266-269).  rank = index among the distinct values.
+  std::vector<float> pr(64 * 16, 0.0f);
+  std::vector<float> uniq;
+  for (int s = 0; s < 64; s++)
+    for (int w = 0; w < 15; w++) {
+      volatile double dd = p->bsf[s] * ddf(w);
+      const float f = (float)(dd / (double)delta_bits(w));
+      pr[s * 16 + w] = f;
+      uniq.push_back(f);
+    }
+  std::sort(uniq.begin(), uniq.end());
+  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  for (int s = 0; s < 64; s++)
+    for (int w = 0; w < 15; w++)
+      p->rank[s * 16 + w] =
+          (uint16_t)(std::lower_bound(uniq.begin(), uniq.end(), pr[s * 16 + w]) - uniq.begin());
+}
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + (bytes >> 3) + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct carta1_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  carta1_tables tables;
+  DevTables *d_tables = nullptr;
+  DevEncParams *d_params = nullptr;  // params of the most recent whole-buffer/device call
+  std::string err;
+  uint64_t launches = 0;
+  DevBuf bands, mags, modes, coefs, inv, scores, stage_pcm, stage_su, dbg;
+};
+
+struct carta1_encoder {
+  carta1_ctx *ctx;
+  int n_streams;
+  carta1_enc_opts opts;
+  double bsf_copy[64];
+  DevEncParams *d_params = nullptr;
+  float *d_hist = nullptr;  // [n_streams][1024]: the last two frames of PCM per stream
+  DevBuf work, su;
+};
+
+struct carta1_decoder {
+  carta1_ctx *ctx;
+  int n_streams;
+  bool has_prev = false;
+  uint8_t *d_prev = nullptr;  // [n_streams][212]: the previous sound unit per stream
+  DevBuf work, pcm;
+};
+
+namespace {
+
+int fail(carta1_ctx *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->err = msg; else g_create_error = msg;
+  return code;
+}
+int cuda_fail(carta1_ctx *ctx, cudaError_t e, const char *what) {
+  return fail(ctx, CARTA1_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(ctx, call)                                              \
+  do {                                                             \
+    cudaError_t e_ = (call);                                       \
+    if (e_ != cudaSuccess) return cuda_fail((ctx), e_, #call);     \
+  } while (0)
+
+int upload_params(carta1_ctx *ctx, const carta1_enc_opts *opts, DevEncParams *d_params) {
+  carta1_enc_opts o;
+  if (opts) o = *opts; else carta1_default_enc_opts(&o);
+  DevEncParams hp;
+  build_enc_params(ctx->tables, o, &hp);
+  CU(ctx, cudaMemcpyAsync(d_params, &hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));  // hp lives on this stack frame
+  return CARTA1_OK;
+}
+
+int ensure_encode_scratch(carta1_ctx *ctx, size_t units, bool auto_modes) {
+  CU(ctx, ctx->bands.ensure(units * 512 * sizeof(float)));
+  CU(ctx, ctx->coefs.ensure(units * 512 * sizeof(float)));
+  CU(ctx, ctx->modes.ensure(units * 4));
+  if (auto_modes) CU(ctx, ctx->mags.ensure(units * 256 * sizeof(float)));
+  return CARTA1_OK;
+}
+int ensure_decode_scratch(carta1_ctx *ctx, size_t units) {
+  CU(ctx, ctx->coefs.ensure(units * 512 * sizeof(float)));
+  CU(ctx, ctx->inv.ensure(units * 512 * sizeof(float)));
+  CU(ctx, ctx->modes.ensure(units * 4));
+  return CARTA1_OK;
+}
+
+// Frames per pass for the chunked host entry points (bounds scratch and staging memory).
+const size_t kMaxUnitsPerPass = 1u << 19;
+
+}  // namespace
+
+extern "C" {
+
+int carta1_abi_version(void) { return 1; }
+
+void carta1_default_tables(carta1_tables *t) {
+  for (int i = 0; i < 32; i++) t->window_short[i] = sin(((i + 0.5) * M_PI) / 64);  // constants.js:60-66
+  for (int i = 0; i < 64; i++) t->scale_factors[i] = pow(2.0, i / 3.0 - 21);       // constants.js:144-150
+  fill_mdct_table(t->mdct_fwd64, 64, 0.5);                                         // mdct.js:215-221
+  fill_mdct_table(t->mdct_fwd256, 256, 0.5);
+  fill_mdct_table(t->mdct_fwd512, 512, 1.0);
+  fill_mdct_table(t->mdct_inv64, 64, 64 * 8);
+  fill_mdct_table(t->mdct_inv256, 256, 256 * 8);
+  fill_mdct_table(t->mdct_inv512, 512, 512 * 4);
+  for (int k = 0; k < 8; k++) {  // fft.js:36-39
+    const int stride = 2 << k;
+    const double angle = (-2 * M_PI) / stride;
+    t->fft_w[k][0] = cos(angle);
+    t->fft_w[k][1] = sin(angle);
+  }
+}
+
+void carta1_default_enc_opts(carta1_enc_opts *o) {  // options.js:17-23
+  memset(o, 0, sizeof(*o));
+  o->transient_threshold_low = 1.0;
+  o->allocation_bias = 1.0;
+  o->use_fixed_block_modes = 0;
+  o->biased_scale_factors = nullptr;
+}
+
+int carta1_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int carta1_ctx_create(int device, const carta1_tables *tables, carta1_ctx **out) {
+  if (!out) return fail(nullptr, CARTA1_ERR_ARG, "carta1_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, CARTA1_ERR_CUDA,
+                std::string("carta1_b200 needs a CUDA device (sm_100a); none usable: ") +
+                    (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  if (device < 0 || device >= n) return fail(nullptr, CARTA1_ERR_ARG, "carta1_ctx_create: bad device index");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+  carta1_ctx *ctx = new carta1_ctx();
+  ctx->device = device;
+  if (tables) ctx->tables = *tables; else carta1_default_tables(&ctx->tables);
+  DevTables *ht = new DevTables();
+  build_dev_tables(ctx->tables, ht);
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_tables, sizeof(DevTables));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_params, sizeof(DevEncParams));
+  if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tables, ht, sizeof(DevTables), cudaMemcpyHostToDevice);
+  delete ht;
+  if (e != cudaSuccess) {
+    cuda_fail(nullptr, e, "carta1_ctx_create");
+    carta1_ctx_destroy(ctx);
+    return CARTA1_ERR_CUDA;
+  }
+  *out = ctx;
+  return CARTA1_OK;
+}
+
+void carta1_ctx_destroy(carta1_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  ctx->bands.release(); ctx->mags.release(); ctx->modes.release(); ctx->coefs.release();
+  ctx->inv.release(); ctx->scores.release(); ctx->stage_pcm.release(); ctx->stage_su.release();
+  ctx->dbg.release();
+  if (ctx->d_tables) cudaFree(ctx->d_tables);
+  if (ctx->d_params) cudaFree(ctx->d_params);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *carta1_last_error(const carta1_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+int carta1_ctx_sync(carta1_ctx *ctx) {
+  if (!ctx) return CARTA1_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return CARTA1_OK;
+}
+void *carta1_ctx_stream(carta1_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+uint64_t carta1_ctx_launch_count(const carta1_ctx *ctx) { return ctx ? ctx->launches : 0; }
+size_t carta1_frame_count(size_t n_samples) { return (n_samples + 511) / 512; }
+
+// ------------------------------------------------------------------ device-resident
+static int encode_device_impl(carta1_ctx *ctx, const void *d_pcm, int pcm_fmt, size_t row_stride,
+                              int n_ch_interleave, int n_streams, size_t valid_samples, size_t halo_frames,
+                              size_t n_frames, const DevEncParams *d_params, bool use_fixed, uint8_t *d_su,
+                              size_t su_frame_stride, size_t su_stream_stride, float *dbg_bands,
+                              float *dbg_mags, uint8_t *dbg_modes, float *dbg_coefs) {
+  const size_t frames_total = halo_frames + n_frames;
+  const size_t units = frames_total * (size_t)n_streams;
+  if (units == 0) return CARTA1_OK;
+  if (units > 0x7fffffffull / 4) return fail(ctx, CARTA1_ERR_ARG, "carta1: too many sound units in one launch");
+  int rc = ensure_encode_scratch(ctx, units, !use_fixed);
+  if (rc) return rc;
+  EncodeLaunch L;
+  memset(&L, 0, sizeof L);
+  L.pcm = d_pcm; L.pcm_fmt = pcm_fmt; L.row_stride = row_stride; L.n_ch_interleave = n_ch_interleave;
+  L.valid_samples = (long long)valid_samples;
+  L.n_streams = n_streams; L.frames_total = (int)frames_total; L.halo_frames = (int)halo_frames;
+  L.n_out_frames = (int)n_frames; L.use_fixed = use_fixed ? 1 : 0;
+  L.tables = ctx->d_tables; L.params = d_params;
+  L.bands = dbg_bands ? dbg_bands : (float *)ctx->bands.p;
+  L.mags = dbg_mags ? dbg_mags : (float *)ctx->mags.p;
+  L.modes = dbg_modes ? dbg_modes : (uint8_t *)ctx->modes.p;
+  L.coefs = dbg_coefs ? dbg_coefs : (float *)ctx->coefs.p;
+  L.scores = nullptr;
+  L.su_out = d_su; L.su_frame_stride = su_frame_stride; L.su_stream_stride = su_stream_stride;
+  CU(ctx, launch_encode(L, ctx->stream, &ctx->launches));
+  return CARTA1_OK;
+}
+
+static int decode_device_impl(carta1_ctx *ctx, const uint8_t *d_su, size_t su_frame_stride,
+                              size_t su_stream_stride, size_t n_su_valid, int n_streams, size_t halo_frames,
+                              size_t n_frames, void *d_pcm, int pcm_fmt, size_t row_stride, int n_ch_interleave,
+                              float *dbg_coefs, float *dbg_bands) {
+  const size_t frames_total = halo_frames + n_frames;
+  const size_t units = frames_total * (size_t)n_streams;
+  if (units == 0) return CARTA1_OK;
+  if (units > 0x7fffffffull / 4) return fail(ctx, CARTA1_ERR_ARG, "carta1: too many sound units in one launch");
+  int rc = ensure_decode_scratch(ctx, units);
+  if (rc) return rc;
+  DecodeLaunch L;
+  memset(&L, 0, sizeof L);
+  L.su = d_su; L.su_frame_stride = su_frame_stride; L.su_stream_stride = su_stream_stride;
+  L.n_su_valid = (long long)n_su_valid; L.n_streams = n_streams; L.frames_total = (int)frames_total;
+  L.halo_frames = (int)halo_frames; L.n_out_frames = (int)n_frames; L.tables = ctx->d_tables;
+  L.coefs = dbg_coefs ? dbg_coefs : (float *)ctx->coefs.p;
+  L.modes = (uint8_t *)ctx->modes.p;
+  L.inv = (float *)ctx->inv.p;
+  L.bands_dbg = dbg_bands;
+  L.pcm = d_pcm; L.pcm_fmt = pcm_fmt; L.row_stride = row_stride; L.n_ch_interleave = n_ch_interleave;
+  CU(ctx, launch_decode(L, ctx->stream, &ctx->launches));
+  return CARTA1_OK;
+}
+
+int carta1_encode_device(carta1_ctx *ctx, const float *d_pcm, size_t row_stride, int n_streams,
+                         size_t valid_samples, size_t halo_frames, size_t n_frames,
+                         const carta1_enc_opts *opts, uint8_t *d_su, size_t su_frame_stride,
+                         size_t su_stream_stride, int sync) {
+  if (!ctx) return CARTA1_ERR_ARG;
+  if (!d_pcm || !d_su || n_streams <= 0) return fail(ctx, CARTA1_ERR_ARG, "carta1_encode_device: bad argument");
+  if (halo_frames == 1) return fail(ctx, CARTA1_ERR_ARG, "carta1_encode_device: halo_frames must be 0 or >= 2");
+  CU(ctx, cudaSetDevice(ctx->device));
+  int rc = upload_params(ctx, opts, ctx->d_params);
+  if (rc) return rc;
+  const bool fixed = opts && opts->use_fixed_block_modes;
+  rc = encode_device_impl(ctx, d_pcm, 0, row_stride, 1, n_streams, valid_samples, halo_frames, n_frames,
+                          ctx->d_params, fixed, d_su, su_frame_stride, su_stream_stride, nullptr, nullptr,
+                          nullptr, nullptr);
+  if (rc) return rc;
+  if (sync) CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return CARTA1_OK;
+}
+
+int carta1_decode_device(carta1_ctx *ctx, const uint8_t *d_su, size_t su_frame_stride,
+                         size_t su_stream_stride, size_t n_su_valid, int n_streams, size_t halo_frames,
+                         size_t n_frames, float *d_pcm, size_t row_stride, int sync) {
+  if (!ctx) return CARTA1_ERR_ARG;
+  if (!d_su || !d_pcm || n_streams <= 0) return fail(ctx, CARTA1_ERR_ARG, "carta1_decode_device: bad argument");
+  CU(ctx, cudaSetDevice(ctx->device));
+  int rc = decode_device_impl(ctx, d_su, su_frame_stride, su_stream_stride, n_su_valid, n_streams, halo_frames,
+                              n_frames, d_pcm, 0, row_stride, 1, nullptr, nullptr);
+  if (rc) return rc;
+  if (sync) CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return CARTA1_OK;
+}
+
+// ------------------------------------------------------------------ whole buffers (host)
+static int encode_host_impl(carta1_ctx *ctx, const float *const *channels, const int16_t *interleaved,
+                            int n_ch, size_t n_samples, const carta1_enc_opts *opts, uint8_t *su_out,
+                            size_t su_capacity_bytes, size_t *n_su_out) {
+  if (!ctx) return CARTA1_ERR_ARG;
+  // processor.js:598-604
+  if ((n_ch != 1 && n_ch != 2) || (!channels && !interleaved))
+    return fail(ctx, CARTA1_ERR_ARG, "ATRAC1 encoding requires one or two Float32 channels");
+  if (channels)
+    for (int c = 0; c < n_ch; c++)
+      if (!channels[c] && n_samples)
+        return fail(ctx, CARTA1_ERR_ARG, "ATRAC1 encoding requires one or two Float32 channels");
+  const size_t frames = carta1_frame_count(n_samples);
+  const size_t n_su = frames * (size_t)n_ch;
+  if (n_su_out) *n_su_out = n_su;
+  if (n_su == 0) return CARTA1_OK;
+  if (!su_out || su_capacity_bytes < n_su * CARTA1_SU_BYTES)
+    return fail(ctx, CARTA1_ERR_ARG, "carta1_encode_pcm: output buffer too small");
+  CU(ctx, cudaSetDevice(ctx->device));
+  int rc = upload_params(ctx, opts, ctx->d_params);
+  if (rc) return rc;
+  const bool fixed = opts && opts->use_fixed_block_modes;
+  const size_t chunk = std::max<size_t>(16, kMaxUnitsPerPass / (size_t)n_ch);
+  for (size_t a = 0; a < frames; a += chunk) {
+    const size_t b = std::min(frames, a + chunk);
+    const size_t halo = a >= 2 ? 2 : 0;  // a is 0 or >= chunk
+    const size_t first = a - halo;
+    const size_t span = (b - first) * 512;                       // samples staged per row
+    const size_t have = std::min(n_samples - first * 512, span); // samples that exist
+    const void *d_in;
+    size_t row_stride = span;
+    if (channels) {
+      CU(ctx, ctx->stage_pcm.ensure((size_t)n_ch * span * sizeof(float)));
+      for (int c = 0; c < n_ch; c++)
+        CU(ctx, cudaMemcpyAsync((float *)ctx->stage_pcm.p + (size_t)c * span, channels[c] + first * 512,
+                                have * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+      d_in = ctx->stage_pcm.p;
+    } else {
+      CU(ctx, ctx->stage_pcm.ensure((size_t)n_ch * span * sizeof(int16_t)));
+      CU(ctx, cudaMemcpyAsync(ctx->stage_pcm.p, interleaved + first * 512 * (size_t)n_ch,
+                              have * (size_t)n_ch * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+      d_in = ctx->stage_pcm.p;
+    }
+    const size_t out_units = (b - a) * (size_t)n_ch;
+    CU(ctx, ctx->stage_su.ensure(out_units * CARTA1_SU_BYTES));
+    rc = encode_device_impl(ctx, d_in, channels ? 0 : 1, row_stride, n_ch, n_ch, have, halo, b - a,
+                            ctx->d_params, fixed, (uint8_t *)ctx->stage_su.p, (size_t)n_ch, 1, nullptr,
+                            nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(su_out + a * (size_t)n_ch * CARTA1_SU_BYTES, ctx->stage_su.p,
+                            out_units * CARTA1_SU_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return CARTA1_OK;
+}
+
+int carta1_encode_pcm(carta1_ctx *ctx, const float *const *channels, int n_ch, size_t n_samples,
+                      const carta1_enc_opts *opts, uint8_t *su_out, size_t su_capacity_bytes,
+                      size_t *n_su_out) {
+  return encode_host_impl(ctx, channels, nullptr, n_ch, n_samples, opts, su_out, su_capacity_bytes, n_su_out);
+}
+
+int carta1_encode_pcm_s16(carta1_ctx *ctx, const int16_t *interleaved, int n_ch, size_t n_samples,
+                          const carta1_enc_opts *opts, uint8_t *su_out, size_t su_capacity_bytes,
+                          size_t *n_su_out) {
+  return encode_host_impl(ctx, nullptr, interleaved, n_ch, n_samples, opts, su_out, su_capacity_bytes, n_su_out);
+}
+
+static int decode_host_impl(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch,
+                            float *const *channels_out, int16_t *interleaved_out) {
+  if (!ctx) return CARTA1_ERR_ARG;
+  if (n_ch != 1 && n_ch != 2) {  // processor.js:147-157
+    char msg[64];
+    snprintf(msg, sizeof msg, "Unsupported channel count: %d", n_ch);
+    return fail(ctx, CARTA1_ERR_ARG, msg);
+  }
+  if (n_su && !su) return fail(ctx, CARTA1_ERR_ARG, "ATRAC1 decoding requires AEA bytes or a Blob");
+  const size_t frames = (n_su + (size_t)n_ch - 1) / (size_t)n_ch;
+  if (frames == 0) return CARTA1_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t chunk = std::max<size_t>(16, kMaxUnitsPerPass / (size_t)n_ch);
+  for (size_t a = 0; a < frames; a += chunk) {
+    const size_t b = std::min(frames, a + chunk);
+    const size_t halo = a >= 1 ? 1 : 0;
+    const size_t first = a - halo;
+    const size_t want_units = (b - first) * (size_t)n_ch;
+    const size_t have_units = std::min(n_su - first * (size_t)n_ch, want_units);
+    CU(ctx, ctx->stage_su.ensure(want_units * CARTA1_SU_BYTES));
+    CU(ctx, cudaMemcpyAsync(ctx->stage_su.p, su + first * (size_t)n_ch * CARTA1_SU_BYTES,
+                            have_units * CARTA1_SU_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t span = (b - a) * 512;
+    int rc;
+    if (channels_out) {
+      CU(ctx, ctx->stage_pcm.ensure((size_t)n_ch * span * sizeof(float)));
+      rc = decode_device_impl(ctx, (const uint8_t *)ctx->stage_su.p, (size_t)n_ch, 1, have_units, n_ch, halo,
+                              b - a, ctx->stage_pcm.p, 0, span, n_ch, nullptr, nullptr);
+      if (rc) return rc;
+      for (int c = 0; c < n_ch; c++)
+        CU(ctx, cudaMemcpyAsync(channels_out[c] + a * 512, (float *)ctx->stage_pcm.p + (size_t)c * span,
+                                span * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      CU(ctx, ctx->stage_pcm.ensure((size_t)n_ch * span * sizeof(int16_t)));
+      rc = decode_device_impl(ctx, (const uint8_t *)ctx->stage_su.p, (size_t)n_ch, 1, have_units, n_ch, halo,
+                              b - a, ctx->stage_pcm.p, 1, span, n_ch, nullptr, nullptr);
+      if (rc) return rc;
+      CU(ctx, cudaMemcpyAsync(interleaved_out + a * 512 * (size_t)n_ch, ctx->stage_pcm.p,
+                              (size_t)n_ch * span * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return CARTA1_OK;
+}
+
+int carta1_decode_su(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch, float *const *channels_out) {
+  if (ctx && !channels_out) return fail(ctx, CARTA1_ERR_ARG, "carta1_decode_su: channels_out is NULL");
+  return decode_host_impl(ctx, su, n_su, n_ch, channels_out, nullptr);
+}
+int carta1_decode_su_s16(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch, int16_t *interleaved_out) {
+  if (ctx && !interleaved_out) return fail(ctx, CARTA1_ERR_ARG, "carta1_decode_su_s16: output is NULL");
+  return decode_host_impl(ctx, su, n_su, n_ch, nullptr, interleaved_out);
+}
+
+// ------------------------------------------------------------------ stateful closures
+int carta1_enc_create(carta1_ctx *ctx, const carta1_enc_opts *opts, int n_streams, carta1_encoder **out) {
+  if (!ctx) return CARTA1_ERR_ARG;
+  if (!out || n_streams <= 0) return fail(ctx, CARTA1_ERR_ARG, "carta1_enc_create: bad argument");
+  CU(ctx, cudaSetDevice(ctx->device));
+  carta1_encoder *e = new carta1_encoder();
+  e->ctx = ctx;
+  e->n_streams = n_streams;
+  if (opts) e->opts = *opts; else carta1_default_enc_opts(&e->opts);
+  if (e->opts.biased_scale_factors) {
+    memcpy(e->bsf_copy, e->opts.biased_scale_factors, sizeof e->bsf_copy);
+    e->opts.biased_scale_factors = e->bsf_copy;
+  }
+  cudaError_t ce = cudaMalloc(&e->d_params, sizeof(DevEncParams));
+  if (ce == cudaSuccess) ce = cudaMalloc(&e->d_hist, (size_t)n_streams * 1024 * sizeof(float));
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(e->d_hist, 0, (size_t)n_streams * 1024 * sizeof(float), ctx->stream);
+  if (ce != cudaSuccess) { carta1_enc_destroy(e); return cuda_fail(ctx, ce, "carta1_enc_create"); }
+  int rc = upload_params(ctx, &e->opts, e->d_params);
+  if (rc) { carta1_enc_destroy(e); return rc; }
+  *out = e;
+  return CARTA1_OK;
+}
+
+void carta1_enc_destroy(carta1_encoder *e) {
+  if (!e) return;
+  cudaSetDevice(e->ctx->device);
+  cudaStreamSynchronize(e->ctx->stream);
+  if (e->d_params) cudaFree(e->d_params);
+  if (e->d_hist) cudaFree(e->d_hist);
+  e->work.release(); e->su.release();
+  delete e;
+}
+
+int carta1_enc_reset(carta1_encoder *e) {
+  if (!e) return CARTA1_ERR_ARG;
+  carta1_ctx *ctx = e->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMemsetAsync(e->d_hist, 0, (size_t)e->n_streams * 1024 * sizeof(float), ctx->stream));
+  return CARTA1_OK;
+}
+
+// The encoder's carried state (BufferPool: QMF delays, MDCT overlap, previous magnitude
+// spectra) is a function of the last 650 PCM samples, so the handle
+// keeps the last two frames of PCM per stream and re-derives it.
+int carta1_enc_frames(carta1_encoder *e, const float *pcm, int n_frames, uint8_t *su_out) {
+  if (!e) return CARTA1_ERR_ARG;
+  carta1_ctx *ctx = e->ctx;
+  if (n_frames < 0 || (n_frames && (!pcm || !su_out))) return fail(ctx, CARTA1_ERR_ARG, "carta1_enc_frames: bad argument");
+  if (n_frames == 0) return CARTA1_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t ns = (size_t)e->n_streams;
+  const size_t row = (size_t)(n_frames + 2) * 512;
+  CU(ctx, e->work.ensure(ns * row * sizeof(float)));
+  CU(ctx, e->su.ensure(ns * (size_t)n_frames * CARTA1_SU_BYTES));
+  float *w = (float *)e->work.p;
+  CU(ctx, cudaMemcpy2DAsync(w, row * sizeof(float), e->d_hist, 1024 * sizeof(float), 1024 * sizeof(float), ns,
+                            cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(ctx, cudaMemcpy2DAsync(w + 1024, row * sizeof(float), pcm, (size_t)n_frames * 512 * sizeof(float),
+                            (size_t)n_frames * 512 * sizeof(float), ns, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = encode_device_impl(ctx, w, 0, row, 1, e->n_streams, row, 2, (size_t)n_frames, e->d_params,
+                              e->opts.use_fixed_block_modes != 0, (uint8_t *)e->su.p, 1, (size_t)n_frames,
+                              nullptr, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  CU(ctx, cudaMemcpy2DAsync(e->d_hist, 1024 * sizeof(float), w + (size_t)n_frames * 512, row * sizeof(float),
+                            1024 * sizeof(float), ns, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(su_out, e->su.p, ns * (size_t)n_frames * CARTA1_SU_BYTES, cudaMemcpyDeviceToHost,
+                          ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return CARTA1_OK;
+}
+
+int carta1_dec_create(carta1_ctx *ctx, int n_streams, carta1_decoder **out) {
+  if (!ctx) return CARTA1_ERR_ARG;
+  if (!out || n_streams <= 0) return fail(ctx, CARTA1_ERR_ARG, "carta1_dec_create: bad argument");
+  CU(ctx, cudaSetDevice(ctx->device));
+  carta1_decoder *d = new carta1_decoder();
+  d->ctx = ctx;
+  d->n_streams = n_streams;
+  cudaError_t ce = cudaMalloc(&d->d_prev, (size_t)n_streams * CARTA1_SU_BYTES);
+  if (ce != cudaSuccess) { delete d; return cuda_fail(ctx, ce, "carta1_dec_create"); }
+  *out = d;
+  return CARTA1_OK;
+}
+
+void carta1_dec_destroy(carta1_decoder *d) {
+  if (!d) return;
+  cudaSetDevice(d->ctx->device);
+  cudaStreamSynchronize(d->ctx->stream);
+  if (d->d_prev) cudaFree(d->d_prev);
+  d->work.release(); d->pcm.release();
+  delete d;
+}
+
+int carta1_dec_reset(carta1_decoder *d) {
+  if (!d) return CARTA1_ERR_ARG;
+  d->has_prev = false;
+  return CARTA1_OK;
+}
+
+// The decoder's carried state (QMF delays, IMDCT tails) is a function of the previous
+// sound unit alone, so the handle keeps that unit per stream.
+int carta1_dec_frames(carta1_decoder *d, const uint8_t *su, int n_frames, float *pcm_out) {
+  if (!d) return CARTA1_ERR_ARG;
+  carta1_ctx *ctx = d->ctx;
+  if (n_frames < 0 || (n_frames && (!su || !pcm_out))) return fail(ctx, CARTA1_ERR_ARG, "carta1_dec_frames: bad argument");
+  if (n_frames == 0) return CARTA1_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t ns = (size_t)d->n_streams;
+  const size_t halo = d->has_prev ? 1 : 0;
+  const size_t fr = (size_t)n_frames + halo;
+  CU(ctx, d->work.ensure(ns * fr * CARTA1_SU_BYTES));
+  CU(ctx, d->pcm.ensure(ns * (size_t)n_frames * 512 * sizeof(float)));
+  uint8_t *w = (uint8_t *)d->work.p;  // [stream][frame][212]
+  if (halo)
+    CU(ctx, cudaMemcpy2DAsync(w, fr * CARTA1_SU_BYTES, d->d_prev, CARTA1_SU_BYTES, CARTA1_SU_BYTES, ns,
+                              cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(ctx, cudaMemcpy2DAsync(w + halo * CARTA1_SU_BYTES, fr * CARTA1_SU_BYTES, su,
+                            (size_t)n_frames * CARTA1_SU_BYTES, (size_t)n_frames * CARTA1_SU_BYTES, ns,
+                            cudaMemcpyHostToDevice, ctx->stream));
+  int rc = decode_device_impl(ctx, w, 1, fr, ns * fr, d->n_streams, halo, (size_t)n_frames, d->pcm.p, 0,
+                              (size_t)n_frames * 512, 1, nullptr, nullptr);
+  if (rc) return rc;
+  CU(ctx, cudaMemcpy2DAsync(d->d_prev, CARTA1_SU_BYTES, w + (fr - 1) * CARTA1_SU_BYTES, fr * CARTA1_SU_BYTES,
+                            CARTA1_SU_BYTES, ns, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(pcm_out, d->pcm.p, ns * (size_t)n_frames * 512 * sizeof(float), cudaMemcpyDeviceToHost,
+                          ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  d->has_prev = true;
+  return CARTA1_OK;
+}
+
+// ------------------------------------------------------------------ stage taps
+int carta1_debug_encode_stages(carta1_ctx *ctx, const float *pcm, size_t n_samples, const carta1_enc_opts *opts,
+                               float *bands, float *mags, int32_t *modes, float *coefs, uint8_t *su) {
+  if (!ctx) return CARTA1_ERR_ARG;
+  const size_t frames = carta1_frame_count(n_samples);
+  if (frames == 0) return CARTA1_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  int rc = upload_params(ctx, opts, ctx->d_params);
+  if (rc) return rc;
+  const bool fixed = opts && opts->use_fixed_block_modes;
+  // layout: pcm | bands | mags | coefs | su | modes
+  const size_t o_bands = frames * 512, o_mags = o_bands + frames * 512, o_coefs = o_mags + frames * 256,
+               o_su = o_coefs + frames * 512, o_modes = o_su + (frames * 212 + 3) / 4 + 1,
+               total = o_modes + frames + 1;
+  CU(ctx, ctx->dbg.ensure(total * sizeof(float)));
+  float *base = (float *)ctx->dbg.p;
+  CU(ctx, cudaMemsetAsync(base, 0, total * sizeof(float), ctx->stream));
+  CU(ctx, cudaMemcpyAsync(base, pcm, n_samples * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  rc = encode_device_impl(ctx, base, 0, frames * 512, 1, 1, n_samples, 0, frames, ctx->d_params, fixed,
+                          (uint8_t *)(base + o_su), 1, frames, base + o_bands, base + o_mags,
+                          (uint8_t *)(base + o_modes), base + o_coefs);
+  if (rc) return rc;
+  if (bands) CU(ctx, cudaMemcpyAsync(bands, base + o_bands, frames * 512 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (mags) CU(ctx, cudaMemcpyAsync(mags, base + o_mags, frames * 256 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (coefs) CU(ctx, cudaMemcpyAsync(coefs, base + o_coefs, frames * 512 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (su) CU(ctx, cudaMemcpyAsync(su, base + o_su, frames * 212, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<uint8_t> m(frames * 4);
+  CU(ctx, cudaMemcpyAsync(m.data(), base + o_modes, frames * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (modes)
+    for (size_t f = 0; f < frames; f++)
+      for (int b = 0; b < 3; b++)
+        modes[f * 3 + b] = fixed ? opts->fixed_block_modes[b] : (int32_t)m[f * 4 + b];
+  return CARTA1_OK;
+}
+
+int carta1_debug_decode_stages(carta1_ctx *ctx, const uint8_t *su, size_t n_su, float *coefs, float *bands,
+                               float *pcm) {
+  if (!ctx) return CARTA1_ERR_ARG;
+  if (n_su == 0) return CARTA1_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t o_coefs = (n_su * 212 + 3) / 4 + 1, o_bands = o_coefs + n_su * 512, o_pcm = o_bands + n_su * 512,
+               total = o_pcm + n_su * 512;
+  CU(ctx, ctx->dbg.ensure(total * sizeof(float)));
+  float *base = (float *)ctx->dbg.p;
+  CU(ctx, cudaMemcpyAsync(base, su, n_su * 212, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = decode_device_impl(ctx, (const uint8_t *)base, 1, n_su, n_su, 1, 0, n_su, base + o_pcm, 0, n_su * 512, 1,
+                              base + o_coefs, base + o_bands);
+  if (rc) return rc;
+  if (coefs) CU(ctx, cudaMemcpyAsync(coefs, base + o_coefs, n_su * 512 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (bands) CU(ctx, cudaMemcpyAsync(bands, base + o_bands, n_su * 512 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (pcm) CU(ctx, cudaMemcpyAsync(pcm, base + o_pcm, n_su * 512 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return CARTA1_OK;
+}
+
+// ------------------------------------------------------------------ AEA container
+int carta1_aea_write_header(const char *title, uint32_t su_count, int n_ch, uint8_t out[CARTA1_AEA_HEADER_BYTES]) {
+  // serialization.js:190-211
+  if (!out) return CARTA1_ERR_ARG;
+  memset(out, 0, CARTA1_AEA_HEADER_BYTES);
+  out[1] = 0x08;
+  if (title) {
+    size_t n = strlen(title);
+    if (n > 255) n = 255;
+    memcpy(out + 4, title, n);
+  }
+  out[260] = (uint8_t)su_count;
+  out[261] = (uint8_t)(su_count >> 8);
+  out[262] = (uint8_t)(su_count >> 16);
+  out[263] = (uint8_t)(su_count >> 24);
+  out[264] = (uint8_t)n_ch;
+  return CARTA1_OK;
+}
+
+int carta1_aea_parse_header(const uint8_t *hdr, size_t len, char title_out[257], uint32_t *su_count, int *n_ch) {
+  // serialization.js:222-253
+  if (!hdr || len != CARTA1_AEA_HEADER_BYTES) return fail(nullptr, CARTA1_ERR_ARG, "Header must be 2048 bytes");
+  if (hdr[0] != 0 || hdr[1] != 8 || hdr[2] != 0 || hdr[3] != 0) return fail(nullptr, CARTA1_ERR_ARG, "Invalid AEA file");
+  size_t end = 4;
+  while (end < CARTA1_AEA_HEADER_BYTES && hdr[end] != 0) end++;
+  size_t tl = end == CARTA1_AEA_HEADER_BYTES ? 256 : end - 4;
+  if (tl > 256) tl = 256;
+  if (title_out) { memcpy(title_out, hdr + 4, tl); title_out[tl] = 0; }
+  if (su_count) *su_count = (uint32_t)hdr[260] | ((uint32_t)hdr[261] << 8) | ((uint32_t)hdr[262] << 16) | ((uint32_t)hdr[263] << 24);
+  if (n_ch) *n_ch = hdr[264];
+  return CARTA1_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// c1_common.cuh -- shared device/host declarations for the carta1_b200 kernels.
+//
+// Numerical contract: "binary64 compute, binary32 store, no FMA".
+// The whole library is compiled with -fmad=false so nvcc never contracts a*b+c; the only
+// fused operations are the explicit fma() calls in the QMF kernels, where both factors are
+// widened binary32 values and the product is therefore exact (Appendix A.2).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace c1 {
+
+constexpr int kFrame = 512;
+constexpr int kSuBytes = 212;
+constexpr int kSuWords = 53;
+constexpr int kNumBfu = 52;
+constexpr int kFrameBits = 1696;
+
+// Format tables (codec/core/constants.js:29-52,141-143).  Device copies live in
+// __constant__ memory (c1_tables.cu); they are indexed warp-uniformly or nearly so.
+struct FormatTables {
+  uint8_t specs[52];        // SPECS_PER_BFU
+  uint16_t start_long[52];  // BFU_START_LONG
+  uint16_t start_short[52]; // BFU_START_SHORT
+  uint8_t bfu_of_long[512]; // inverse maps: coefficient position -> BFU index
+  uint8_t bfu_of_short[512];
+};
+
+// libm-derived tables, uploaded once per context (global memory, read through L1).
+struct DevTables {
+  double qmf_even[24];  // QMF_EVEN / QMF_ODD widened to binary64 (exact)
+  double qmf_odd[24];
+  double win[32];       // WINDOW_SHORT
+  double sf[64];        // SCALE_FACTORS
+  double mdct_fwd64[32], mdct_fwd256[128], mdct_fwd512[256];
+  double mdct_inv64[32], mdct_inv256[128], mdct_inv512[256];
+  // FFT twiddles by the reference's recurrence (codec/transforms/fft.js:42-65): for half
+  // stride h the k-th twiddle sits at index (h - 1 + k); (re, im) pairs.
+  double2 fft_tw[255];
+  float sf_thr[64];     // 63 thresholds of the exact findScaleFactor table (+1 pad)
+  double log1p10;       // fdlibm log1p(10), the constant divisor of transient.js:211
+  FormatTables fmt;
+};
+
+// Per-encoder parameters (EncoderOptions + tables derived from allocationBias).
+struct DevEncParams {
+  double threshold;
+  double bsf[64];        // biased scale factors
+  float zero_scale[64];  // unused pad / reserved
+  uint16_t rank[64 * 16];// priority rank of (sfi, wl): order-isomorphic to the f32 priority
+  int32_t use_fixed;
+  int32_t fixed[3];
+};
+
+// ECMAScript ToInt32 (`| 0`, codec/coding/quantization.js:51).
+__device__ __forceinline__ int js_to_int32(double x) {
+  if (fabs(x) < 2147483648.0) return __double2int_rz(x);  // also false for NaN
+  if (!isfinite(x)) return 0;
+  double t = trunc(x);
+  double m = fmod(t, 4294967296.0);
+  if (m < 0) m += 4294967296.0;
+  return (int)(unsigned int)(unsigned long long)m;
+}
+
+__device__ __forceinline__ int band_of_bfu(int b) { return b < 20 ? 0 : (b < 36 ? 1 : 2); }
+__device__ __forceinline__ int band_of_coef(int c) { return c < 128 ? 0 : (c < 256 ? 1 : 2); }
+__device__ __forceinline__ int wl_bits(int wl) { return wl == 0 ? 0 : wl + 1; }  // WORD_LENGTH_BITS
+
+}  // namespace c1

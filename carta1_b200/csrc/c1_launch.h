@@ -1,0 +1,62 @@
+// c1_launch.h -- host-side launch descriptors shared by the ABI layer and the kernel files.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace c1 {
+
+struct DevTables;
+struct DevEncParams;
+
+// One encode pass over `n_streams` rows of (halo_frames + n_out_frames) frames each.
+struct EncodeLaunch {
+  const void *pcm;          // f32 planar rows (pcm_fmt 0) or s16 interleaved (pcm_fmt 1)
+  int pcm_fmt;
+  size_t row_stride;        // floats between rows (pcm_fmt 0)
+  int n_ch_interleave;      // channel count of the interleaved s16 source (pcm_fmt 1)
+  long long valid_samples;  // samples present per row; the rest reads as zero
+  int n_streams;
+  int frames_total;         // halo_frames + n_out_frames
+  int halo_frames;
+  int n_out_frames;
+  int use_fixed;
+  const DevTables *tables;
+  const DevEncParams *params;
+  // scratch, [n_streams][frames_total][...]
+  float *bands;             // 512 per unit
+  float *mags;              // 256 per unit (auto modes only)
+  uint8_t *modes;           // 4 per unit   (auto modes only)
+  double *scores;           // 3 per unit, optional
+  float *coefs;             // 512 per unit
+  // output
+  uint8_t *su_out;          // may be NULL (stage taps only)
+  size_t su_frame_stride, su_stream_stride;
+};
+
+struct DecodeLaunch {
+  const uint8_t *su;        // unit (f, s) at su + (f*su_frame_stride + s*su_stream_stride)*212
+  size_t su_frame_stride, su_stream_stride;
+  long long n_su_valid;     // linear unit indices >= this decode as the dummy frame
+  int n_streams;
+  int frames_total;         // halo_frames + n_out_frames
+  int halo_frames;
+  int n_out_frames;
+  const DevTables *tables;
+  // scratch, [n_streams][frames_total][...]
+  float *coefs;             // 512 per unit
+  uint8_t *modes;           // 4 per unit
+  float *inv;               // 512 per unit: IMDCT output before overlap-add
+  float *bands_dbg;         // optional 512 per unit: time-domain bands (stage tap)
+  // output
+  void *pcm;                // f32 planar rows (pcm_fmt 0) or s16 interleaved (pcm_fmt 1); may be NULL
+  int pcm_fmt;
+  size_t row_stride;
+  int n_ch_interleave;
+};
+
+cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, uint64_t *launches);
+cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, uint64_t *launches);
+
+}  // namespace c1

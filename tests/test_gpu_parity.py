@@ -1,0 +1,208 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  Bit-exact for sound units, block modes and every f32 intermediate."""
+import numpy as np
+import pytest
+
+import signals as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import carta1_b200
+
+    c = carta1_b200.Context(0)
+    yield c
+    c.close()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def oracle_encode_stages(O, pcm, options):
+    enc = O.FrameEncoder(options)
+    nf = O.frame_count(len(pcm))
+    x = np.zeros(nf * 512, np.float32)
+    x[:len(pcm)] = pcm
+    out = dict(bands=[], mags=[], modes=[], coefs=[], su=[])
+    for f in range(nf):
+        fr, dbg = enc(x[512 * f:512 * f + 512], debug=True)
+        out["bands"].append(np.array(dbg.bands, np.float32))
+        out["mags"].append(np.array(dbg.mags, np.float32))
+        out["coefs"].append(np.array(dbg.coefs, np.float32))
+        out["modes"].append(list(fr.modes))
+        out["su"].append(O.serialize_frame(fr))
+    return {k: np.array(v) for k, v in out.items()}
+
+
+def mono_signals():
+    rng = np.random.default_rng(11)
+    sigs = {
+        "transients": S.cfg3_transients(0.6, n_ch=1)[0],
+        "sine_noise": S.cfg1_stereo(0.4)[0],
+        "chirp": S.cfg2_stereo(0.4)[1],
+        "white": (rng.uniform(-1, 1, 512 * 9)).astype(np.float32),
+        "silence": np.zeros(512 * 4, np.float32),
+        "tiny": (1e-7 * rng.standard_normal(512 * 5)).astype(np.float32),
+        "loud": (4.0 * rng.standard_normal(512 * 5)).astype(np.float32),
+        "sparse": np.where(rng.uniform(size=512 * 6) > 0.97, rng.standard_normal(512 * 6), 0).astype(np.float32),
+        "ragged": (0.3 * rng.standard_normal(512 * 3 + 77)).astype(np.float32),
+    }
+    return sigs
+
+
+OPTION_SETS = [
+    dict(),
+    dict(fixed_modes=[0, 0, 0]),
+    dict(fixed_modes=[2, 2, 3]),
+    dict(fixed_modes=[0, 2, 0]),
+    dict(threshold=0.3),
+    dict(bias=0.0),
+    dict(bias=0.5),
+    dict(bias=2.5),
+    dict(bias=5.0, threshold=0.6),
+]
+
+
+def both_opts(O, kw):
+    import carta1_b200
+
+    o = O.make_options(threshold=kw.get("threshold", 1.0), bias=kw.get("bias", 1.0), fixed_modes=kw.get("fixed_modes"))
+    g = carta1_b200.make_enc_opts(kw.get("threshold", 1.0), kw.get("bias", 1.0), kw.get("fixed_modes"))
+    return o, g
+
+
+@pytest.mark.parametrize("kw", OPTION_SETS, ids=[str(k) for k in OPTION_SETS])
+def test_encode_stages_match_oracle(ctx, oracle, kw):
+    o_opt, g_opt = both_opts(oracle, kw)
+    for name, pcm in mono_signals().items():
+        want = oracle_encode_stages(oracle, pcm, o_opt)
+        got = ctx.debug_encode_stages(pcm, g_opt)
+        assert np.array_equal(bits(got["bands"]), bits(want["bands"])), (name, "bands")
+        if "fixed_modes" not in kw:
+            assert np.array_equal(bits(got["mags"]), bits(want["mags"])), (name, "mags")
+        assert np.array_equal(got["modes"], want["modes"]), (name, "modes")
+        assert np.array_equal(bits(got["coefs"]), bits(want["coefs"])), (name, "coefs")
+        assert np.array_equal(got["su"], want["su"]), (name, "sound units")
+
+
+def test_decode_stages_match_oracle(ctx, oracle):
+    for name, pcm in mono_signals().items():
+        su = oracle.encode_pcm([pcm])
+        dec = oracle.FrameDecoder()
+        coefs, bands, out = [], [], []
+        for u in su:
+            p, dbg = dec(oracle.deserialize_frame(u), debug=True)
+            coefs.append(np.array(dbg.coefs, np.float32))
+            bands.append(np.array(dbg.bands, np.float32))
+            out.append(p)
+        got = ctx.debug_decode_stages(su)
+        assert np.array_equal(bits(got["coefs"]), bits(np.array(coefs))), (name, "coefs")
+        assert np.array_equal(bits(got["bands"]), bits(np.array(bands))), (name, "bands")
+        assert np.array_equal(bits(got["pcm"]), bits(np.array(out))), (name, "pcm")
+
+
+def test_decode_arbitrary_bytes(ctx, oracle):
+    """Malformed input fidelity: random bytes exercise every header value,
+    word lengths that run past the 212-byte buffer and scale-factor index 0."""
+    rng = np.random.default_rng(5)
+    su = rng.integers(0, 256, (64, 212), dtype=np.uint8)
+    su[::7, 2:30] = 0xFF  # maximal word lengths -> reads beyond the buffer
+    want = oracle.decode_su(su, 1)[0]
+    got = ctx.decode_su(su, 1)[0]
+    assert np.array_equal(bits(got), bits(want))
+
+
+@pytest.mark.parametrize("n", [0, 1, 511, 512, 513, 1024, 5000])
+def test_whole_buffer_lengths(ctx, oracle, n):
+    rng = np.random.default_rng(n)
+    a = (0.4 * rng.standard_normal(n)).astype(np.float32)
+    b = (0.4 * rng.standard_normal(max(n - 100, 0))).astype(np.float32)
+    for chans in ([a], [a, b]):
+        if n == 0:
+            assert len(ctx.encode_pcm(chans)) == 0
+            continue
+        su = ctx.encode_pcm(chans)
+        want = oracle.encode_pcm(chans)
+        assert np.array_equal(su, want)
+        pcm = ctx.decode_su(su, len(chans))
+        ref = oracle.decode_su(want, len(chans))
+        for x, y in zip(pcm, ref):
+            assert np.array_equal(bits(x), bits(y))
+
+
+def test_cfg1_stereo_bitexact(ctx, oracle):
+    """BASELINE config 1: 10 s stereo sine+noise, default bias, auto block modes."""
+    chans = S.cfg1_stereo(10.0)
+    su = ctx.encode_pcm(chans)
+    want = oracle.encode_pcm(chans, threads=8, chunk_frames=64)
+    assert su.shape == (1724, 212)
+    assert np.array_equal(su, want)
+    pcm = ctx.decode_su(su, 2)
+    ref = oracle.decode_su(want, 2, threads=8, chunk_frames=64)
+    for x, y in zip(pcm, ref):
+        assert np.array_equal(bits(x), bits(y))
+    # 16-bit WAV quantisation is bit-exact as well (processor.js:382-389)
+    s16 = ctx.decode_su_s16(su, 2).reshape(-1, 2)
+    for c in range(2):
+        assert np.array_equal(s16[:, c], oracle.pcm_to_int16(ref[c]))
+
+
+def test_stereo_odd_unit_count_uses_dummy_frame(ctx, oracle):
+    chans = S.cfg1_stereo(0.1)
+    su = oracle.encode_pcm(chans)[:-1]
+    pcm = ctx.decode_su(su, 2)
+    ref = oracle.decode_su(su, 2)
+    for x, y in zip(pcm, ref):
+        assert np.array_equal(bits(x), bits(y))
+
+
+def test_s16_ingest(ctx, oracle):
+    rng = np.random.default_rng(3)
+    x = rng.integers(-32768, 32768, (4000, 2), dtype=np.int16)
+    su = ctx.encode_pcm_s16(x, 2)
+    chans = [oracle.int16_to_pcm(x[:, 0].copy()), oracle.int16_to_pcm(x[:, 1].copy())]
+    assert np.array_equal(su, oracle.encode_pcm(chans))
+
+
+def test_stateful_streams_match_whole_buffer(ctx, oracle):
+    """The batched closure API (config 4 shape): any split into calls gives the whole-stream bytes."""
+    import carta1_b200
+
+    x = S.cfg4_mono_streams(6, 0.35)
+    nf = x.shape[1] // 512
+    x = x[:, :nf * 512]
+    want = np.stack([oracle.encode_pcm([x[s]]) for s in range(6)])
+    for split in ([nf], [1] * nf, [1, 2, 5, nf - 8]):
+        enc = carta1_b200.StreamEncoder(ctx, None, 6)
+        dec = carta1_b200.StreamDecoder(ctx, 6)
+        outs, pcms, pos = [], [], 0
+        for k in split:
+            su = enc.frames(x[:, 512 * pos:512 * (pos + k)])
+            outs.append(su)
+            pcms.append(dec.frames(su))
+            pos += k
+        got = np.concatenate(outs, axis=1)
+        assert np.array_equal(got, want), split
+        pcm = np.concatenate(pcms, axis=1).reshape(6, -1)
+        for s in range(6):
+            assert np.array_equal(bits(pcm[s]), bits(oracle.decode_su(want[s], 1)[0])), split
+        enc.close()
+        dec.close()
+
+
+def test_chunked_host_path(ctx, oracle, monkeypatch):
+    """More frames than one pass holds: the halo logic of the chunked entry points."""
+    chans = S.cfg3_transients(3.0, n_ch=2)
+    su = ctx.encode_pcm(chans)
+    want = oracle.encode_pcm(chans, threads=8, chunk_frames=32)
+    assert np.array_equal(su, want)
+
+
+def test_error_messages(ctx):
+    with pytest.raises(TypeError, match="one or two Float32 channels"):
+        ctx.encode_pcm([np.zeros(10, np.float32)] * 3)
+    with pytest.raises(ValueError, match="Unsupported channel count: 3"):
+        ctx.decode_su(np.zeros((3, 212), np.uint8), 3)
