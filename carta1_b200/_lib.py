@@ -55,7 +55,8 @@ EXPORTED_SYMBOLS = [
     "carta1_dec_create", "carta1_dec_destroy", "carta1_dec_reset", "carta1_dec_frames",
     "carta1_encode_device", "carta1_decode_device", "carta1_ctx_sync", "carta1_ctx_stream",
     "carta1_ctx_launch_count", "carta1_debug_encode_stages", "carta1_debug_decode_stages",
-    "carta1_aea_write_header", "carta1_aea_parse_header",
+    "carta1_aea_write_header", "carta1_aea_parse_header", "carta1_kernel_count", "carta1_kernel_name",
+    "carta1_ctx_profile", "carta1_ctx_profile_read",
 ]
 
 _lib = None
@@ -107,6 +108,11 @@ def load():
     L.carta1_ctx_stream.restype = vp
     L.carta1_ctx_launch_count.argtypes = [vp]
     L.carta1_ctx_launch_count.restype = C.c_uint64
+    L.carta1_kernel_count.restype = C.c_int
+    L.carta1_kernel_name.argtypes = [C.c_int]
+    L.carta1_kernel_name.restype = C.c_char_p
+    L.carta1_ctx_profile.argtypes = [vp, C.c_int]
+    L.carta1_ctx_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
     L.carta1_debug_encode_stages.argtypes = [vp, vp, sz, C.POINTER(EncOpts), vp, vp, vp, vp, vp]
     L.carta1_debug_decode_stages.argtypes = [vp, vp, sz, vp, vp, vp]
     L.carta1_aea_write_header.argtypes = [C.c_char_p, C.c_uint32, C.c_int, vp]
@@ -239,6 +245,30 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.L.carta1_ctx_launch_count(self.h))
+
+    def profile(self, enable: bool):
+        self._check(self.L.carta1_ctx_profile(self.h, int(enable)))
+
+    def profile_read(self) -> dict:
+        """{kernel name: (total ms, launches)} since the last read; synchronises."""
+        n = self.L.carta1_kernel_count()
+        ms = (C.c_double * n)()
+        cnt = (C.c_uint64 * n)()
+        self._check(self.L.carta1_ctx_profile_read(self.h, ms, cnt, n))
+        return {self.L.carta1_kernel_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n) if cnt[i]}
+
+    # ---- whole buffers into caller-provided (e.g. pinned) arrays
+    def encode_pcm_into(self, chans, su_out: np.ndarray, opts: EncOpts | None = None) -> int:
+        n = len(chans[0])
+        ptrs = (C.POINTER(C.c_float) * len(chans))(*[c.ctypes.data_as(C.POINTER(C.c_float)) for c in chans])
+        n_su = C.c_size_t()
+        self._check(self.L.carta1_encode_pcm(self.h, ptrs, len(chans), n, C.byref(opts) if opts is not None else None,
+                                             _ptr(su_out), su_out.nbytes, C.byref(n_su)))
+        return n_su.value
+
+    def decode_su_into(self, su: np.ndarray, n_su: int, n_ch: int, outs) -> None:
+        ptrs = (C.POINTER(C.c_float) * len(outs))(*[c.ctypes.data_as(C.POINTER(C.c_float)) for c in outs])
+        self._check(self.L.carta1_decode_su(self.h, _ptr(su), n_su, n_ch, ptrs))
 
     # ---- stage taps
     def debug_encode_stages(self, pcm: np.ndarray, opts: EncOpts | None = None):

@@ -186,7 +186,11 @@ struct carta1_ctx {
   DevTables *d_tables = nullptr;
   DevEncParams *d_params = nullptr;  // params of the most recent whole-buffer/device call
   std::string err;
-  uint64_t launches = 0;
+  Prof prof;
+  // cache of the parameters resident in d_params
+  bool params_valid = false;
+  carta1_enc_opts params_opts;
+  double params_bsf[64];
   DevBuf bands, mags, modes, coefs, inv, scores, stage_pcm, stage_su, dbg;
 };
 
@@ -226,6 +230,19 @@ int cuda_fail(carta1_ctx *ctx, cudaError_t e, const char *what) {
 int upload_params(carta1_ctx *ctx, const carta1_enc_opts *opts, DevEncParams *d_params) {
   carta1_enc_opts o;
   if (opts) o = *opts; else carta1_default_enc_opts(&o);
+  if (d_params == ctx->d_params) {  // skip the rebuild + upload when nothing changed
+    const carta1_enc_opts &c = ctx->params_opts;
+    bool same = ctx->params_valid && c.transient_threshold_low == o.transient_threshold_low &&
+                c.allocation_bias == o.allocation_bias && c.use_fixed_block_modes == o.use_fixed_block_modes &&
+                memcmp(c.fixed_block_modes, o.fixed_block_modes, sizeof c.fixed_block_modes) == 0 &&
+                (c.biased_scale_factors != nullptr) == (o.biased_scale_factors != nullptr);
+    if (same && o.biased_scale_factors)
+      same = memcmp(ctx->params_bsf, o.biased_scale_factors, sizeof ctx->params_bsf) == 0;
+    if (same) return CARTA1_OK;
+    ctx->params_valid = true;
+    ctx->params_opts = o;
+    if (o.biased_scale_factors) memcpy(ctx->params_bsf, o.biased_scale_factors, sizeof ctx->params_bsf);
+  }
   DevEncParams hp;
   build_enc_params(ctx->tables, o, &hp);
   CU(ctx, cudaMemcpyAsync(d_params, &hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
@@ -339,7 +356,38 @@ int carta1_ctx_sync(carta1_ctx *ctx) {
   return CARTA1_OK;
 }
 void *carta1_ctx_stream(carta1_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
-uint64_t carta1_ctx_launch_count(const carta1_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t carta1_ctx_launch_count(const carta1_ctx *ctx) { return ctx ? ctx->prof.launches : 0; }
+
+int carta1_kernel_count(void) { return K_COUNT; }
+const char *carta1_kernel_name(int id) { return kernel_name(id); }
+
+int carta1_ctx_profile(carta1_ctx *ctx, int enable) {
+  if (!ctx) return CARTA1_ERR_ARG;
+  ctx->prof.on = enable != 0;
+  return CARTA1_OK;
+}
+
+int carta1_ctx_profile_read(carta1_ctx *ctx, double *ms_out, uint64_t *count_out, int n) {
+  if (!ctx) return CARTA1_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int id = 0; id < K_COUNT; id++) {
+    double total = 0.0;
+    for (auto &pr : ctx->prof.ev[id]) {
+      float ms = 0.0f;
+      cudaEventElapsedTime(&ms, pr.first, pr.second);
+      total += ms;
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    if (id < n) {
+      if (ms_out) ms_out[id] = total;
+      if (count_out) count_out[id] = ctx->prof.ev[id].size();
+    }
+    ctx->prof.ev[id].clear();
+  }
+  return CARTA1_OK;
+}
 size_t carta1_frame_count(size_t n_samples) { return (n_samples + 511) / 512; }
 
 // ------------------------------------------------------------------ device-resident
@@ -367,7 +415,7 @@ static int encode_device_impl(carta1_ctx *ctx, const void *d_pcm, int pcm_fmt, s
   L.coefs = dbg_coefs ? dbg_coefs : (float *)ctx->coefs.p;
   L.scores = nullptr;
   L.su_out = d_su; L.su_frame_stride = su_frame_stride; L.su_stream_stride = su_stream_stride;
-  CU(ctx, launch_encode(L, ctx->stream, &ctx->launches));
+  CU(ctx, launch_encode(L, ctx->stream, &ctx->prof));
   return CARTA1_OK;
 }
 
@@ -391,7 +439,7 @@ static int decode_device_impl(carta1_ctx *ctx, const uint8_t *d_su, size_t su_fr
   L.inv = (float *)ctx->inv.p;
   L.bands_dbg = dbg_bands;
   L.pcm = d_pcm; L.pcm_fmt = pcm_fmt; L.row_stride = row_stride; L.n_ch_interleave = n_ch_interleave;
-  CU(ctx, launch_decode(L, ctx->stream, &ctx->launches));
+  CU(ctx, launch_decode(L, ctx->stream, &ctx->prof));
   return CARTA1_OK;
 }
 

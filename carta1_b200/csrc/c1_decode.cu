@@ -324,27 +324,32 @@ synth_kernel(const float *__restrict__ inv, const uint8_t *__restrict__ modes, i
   }
 }
 
-cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, uint64_t *launches) {
+cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, Prof *prof) {
   const int n_units = L.n_streams * L.frames_total;
   if (n_units == 0) return cudaSuccess;
+  prof->begin(K_UNPACK_DEQUANT, st);
   unpack_dequant_kernel<<<(n_units + 3) / 4, 128, 0, st>>>(L.su, L.su_frame_stride, L.su_stream_stride,
                                                          L.n_su_valid, L.frames_total, n_units, L.tables,
                                                          L.coefs, L.modes);
+  prof->end(K_UNPACK_DEQUANT, st);
+  prof->begin(K_IMDCT, st);
   imdct_kernel<<<(n_units + 3) / 4, 128, 0, st>>>(L.coefs, L.modes, n_units, L.tables, L.inv);
-  (*launches) += 2;
+  prof->end(K_IMDCT, st);
   if (L.bands_dbg) {
+    prof->begin(K_BANDS_TIME, st);
     bands_time_kernel<<<n_units, 256, 0, st>>>(L.inv, L.modes, L.frames_total, n_units, L.tables, L.bands_dbg);
-    (*launches)++;
+    prof->end(K_BANDS_TIME, st);
   }
   if (L.pcm) {
     dim3 grid((L.frames_total + kSynTile - 1) / kSynTile, L.n_streams);
+    prof->begin(K_SYNTH, st);
     if (L.pcm_fmt == 0)
       synth_kernel<0><<<grid, 256, 0, st>>>(L.inv, L.modes, L.frames_total, L.halo_frames, L.tables, L.pcm,
                                            L.row_stride, L.n_ch_interleave);
     else
       synth_kernel<1><<<grid, 256, 0, st>>>(L.inv, L.modes, L.frames_total, L.halo_frames, L.tables, L.pcm,
                                            L.row_stride, L.n_ch_interleave);
-    (*launches)++;
+    prof->end(K_SYNTH, st);
   }
   return cudaGetLastError();
 }

@@ -603,41 +603,49 @@ alloc_quant_pack_kernel(const float *__restrict__ coefs, const uint8_t *__restri
 // ------------------------------------------------------------------------------------
 size_t alloc_quant_pack_smem_bytes() { return sizeof(AqSmem); }
 
-cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, uint64_t *launches) {
+const char *kernel_name(int id) {
+  static const char *names[K_COUNT] = {"qmf_analysis", "band_mags", "transient_modes", "mdct",
+                                       "alloc_quant_pack", "unpack_dequant", "imdct", "bands_time", "synth"};
+  return id >= 0 && id < K_COUNT ? names[id] : "?";
+}
+
+cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
   const int frames = L.frames_total;
   const int n_su = L.n_streams * frames;
   if (n_su == 0) return cudaSuccess;
   {
     dim3 grid((frames + kQmfTile - 1) / kQmfTile, L.n_streams);
+    prof->begin(K_QMF_ANALYSIS, st);
     if (L.pcm_fmt == 0)
       qmf_analysis_kernel<0><<<grid, 256, 0, st>>>(L.pcm, L.row_stride, L.n_ch_interleave, L.valid_samples,
                                                   frames, L.tables, L.bands);
     else
       qmf_analysis_kernel<1><<<grid, 256, 0, st>>>(L.pcm, L.row_stride, L.n_ch_interleave, L.valid_samples,
                                                   frames, L.tables, L.bands);
-    (*launches)++;
+    prof->end(K_QMF_ANALYSIS, st);
   }
   if (!L.use_fixed) {
+    prof->begin(K_BAND_MAGS, st);
     band_mags_kernel<<<(n_su + 3) / 4, 128, 0, st>>>(L.bands, n_su, L.tables, L.mags);
+    prof->end(K_BAND_MAGS, st);
+    prof->begin(K_TRANSIENT_MODES, st);
     transient_modes_kernel<<<(n_su * 3 + 127) / 128, 128, 0, st>>>(L.mags, frames, n_su, L.tables, L.params,
                                                                   L.modes, L.scores);
-    (*launches) += 2;
+    prof->end(K_TRANSIENT_MODES, st);
   }
+  prof->begin(K_MDCT, st);
   mdct_kernel<<<(n_su + 3) / 4, 128, 0, st>>>(L.bands, L.modes, frames, n_su, L.tables, L.params, L.coefs);
-  (*launches)++;
+  prof->end(K_MDCT, st);
   const long long n_units = (long long)L.n_streams * L.n_out_frames;
   if (n_units > 0 && L.su_out) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(alloc_quant_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(AqSmem));
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
+    cudaError_t e = cudaFuncSetAttribute(alloc_quant_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(AqSmem));
+    if (e != cudaSuccess) return e;
+    prof->begin(K_ALLOC_QUANT_PACK, st);
     alloc_quant_pack_kernel<<<(unsigned)((n_units + kAqSu - 1) / kAqSu), kAqThreads, sizeof(AqSmem), st>>>(
         L.coefs, L.modes, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params, L.su_out,
         L.su_frame_stride, L.su_stream_stride);
-    (*launches)++;
+    prof->end(K_ALLOC_QUANT_PACK, st);
   }
   return cudaGetLastError();
 }

@@ -5,6 +5,9 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <utility>
+#include <vector>
+
 namespace c1 {
 
 struct DevTables;
@@ -56,7 +59,32 @@ struct DecodeLaunch {
   int n_ch_interleave;
 };
 
-cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, uint64_t *launches);
-cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, uint64_t *launches);
+// Launch accounting and optional per-kernel CUDA-event timing (bench.py's roofline leg).
+enum KernelId {
+  K_QMF_ANALYSIS = 0, K_BAND_MAGS, K_TRANSIENT_MODES, K_MDCT, K_ALLOC_QUANT_PACK,
+  K_UNPACK_DEQUANT, K_IMDCT, K_BANDS_TIME, K_SYNTH, K_COUNT
+};
+const char *kernel_name(int id);
+
+struct Prof {
+  bool on = false;
+  uint64_t launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[K_COUNT];
+  void begin(int id, cudaStream_t st) {
+    launches++;
+    if (!on) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+    ev[id].push_back({a, b});
+  }
+  void end(int id, cudaStream_t st) {
+    if (on) cudaEventRecord(ev[id].back().second, st);
+  }
+};
+
+cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof);
+cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, Prof *prof);
 
 }  // namespace c1

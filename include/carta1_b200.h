@@ -141,6 +141,15 @@ void *carta1_ctx_stream(carta1_ctx *ctx); /* cudaStream_t the work is enqueued o
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 uint64_t carta1_ctx_launch_count(const carta1_ctx *ctx);
 
+/* Per-kernel CUDA-event timing (bench.py's roofline leg).  While enabled every kernel launch
+ * is bracketed by events on the context's stream; profile_read synchronises, returns the
+ * summed milliseconds and launch counts per kernel id (0 .. carta1_kernel_count()-1) and
+ * clears the records. */
+int carta1_kernel_count(void);
+const char *carta1_kernel_name(int id);
+int carta1_ctx_profile(carta1_ctx *ctx, int enable);
+int carta1_ctx_profile_read(carta1_ctx *ctx, double *ms_out, uint64_t *count_out, int n);
+
 /* ---- stage-level taps for parity tests (host memory, small inputs) ---------------
  * Run the encode path on one row of PCM and return the intermediates the oracle also
  * exposes: bands [n_frames][512], transient magnitudes [n_frames][256], block modes
