@@ -126,6 +126,9 @@ void build_dev_tables(const carta1_tables &t, DevTables *d) {
       d->fmt.bfu_of_long[kStartLong[b] + j] = (uint8_t)b;
       d->fmt.bfu_of_short[kStartShort[b] + j] = (uint8_t)b;
     }
+    static const int kSizes[8] = {4, 6, 7, 8, 9, 10, 12, 20};
+    for (int c = 0; c < 8; c++)
+      if (kSizes[c] == kSpecs[b]) d->fmt.size_class[b] = (uint8_t)c;
   }
 }
 
@@ -133,7 +136,10 @@ void build_dev_tables(const carta1_tables &t, DevTables *d) {
 double ddf(int i) { return i == 0 ? 2.0 - 0.25 : ldexp(1.0, -(i + 1)) - ldexp(1.0, -(i + 2)); }
 int delta_bits(int i) { return i == 0 ? 2 : 1; }
 
-void build_enc_params(const carta1_tables &t, const carta1_enc_opts &o, DevEncParams *p) {
+// Returns false if the priorities cannot be represented by the 15-bit keys (only possible
+// with pathological injected scale factors: zero, negative, non-finite or f32-subnormal).
+bool build_enc_params(const carta1_tables &t, const carta1_enc_opts &o, DevEncParams *p) {
+  static const int kSizes[8] = {4, 6, 7, 8, 9, 10, 12, 20};
   memset(p, 0, sizeof(*p));
   p->threshold = o.transient_threshold_low;
   for (int i = 0; i < 64; i++) {  // bitallocation.js:46-61
@@ -142,23 +148,38 @@ void build_enc_params(const carta1_tables &t, const carta1_enc_opts &o, DevEncPa
   }
   p->use_fixed = o.use_fixed_block_modes ? 1 : 0;
   for (int i = 0; i < 3; i++) p->fixed[i] = o.fixed_block_modes[i];
-  // Heap priorities as the reference stores them: f32((bsf[sfi] * DDF[wl]) / deltaBits[wl])
-  // (bitallocation.js:226-230,266-269).  rank = index among the distinct values.
-  std::vector<float> pr(64 * 16, 0.0f);
-  std::vector<float> uniq;
   for (int s = 0; s < 64; s++)
+    for (int c = 0; c < 8; c++) {  // bitallocation.js:86-87
+      volatile double twice = p->bsf[s] * 2.0;
+      p->zero_bit[s * 8 + c] = (float)(twice * (double)kSizes[c]);
+    }
+  // Heap priorities as the reference stores them: f32((bsf[sfi] * DDF[wl]) / deltaBits[wl])
+  // (bitallocation.js:226-230,266-269).
+  uint32_t pr[64][15];
+  std::vector<uint32_t> mant;
+  for (int s = 1; s < 64; s++) {
     for (int w = 0; w < 15; w++) {
       volatile double dd = p->bsf[s] * ddf(w);
       const float f = (float)(dd / (double)delta_bits(w));
-      pr[s * 16 + w] = f;
-      uniq.push_back(f);
+      uint32_t bits;
+      memcpy(&bits, &f, 4);
+      const uint32_t e = (bits >> 23) & 0xFF;
+      if ((bits >> 31) || e == 0 || e == 0xFF) return false;
+      pr[s][w] = bits;
+      if (w >= 2 && bits != pr[s][w - 1] - (1u << 23)) return false;  // halves exactly
     }
-  std::sort(uniq.begin(), uniq.end());
-  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
-  for (int s = 0; s < 64; s++)
-    for (int w = 0; w < 15; w++)
-      p->rank[s * 16 + w] =
-          (uint16_t)(std::lower_bound(uniq.begin(), uniq.end(), pr[s * 16 + w]) - uniq.begin());
+    mant.push_back(pr[s][0] & 0x7FFFFF);
+    mant.push_back(pr[s][1] & 0x7FFFFF);
+  }
+  std::sort(mant.begin(), mant.end());
+  mant.erase(std::unique(mant.begin(), mant.end()), mant.end());
+  for (int s = 1; s < 64; s++)
+    for (int w = 0; w < 2; w++) {
+      const uint32_t m = (uint32_t)(std::lower_bound(mant.begin(), mant.end(), pr[s][w] & 0x7FFFFF) - mant.begin());
+      const uint16_t key = (uint16_t)((((pr[s][w] >> 23) & 0xFF) << 7) | m);
+      (w == 0 ? p->key0 : p->key1)[s] = key;
+    }
+  return true;
 }
 
 struct DevBuf {
@@ -191,7 +212,7 @@ struct carta1_ctx {
   bool params_valid = false;
   carta1_enc_opts params_opts;
   double params_bsf[64];
-  DevBuf bands, mags, modes, coefs, inv, scores, stage_pcm, stage_su, dbg;
+  DevBuf bands, mags, modes, coefs, inv, scores, stage_pcm, stage_su, dbg, recs;
 };
 
 struct carta1_encoder {
@@ -244,7 +265,10 @@ int upload_params(carta1_ctx *ctx, const carta1_enc_opts *opts, DevEncParams *d_
     if (o.biased_scale_factors) memcpy(ctx->params_bsf, o.biased_scale_factors, sizeof ctx->params_bsf);
   }
   DevEncParams hp;
-  build_enc_params(ctx->tables, o, &hp);
+  if (!build_enc_params(ctx->tables, o, &hp)) {
+    if (d_params == ctx->d_params) ctx->params_valid = false;
+    return fail(ctx, CARTA1_ERR_ARG, "carta1: biased scale factors must be positive, finite and normal in binary32");
+  }
   CU(ctx, cudaMemcpyAsync(d_params, &hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));  // hp lives on this stack frame
   return CARTA1_OK;
@@ -341,7 +365,7 @@ void carta1_ctx_destroy(carta1_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->bands.release(); ctx->mags.release(); ctx->modes.release(); ctx->coefs.release();
   ctx->inv.release(); ctx->scores.release(); ctx->stage_pcm.release(); ctx->stage_su.release();
-  ctx->dbg.release();
+  ctx->dbg.release(); ctx->recs.release();
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_params) cudaFree(ctx->d_params);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -402,6 +426,7 @@ static int encode_device_impl(carta1_ctx *ctx, const void *d_pcm, int pcm_fmt, s
   if (units > 0x7fffffffull / 4) return fail(ctx, CARTA1_ERR_ARG, "carta1: too many sound units in one launch");
   int rc = ensure_encode_scratch(ctx, units, !use_fixed);
   if (rc) return rc;
+  CU(ctx, ctx->recs.ensure((size_t)n_streams * n_frames * alloc_rec_bytes()));
   EncodeLaunch L;
   memset(&L, 0, sizeof L);
   L.pcm = d_pcm; L.pcm_fmt = pcm_fmt; L.row_stride = row_stride; L.n_ch_interleave = n_ch_interleave;
@@ -414,6 +439,7 @@ static int encode_device_impl(carta1_ctx *ctx, const void *d_pcm, int pcm_fmt, s
   L.modes = dbg_modes ? dbg_modes : (uint8_t *)ctx->modes.p;
   L.coefs = dbg_coefs ? dbg_coefs : (float *)ctx->coefs.p;
   L.scores = nullptr;
+  L.alloc_recs = ctx->recs.p;
   L.su_out = d_su; L.su_frame_stride = su_frame_stride; L.su_stream_stride = su_stream_stride;
   CU(ctx, launch_encode(L, ctx->stream, &ctx->prof));
   return CARTA1_OK;

@@ -17,14 +17,14 @@ constexpr int kSuWords = 53;
 constexpr int kNumBfu = 52;
 constexpr int kFrameBits = 1696;
 
-// Format tables (codec/core/constants.js:29-52,141-143).  Device copies live in
-// __constant__ memory (c1_tables.cu); they are indexed warp-uniformly or nearly so.
+// Format tables (codec/core/constants.js:29-52,141-143), part of DevTables.
 struct FormatTables {
   uint8_t specs[52];        // SPECS_PER_BFU
   uint16_t start_long[52];  // BFU_START_LONG
   uint16_t start_short[52]; // BFU_START_SHORT
   uint8_t bfu_of_long[512]; // inverse maps: coefficient position -> BFU index
   uint8_t bfu_of_short[512];
+  uint8_t size_class[52];   // index of SPECS_PER_BFU[b] in {4,6,7,8,9,10,12,20}
 };
 
 // libm-derived tables, uploaded once per context (global memory, read through L1).
@@ -47,8 +47,11 @@ struct DevTables {
 struct DevEncParams {
   double threshold;
   double bsf[64];        // biased scale factors
-  float zero_scale[64];  // unused pad / reserved
-  uint16_t rank[64 * 16];// priority rank of (sfi, wl): order-isomorphic to the f32 priority
+  // zero_bit[sfi*8 + size_class] = f32((bsf[sfi] * 2.0) * size)   (bitallocation.js:86-87)
+  float zero_bit[64 * 8];
+  // 15-bit order-isomorphic images of the f32 heap priorities (bitallocation.js:226-230,
+  // 266-269): key0 for word length 0, key1 for word length 1; each further step is -128.
+  uint16_t key0[64], key1[64];
   int32_t use_fixed;
   int32_t fixed[3];
 };

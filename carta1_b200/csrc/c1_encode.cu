@@ -328,58 +328,215 @@ mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, 
 }
 
 // ------------------------------------------------------------------------------------
-// K4: scale factors, RDO bit allocation (literal max-heap emulation), quantisation and
-// 212-byte packing.  One CTA = 128 threads = 16 sound units; 8 threads per unit run the 8
-// candidate BFU counts' heaps concurrently.
+// K4a: scale factors + RDO bit allocation by literal max-heap emulation
+// (bitallocation.js:74-341).  One CTA = 256 threads = 32 sound units; warp w runs candidate
+// BFU count BFU_AMOUNTS[w] for all 32 units (lane = unit), so the lanes of a warp execute
+// loops of similar length.
 //
-// Heap entries are one 32-bit word: rank[31:22] | sfi[21:16] | wl[11:8] | bfu[5:0].  `rank`
-// is the position of the entry's f32 priority among all distinct priorities of this
-// encoder (DevEncParams::rank), so comparing ranks is comparing the reference's
-// Float32Array priorities, ties included.  The heap is stored node-major / thread-minor, so
-// the 32 lanes of a warp always hit 32 different banks.
+// Heap entries are one 32-bit word: key[24:10] | wl[9:6] | bfu[5:0].  `key` is an
+// order-isomorphic 15-bit image of the reference's Float32Array priority (DevEncParams::key0/
+// key1): f32 exponent (8 bits) over the rank of the f32 mantissa among the 126 possible
+// ones.  For wl >= 1 the priority halves exactly with every step, i.e. key -= 128.
+// Heaps are stored node-major / lane-minor: a warp's 32 lanes always hit 32 distinct banks.
 // ------------------------------------------------------------------------------------
-constexpr int kAqSu = 16;
-constexpr int kAqThreads = 128;
+constexpr int kAlSu = 32;
+constexpr int kAlThreads = 256;
+constexpr int kAlHeapSlots = 308;  // sum over candidates of (cand + 1)
+constexpr int kAlWlSlots = 300;    // sum over candidates of cand
 
-struct AqSmem {
-  float coef[kAqSu][512];
-  uint32_t heap[52][kAqThreads];
-  uint8_t wl[52][kAqThreads];
-  double nf[kAqSu][52];
-  float zero_bit[kAqSu][52];
-  uint32_t words[kAqSu][56];
-  uint16_t rank[1024];
-  uint16_t base[kAqSu][52];
-  uint8_t sfi[kAqSu][52];
-  uint8_t wlf[kAqSu][52];
-  uint8_t mode[kAqSu][4];
-  int nbfu[kAqSu];
+struct AllocRec {  // per sound unit, global scratch between K4a and K4b
+  uint8_t n_bfu, pad[3];
+  uint8_t wl[52];
+  uint8_t sfi[52];
+  uint8_t pad2[4];
+};
+static_assert(sizeof(AllocRec) == 112, "AllocRec layout");
+
+struct AlSmem {
+  uint32_t heap[kAlHeapSlots][32];
+  uint8_t wl[kAlWlSlots][32];
+  double dist[8][32];
+  uint16_t key0[64], key1[64];
+  uint8_t sfi[kAlSu][52];
+  uint8_t mode[kAlSu][4];
+  uint8_t specs[52];
+  int best[kAlSu];
 };
 
-__device__ __forceinline__ void heap_sift(uint32_t *H, int start, int size) {  // bitallocation.js:314-341
+__device__ __forceinline__ void heap_sift(uint32_t (*H)[32], int lane, int start, int size, uint32_t v) {
+  // bitallocation.js:314-341; v is the entry being placed, H[start] is the hole
   int i = start;
-  const uint32_t v = H[i * kAqThreads];
-  const uint32_t vr = v >> 22;
+  const uint32_t vm = v | 0x3FFu;
   for (;;) {
     const int l = 2 * i + 1;
     if (l >= size) break;
-    const int r = l + 1;
-    const uint32_t cl = H[l * kAqThreads];
-    int max_i = i;
-    uint32_t max_r = vr;
-    uint32_t moved = cl;
-    if ((cl >> 22) > max_r) { max_i = l; max_r = cl >> 22; }
-    if (r < size) {
-      const uint32_t cr = H[r * kAqThreads];
-      if ((cr >> 22) > max_r) { max_i = r; moved = cr; }
-    }
-    if (max_i == i) break;
-    H[i * kAqThreads] = moved;
-    i = max_i;
+    const uint32_t cl = H[l][lane];
+    const uint32_t cr = H[l + 1][lane];  // slot `size` is kept zero
+    const bool pl = cl > vm;
+    const uint32_t m = pl ? (cl | 0x3FFu) : vm;
+    const bool pr = cr > m;
+    if (!(pl || pr)) break;
+    H[i][lane] = pr ? cr : cl;
+    i = pr ? l + 1 : l;
   }
-  H[i * kAqThreads] = v;
+  H[i][lane] = v;
 }
 
+__global__ void __launch_bounds__(kAlThreads)
+alloc_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes, int frames, int halo,
+             int n_out_frames, int n_streams, const DevTables *__restrict__ T,
+             const DevEncParams *__restrict__ P, AllocRec *__restrict__ recs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  AlSmem &S = *reinterpret_cast<AlSmem *>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long n_units = (long long)n_streams * n_out_frames;
+  const long long unit0 = (long long)blockIdx.x * kAlSu;
+  const FormatTables &F = T->fmt;
+
+  if (tid < 64) { S.key0[tid] = P->key0[tid]; S.key1[tid] = P->key1[tid]; }
+  if (tid < 52) S.specs[tid] = F.specs[tid];
+  if (tid < kAlSu * 3) {
+    const int u = tid / 3, b = tid - u * 3;
+    const long long unit = unit0 + u;
+    uint8_t m = 0;
+    if (unit < n_units) {
+      const size_t su = (size_t)(unit / n_out_frames) * frames + halo + (size_t)(unit % n_out_frames);
+      m = P->use_fixed ? (uint8_t)(P->fixed[b] != 0) : modes[su * 4 + b];
+    }
+    S.mode[u][b] = m;
+  }
+  __syncthreads();
+
+  // ---- phase A: scale-factor index per BFU (bitallocation.js:290-299).  The log2/ceil of
+  // the reference equals 3*(E+21) + #{thresholds of the binade below max} (DevTables::sf_thr).
+  for (int item = tid; item < kAlSu * 52; item += kAlThreads) {
+    const int u = item / 52, b = item - u * 52;
+    const long long unit = unit0 + u;
+    int sfi = 0;
+    if (unit < n_units) {
+      const size_t su = (size_t)(unit / n_out_frames) * frames + halo + (size_t)(unit % n_out_frames);
+      const int sz = F.specs[b];
+      const int start = S.mode[u][band_of_bfu(b)] == 0 ? F.start_long[b] : F.start_short[b];
+      const float *src = coefs + su * 512 + start;
+      float mx = 0.0f;
+      for (int j = 0; j < sz; j++) {
+        const float a = fabsf(src[j]);
+        if (a > mx) mx = a;  // NaN never wins, as in the reference
+      }
+      if (mx > 0.0f) {
+        const uint32_t bits = __float_as_uint(mx);
+        const int e3 = 3 * ((int)(bits >> 23) - 127 + 21);
+        if (e3 >= 63) sfi = 63;
+        else if (e3 >= 0) {
+          sfi = e3 + (mx > T->sf_thr[e3]) + (mx > T->sf_thr[e3 + 1]) + (mx > T->sf_thr[e3 + 2]);
+          if (sfi > 63) sfi = 63;
+        }
+      }
+    }
+    S.sfi[u][b] = (uint8_t)sfi;
+  }
+  __syncthreads();
+
+  // ---- phase B: warp = candidate, lane = unit
+  {
+    const int u = lane;
+    const int c = warp;
+    const int cand = c == 0 ? 20 : 24 + 4 * c;               // BFU_AMOUNTS
+    const int hbase = c == 0 ? 0 : (21 + (c - 1) * 29 + 2 * (c - 1) * (c - 2));  // prefix of (cand+1)
+    const int wbase = hbase - c;                              // prefix of cand
+    uint32_t (*H)[32] = &S.heap[hbase];
+    uint8_t (*W)[32] = &S.wl[wbase];
+    const bool live = unit0 + u < n_units;
+    double total = 0.0;
+    if (live) {
+      int remaining = kFrameBits - 40 - 10 * cand;  // bitallocation.js:97-100
+      int count = 0;
+      for (int b = 0; b < cand; b++) {               // bitallocation.js:216-232
+        W[b][lane] = 0;
+        const uint32_t sfi = S.sfi[u][b];
+        if (sfi) {
+          H[count][lane] = ((uint32_t)S.key0[sfi] << 10) | (uint32_t)b;
+          count++;
+        }
+      }
+      for (int i = count; i <= cand; i++) H[i][lane] = 0;
+      if (count) {
+        for (int i = (count >> 1) - 1; i >= 0; i--) heap_sift(H, lane, i, count, H[i][lane]);
+        int size = count;
+        uint32_t e = H[0][lane];
+        while (remaining > 0 && size > 0) {  // bitallocation.js:244-278
+          const int b = e & 63;
+          const int wl = (e >> 6) & 15;
+          const int cost = (int)S.specs[b] << (wl == 0);
+          bool pop = cost > remaining;
+          if (!pop) {
+            remaining -= cost;
+            if (wl == 0) e = ((uint32_t)S.key1[S.sfi[u][b]] << 10) | (1u << 6) | (uint32_t)b;
+            else e += 64u - (128u << 10);  // wl + 1, priority halves exactly
+            pop = wl == 14;                // reached MAX_WORD_LENGTH_INDEX
+          }
+          if (pop) {
+            W[b][lane] = (uint8_t)((e >> 6) & 15);
+            size--;
+            e = H[size][lane];
+            H[size][lane] = 0;
+            if (size == 0) break;
+          }
+          heap_sift(H, lane, 0, size, e);
+          e = H[0][lane];
+        }
+        for (int i = 0; i < size; i++) {
+          const uint32_t x = H[i][lane];
+          W[x & 63][lane] = (uint8_t)((x >> 6) & 15);
+        }
+      }
+      // total distortion of this candidate (bitallocation.js:157-190), index order
+      for (int i = 0; i < 52; i++) {
+        const int sfi = S.sfi[u][i];
+        if (sfi == 0) continue;  // contributes +0.0 or is skipped by the reference
+        const int bits = i < cand ? wl_bits(W[i][lane]) : 0;
+        if (bits == 0) {
+          total += (double)P->zero_bit[sfi * 8 + F.size_class[i]];
+        } else {
+          const double inv = __hiloint2double((1023 - bits) << 20, 0);
+          total += P->bsf[sfi] * inv * (double)S.specs[i];
+        }
+      }
+    }
+    S.dist[c][u] = total;
+    __syncthreads();
+    if (warp == 0 && live) {  // first strict minimum over ascending candidates (:122-129)
+      double min_total = __longlong_as_double(0x7ff0000000000000ll);
+      int best = -1;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const double t = S.dist[k][u];
+        if (t < min_total) { min_total = t; best = k; }
+      }
+      S.best[u] = best;
+    }
+    __syncthreads();
+    if (live) {
+      const int best = S.best[u];
+      AllocRec *r = recs + (unit0 + u);
+      if (best == c) {
+        r->n_bfu = (uint8_t)cand;
+        for (int b = 0; b < 52; b++) {
+          r->wl[b] = b < cand ? W[b][lane] : 0;
+          r->sfi[b] = S.sfi[u][b];
+        }
+      } else if (best < 0 && c == 0) {  // bitallocation.js:132-139
+        r->n_bfu = 20;
+        for (int b = 0; b < 52; b++) { r->wl[b] = 0; r->sfi[b] = 0; }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// K4b: quantise (quantization.js:34-56) and pack the 212-byte unit
+// (serialization.js:41-98, bitstream.js:15-39).  One warp per sound unit.
+// ------------------------------------------------------------------------------------
 __device__ __forceinline__ void put_bits(uint32_t *words, int pos, uint32_t value, int bits) {
   const int w = pos >> 5, off = pos & 31;
   const unsigned long long v = (unsigned long long)value << (64 - off - bits);
@@ -388,224 +545,103 @@ __device__ __forceinline__ void put_bits(uint32_t *words, int pos, uint32_t valu
   if (lo) atomicOr(&words[w + 1], lo);
 }
 
-__global__ void __launch_bounds__(kAqThreads)
-alloc_quant_pack_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes, int frames,
-                        int halo, int n_out_frames, int n_streams, const DevTables *__restrict__ T,
-                        const DevEncParams *__restrict__ P, uint8_t *__restrict__ su_out,
-                        size_t su_frame_stride, size_t su_stream_stride) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  AqSmem &S = *reinterpret_cast<AqSmem *>(smem_raw);
-  const int tid = threadIdx.x;
-  const long long n_units = (long long)n_streams * n_out_frames;
-  const long long unit0 = (long long)blockIdx.x * kAqSu;
+constexpr int kQpWarps = 8;
+
+__global__ void __launch_bounds__(kQpWarps * 32)
+quant_pack_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes,
+                  const AllocRec *__restrict__ recs, int frames, int halo, int n_out_frames, int n_streams,
+                  const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
+                  uint8_t *__restrict__ su_out, size_t su_frame_stride, size_t su_stream_stride) {
+  __shared__ uint32_t s_words[kQpWarps][56];
+  __shared__ double s_nf[kQpWarps][52];
+  __shared__ uint16_t s_base[kQpWarps][52];
+  __shared__ uint8_t s_bits[kQpWarps][52];
+  __shared__ uint8_t s_bfu_long[512], s_bfu_short[512];
+  __shared__ uint16_t s_start_long[52], s_start_short[52];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const FormatTables &F = T->fmt;
-
-  // ---- load: coefficients, modes, rank table
-  for (int i = tid; i < 1024; i += kAqThreads) S.rank[i] = P->rank[i];
-  for (int u = 0; u < kAqSu; u++) {
-    const long long unit = unit0 + u;
-    if (unit >= n_units) break;
-    const int stream = (int)(unit / n_out_frames);
-    const int frame = halo + (int)(unit % n_out_frames);
-    const size_t su = (size_t)stream * frames + frame;
-    const float4 v = reinterpret_cast<const float4 *>(coefs + su * 512)[tid];
-    reinterpret_cast<float4 *>(S.coef[u])[tid] = v;
-    if (tid < 3) S.mode[u][tid] = P->use_fixed ? (uint8_t)(P->fixed[tid] != 0) : modes[su * 4 + tid];
-  }
+  for (int i = tid; i < 512; i += kQpWarps * 32) { s_bfu_long[i] = F.bfu_of_long[i]; s_bfu_short[i] = F.bfu_of_short[i]; }
+  if (tid < 52) { s_start_long[tid] = F.start_long[tid]; s_start_short[tid] = F.start_short[tid]; }
   __syncthreads();
-
-  // ---- phase A: scale factor per BFU (bitallocation.js:290-299 via the exact threshold
-  // table) and its zero-bit distortion (bitallocation.js:83-88)
-  for (int item = tid; item < kAqSu * 52; item += kAqThreads) {
-    const int u = item / 52, b = item - u * 52;
-    if (unit0 + u >= n_units) continue;
-    const int sz = F.specs[b];
-    const int start = S.mode[u][band_of_bfu(b)] == 0 ? F.start_long[b] : F.start_short[b];
-    float mx = 0.0f;
-    for (int j = 0; j < sz; j++) {
-      const float a = fabsf(S.coef[u][start + j]);
-      if (a > mx) mx = a;
-    }
-    int sfi = 0;
-    if (mx > 0.0f) {
-#pragma unroll 7
-      for (int k = 0; k < 63; k++) sfi += (mx > T->sf_thr[k]);
-    }
-    S.sfi[u][b] = (uint8_t)sfi;
-    S.zero_bit[u][b] = sfi > 0 ? (float)(P->bsf[sfi] * 2.0 * (double)sz) : 0.0f;
-  }
-  __syncthreads();
-
-  // ---- phase B: one thread per (unit, candidate BFU count)
-  {
-    const int u = tid >> 3, c = tid & 7;
-    const int cand = c == 0 ? 20 : 24 + 4 * c;  // BFU_AMOUNTS = 20,28,32,...,52
-    const bool live = unit0 + u < n_units;
-    double total = 0.0;
-    if (live) {
-      int remaining = kFrameBits - 40 - 10 * cand;  // bitallocation.js:97-100
-      uint32_t *H = &S.heap[0][tid];
-      int count = 0;
-      for (int b = 0; b < 52; b++) S.wl[b][tid] = 0;
-      for (int b = 0; b < cand; b++) {  // bitallocation.js:216-232
-        const uint32_t sfi = S.sfi[u][b];
-        if (sfi) {
-          H[count * kAqThreads] = ((uint32_t)S.rank[sfi * 16] << 22) | (sfi << 16) | (uint32_t)b;
-          count++;
-        }
-      }
-      if (count) {
-        for (int i = (count >> 1) - 1; i >= 0; i--) heap_sift(H, i, count);
-        int size = count;
-        while (remaining > 0 && size > 0) {  // bitallocation.js:244-278
-          uint32_t e = H[0];
-          const int b = e & 63;
-          int wl = (e >> 8) & 15;
-          const int cost = (wl == 0 ? 2 : 1) * (int)F.specs[b];
-          bool pop;
-          if (cost > remaining) {
-            pop = true;
-          } else {
-            remaining -= cost;
-            wl++;
-            e = (e & 0xFFFFF0FFu) | ((uint32_t)wl << 8);
-            if (wl < 15) {
-              const uint32_t sfi = (e >> 16) & 63;
-              e = (e & 0x003FFFFFu) | ((uint32_t)S.rank[sfi * 16 + wl] << 22);
-              H[0] = e;
-              heap_sift(H, 0, size);
-              pop = false;
-            } else {
-              pop = true;
-            }
-          }
-          if (pop) {  // retired entries are parked behind the live heap
-            size--;
-            const uint32_t last = H[size * kAqThreads];
-            H[size * kAqThreads] = e;
-            if (size > 0) {
-              H[0] = last;
-              heap_sift(H, 0, size);
-            }
-          }
-        }
-        for (int i = 0; i < count; i++) {
-          const uint32_t e = H[i * kAqThreads];
-          S.wl[e & 63][tid] = (uint8_t)((e >> 8) & 15);
-        }
-      }
-      // total distortion of this candidate (bitallocation.js:157-190), index order
-      for (int i = 0; i < cand; i++) {
-        const int bits = wl_bits(S.wl[i][tid]);
-        if (bits == 0) { total += (double)S.zero_bit[u][i]; continue; }
-        const int sfi = S.sfi[u][i];
-        if (sfi == 0) continue;
-        const double inv = __hiloint2double((1023 - bits) << 20, 0);
-        total += P->bsf[sfi] * inv * (double)F.specs[i];
-      }
-      for (int i = cand; i < 52; i++) total += (double)S.zero_bit[u][i];
-    }
-    // first strict minimum over ascending candidates (bitallocation.js:122-129)
-    const double inf = __longlong_as_double(0x7ff0000000000000ll);
-    double key = (live && total < inf) ? total : inf;
-    int best = c;
+  const long long n_units = (long long)n_streams * n_out_frames;
+  const long long unit = (long long)blockIdx.x * kQpWarps + warp;
+  if (unit >= n_units) return;
+  const int stream = (int)(unit / n_out_frames);
+  const int frame_out = (int)(unit % n_out_frames);
+  const size_t su = (size_t)stream * frames + halo + frame_out;
+  const AllocRec *r = recs + unit;
+  const int n = r->n_bfu;
+  uint32_t *words = s_words[warp];
+  for (int i = lane; i < 56; i += 32) words[i] = 0;
+  int m0, m1, m2, l0, l1, l2;
+  if (P->use_fixed) { m0 = P->fixed[0]; m1 = P->fixed[1]; m2 = P->fixed[2]; }
+  else { m0 = modes[su * 4]; m1 = modes[su * 4 + 1]; m2 = modes[su * 4 + 2]; }
+  l0 = m0 == 0; l1 = m1 == 0; l2 = m2 == 0;
+  // per-BFU bit widths, offsets (exclusive scan over bits*size) and 1/step factors
+  int run = 16 + 10 * n;
 #pragma unroll
-    for (int off = 4; off >= 1; off >>= 1) {
-      const double ok = __shfl_xor_sync(0xffffffffu, key, off, 8);
-      const int oi = __shfl_xor_sync(0xffffffffu, best, off, 8);
-      if (ok < key || (ok == key && oi < best)) { key = ok; best = oi; }
+  for (int h = 0; h < 2; h++) {
+    const int b = lane + 32 * h;
+    int wl = 0, sfi = 0, sz = 0;
+    if (b < 52) { wl = r->wl[b]; sfi = r->sfi[b]; sz = F.specs[b]; }
+    const int bits = b < n ? wl_bits(wl) : 0;
+    int incl = bits * sz;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
     }
-    if (live) {
-      if (key < inf) {
-        if (best == c) {
-          S.nbfu[u] = cand;
-          for (int b = 0; b < 52; b++) S.wlf[u][b] = b < cand ? S.wl[b][tid] : 0;
-        }
-      } else if (c == 0) {  // bitallocation.js:132-139
-        S.nbfu[u] = 20;
-        for (int b = 0; b < 52; b++) S.wlf[u][b] = 0;
+    if (b < 52) {
+      s_base[warp][b] = (uint16_t)(run + incl - bits * sz);
+      s_bits[warp][b] = (uint8_t)bits;
+      s_nf[warp][b] = (bits > 0 && sfi > 0) ? (double)((1 << (bits - 1)) - 1) / T->sf[sfi] : 0.0;
+      if (b < n) {
+        put_bits(words, 16 + 4 * b, (uint32_t)wl, 4);
+        put_bits(words, 16 + 4 * n + 6 * b, (uint32_t)sfi, 6);
       }
     }
-    __syncwarp();
-    if (live && !(key < inf) && c == 0)
-      for (int b = 0; b < 52; b++) S.sfi[u][b] = 0;
+    run += __shfl_sync(0xffffffffu, incl, 31);
   }
-  __syncthreads();
-
-  // ---- phase C: quantise (quantization.js:34-56) and pack (serialization.js:41-98)
-  {
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int uu = 0; uu < 4; uu++) {
-      const int u = warp * 4 + uu;
-      const long long unit = unit0 + u;
-      if (unit >= n_units) break;
-      const int n = S.nbfu[u];
-      uint32_t *words = S.words[u];
-      for (int i = lane; i < 56; i += 32) words[i] = 0;
-      for (int b = lane; b < 52; b += 32) {
-        const int bits = wl_bits(S.wlf[u][b]);
-        const int sfi = S.sfi[u][b];
-        double nf = 0.0;
-        if (b < n && bits > 0 && sfi > 0) nf = (double)((1 << (bits - 1)) - 1) / T->sf[sfi];
-        S.nf[u][b] = nf;
-      }
-      if (lane == 0) {
-        int pos = 16 + 10 * n;
-        for (int b = 0; b < n; b++) {
-          S.base[u][b] = (uint16_t)pos;
-          pos += wl_bits(S.wlf[u][b]) * (int)F.specs[b];
-        }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        const int idx = n == 20 ? 0 : (n - 24) / 4;
-        int m0, m1, m2;
-        if (P->use_fixed) { m0 = P->fixed[0]; m1 = P->fixed[1]; m2 = P->fixed[2]; }
-        else { m0 = S.mode[u][0]; m1 = S.mode[u][1]; m2 = S.mode[u][2]; }
-        const uint32_t header = (((uint32_t)(2 - m0) << 14) | ((uint32_t)(2 - m1) << 12) |
-                                 ((uint32_t)(3 - m2) << 10) | ((uint32_t)idx << 5)) & 0xFFFFu;
-        atomicOr(&words[0], header << 16);
-      }
-      for (int i = lane; i < n; i += 32) {
-        put_bits(words, 16 + 4 * i, S.wlf[u][i], 4);
-        put_bits(words, 16 + 4 * n + 6 * i, S.sfi[u][i], 6);
-      }
-      for (int k = 0; k < 16; k++) {
-        const int cidx = lane + 32 * k;
-        const int long_mode = S.mode[u][band_of_coef(cidx)] == 0;
-        const int b = long_mode ? F.bfu_of_long[cidx] : F.bfu_of_short[cidx];
-        if (b >= n) continue;
-        const int bits = wl_bits(S.wlf[u][b]);
-        if (bits == 0) continue;
-        int q = 0;
-        if (S.sfi[u][b] != 0) {
-          const int range = (1 << (bits - 1)) - 1;
-          const double x = (double)S.coef[u][cidx] * S.nf[u][b];
-          const int y = js_to_int32(x + (x >= 0.0 ? 0.5 : -0.5));
-          q = y > range ? range : (y < -range ? -range : y);
-        }
-        const int j = cidx - (long_mode ? F.start_long[b] : F.start_short[b]);
-        put_bits(words, S.base[u][b] + j * bits, (uint32_t)q & ((1u << bits) - 1u), bits);
-      }
-      __syncwarp();
-      const int stream = (int)(unit / n_out_frames);
-      const int frame_out = (int)(unit % n_out_frames);
-      uint32_t *dst = reinterpret_cast<uint32_t *>(
-          su_out + ((size_t)frame_out * su_frame_stride + (size_t)stream * su_stream_stride) * kSuBytes);
-      for (int i = lane; i < kSuWords; i += 32) dst[i] = __byte_perm(words[i], 0, 0x0123);
-      __syncwarp();
-    }
+  if (lane == 0) {
+    const int idx = n == 20 ? 0 : (n - 24) / 4;
+    const uint32_t header = (((uint32_t)(2 - m0) << 14) | ((uint32_t)(2 - m1) << 12) |
+                             ((uint32_t)(3 - m2) << 10) | ((uint32_t)idx << 5)) & 0xFFFFu;
+    atomicOr(&words[0], header << 16);
   }
+  __syncwarp();
+  const float *src = coefs + su * 512;
+#pragma unroll 4
+  for (int k = 0; k < 16; k++) {
+    const int cidx = lane + 32 * k;
+    const int long_mode = k < 4 ? l0 : (k < 8 ? l1 : l2);
+    const int b = long_mode ? s_bfu_long[cidx] : s_bfu_short[cidx];
+    const int bits = s_bits[warp][b];
+    if (bits == 0) continue;
+    const double nf = s_nf[warp][b];
+    int q = 0;
+    if (nf != 0.0) {
+      const int range = (1 << (bits - 1)) - 1;
+      const double x = (double)src[cidx] * nf;
+      const int y = js_to_int32(x + (x >= 0.0 ? 0.5 : -0.5));
+      q = y > range ? range : (y < -range ? -range : y);
+    }
+    const int j = cidx - (long_mode ? s_start_long[b] : s_start_short[b]);
+    put_bits(words, s_base[warp][b] + j * bits, (uint32_t)q & ((1u << bits) - 1u), bits);
+  }
+  __syncwarp();
+  uint32_t *dst = reinterpret_cast<uint32_t *>(
+      su_out + ((size_t)frame_out * su_frame_stride + (size_t)stream * su_stream_stride) * kSuBytes);
+  for (int i = lane; i < kSuWords; i += 32) dst[i] = __byte_perm(words[i], 0, 0x0123);
 }
 
 // ------------------------------------------------------------------------------------
 // Host-side launchers
 // ------------------------------------------------------------------------------------
-size_t alloc_quant_pack_smem_bytes() { return sizeof(AqSmem); }
+size_t alloc_rec_bytes() { return sizeof(AllocRec); }
 
 const char *kernel_name(int id) {
   static const char *names[K_COUNT] = {"qmf_analysis", "band_mags", "transient_modes", "mdct",
-                                       "alloc_quant_pack", "unpack_dequant", "imdct", "bands_time", "synth"};
+                                       "alloc", "quant_pack", "unpack_dequant", "imdct", "bands_time", "synth"};
   return id >= 0 && id < K_COUNT ? names[id] : "?";
 }
 
@@ -638,14 +674,19 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
   prof->end(K_MDCT, st);
   const long long n_units = (long long)L.n_streams * L.n_out_frames;
   if (n_units > 0 && L.su_out) {
-    cudaError_t e = cudaFuncSetAttribute(alloc_quant_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(AqSmem));
+    cudaError_t e = cudaFuncSetAttribute(alloc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(AlSmem));
     if (e != cudaSuccess) return e;
-    prof->begin(K_ALLOC_QUANT_PACK, st);
-    alloc_quant_pack_kernel<<<(unsigned)((n_units + kAqSu - 1) / kAqSu), kAqThreads, sizeof(AqSmem), st>>>(
-        L.coefs, L.modes, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params, L.su_out,
-        L.su_frame_stride, L.su_stream_stride);
-    prof->end(K_ALLOC_QUANT_PACK, st);
+    AllocRec *recs = static_cast<AllocRec *>(L.alloc_recs);
+    prof->begin(K_ALLOC, st);
+    alloc_kernel<<<(unsigned)((n_units + kAlSu - 1) / kAlSu), kAlThreads, sizeof(AlSmem), st>>>(
+        L.coefs, L.modes, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params, recs);
+    prof->end(K_ALLOC, st);
+    prof->begin(K_QUANT_PACK, st);
+    quant_pack_kernel<<<(unsigned)((n_units + kQpWarps - 1) / kQpWarps), kQpWarps * 32, 0, st>>>(
+        L.coefs, L.modes, recs, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params,
+        L.su_out, L.su_frame_stride, L.su_stream_stride);
+    prof->end(K_QUANT_PACK, st);
   }
   return cudaGetLastError();
 }

@@ -33,6 +33,7 @@ struct EncodeLaunch {
   uint8_t *modes;           // 4 per unit   (auto modes only)
   double *scores;           // 3 per unit, optional
   float *coefs;             // 512 per unit
+  void *alloc_recs;         // alloc_rec_bytes() per emitted unit
   // output
   uint8_t *su_out;          // may be NULL (stage taps only)
   size_t su_frame_stride, su_stream_stride;
@@ -61,7 +62,7 @@ struct DecodeLaunch {
 
 // Launch accounting and optional per-kernel CUDA-event timing (bench.py's roofline leg).
 enum KernelId {
-  K_QMF_ANALYSIS = 0, K_BAND_MAGS, K_TRANSIENT_MODES, K_MDCT, K_ALLOC_QUANT_PACK,
+  K_QMF_ANALYSIS = 0, K_BAND_MAGS, K_TRANSIENT_MODES, K_MDCT, K_ALLOC, K_QUANT_PACK,
   K_UNPACK_DEQUANT, K_IMDCT, K_BANDS_TIME, K_SYNTH, K_COUNT
 };
 const char *kernel_name(int id);
@@ -84,6 +85,7 @@ struct Prof {
   }
 };
 
+size_t alloc_rec_bytes();
 cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof);
 cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, Prof *prof);
 
