@@ -349,6 +349,8 @@ int carta1_ctx_create(int device, const carta1_tables *tables, carta1_ctx **out)
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_tables, sizeof(DevTables));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_params, sizeof(DevEncParams));
   if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tables, ht, sizeof(DevTables), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = upload_encode_constants(ht->qmf_even, ht->qmf_odd);
+  if (e == cudaSuccess) e = upload_decode_constants(ht->qmf_even, ht->qmf_odd);
   delete ht;
   if (e != cudaSuccess) {
     cuda_fail(nullptr, e, "carta1_ctx_create");
@@ -766,7 +768,7 @@ int carta1_debug_encode_stages(carta1_ctx *ctx, const float *pcm, size_t n_sampl
   const bool fixed = opts && opts->use_fixed_block_modes;
   // layout: pcm | bands | mags | coefs | su | modes
   const size_t o_bands = frames * 512, o_mags = o_bands + frames * 512, o_coefs = o_mags + frames * 256,
-               o_su = o_coefs + frames * 512, o_modes = o_su + (frames * 212 + 3) / 4 + 1,
+               o_su = o_coefs + frames * 512, o_modes = (o_su + (frames * 212 + 3) / 4 + 4) & ~(size_t)3,
                total = o_modes + frames + 1;
   CU(ctx, ctx->dbg.ensure(total * sizeof(float)));
   float *base = (float *)ctx->dbg.p;
@@ -795,7 +797,7 @@ int carta1_debug_decode_stages(carta1_ctx *ctx, const uint8_t *su, size_t n_su, 
   if (!ctx) return CARTA1_ERR_ARG;
   if (n_su == 0) return CARTA1_OK;
   CU(ctx, cudaSetDevice(ctx->device));
-  const size_t o_coefs = (n_su * 212 + 3) / 4 + 1, o_bands = o_coefs + n_su * 512, o_pcm = o_bands + n_su * 512,
+  const size_t o_coefs = ((n_su * 212 + 3) / 4 + 4) & ~(size_t)3, o_bands = o_coefs + n_su * 512, o_pcm = o_bands + n_su * 512,
                total = o_pcm + n_su * 512;
   CU(ctx, ctx->dbg.ensure(total * sizeof(float)));
   float *base = (float *)ctx->dbg.p;

@@ -210,119 +210,155 @@ bands_time_kernel(const float *__restrict__ inv, const uint8_t *__restrict__ mod
 
 // ------------------------------------------------------------------------------------
 // K7: overlap-add + QMF synthesis for a tile of frames of one row.
-//   M2[2m], M2[2m+1] = f32(.5(L[m] +- M[m]))                         (qmf.js:77-83)
-//   out2[2i]   = f32(sum_j M2[2i-45+2j] * ODD[j]),  out2[2i+1] = f32(sum_j M2[2i-46+2j] * EVEN[j])
-//   M1[2n], M1[2n+1] = f32(.5(out2[n] +- H[n-39]))                    (decoder.js:362-367)
-//   pcm likewise from M1.  Negative indices are the zero-initialised delay lines.
+//   S[m], D[m]   = f32(.5(L[m] +- M[m]))                              (qmf.js:77-83)
+//   out2[2i]     = f32(sum_j D[i-23+j] * ODD[j]),  out2[2i+1] = f32(sum_j S[i-23+j] * EVEN[j])
+//   S1[n], D1[n] = f32(.5(out2[n] +- H[n-39]))                        (decoder.js:362-367)
+//   pcm[2n]      = f32(sum_j D1[n-23+j] * ODD[j]), pcm[2n+1]  = f32(sum_j S1[n-23+j] * EVEN[j])
+// Negative indices are the zero-initialised delay lines.  As in K1 the sequences live in
+// shared memory as binary64, row kk&7 / column kk>>3, and every thread produces 8 outputs
+// of each polyphase from a 31-value register window.
 // ------------------------------------------------------------------------------------
-constexpr int kSynTile = 4;
+constexpr int kSynTile = 8;
+constexpr int kSynThreads = 256;
+constexpr int kSynS2Threads = 16 * kSynTile + 2;
+constexpr int kSynStrideA = 146;  // >= (8*kSynS2Threads + 31)/8 + 1, == 2 mod 16
+constexpr int kSynStrideB = 274;  // >= (8*32*kSynTile + 31)/8 + 1,   == 2 mod 16
+constexpr int kSynHd = 256 * kSynTile + 24;
+
+__constant__ double c_syn_even[24];
+__constant__ double c_syn_odd[24];
+
+cudaError_t upload_decode_constants(const double *even24, const double *odd24) {
+  cudaError_t e = cudaMemcpyToSymbol(c_syn_even, even24, 24 * sizeof(double));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyToSymbol(c_syn_odd, odd24, 24 * sizeof(double));
+}
+
+// acc[r] = sum_j w[8t + 1 + r + j] * taps[j], j ascending, for r = 0..7 (thread t)
+template <int kStride>
+__device__ __forceinline__ void fir8_synthesis(const double *__restrict__ seq, int t, const double *taps,
+                                               double (&acc)[8]) {
+#pragma unroll
+  for (int r = 0; r < 8; r++) acc[r] = 0.0;
+#pragma unroll
+  for (int j = 0; j < 24; j++) {
+    const double c = taps[j];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const int i = r + j + 1;
+      acc[r] = fma(seq[(i & 7) * kStride + t + (i >> 3)], c, acc[r]);
+    }
+  }
+}
 
 template <int kFmt>  // 0: f32 planar rows, 1: s16 interleaved (processor.js:382-389)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kSynThreads)
 synth_kernel(const float *__restrict__ inv, const uint8_t *__restrict__ modes, int frames, int halo,
              const DevTables *__restrict__ T, void *__restrict__ pcm_v, size_t row_stride, int n_ch) {
-  __shared__ float m2[kSynTile * 256 + 72];
-  __shared__ float o2[kSynTile * 256 + 24];
-  __shared__ float m1[kSynTile * 512 + 48];
-  __shared__ double ce[24], co[24], win[32];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sa = reinterpret_cast<double *>(smem_raw);  // [2][8*kSynStrideA]: D, S of stage 2
+  double *sb = sa + 2 * 8 * kSynStrideA;               // [2][8*kSynStrideB]: D1, S1 of stage 1
+  float *hd = reinterpret_cast<float *>(sb + 2 * 8 * kSynStrideB);  // delayed high band, n >= 256*f0 - 24
+  __shared__ double win[32];
   const int tid = threadIdx.x;
   const int f0 = blockIdx.x * kSynTile;
   const int stream = blockIdx.y;
-  if (tid < 24) { ce[tid] = T->qmf_even[tid]; co[tid] = T->qmf_odd[tid]; }
   if (tid < 32) win[tid] = T->win[tid];
   __syncthreads();
   const float *inv_row = inv + (size_t)stream * frames * 512;
   const uint8_t *mode_row = modes + (size_t)stream * frames * 4;
   const int f_end = min(f0 + kSynTile, frames);
 
-  // step 1: merged low/mid pairs, m in [128*f0 - 35, 128*f_end)
-  const int m_lo = 128 * f0 - 35;
-  for (int t = tid; t < kSynTile * 128 + 35; t += 256) {
-    const int m = m_lo + t;
-    float a = 0.0f, b = 0.0f;
+  // merged low/mid pairs: kk -> m = 128*f0 - 40 + kk
+  const int m_lo = 128 * f0 - 40;
+  for (int kk = tid; kk < 8 * kSynS2Threads + 32; kk += kSynThreads) {
+    const int m = m_lo + kk;
+    float sum = 0.0f, dif = 0.0f;
     if (m >= 0 && m < 128 * f_end) {
       const int fr = m >> 7, p = m & 127;
       const float *fl = inv_row + (size_t)fr * 512;
       const float l = band_sample(fl, fr > 0 ? fl - 512 : nullptr, 128, mode_row[fr * 4 + 0] == 0, p, win);
       const float h = band_sample(fl + 128, fr > 0 ? fl - 384 : nullptr, 128, mode_row[fr * 4 + 1] == 0, p, win);
-      a = (float)(0.5 * ((double)l + (double)h));
-      b = (float)(0.5 * ((double)l - (double)h));
+      sum = (float)(0.5 * ((double)l + (double)h));
+      dif = (float)(0.5 * ((double)l - (double)h));
     }
-    m2[2 * t] = a;
-    m2[2 * t + 1] = b;
+    const int at = (kk & 7) * kSynStrideA + (kk >> 3);
+    sa[at] = (double)dif;
+    sa[8 * kSynStrideA + at] = (double)sum;
+  }
+  // delayed high band: hd[q] = H[n - 39], n = 256*f0 - 24 + q
+  for (int q = tid; q < kSynHd; q += kSynThreads) {
+    const int g = 256 * f0 - 24 + q - 39;
+    float h = 0.0f;
+    if (g >= 0 && g < 256 * f_end) {
+      const int fr = g >> 8, p = g & 255;
+      const float *fh = inv_row + (size_t)fr * 512 + 256;
+      h = band_sample(fh, fr > 0 ? fh - 512 : nullptr, 256, mode_row[fr * 4 + 2] == 0, p, win);
+    }
+    hd[q] = h;
   }
   __syncthreads();
-  // step 2: stage-2 synthesis output, n in [256*f0 - 24, 256*f_end)
-  const int n_lo = 256 * f0 - 24;
-  for (int t = tid; t < kSynTile * 256 + 24; t += 256) {
-    const int n = n_lo + t;
-    float v = 0.0f;
-    if (n >= 0 && n < 256 * f_end) {
-      // M2 global index k -> m2[k - (256*f0 - 70)];  n = 2i (+1), k starts at 2i-45 / 2i-46
-      const int i2 = n & ~1;
-      double s = 0.0;
-      if ((n & 1) == 0) {
-        const int base = i2 - 45 - (256 * f0 - 70);
+  // stage 2 (low + mid -> 256-rate signal) and the merge with the delayed high band
+  if (tid < kSynS2Threads) {
+    double ev[8], od[8];
+    fir8_synthesis<kSynStrideA>(sa, tid, c_syn_odd, od);                     // out2[2i]
+    fir8_synthesis<kSynStrideA>(sa + 8 * kSynStrideA, tid, c_syn_even, ev);  // out2[2i+1]
 #pragma unroll
-        for (int j = 0; j < 24; j++) s = fma((double)m2[base + 2 * j], co[j], s);
+    for (int r = 0; r < 8; r++) {
+#pragma unroll
+      for (int par = 0; par < 2; par++) {
+        const int n = 2 * (128 * f0 - 16 + 8 * tid + r) + par;
+        const int kk1 = n - (256 * f0 - 24);
+        if (kk1 < 0) continue;
+        float s1 = 0.0f, d1 = 0.0f;
+        if (n >= 0 && n < 256 * f_end) {
+          const float x = (float)(par ? ev[r] : od[r]);
+          const float h = hd[kk1];
+          s1 = (float)(0.5 * ((double)x + (double)h));
+          d1 = (float)(0.5 * ((double)x - (double)h));
+        }
+        const int at = (kk1 & 7) * kSynStrideB + (kk1 >> 3);
+        sb[at] = (double)d1;
+        sb[8 * kSynStrideB + at] = (double)s1;
+      }
+    }
+  }
+  __syncthreads();
+  // stage 1 -> PCM: thread t covers samples [16t, 16t+16) of the tile
+  {
+    const int fr = f0 + (tid >> 5);
+    if (fr < frames && fr >= halo) {
+      double ev[8], od[8];
+      fir8_synthesis<kSynStrideB>(sb, tid, c_syn_odd, od);
+      fir8_synthesis<kSynStrideB>(sb + 8 * kSynStrideB, tid, c_syn_even, ev);
+      const size_t sample = (size_t)(fr - halo) * 512 + 16 * (tid & 31);
+      if (kFmt == 0) {
+        float *dstf = static_cast<float *>(pcm_v) + (size_t)stream * row_stride + sample;
+        if ((reinterpret_cast<uintptr_t>(dstf) & 15) == 0) {
+          float4 *dst = reinterpret_cast<float4 *>(dstf);
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            dst[q] = make_float4((float)od[2 * q], (float)ev[2 * q], (float)od[2 * q + 1], (float)ev[2 * q + 1]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; q++) { dstf[2 * q] = (float)od[q]; dstf[2 * q + 1] = (float)ev[q]; }
+        }
       } else {
-        const int base = i2 - 46 - (256 * f0 - 70);
+        short *dst = static_cast<short *>(pcm_v);
 #pragma unroll
-        for (int j = 0; j < 24; j++) s = fma((double)m2[base + 2 * j], ce[j], s);
+        for (int r = 0; r < 16; r++) {
+          double d = (double)(float)((r & 1) ? ev[r >> 1] : od[r >> 1]);  // Math.max(-1, Math.min(1, x))
+          d = d > 1.0 ? 1.0 : d;
+          d = d < -1.0 ? -1.0 : d;
+          const double w = d < 0.0 ? d * 32768.0 : d * 32767.0;
+          dst[(sample + r) * n_ch + stream] = (short)(isnan(w) ? 0 : __double2int_rz(w));
+        }
       }
-      v = (float)s;
-    }
-    o2[t] = v;
-  }
-  __syncthreads();
-  // step 3: merged (stage-2 output, delayed high) pairs, n in [256*f0 - 23, 256*f_end)
-  for (int t = tid; t < kSynTile * 256 + 23; t += 256) {
-    const int n = 256 * f0 - 23 + t;
-    float a = 0.0f, b = 0.0f;
-    if (n >= 0 && n < 256 * f_end) {
-      const float x = o2[n - n_lo];
-      float h = 0.0f;
-      const int g = n - 39;
-      if (g >= 0) {
-        const int fr = g >> 8, p = g & 255;
-        const float *fh = inv_row + (size_t)fr * 512 + 256;
-        h = band_sample(fh, fr > 0 ? fh - 512 : nullptr, 256, mode_row[fr * 4 + 2] == 0, p, win);
-      }
-      a = (float)(0.5 * ((double)x + (double)h));
-      b = (float)(0.5 * ((double)x - (double)h));
-    }
-    m1[2 * t] = a;      // M1 global index 2n   -> m1[2n - (512*f0 - 46)]
-    m1[2 * t + 1] = b;
-  }
-  __syncthreads();
-  // step 4: stage-1 synthesis -> PCM
-  for (int t = tid; t < kSynTile * 512; t += 256) {
-    const int fr = f0 + (t >> 9);
-    if (fr >= frames || fr < halo) continue;
-    const int i2 = t & ~1;
-    double s = 0.0;
-    if ((t & 1) == 0) {
-      const int base = i2 + 1;  // (512*f0 + i2) - 45 - (512*f0 - 46)
-#pragma unroll
-      for (int j = 0; j < 24; j++) s = fma((double)m1[base + 2 * j], co[j], s);
-    } else {
-      const int base = i2;
-#pragma unroll
-      for (int j = 0; j < 24; j++) s = fma((double)m1[base + 2 * j], ce[j], s);
-    }
-    const float v = (float)s;
-    const size_t sample = (size_t)(fr - halo) * 512 + (t & 511);
-    if (kFmt == 0) {
-      static_cast<float *>(pcm_v)[(size_t)stream * row_stride + sample] = v;
-    } else {
-      double d = (double)v;  // Math.max(-1, Math.min(1, x)); NaN -> 0 through ToInt16
-      d = d > 1.0 ? 1.0 : d;
-      d = d < -1.0 ? -1.0 : d;
-      const double w = d < 0.0 ? d * 32768.0 : d * 32767.0;
-      static_cast<short *>(pcm_v)[sample * n_ch + stream] = (short)(isnan(w) ? 0 : __double2int_rz(w));
     }
   }
 }
+constexpr size_t kSynSmemBytes =
+    (size_t)(2 * 8 * kSynStrideA + 2 * 8 * kSynStrideB) * sizeof(double) + (size_t)kSynHd * sizeof(float);
 
 cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, Prof *prof) {
   const int n_units = L.n_streams * L.frames_total;
@@ -342,13 +378,17 @@ cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, Prof *prof) {
   }
   if (L.pcm) {
     dim3 grid((L.frames_total + kSynTile - 1) / kSynTile, L.n_streams);
+    cudaError_t e0 = cudaFuncSetAttribute(synth_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSynSmemBytes);
+    if (e0 == cudaSuccess)
+      e0 = cudaFuncSetAttribute(synth_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSynSmemBytes);
+    if (e0 != cudaSuccess) return e0;
     prof->begin(K_SYNTH, st);
     if (L.pcm_fmt == 0)
-      synth_kernel<0><<<grid, 256, 0, st>>>(L.inv, L.modes, L.frames_total, L.halo_frames, L.tables, L.pcm,
-                                           L.row_stride, L.n_ch_interleave);
+      synth_kernel<0><<<grid, kSynThreads, kSynSmemBytes, st>>>(L.inv, L.modes, L.frames_total, L.halo_frames,
+                                                                 L.tables, L.pcm, L.row_stride, L.n_ch_interleave);
     else
-      synth_kernel<1><<<grid, 256, 0, st>>>(L.inv, L.modes, L.frames_total, L.halo_frames, L.tables, L.pcm,
-                                           L.row_stride, L.n_ch_interleave);
+      synth_kernel<1><<<grid, kSynThreads, kSynSmemBytes, st>>>(L.inv, L.modes, L.frames_total, L.halo_frames,
+                                                                 L.tables, L.pcm, L.row_stride, L.n_ch_interleave);
     prof->end(K_SYNTH, st);
   }
   return cudaGetLastError();

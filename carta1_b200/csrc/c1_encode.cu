@@ -47,66 +47,115 @@ __device__ __forceinline__ int bitrev(int x, int log2n) { return (int)(__brev((u
 //   S1lo/S1hi[n] = f32(E +- O), E = sum_j x[2n+1-2j]*EVEN[j], O = sum_j x[2n-2j]*ODD[j]
 //   L/M[m]       = the same filter applied to S1lo;  H[n] = S1hi[n-39].
 // fma() is exact-product here (both factors are widened f32), so it equals mul-then-add.
+//
+// Layout: the input is widened to binary64 once and kept in shared memory as its two
+// polyphase sequences xo[k] = x[2k+1], xe[k] = x[2k].  Each thread produces 8 consecutive
+// outputs, so a 24-tap filter needs a window of 31 polyphase values for 192 DFMA.  Element
+// kk of a sequence lives at row kk&7, column kk>>3 (row stride == 2 mod 16 doubles): a warp's
+// window reads and the tile fill are both bank-conflict free.
 // ------------------------------------------------------------------------------------
-constexpr int kQmfTile = 4;  // frames per CTA
+constexpr int kQmfTile = 8;                       // frames per CTA
+constexpr int kQmfS1Threads = 32 * kQmfTile + 6;  // stage-1 work items (8 outputs each)
+constexpr int kQmfThreads = 288;
+constexpr int kQmfStride1 = 274;                  // >= (8*kQmfS1Threads + 31)/8 + 1, == 2 mod 16
+constexpr int kQmfStride2 = 146;                  // >= (8*16*kQmfTile + 31)/8 + 1,   == 2 mod 16
+static_assert(kQmfS1Threads <= kQmfThreads, "stage 1 must fit the block");
+
+__constant__ double c_qmf_even[24];
+__constant__ double c_qmf_odd[24];
+
+cudaError_t upload_encode_constants(const double *even24, const double *odd24) {
+  cudaError_t e = cudaMemcpyToSymbol(c_qmf_even, even24, 24 * sizeof(double));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyToSymbol(c_qmf_odd, odd24, 24 * sizeof(double));
+}
+
+// acc[r] = sum_j w[8t + 24 + r - j] * taps[j], j ascending, for r = 0..7 (thread t)
+template <int kStride>
+__device__ __forceinline__ void fir8_analysis(const double *__restrict__ seq, int t, const double *taps,
+                                              double (&acc)[8]) {
+#pragma unroll
+  for (int r = 0; r < 8; r++) acc[r] = 0.0;
+#pragma unroll
+  for (int j = 0; j < 24; j++) {
+    const double c = taps[j];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const int i = r - j + 24;  // kk = 8t + i, i in 1..31
+      acc[r] = fma(seq[(i & 7) * kStride + t + (i >> 3)], c, acc[r]);
+    }
+  }
+}
 
 template <int kFmt>  // 0: f32 planar rows, 1: s16 interleaved
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kQmfThreads)
 qmf_analysis_kernel(const void *__restrict__ pcm_v, size_t row_stride, int n_ch, long long valid_samples,
-                    int frames, const DevTables *__restrict__ T, float *__restrict__ bands) {
-  __shared__ float xs[kQmfTile * 512 + 138 + 2];
-  __shared__ float s1[kQmfTile * 256 + 46 + 2];
-  __shared__ double ce[24], co[24];
+                    int frames, float *__restrict__ bands) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *x1 = reinterpret_cast<double *>(smem_raw);  // [2][8*kQmfStride1]: odd, even polyphase of x
+  double *x2 = x1 + 2 * 8 * kQmfStride1;               // [2][8*kQmfStride2]: odd, even polyphase of S1lo
   const int tid = threadIdx.x;
   const int f0 = blockIdx.x * kQmfTile;
   const int stream = blockIdx.y;
-  if (tid < 24) { ce[tid] = T->qmf_even[tid]; co[tid] = T->qmf_odd[tid]; }
-  const long long x0 = 512ll * f0 - 138;
-  for (int i = tid; i < kQmfTile * 512 + 138; i += 256) {
-    const long long g = x0 + i;
+  const int nb = 256 * f0 - 48;  // first stage-1 output of the tile
+  const int kb = nb - 24;        // polyphase index of kk == 0
+  // fill: kk in [0, 8*kQmfS1Threads + 32), both polyphases
+  for (int idx = tid; idx < 2 * (8 * kQmfS1Threads + 32); idx += kQmfThreads) {
+    const int kk = idx >> 1, par = idx & 1;
+    const long long g = 2ll * (kb + kk) + par;
     float v = 0.0f;
     if (g >= 0 && g < valid_samples) {
       if (kFmt == 0) {
         v = static_cast<const float *>(pcm_v)[(size_t)stream * row_stride + (size_t)g];
       } else {  // bin/cli.js:395  readInt16LE / 32768.0 -> Float32Array
-        const short s = static_cast<const short *>(pcm_v)[(size_t)g * n_ch + stream];
-        v = (float)((double)s / 32768.0);
+        const short sv = static_cast<const short *>(pcm_v)[(size_t)g * n_ch + stream];
+        v = (float)((double)sv / 32768.0);
       }
     }
-    xs[i] = v;
+    x1[(par ? 0 : 8 * kQmfStride1) + (kk & 7) * kQmfStride1 + (kk >> 3)] = (double)v;
   }
   __syncthreads();
   float *out = bands + ((size_t)stream * frames) * 512;
-  const int n_lo = 256 * f0 - 46;
-  for (int t = tid; t < kQmfTile * 256 + 46; t += 256) {
-    double e = 0.0, o = 0.0;
+  const int mb = 128 * f0;
+  if (tid < kQmfS1Threads) {
+    double e[8], o[8];
+    fir8_analysis<kQmfStride1>(x1, tid, c_qmf_even, e);
+    fir8_analysis<kQmfStride1>(x1 + 8 * kQmfStride1, tid, c_qmf_odd, o);
 #pragma unroll
-    for (int j = 0; j < 24; j++) {
-      e = fma((double)xs[47 + 2 * t - 2 * j], ce[j], e);
-      o = fma((double)xs[46 + 2 * t - 2 * j], co[j], o);
-    }
-    s1[t] = (float)(e + o);
-    const int nh = n_lo + t + 39;  // delayed high-band index (encoder.js:84-90)
-    if (nh >= 256 * f0 && nh < 256 * (f0 + kQmfTile)) {
-      const int fr = nh >> 8;
-      if (fr < frames) out[(size_t)fr * 512 + 256 + (nh & 255)] = (float)(e - o);
+    for (int r = 0; r < 8; r++) {
+      const int n = nb + 8 * tid + r;
+      const float lo = (float)(e[r] + o[r]);
+      const float hi = (float)(e[r] - o[r]);
+      // S1lo[n] feeds stage 2: polyphase (n & 1), index (n >> 1) - (mb - 24)
+      const int kk2 = (n >> 1) - (mb - 24);
+      x2[((n & 1) ? 0 : 8 * kQmfStride2) + (kk2 & 7) * kQmfStride2 + (kk2 >> 3)] = (double)lo;
+      const int nh = n + 39;  // delayed high band (encoder.js:84-90)
+      if (nh >= 256 * f0 && nh < 256 * (f0 + kQmfTile)) {
+        const int fr = nh >> 8;
+        if (fr < frames) out[(size_t)fr * 512 + 256 + (nh & 255)] = hi;
+      }
     }
   }
   __syncthreads();
-  for (int u = tid; u < kQmfTile * 128; u += 256) {
-    double e = 0.0, o = 0.0;
-#pragma unroll
-    for (int j = 0; j < 24; j++) {
-      e = fma((double)s1[47 + 2 * u - 2 * j], ce[j], e);
-      o = fma((double)s1[46 + 2 * u - 2 * j], co[j], o);
-    }
-    const int fr = f0 + (u >> 7);
+  if (tid < 16 * kQmfTile) {
+    double e[8], o[8];
+    fir8_analysis<kQmfStride2>(x2, tid, c_qmf_even, e);
+    fir8_analysis<kQmfStride2>(x2 + 8 * kQmfStride2, tid, c_qmf_odd, o);
+    const int fr = f0 + (tid >> 4);
     if (fr < frames) {
-      out[(size_t)fr * 512 + (u & 127)] = (float)(e + o);
-      out[(size_t)fr * 512 + 128 + (u & 127)] = (float)(e - o);
+      float lo[8], hi[8];
+#pragma unroll
+      for (int r = 0; r < 8; r++) { lo[r] = (float)(e[r] + o[r]); hi[r] = (float)(e[r] - o[r]); }
+      float4 *dl = reinterpret_cast<float4 *>(out + (size_t)fr * 512 + 8 * (tid & 15));
+      float4 *dm = reinterpret_cast<float4 *>(out + (size_t)fr * 512 + 128 + 8 * (tid & 15));
+      dl[0] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      dl[1] = make_float4(lo[4], lo[5], lo[6], lo[7]);
+      dm[0] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      dm[1] = make_float4(hi[4], hi[5], hi[6], hi[7]);
     }
   }
 }
+constexpr size_t kQmfSmemBytes = (size_t)(2 * 8 * kQmfStride1 + 2 * 8 * kQmfStride2) * sizeof(double);
 
 // ------------------------------------------------------------------------------------
 // K2a: magnitude spectra for transient detection, one warp per sound unit.
@@ -328,21 +377,29 @@ mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, 
 }
 
 // ------------------------------------------------------------------------------------
-// K4a: scale factors + RDO bit allocation by literal max-heap emulation
-// (bitallocation.js:74-341).  One CTA = 256 threads = 32 sound units; warp w runs candidate
-// BFU count BFU_AMOUNTS[w] for all 32 units (lane = unit), so the lanes of a warp execute
-// loops of similar length.
+// K4a: scale factors + RDO bit allocation (bitallocation.js:74-341).
+//
+// The reference runs a greedy max-heap bit spend for each of the 8 candidate BFU counts and
+// keeps the first candidate with the strictly smallest total distortion.  Ties between equal
+// Float32Array priorities are resolved by the heap's structure, so the heap is emulated
+// literally (same array layout, same sift-down, same strict comparisons).
+//
+// Candidate pruning (exact): candidate n leaves BFUs >= n uncoded, which alone costs
+// tail(n) = sum_{i>=n} zeroBit[i].  The 52-BFU candidate has no tail.  If tail(n), deflated
+// by the worst-case rounding of the reference's own summation, already exceeds the 52-BFU
+// total, candidate n can neither win nor tie and is not run.  On broadband material fewer
+// than 1 % of the smaller candidates survive; on silence all do (and cost nothing).
+//
+// One CTA = 128 threads = 128 sound units.  Pass 1: thread u runs the 52-BFU candidate of
+// unit u.  Survivors of all units are compacted into a CTA-wide list and run 128 at a time.
 //
 // Heap entries are one 32-bit word: key[24:10] | wl[9:6] | bfu[5:0].  `key` is an
-// order-isomorphic 15-bit image of the reference's Float32Array priority (DevEncParams::key0/
-// key1): f32 exponent (8 bits) over the rank of the f32 mantissa among the 126 possible
-// ones.  For wl >= 1 the priority halves exactly with every step, i.e. key -= 128.
-// Heaps are stored node-major / lane-minor: a warp's 32 lanes always hit 32 distinct banks.
+// order-isomorphic 15-bit image of the reference's f32 priority (DevEncParams::key0/key1):
+// f32 exponent (8 bits) over the rank of the f32 mantissa among the 126 possible ones.  For
+// wl >= 1 the priority halves exactly with every step, i.e. key -= 128.  Heaps are stored
+// node-major / thread-minor, so a warp's 32 lanes always hit 32 distinct banks.
 // ------------------------------------------------------------------------------------
-constexpr int kAlSu = 32;
-constexpr int kAlThreads = 256;
-constexpr int kAlHeapSlots = 308;  // sum over candidates of (cand + 1)
-constexpr int kAlWlSlots = 300;    // sum over candidates of cand
+constexpr int kAlThreads = 128;
 
 struct AllocRec {  // per sound unit, global scratch between K4a and K4b
   uint8_t n_bfu, pad[3];
@@ -352,64 +409,149 @@ struct AllocRec {  // per sound unit, global scratch between K4a and K4b
 };
 static_assert(sizeof(AllocRec) == 112, "AllocRec layout");
 
+struct AllocCand {  // per sound unit: results of surviving smaller candidates
+  double total[7];
+  uint8_t wl[7][52];
+  uint8_t pad[4];
+};
+static_assert(sizeof(AllocCand) == 424, "AllocCand layout");
+
 struct AlSmem {
-  uint32_t heap[kAlHeapSlots][32];
-  uint8_t wl[kAlWlSlots][32];
-  double dist[8][32];
+  uint32_t heap[53][kAlThreads];
+  uint8_t wl[52][kAlThreads];
+  uint8_t sfi[kAlThreads][52];
+  uint16_t list[kAlThreads * 7];
   uint16_t key0[64], key1[64];
-  uint8_t sfi[kAlSu][52];
-  uint8_t mode[kAlSu][4];
+  uint8_t mode[kAlThreads][4];
   uint8_t specs[52];
-  int best[kAlSu];
+  int n_list;
 };
 
-__device__ __forceinline__ void heap_sift(uint32_t (*H)[32], int lane, int start, int size, uint32_t v) {
-  // bitallocation.js:314-341; v is the entry being placed, H[start] is the hole
-  int i = start;
+// Shared-memory byte addresses (32-bit) keep the sift loop free of 64-bit pointer math.
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+constexpr uint32_t kNode = kAlThreads * 4;  // byte stride between heap nodes
+
+// bitallocation.js:314-341.  `hole` is the address of the node being filled, `end` the
+// address of node `size`, `h0` the address of node 0; v is the entry being placed.
+__device__ __forceinline__ void heap_sift(uint32_t h0, uint32_t hole, uint32_t end, uint32_t v) {
   const uint32_t vm = v | 0x3FFu;
   for (;;) {
-    const int l = 2 * i + 1;
-    if (l >= size) break;
-    const uint32_t cl = H[l][lane];
-    const uint32_t cr = H[l + 1][lane];  // slot `size` is kept zero
+    const uint32_t l = 2u * hole - h0 + kNode;  // node 2i+1
+    if (l >= end) break;
+    const uint32_t cl = lds32(l);
+    const uint32_t cr = lds32(l + kNode);  // node `size` is kept zero
     const bool pl = cl > vm;
     const uint32_t m = pl ? (cl | 0x3FFu) : vm;
     const bool pr = cr > m;
     if (!(pl || pr)) break;
-    H[i][lane] = pr ? cr : cl;
-    i = pr ? l + 1 : l;
+    sts32(hole, pr ? cr : cl);
+    hole = pr ? l + kNode : l;
   }
-  H[i][lane] = v;
+  sts32(hole, v);
+}
+
+// Greedy spend for one candidate (bitallocation.js:203-281) followed by its total
+// distortion (:157-190).  col = this thread's column in the heap / wl arrays.
+__device__ __forceinline__ double run_candidate(AlSmem &S, const DevEncParams *__restrict__ P,
+                                                const FormatTables &F, const uint8_t *sfi_row, int cand,
+                                                int col) {
+  const uint32_t h0 = (uint32_t)__cvta_generic_to_shared(&S.heap[0][col]);
+  uint8_t *W = &S.wl[0][col];
+  int remaining = kFrameBits - 40 - 10 * cand;  // bitallocation.js:97-100
+  int count = 0;
+  for (int b = 0; b < cand; b++) {  // bitallocation.js:216-232
+    W[b * kAlThreads] = 0;
+    const uint32_t sfi = sfi_row[b];
+    if (sfi) {
+      sts32(h0 + count * kNode, ((uint32_t)S.key0[sfi] << 10) | (uint32_t)b);
+      count++;
+    }
+  }
+  sts32(h0 + count * kNode, 0);
+  if (count) {
+    uint32_t end = h0 + count * kNode;
+    for (int i = (count >> 1) - 1; i >= 0; i--) heap_sift(h0, h0 + i * kNode, end, lds32(h0 + i * kNode));
+    uint32_t e = lds32(h0);
+    while (remaining > 0) {  // bitallocation.js:244-278 (size > 0 is the loop's other exit)
+      const int b = e & 63;
+      const int wl = (e >> 6) & 15;
+      const int cost = (int)S.specs[b] << (wl == 0);
+      bool pop = cost > remaining;
+      if (!pop) {
+        remaining -= cost;
+        if (wl == 0) e = ((uint32_t)S.key1[sfi_row[b]] << 10) | (1u << 6) | (uint32_t)b;
+        else e += 64u - (128u << 10);  // wl + 1, priority halves exactly
+        pop = wl == 14;                // reached MAX_WORD_LENGTH_INDEX
+      }
+      if (pop) {
+        W[b * kAlThreads] = (uint8_t)((e >> 6) & 15);
+        end -= kNode;
+        if (end == h0) break;
+        e = lds32(end);
+        sts32(end, 0);
+      }
+      heap_sift(h0, h0, end, e);
+      e = lds32(h0);
+    }
+    for (uint32_t a = h0; a < end; a += kNode) {  // entries still in the heap keep their wl
+      const uint32_t x = lds32(a);
+      W[(x & 63) * kAlThreads] = (uint8_t)((x >> 6) & 15);
+    }
+  }
+  double total = 0.0;
+  for (int i = 0; i < 52; i++) {
+    const int sfi = sfi_row[i];
+    if (sfi == 0) continue;  // the reference adds +0.0 or skips
+    const int bits = i < cand ? wl_bits(W[i * kAlThreads]) : 0;
+    if (bits == 0) {
+      total += (double)P->zero_bit[sfi * 8 + F.size_class[i]];
+    } else {
+      const double inv = __hiloint2double((1023 - bits) << 20, 0);
+      total += P->bsf[sfi] * inv * (double)S.specs[i];
+    }
+  }
+  return total;
 }
 
 __global__ void __launch_bounds__(kAlThreads)
 alloc_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes, int frames, int halo,
              int n_out_frames, int n_streams, const DevTables *__restrict__ T,
-             const DevEncParams *__restrict__ P, AllocRec *__restrict__ recs) {
+             const DevEncParams *__restrict__ P, AllocRec *__restrict__ recs, AllocCand *__restrict__ cands) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AlSmem &S = *reinterpret_cast<AlSmem *>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
   const long long n_units = (long long)n_streams * n_out_frames;
-  const long long unit0 = (long long)blockIdx.x * kAlSu;
+  const long long unit0 = (long long)blockIdx.x * kAlThreads;
   const FormatTables &F = T->fmt;
 
   if (tid < 64) { S.key0[tid] = P->key0[tid]; S.key1[tid] = P->key1[tid]; }
   if (tid < 52) S.specs[tid] = F.specs[tid];
-  if (tid < kAlSu * 3) {
-    const int u = tid / 3, b = tid - u * 3;
-    const long long unit = unit0 + u;
-    uint8_t m = 0;
+  if (tid == 0) S.n_list = 0;
+  {
+    const long long unit = unit0 + tid;
+    uint8_t m0 = 0, m1 = 0, m2 = 0;
     if (unit < n_units) {
-      const size_t su = (size_t)(unit / n_out_frames) * frames + halo + (size_t)(unit % n_out_frames);
-      m = P->use_fixed ? (uint8_t)(P->fixed[b] != 0) : modes[su * 4 + b];
+      if (P->use_fixed) {
+        m0 = P->fixed[0] != 0; m1 = P->fixed[1] != 0; m2 = P->fixed[2] != 0;
+      } else {
+        const size_t su = (size_t)(unit / n_out_frames) * frames + halo + (size_t)(unit % n_out_frames);
+        m0 = modes[su * 4]; m1 = modes[su * 4 + 1]; m2 = modes[su * 4 + 2];
+      }
     }
-    S.mode[u][b] = m;
+    S.mode[tid][0] = m0; S.mode[tid][1] = m1; S.mode[tid][2] = m2;
   }
   __syncthreads();
 
   // ---- phase A: scale-factor index per BFU (bitallocation.js:290-299).  The log2/ceil of
   // the reference equals 3*(E+21) + #{thresholds of the binade below max} (DevTables::sf_thr).
-  for (int item = tid; item < kAlSu * 52; item += kAlThreads) {
+  for (int item = tid; item < kAlThreads * 52; item += kAlThreads) {
     const int u = item / 52, b = item - u * 52;
     const long long unit = unit0 + u;
     int sfi = 0;
@@ -437,99 +579,83 @@ alloc_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes,
   }
   __syncthreads();
 
-  // ---- phase B: warp = candidate, lane = unit
+  // ---- pass 1: the 52-BFU candidate of unit `tid`; its result is the provisional record
+  const bool live = unit0 + tid < n_units;
+  double total52 = 0.0;
+  uint32_t survive = 0;
+  if (live) {
+    total52 = run_candidate(S, P, F, S.sfi[tid], 52, tid);
+    AllocRec *r = recs + (unit0 + tid);
+    r->n_bfu = 52;
+    for (int b = 0; b < 52; b++) { r->wl[b] = S.wl[b][tid]; r->sfi[b] = S.sfi[tid][b]; }
+    // tails of the smaller candidates, from the top BFU down
+    double tail = 0.0;
+    int c = 6;
+    for (int i = 51; i >= 20; i--) {
+      const int sfi = S.sfi[tid][i];
+      if (sfi) tail += (double)P->zero_bit[sfi * 8 + F.size_class[i]];
+      const int bound = c == 0 ? 20 : 24 + 4 * c;  // BFU_AMOUNTS[c]
+      if (i == bound) {
+        // 1 - 2^-40 covers the rounding of the reference's own 52-term summation
+        if (!(tail * (1.0 - 9.094947017729282e-13) > total52)) survive |= 1u << c;
+        c--;
+      }
+    }
+  }
+  // ---- compact the surviving (unit, candidate) pairs of the CTA
   {
-    const int u = lane;
-    const int c = warp;
-    const int cand = c == 0 ? 20 : 24 + 4 * c;               // BFU_AMOUNTS
-    const int hbase = c == 0 ? 0 : (21 + (c - 1) * 29 + 2 * (c - 1) * (c - 2));  // prefix of (cand+1)
-    const int wbase = hbase - c;                              // prefix of cand
-    uint32_t (*H)[32] = &S.heap[hbase];
-    uint8_t (*W)[32] = &S.wl[wbase];
-    const bool live = unit0 + u < n_units;
-    double total = 0.0;
-    if (live) {
-      int remaining = kFrameBits - 40 - 10 * cand;  // bitallocation.js:97-100
-      int count = 0;
-      for (int b = 0; b < cand; b++) {               // bitallocation.js:216-232
-        W[b][lane] = 0;
-        const uint32_t sfi = S.sfi[u][b];
-        if (sfi) {
-          H[count][lane] = ((uint32_t)S.key0[sfi] << 10) | (uint32_t)b;
-          count++;
-        }
-      }
-      for (int i = count; i <= cand; i++) H[i][lane] = 0;
-      if (count) {
-        for (int i = (count >> 1) - 1; i >= 0; i--) heap_sift(H, lane, i, count, H[i][lane]);
-        int size = count;
-        uint32_t e = H[0][lane];
-        while (remaining > 0 && size > 0) {  // bitallocation.js:244-278
-          const int b = e & 63;
-          const int wl = (e >> 6) & 15;
-          const int cost = (int)S.specs[b] << (wl == 0);
-          bool pop = cost > remaining;
-          if (!pop) {
-            remaining -= cost;
-            if (wl == 0) e = ((uint32_t)S.key1[S.sfi[u][b]] << 10) | (1u << 6) | (uint32_t)b;
-            else e += 64u - (128u << 10);  // wl + 1, priority halves exactly
-            pop = wl == 14;                // reached MAX_WORD_LENGTH_INDEX
-          }
-          if (pop) {
-            W[b][lane] = (uint8_t)((e >> 6) & 15);
-            size--;
-            e = H[size][lane];
-            H[size][lane] = 0;
-            if (size == 0) break;
-          }
-          heap_sift(H, lane, 0, size, e);
-          e = H[0][lane];
-        }
-        for (int i = 0; i < size; i++) {
-          const uint32_t x = H[i][lane];
-          W[x & 63][lane] = (uint8_t)((x >> 6) & 15);
-        }
-      }
-      // total distortion of this candidate (bitallocation.js:157-190), index order
-      for (int i = 0; i < 52; i++) {
-        const int sfi = S.sfi[u][i];
-        if (sfi == 0) continue;  // contributes +0.0 or is skipped by the reference
-        const int bits = i < cand ? wl_bits(W[i][lane]) : 0;
-        if (bits == 0) {
-          total += (double)P->zero_bit[sfi * 8 + F.size_class[i]];
-        } else {
-          const double inv = __hiloint2double((1023 - bits) << 20, 0);
-          total += P->bsf[sfi] * inv * (double)S.specs[i];
-        }
-      }
-    }
-    S.dist[c][u] = total;
-    __syncthreads();
-    if (warp == 0 && live) {  // first strict minimum over ascending candidates (:122-129)
-      double min_total = __longlong_as_double(0x7ff0000000000000ll);
-      int best = -1;
+    const int n = __popc(survive);
+    int incl = n;
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const double t = S.dist[k][u];
-        if (t < min_total) { min_total = t; best = k; }
-      }
-      S.best[u] = best;
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
     }
-    __syncthreads();
-    if (live) {
-      const int best = S.best[u];
-      AllocRec *r = recs + (unit0 + u);
-      if (best == c) {
-        r->n_bfu = (uint8_t)cand;
-        for (int b = 0; b < 52; b++) {
-          r->wl[b] = b < cand ? W[b][lane] : 0;
-          r->sfi[b] = S.sfi[u][b];
-        }
-      } else if (best < 0 && c == 0) {  // bitallocation.js:132-139
-        r->n_bfu = 20;
-        for (int b = 0; b < 52; b++) { r->wl[b] = 0; r->sfi[b] = 0; }
-      }
+    int base = 0;
+    if (lane == 31 && incl) base = atomicAdd(&S.n_list, incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    int at = base + incl - n;
+    for (uint32_t m = survive; m; m &= m - 1) S.list[at++] = (uint16_t)((tid << 3) | (__ffs(m) - 1));
+  }
+  __syncthreads();
+  const int n_list = S.n_list;
+  for (int base = 0; base < n_list; base += kAlThreads) {  // uniform trip count
+    const int k = base + tid;
+    if (k < n_list) {
+      const int u = S.list[k] >> 3, c = S.list[k] & 7;
+      const int cand = c == 0 ? 20 : 24 + 4 * c;
+      const double total = run_candidate(S, P, F, S.sfi[u], cand, tid);
+      AllocCand *ac = cands + (unit0 + u);
+      ac->total[c] = total;
+      for (int b = 0; b < cand; b++) ac->wl[c][b] = S.wl[b][tid];
     }
+    __syncthreads();  // also orders the global writes before the selection below
+  }
+  __threadfence_block();
+  // ---- first strict minimum over ascending candidates (bitallocation.js:91-130)
+  if (live && survive) {
+    const AllocCand *ac = cands + (unit0 + tid);
+    double min_total = __longlong_as_double(0x7ff0000000000000ll);
+    int best = -1;
+    for (int c = 0; c < 7; c++) {
+      if (!(survive >> c & 1)) continue;
+      const double t = ac->total[c];
+      if (t < min_total) { min_total = t; best = c; }
+    }
+    if (total52 < min_total) best = 7;
+    AllocRec *r = recs + (unit0 + tid);
+    if (best < 0) {  // bitallocation.js:132-139
+      r->n_bfu = 20;
+      for (int b = 0; b < 52; b++) { r->wl[b] = 0; r->sfi[b] = 0; }
+    } else if (best < 7) {
+      const int cand = best == 0 ? 20 : 24 + 4 * best;
+      r->n_bfu = (uint8_t)cand;
+      for (int b = 0; b < 52; b++) r->wl[b] = b < cand ? ac->wl[best][b] : 0;
+    }
+  } else if (live && !(total52 < __longlong_as_double(0x7ff0000000000000ll))) {
+    AllocRec *r = recs + (unit0 + tid);  // no finite candidate at all: the reference's fallback
+    r->n_bfu = 20;
+    for (int b = 0; b < 52; b++) { r->wl[b] = 0; r->sfi[b] = 0; }
   }
 }
 
@@ -637,7 +763,7 @@ quant_pack_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ m
 // ------------------------------------------------------------------------------------
 // Host-side launchers
 // ------------------------------------------------------------------------------------
-size_t alloc_rec_bytes() { return sizeof(AllocRec); }
+size_t alloc_rec_bytes() { return sizeof(AllocRec) + sizeof(AllocCand); }
 
 const char *kernel_name(int id) {
   static const char *names[K_COUNT] = {"qmf_analysis", "band_mags", "transient_modes", "mdct",
@@ -651,13 +777,17 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
   if (n_su == 0) return cudaSuccess;
   {
     dim3 grid((frames + kQmfTile - 1) / kQmfTile, L.n_streams);
+    cudaError_t e0 = cudaFuncSetAttribute(qmf_analysis_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQmfSmemBytes);
+    if (e0 == cudaSuccess)
+      e0 = cudaFuncSetAttribute(qmf_analysis_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQmfSmemBytes);
+    if (e0 != cudaSuccess) return e0;
     prof->begin(K_QMF_ANALYSIS, st);
     if (L.pcm_fmt == 0)
-      qmf_analysis_kernel<0><<<grid, 256, 0, st>>>(L.pcm, L.row_stride, L.n_ch_interleave, L.valid_samples,
-                                                  frames, L.tables, L.bands);
+      qmf_analysis_kernel<0><<<grid, kQmfThreads, kQmfSmemBytes, st>>>(L.pcm, L.row_stride, L.n_ch_interleave,
+                                                                        L.valid_samples, frames, L.bands);
     else
-      qmf_analysis_kernel<1><<<grid, 256, 0, st>>>(L.pcm, L.row_stride, L.n_ch_interleave, L.valid_samples,
-                                                  frames, L.tables, L.bands);
+      qmf_analysis_kernel<1><<<grid, kQmfThreads, kQmfSmemBytes, st>>>(L.pcm, L.row_stride, L.n_ch_interleave,
+                                                                        L.valid_samples, frames, L.bands);
     prof->end(K_QMF_ANALYSIS, st);
   }
   if (!L.use_fixed) {
@@ -678,9 +808,10 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
                                          (int)sizeof(AlSmem));
     if (e != cudaSuccess) return e;
     AllocRec *recs = static_cast<AllocRec *>(L.alloc_recs);
+    AllocCand *cands = reinterpret_cast<AllocCand *>(recs + n_units);
     prof->begin(K_ALLOC, st);
-    alloc_kernel<<<(unsigned)((n_units + kAlSu - 1) / kAlSu), kAlThreads, sizeof(AlSmem), st>>>(
-        L.coefs, L.modes, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params, recs);
+    alloc_kernel<<<(unsigned)((n_units + kAlThreads - 1) / kAlThreads), kAlThreads, sizeof(AlSmem), st>>>(
+        L.coefs, L.modes, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params, recs, cands);
     prof->end(K_ALLOC, st);
     prof->begin(K_QUANT_PACK, st);
     quant_pack_kernel<<<(unsigned)((n_units + kQpWarps - 1) / kQpWarps), kQpWarps * 32, 0, st>>>(

@@ -779,6 +779,9 @@ static const int *bfu_starts(const int *modes, int bfu) { /* quantization.js:113
   return modes[band] == 0 ? BFU_START_LONG : BFU_START_SHORT;
 }
 
+static double g_dbg_totals[8];
+const double *c1o_debug_last_totals(void) { return g_dbg_totals; } /* not thread safe: tests only */
+
 void c1o_allocate_bits(const float *coefs, const int *modes, const c1o_options *o, int *n_bfu,
                        int *sfi52, int *wl52) {
   /* quantization.js:106-149 (groupIntoBFUs: every BFU slice lies inside its band, so the
@@ -802,6 +805,7 @@ void c1o_allocate_bits(const float *coefs, const int *modes, const c1o_options *
     int wl[52];
     distribute_bits_rdo(cand, SPECS_PER_BFU, avail, o->biased_sf, sfi52, wl);
     const double total = total_distortion(cand, 52, SPECS_PER_BFU, wl, sfi52, o->biased_sf, zero_bit);
+    g_dbg_totals[c] = total;
     if (total < min_total) {
       min_total = total;
       best = cand;

@@ -122,6 +122,7 @@ int c1o_find_scale_factor_table(float max_abs);  /* exact threshold-table varian
 const float *c1o_sf_thresholds(void);            /* 63 f32 thresholds */
 void c1o_allocate_bits(const float *coefs, const int *modes, const c1o_options *o,
                        int *n_bfu, int *sfi52, int *wl52);
+const double *c1o_debug_last_totals(void); /* per-candidate totals of the last c1o_allocate_bits */
 void c1o_quantize(const float *c, int n, int sfi, int bits, const c1o_tables *t, int *out);
 void c1o_dequantize(const int *q, int n, int sfi, int bits, const c1o_tables *t, float *out);
 void c1o_pack_bits(uint8_t *buf, size_t buf_len, int bit_pos, int value, int bit_count);
