@@ -56,7 +56,7 @@ EXPORTED_SYMBOLS = [
     "carta1_encode_device", "carta1_decode_device", "carta1_ctx_sync", "carta1_ctx_stream",
     "carta1_ctx_launch_count", "carta1_debug_encode_stages", "carta1_debug_decode_stages",
     "carta1_aea_write_header", "carta1_aea_parse_header", "carta1_kernel_count", "carta1_kernel_name",
-    "carta1_ctx_profile", "carta1_ctx_profile_read",
+    "carta1_ctx_profile", "carta1_ctx_profile_read", "carta1_debug_selftest",
 ]
 
 _lib = None
@@ -113,6 +113,7 @@ def load():
     L.carta1_kernel_name.restype = C.c_char_p
     L.carta1_ctx_profile.argtypes = [vp, C.c_int]
     L.carta1_ctx_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
+    L.carta1_debug_selftest.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.carta1_debug_encode_stages.argtypes = [vp, vp, sz, C.POINTER(EncOpts), vp, vp, vp, vp, vp]
     L.carta1_debug_decode_stages.argtypes = [vp, vp, sz, vp, vp, vp]
     L.carta1_aea_write_header.argtypes = [C.c_char_p, C.c_uint32, C.c_int, vp]
@@ -269,6 +270,11 @@ class Context:
     def decode_su_into(self, su: np.ndarray, n_su: int, n_ch: int, outs) -> None:
         ptrs = (C.POINTER(C.c_float) * len(outs))(*[c.ctypes.data_as(C.POINTER(C.c_float)) for c in outs])
         self._check(self.L.carta1_decode_su(self.h, _ptr(su), n_su, n_ch, ptrs))
+
+    def selftest(self) -> int:
+        bad = C.c_uint64()
+        self._check(self.L.carta1_debug_selftest(self.h, C.byref(bad)))
+        return int(bad.value)
 
     # ---- stage taps
     def debug_encode_stages(self, pcm: np.ndarray, opts: EncOpts | None = None):

@@ -282,7 +282,6 @@ int ensure_encode_scratch(carta1_ctx *ctx, size_t units, bool auto_modes) {
   return CARTA1_OK;
 }
 int ensure_decode_scratch(carta1_ctx *ctx, size_t units) {
-  CU(ctx, ctx->coefs.ensure(units * 512 * sizeof(float)));
   CU(ctx, ctx->inv.ensure(units * 512 * sizeof(float)));
   CU(ctx, ctx->modes.ensure(units * 4));
   return CARTA1_OK;
@@ -462,7 +461,7 @@ static int decode_device_impl(carta1_ctx *ctx, const uint8_t *d_su, size_t su_fr
   L.su = d_su; L.su_frame_stride = su_frame_stride; L.su_stream_stride = su_stream_stride;
   L.n_su_valid = (long long)n_su_valid; L.n_streams = n_streams; L.frames_total = (int)frames_total;
   L.halo_frames = (int)halo_frames; L.n_out_frames = (int)n_frames; L.tables = ctx->d_tables;
-  L.coefs = dbg_coefs ? dbg_coefs : (float *)ctx->coefs.p;
+  L.coefs_dbg = dbg_coefs;
   L.modes = (uint8_t *)ctx->modes.p;
   L.inv = (float *)ctx->inv.p;
   L.bands_dbg = dbg_bands;
@@ -809,6 +808,19 @@ int carta1_debug_decode_stages(carta1_ctx *ctx, const uint8_t *su, size_t n_su, 
   if (bands) CU(ctx, cudaMemcpyAsync(bands, base + o_bands, n_su * 512 * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (pcm) CU(ctx, cudaMemcpyAsync(pcm, base + o_pcm, n_su * 512 * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return CARTA1_OK;
+}
+
+int carta1_debug_selftest(carta1_ctx *ctx, uint64_t *mismatches) {
+  if (!ctx || !mismatches) return CARTA1_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, ctx->dbg.ensure(64));
+  CU(ctx, cudaMemsetAsync(ctx->dbg.p, 0, 8, ctx->stream));
+  CU(ctx, launch_selftest(ctx->d_tables, (unsigned long long *)ctx->dbg.p, ctx->stream));
+  unsigned long long bad = 0;
+  CU(ctx, cudaMemcpyAsync(&bad, ctx->dbg.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  *mismatches = bad;
   return CARTA1_OK;
 }
 

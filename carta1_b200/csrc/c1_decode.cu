@@ -9,34 +9,16 @@
 // Frame f of a row depends on units f-1 and f only: every kernel
 // treats the row as starting from the decoder's zero state and K7 recomputes the halo.
 #include "c1_common.cuh"
+#include "c1_fft.cuh"
 #include "c1_launch.h"
 
 namespace c1 {
 
-__device__ __forceinline__ int bitrev_d(int x, int log2n) { return (int)(__brev((unsigned)x) >> (32 - log2n)); }
-
-__device__ __forceinline__ void warp_fft_d(float *re, float *im, int n, const double2 *__restrict__ tw,
-                                           int lane) {  // fft.js:35-66
-  for (int half = 1; half < n; half <<= 1) {
-    for (int b = lane; b < (n >> 1); b += 32) {
-      const int k = b & (half - 1);
-      const int e = ((b - k) << 1) + k;
-      const int o = e + half;
-      const double2 w = tw[half - 1 + k];
-      const double er = re[e], ei = im[e], orr = re[o], oi = im[o];
-      const double tr = orr * w.x - oi * w.y;
-      const double ti = orr * w.y + oi * w.x;
-      re[e] = (float)(er + tr);
-      im[e] = (float)(ei + ti);
-      re[o] = (float)(er - tr);
-      im[o] = (float)(ei - ti);
-    }
-    __syncwarp();
-  }
-}
-
 // ------------------------------------------------------------------------------------
-// K5: one warp per sound unit.
+// K5+K6 fused: one warp per sound unit.  The unit is unpacked and dequantised into a
+// shared-memory row of 512 coefficients, each band is inverse-transformed in registers
+// (c1_fft.cuh) and the IMDCT middle halves replace the coefficients in the same row.
+// Only inv[N/4 .. N/4 + N/2) is ever used by the decoder (decoder.js:186-194,268-276).
 // ------------------------------------------------------------------------------------
 // unpackBits (bitstream.js:48-69) on big-endian words: a read that runs past byte 212
 // returns only the bits that were there, unshifted.
@@ -49,130 +31,183 @@ __device__ __forceinline__ uint32_t get_bits(const uint32_t *words, int pos, int
   return (uint32_t)((v << off) >> (64 - nb));
 }
 
-__global__ void __launch_bounds__(128)
-unpack_dequant_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_stream_stride,
-                      long long n_su_valid, int frames, int n_units, const DevTables *__restrict__ T,
-                      float *__restrict__ coefs, uint8_t *__restrict__ modes) {
-  __shared__ uint32_t s_words[4][56];
-  __shared__ uint16_t s_base[4][52];
-  __shared__ uint8_t s_wl[4][52], s_sfi[4][52];
+// f32((q * SF) / R) (quantization.js:75).  The division by the small integer R uses the
+// correctly rounded reciprocal and one residual correction (Markstein): q0 = x*rcp,
+// rem = x - q0*R exactly (fma), result = RN(q0 + rem*rcp) == RN(x / R).  R = 2^k - 1 is never
+// the all-ones significand the theorem excludes; carta1_debug_selftest checks every
+// (q, R, SF) against the IEEE division.
+__device__ __forceinline__ double div_by_range(double x, double range, double rcp) {
+  const double q0 = x * rcp;
+  const double rem = fma(-q0, range, x);
+  return fma(rem, rcp, q0);
+}
+__device__ __forceinline__ double int_to_double(int q) {  // exact, no conversion pipe
+  return __hiloint2double(0x43300000, (int)((unsigned)q ^ 0x80000000u)) - 4503601774854144.0;
+}
+
+// mdct.js:161-170: pre-twiddle of FFT input i (natural order)
+template <typename In>
+__device__ __forceinline__ Cplx imdct_pre(int i, int n, const In &in, const double *__restrict__ tab) {
+  const int i2 = 2 * i, half = n >> 1;
+  const double r = -in(i2);
+  const double m = -in(half - 1 - i2);
+  const double c = __ldg(&tab[i2]), s = __ldg(&tab[i2 + 1]);
+  Cplx z;
+  z.re = rnd32(m * s + r * c);
+  z.im = rnd32(m * c - r * s);
+  return z;
+}
+
+// mdct.js:177-208 restricted to output[n4 .. 3*n4): out[] is that middle half
+__device__ __forceinline__ void imdct_post(const Cplx z, int i, int n, const double *__restrict__ tab, float *out) {
+  const int half = n >> 1, n4 = n >> 2, fft_n = n >> 2;
+  const double c = __ldg(&tab[2 * i]), s = __ldg(&tab[2 * i + 1]);
+  const float r1 = (float)(z.re * c + z.im * s);
+  const float i1 = (float)(z.re * s - z.im * c);
+  const int idx = i < (fft_n >> 1) ? 2 * i : (i - (fft_n >> 1)) * 2 + n4;
+  out[half - 1 - idx] = r1;  // output[n34 - 1 - idx]
+  out[idx] = i1;             // output[n4 + idx]
+}
+
+constexpr int kUiWarps = 8;
+
+__global__ void __launch_bounds__(kUiWarps * 32)
+unpack_imdct_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_stream_stride,
+                    long long n_su_valid, int frames, int n_units, const DevTables *__restrict__ T,
+                    float *__restrict__ coefs_dbg, uint8_t *__restrict__ modes, float *__restrict__ inv) {
+  __shared__ __align__(16) float s_row[kUiWarps][512];
+  __shared__ double s_rcp[kUiWarps][52];
+  __shared__ uint32_t s_words[kUiWarps][56];
+  __shared__ uint16_t s_base[kUiWarps][52];
+  __shared__ uint8_t s_wl[kUiWarps][52], s_sfi[kUiWarps][52];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * 4 + warp;
+  const int unit = blockIdx.x * kUiWarps + warp;
   if (unit >= n_units) return;
   const int stream = unit / frames, frame = unit - stream * frames;
   const long long lin = (long long)frame * (long long)su_frame_stride + (long long)stream * (long long)su_stream_stride;
-  float *dst = coefs + (size_t)unit * 512;
   const FormatTables &F = T->fmt;
+  float *row = s_row[warp];
+  float4 *dst4 = reinterpret_cast<float4 *>(inv + (size_t)unit * 512);
+  int short_mask = 0;  // bit b: band b uses short blocks (any non-zero mode, decoder.js:82-83)
   if (lin >= n_su_valid) {  // dummy frame {nBfu: 0, blockModes: [0,0,0]} (processor.js:299-307)
-    for (int k = 0; k < 16; k++) dst[lane + 32 * k] = 0.0f;
+    // all-zero coefficients: every IMDCT output is +0 or -0; run the transform for the signs
+    for (int k = 0; k < 16; k++) row[lane + 32 * k] = 0.0f;
     if (lane < 4) modes[(size_t)unit * 4 + lane] = 0;
-    return;
-  }
-  uint32_t *words = s_words[warp];
-  const uint32_t *src = reinterpret_cast<const uint32_t *>(su + (size_t)lin * kSuBytes);
-  for (int i = lane; i < 56; i += 32) words[i] = i < kSuWords ? __byte_perm(src[i], 0, 0x0123) : 0u;
-  __syncwarp();
-  const uint32_t header = words[0] >> 16;
-  const int m0 = 2 - (int)((header >> 14) & 3), m1 = 2 - (int)((header >> 12) & 3),
-            m2 = 3 - (int)((header >> 10) & 3);
-  const int idx = (header >> 5) & 7;
-  const int n = idx == 0 ? 20 : 24 + 4 * idx;  // BFU_AMOUNTS
-  for (int i = lane; i < n; i += 32) {
-    s_wl[warp][i] = (uint8_t)get_bits(words, 16 + 4 * i, 4);
-    s_sfi[warp][i] = (uint8_t)get_bits(words, 16 + 4 * n + 6 * i, 6);
-  }
-  __syncwarp();
-  if (lane == 0) {
-    int pos = 16 + 10 * n;
-    for (int b = 0; b < n; b++) {
-      s_base[warp][b] = (uint16_t)pos;
-      pos += wl_bits(s_wl[warp][b]) * (int)F.specs[b];
+  } else {
+    uint32_t *words = s_words[warp];
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(su + (size_t)lin * kSuBytes);
+    for (int i = lane; i < 56; i += 32) words[i] = i < kSuWords ? __byte_perm(src[i], 0, 0x0123) : 0u;
+    __syncwarp();
+    const uint32_t header = words[0] >> 16;  // serialization.js:118-126
+    const int m0 = 2 - (int)((header >> 14) & 3), m1 = 2 - (int)((header >> 12) & 3),
+              m2 = 3 - (int)((header >> 10) & 3);
+    const int idx = (header >> 5) & 7;
+    const int n = idx == 0 ? 20 : 24 + 4 * idx;  // BFU_AMOUNTS
+    int run = 16 + 10 * n;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {  // word lengths, scale factors, bit offsets (exclusive scan)
+      const int b = lane + 32 * h;
+      int wl = 0, sfi = 0;
+      if (b < n) {
+        wl = (int)get_bits(words, 16 + 4 * b, 4);
+        sfi = (int)get_bits(words, 16 + 4 * n + 6 * b, 6);
+      }
+      const int bits = wl_bits(wl);
+      const int cost = b < n ? bits * (int)F.specs[b < 52 ? b : 0] : 0;
+      int incl = cost;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (b < 52) {
+        s_wl[warp][b] = (uint8_t)(b < n ? wl : 0);
+        s_sfi[warp][b] = (uint8_t)sfi;
+        s_base[warp][b] = (uint16_t)(run + incl - cost);
+        s_rcp[warp][b] = bits > 0 ? 1.0 / (double)((1 << (bits - 1)) - 1) : 0.0;
+      }
+      run += __shfl_sync(0xffffffffu, incl, 31);
     }
-  }
-  __syncwarp();
-  if (lane < 4) modes[(size_t)unit * 4 + lane] = (uint8_t)(lane == 0 ? m0 != 0 : lane == 1 ? m1 != 0 : lane == 2 ? m2 != 0 : 0);
-  for (int k = 0; k < 16; k++) {
-    const int c = lane + 32 * k;
-    const int mode = c < 128 ? m0 : (c < 256 ? m1 : m2);
-    const int b = mode == 0 ? F.bfu_of_long[c] : F.bfu_of_short[c];
-    float val = 0.0f;
-    if (b < n) {
-      const int bits = wl_bits(s_wl[warp][b]);
+    __syncwarp();
+    short_mask = (m0 != 0) | ((m1 != 0) << 1) | ((m2 != 0) << 2);
+    if (lane < 4) modes[(size_t)unit * 4 + lane] = (uint8_t)((short_mask >> lane) & 1);
+#pragma unroll 4
+    for (int k = 0; k < 16; k++) {  // serialization.js:153-166 + decoder.js:65-94
+      const int c = lane + 32 * k;
+      const int mode = k < 4 ? m0 : (k < 8 ? m1 : m2);
+      const int b = mode == 0 ? F.bfu_of_long[c] : F.bfu_of_short[c];
+      float val = 0.0f;
+      const int bits = wl_bits(s_wl[warp][b]);  // 0 for b >= n
       if (bits > 0) {
         const int j = c - (mode == 0 ? F.start_long[b] : F.start_short[b]);
         const int v = (int)get_bits(words, (int)s_base[warp][b] + j * bits, bits);
         const int q = v >= (1 << (bits - 1)) ? v - (1 << bits) : v;  // bitstream.js:78-82
         const int sfi = s_sfi[warp][b];
         if (sfi != 0) {
-          const int range = (1 << (bits - 1)) - 1;
-          val = (float)(((double)q * T->sf[sfi]) / (double)range);  // quantization.js:75
+          const double range = (double)((1 << (bits - 1)) - 1);
+          val = (float)div_by_range(int_to_double(q) * T->sf[sfi], range, s_rcp[warp][b]);
         }
       }
-    }
-    dst[c] = val;
-  }
-}
-
-// ------------------------------------------------------------------------------------
-// K6: IMDCT, one warp per sound unit.  Only inv[N/4 .. N/4 + N/2) is ever used by the
-// decoder (decoder.js:186-194,268-276), so only that half is produced.
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ void imdct_warp(const float *__restrict__ in, bool reverse, int n, int lg_fft,
-                                           const double *__restrict__ tab, const double2 *__restrict__ tw,
-                                           float *re, float *im, float *__restrict__ out, int lane) {
-  const int n4 = n >> 2, half = n >> 1, fft_n = n >> 2;
-  for (int i = lane; i < fft_n; i += 32) {  // mdct.js:161-170
-    const int i2 = 2 * i;
-    const int ia = reverse ? half - 1 - i2 : i2;
-    const int ib = reverse ? i2 : half - 1 - i2;
-    const double r = -(double)in[ia];
-    const double m = -(double)in[ib];
-    const double c = tab[i2], s = tab[i2 + 1];
-    const int q = bitrev_d(i, lg_fft);
-    re[q] = (float)(m * s + r * c);
-    im[q] = (float)(m * c - r * s);
-  }
-  __syncwarp();
-  warp_fft_d(re, im, fft_n, tw, lane);
-  for (int i = lane; i < fft_n; i += 32) {  // mdct.js:177-208, restricted to [n4, 3*n4)
-    const int i2 = 2 * i;
-    const double c = tab[i2], s = tab[i2 + 1];
-    const double r = re[i], m = im[i];
-    const float r1 = (float)(r * c + m * s);
-    const float i1 = (float)(r * s - m * c);
-    if (i < (fft_n >> 1)) {
-      out[half - 1 - i2] = r1;  // output[n34 - 1 - i2]
-      out[i2] = i1;             // output[n4 + i2]
-    } else {
-      const int idx = (i - (fft_n >> 1)) * 2 + n4;
-      out[half - 1 - idx] = r1;  // output[n34 - 1 - idx]
-      out[idx] = i1;             // output[n4 + idx]
+      row[c] = val;
     }
   }
   __syncwarp();
-}
-
-__global__ void __launch_bounds__(128)
-imdct_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes, int n_units,
-             const DevTables *__restrict__ T, float *__restrict__ inv) {
-  __shared__ float s_re[4][128], s_im[4][128];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * 4 + warp;
-  if (unit >= n_units) return;
-  float *re = s_re[warp], *im = s_im[warp];
+  if (coefs_dbg) {
+    float4 *d = reinterpret_cast<float4 *>(coefs_dbg + (size_t)unit * 512);
+    const float4 *s4 = reinterpret_cast<const float4 *>(row);
+#pragma unroll
+    for (int k = 0; k < 4; k++) d[lane + 32 * k] = s4[lane + 32 * k];
+  }
+  const double2 *tw = T->fft_tw;
   for (int band = 0; band < 3; band++) {
     const int size = band == 2 ? 256 : 128;
     const int off = band == 0 ? 0 : band == 1 ? 128 : 256;
-    const float *src = coefs + (size_t)unit * 512 + off;
-    float *dst = inv + (size_t)unit * 512 + off;
-    if (modes[(size_t)unit * 4 + band] == 0) {
-      imdct_warp(src, band > 0, band == 2 ? 512 : 256, band == 2 ? 7 : 6,
-                 band == 2 ? T->mdct_inv512 : T->mdct_inv256, T->fft_tw, re, im, dst, lane);
+    float *x = row + off;
+    const bool rev = band > 0;  // utils.js:42-48: un-reverse mid / high spectra
+    if (!((short_mask >> band) & 1)) {
+      auto in = [&](int k) -> double { return (double)x[rev ? size - 1 - k : k]; };
+      if (band < 2) {
+        const double *tab = T->mdct_inv256;
+        const int r5 = brev_bits(lane, 5);
+        Cplx a = imdct_pre(r5, 256, in, tab);
+        Cplx b = imdct_pre(32 + r5, 256, in, tab);
+        __syncwarp();
+        warp_fft_regs<5>(a, b, tw, lane);
+        imdct_post(a, lane, 256, tab, x);
+        imdct_post(b, lane + 32, 256, tab, x);
+      } else {
+        const double *tab = T->mdct_inv512;
+        const int r5 = brev_bits(lane, 5);
+        Cplx a0 = imdct_pre(2 * r5, 512, in, tab);
+        Cplx b0 = imdct_pre(64 + 2 * r5, 512, in, tab);
+        Cplx a1 = imdct_pre(2 * r5 + 1, 512, in, tab);
+        Cplx b1 = imdct_pre(64 + 2 * r5 + 1, 512, in, tab);
+        __syncwarp();
+        warp_fft128_regs(a0, b0, a1, b1, tw, lane);
+        imdct_post(a0, lane, 512, tab, x);
+        imdct_post(b0, lane + 32, 512, tab, x);
+        imdct_post(a1, lane + 64, 512, tab, x);
+        imdct_post(b1, lane + 96, 512, tab, x);
+      }
     } else {
-      for (int b = 0; b < (size >> 5); b++)
-        imdct_warp(src + 32 * b, band > 0, 64, 4, T->mdct_inv64, T->fft_tw, re, im, dst + 32 * b, lane);
+      const double *tab = T->mdct_inv64;
+      const int g = lane & 7, r3 = brev_bits(g, 3);
+      for (int b0 = 0; b0 < (size >> 5); b0 += 4) {
+        float *xb = x + 32 * (b0 + (lane >> 3));
+        auto in = [&](int k) -> double { return (double)xb[rev ? 31 - k : k]; };
+        Cplx a = imdct_pre(r3, 64, in, tab);
+        Cplx b = imdct_pre(8 + r3, 64, in, tab);
+        __syncwarp();
+        warp_fft_regs<3>(a, b, tw, lane);
+        imdct_post(a, g, 64, tab, xb);
+        imdct_post(b, g + 8, 64, tab, xb);
+      }
     }
+    __syncwarp();
   }
+  const float4 *s4 = reinterpret_cast<const float4 *>(row);
+#pragma unroll
+  for (int k = 0; k < 4; k++) dst4[lane + 32 * k] = s4[lane + 32 * k];
 }
 
 // ------------------------------------------------------------------------------------
@@ -360,17 +395,61 @@ synth_kernel(const float *__restrict__ inv, const uint8_t *__restrict__ modes, i
 constexpr size_t kSynSmemBytes =
     (size_t)(2 * 8 * kSynStrideA + 2 * 8 * kSynStrideB) * sizeof(double) + (size_t)kSynHd * sizeof(float);
 
+// ------------------------------------------------------------------------------------
+// Self-test of the two arithmetic shortcuts against the IEEE operations they replace:
+// div_by_range vs '/', for every (word length, quantised value, scale factor); rnd32 vs the
+// cvt round trip on values at and around f32 rounding ties in every binade.
+// ------------------------------------------------------------------------------------
+__global__ void selftest_kernel(const DevTables *__restrict__ T, unsigned long long *bad) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  unsigned long long local = 0;
+  // (a) division: bits 2..16, q in [-2^(bits-1), 2^(bits-1)), sfi 1..63
+  for (int bits = 2; bits <= 16; bits++) {
+    const int range_i = (1 << (bits - 1)) - 1;
+    const double range = (double)range_i;
+    const double rcp = 1.0 / range;
+    const long long total = (long long)(1 << bits) * 63;
+    for (long long k = tid; k < total; k += stride) {
+      const int q = (int)(k / 63) - (1 << (bits - 1));
+      const int sfi = (int)(k % 63) + 1;
+      const double x = int_to_double(q) * T->sf[sfi];
+      const double want = ((double)q * T->sf[sfi]) / range;
+      const double got = div_by_range(x, range, rcp);
+      if (__double_as_longlong(want) != __double_as_longlong(got)) local++;
+    }
+  }
+  // (b) rounding: f32 patterns stepped through all exponents, offsets of k/8 f32-ulp
+  for (long long k = tid; k < (1ll << 24); k += stride) {
+    const unsigned fb = (unsigned)(k * 251u) ^ (unsigned)(k << 9);
+    const float f = __uint_as_float(fb);
+    if (!isfinite(f)) continue;
+    const double d = (double)f;
+    const double ulp = (double)__uint_as_float(((fb & 0x7F800000u) ? (fb & 0x7F800000u) : 0x00800000u)) * 1.1920928955078125e-07;
+#pragma unroll
+    for (int j = -9; j <= 9; j++) {
+      const double v = d + ulp * (0.125 * j) + ((j & 1) ? ulp * 1e-9 : 0.0);
+      const double want = (double)(float)v;
+      const double got = rnd32(v);
+      if (__double_as_longlong(want) != __double_as_longlong(got)) local++;
+    }
+  }
+  if (local) atomicAdd(bad, local);
+}
+
+cudaError_t launch_selftest(const DevTables *tables, unsigned long long *d_bad, cudaStream_t st) {
+  selftest_kernel<<<592, 256, 0, st>>>(tables, d_bad);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, Prof *prof) {
   const int n_units = L.n_streams * L.frames_total;
   if (n_units == 0) return cudaSuccess;
-  prof->begin(K_UNPACK_DEQUANT, st);
-  unpack_dequant_kernel<<<(n_units + 3) / 4, 128, 0, st>>>(L.su, L.su_frame_stride, L.su_stream_stride,
-                                                         L.n_su_valid, L.frames_total, n_units, L.tables,
-                                                         L.coefs, L.modes);
-  prof->end(K_UNPACK_DEQUANT, st);
-  prof->begin(K_IMDCT, st);
-  imdct_kernel<<<(n_units + 3) / 4, 128, 0, st>>>(L.coefs, L.modes, n_units, L.tables, L.inv);
-  prof->end(K_IMDCT, st);
+  prof->begin(K_UNPACK_IMDCT, st);
+  unpack_imdct_kernel<<<(n_units + kUiWarps - 1) / kUiWarps, kUiWarps * 32, 0, st>>>(
+      L.su, L.su_frame_stride, L.su_stream_stride, L.n_su_valid, L.frames_total, n_units, L.tables, L.coefs_dbg,
+      L.modes, L.inv);
+  prof->end(K_UNPACK_IMDCT, st);
   if (L.bands_dbg) {
     prof->begin(K_BANDS_TIME, st);
     bands_time_kernel<<<n_units, 256, 0, st>>>(L.inv, L.modes, L.frames_total, n_units, L.tables, L.bands_dbg);

@@ -11,6 +11,7 @@
 // store.  Compiled with -fmad=false.
 #include "c1_common.cuh"
 #include "c1_fdlibm.cuh"
+#include "c1_fft.cuh"
 #include "c1_launch.h"
 
 namespace c1 {
@@ -284,96 +285,138 @@ transient_modes_kernel(const float *__restrict__ mags, int frames, int n_su,
 
 // ------------------------------------------------------------------------------------
 // K3: windowed MDCT, one warp per sound unit (mdct.js:54-122, encoder.js:228-316).
+// Long blocks: FFT64 (low, mid) / FFT128 (high) in registers; short blocks: four FFT16 per
+// warp pass.  All values are binary64 registers holding f32-representable numbers
+// (c1_fft.cuh); the only f64->f32 conversions are the final coefficient stores.
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ void mdct_warp(const float *in, int n, int lg_fft, const double *__restrict__ tab,
-                                          const double2 *__restrict__ tw, float *re, float *im,
-                                          float *__restrict__ out, bool reverse, int lane) {
-  const int n4 = n >> 2, n34 = 3 * n4, half = n >> 1, fft_n = n >> 2;
-  for (int p = lane; p < fft_n; p += 32) {
-    const int i = 2 * p;
-    double r, m;
-    if (i < n4) {  // mdct.js:76-89
-      r = (double)in[n34 - 1 - i] + (double)in[n34 + i];
-      m = (double)in[n4 + i] - (double)in[n4 - 1 - i];
-    } else {       // mdct.js:91-105
-      r = (double)in[n34 - 1 - i] - (double)in[i - n4];
-      m = (double)in[n4 + i] + (double)in[5 * n4 - 1 - i];
-    }
-    const double c = tab[i], s = tab[i + 1];
-    const int q = bitrev(p, lg_fft);
-    re[q] = (float)(r * c + m * s);
-    im[q] = (float)(m * c - r * s);
+// mdct.js:76-105: pre-twiddle of FFT input q (natural order) of an N-point MDCT
+template <typename In>
+__device__ __forceinline__ Cplx mdct_pre(int q, int n, const In &in, const double *__restrict__ tab) {
+  const int i = 2 * q, n4 = n >> 2, n34 = 3 * n4;
+  double r, m;
+  if (i < n4) {
+    r = in(n34 - 1 - i) + in(n34 + i);
+    m = in(n4 + i) - in(n4 - 1 - i);
+  } else {
+    r = in(n34 - 1 - i) - in(i - n4);
+    m = in(n4 + i) + in(5 * n4 - 1 - i);
   }
-  __syncwarp();
-  warp_fft(re, im, fft_n, tw, lane);
-  for (int i = lane; i < fft_n; i += 32) {  // mdct.js:111-119
-    const double c = tab[2 * i], s = tab[2 * i + 1];
-    const double r = re[i], m = im[i];
-    const float o0 = (float)(-r * c - m * s);
-    const float o1 = (float)(-r * s + m * c);
-    int i0 = 2 * i, i1 = half - 1 - 2 * i;
-    if (reverse) { i0 = half - 1 - i0; i1 = half - 1 - i1; }  // utils.js:42-48
-    out[i0] = o0;
-    out[i1] = o1;
-  }
-  __syncwarp();
+  const double c = __ldg(&tab[i]), s = __ldg(&tab[i + 1]);
+  Cplx z;
+  z.re = rnd32(r * c + m * s);
+  z.im = rnd32(m * c - r * s);
+  return z;
 }
 
-__global__ void __launch_bounds__(128)
+// mdct.js:111-119: FFT output i -> coefficients 2i and N/2-1-2i (spectrum reversed for
+// bands 1 and 2, utils.js:42-48); `out` is the f32 staging row of this block
+__device__ __forceinline__ void mdct_post(const Cplx z, int i, int n, const double *__restrict__ tab,
+                                          float *out, bool reverse) {
+  const int half = n >> 1;
+  const double c = __ldg(&tab[2 * i]), s = __ldg(&tab[2 * i + 1]);
+  const double o0 = rnd32(-z.re * c - z.im * s);
+  const double o1 = rnd32(-z.re * s + z.im * c);
+  int i0 = 2 * i, i1 = half - 1 - 2 * i;
+  if (reverse) { i0 = half - 1 - i0; i1 = half - 1 - i1; }
+  out[i0] = (float)o0;
+  out[i1] = (float)o1;
+}
+
+constexpr int kMdctWarps = 8;
+
+__global__ void __launch_bounds__(kMdctWarps * 32)
 mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, int frames, int n_su,
             const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
             float *__restrict__ coefs) {
-  __shared__ float s_buf[4][512], s_re[4][128], s_im[4][128];
+  __shared__ double s_arr[kMdctWarps][512];
+  __shared__ __align__(16) float s_out[kMdctWarps][512];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int su = blockIdx.x * 4 + warp;
+  const int su = blockIdx.x * kMdctWarps + warp;
   if (su >= n_su) return;
+  const double w_fwd = T->win[lane], w_rev = T->win[31 - lane];  // WINDOW_SHORT[i], [31 - i]
   const int frame = su % frames;
-  float *buf = s_buf[warp], *re = s_re[warp], *im = s_im[warp];
-  const double *win = T->win;
+  double *arr = s_arr[warp];
+  float *out = s_out[warp];
+  const double2 *tw = T->fft_tw;
   for (int band = 0; band < 3; band++) {
     const int size = band == 2 ? 256 : 128;
     const int off = band == 0 ? 0 : band == 1 ? 128 : 256;
     const float *cur = bands + (size_t)su * 512 + off;
     const float *prev = frame > 0 ? cur - 512 : nullptr;
     const int mode = P->use_fixed ? P->fixed[band] : (int)modes[(size_t)su * 4 + band];
-    float *dst = coefs + (size_t)su * 512 + off;
+    const bool rev = band > 0;
     if (mode == 0) {
-      const int n = band == 2 ? 512 : 256;
-      const int ws = band == 2 ? 112 : 48;  // constants.js:115-119
-      for (int k = lane; k < n; k += 32) {
-        float v = 0.0f;
-        const int a = k - ws;
-        if (a >= 0 && a < 32) {  // overlap saved by the previous frame's tail windowing
-          v = prev ? (float)(win[a] * (double)prev[size - 32 + a]) : 0.0f;
-        } else if (a >= 32 && a < 32 + size) {
-          const int sidx = a - 32;
-          const float x = cur[sidx];
-          const int t = sidx - (size - 32);
-          v = t >= 0 ? (float)((double)x * win[31 - t]) : x;
-        }
-        buf[k] = v;
+      // arr = [overlap saved by the previous frame (32) | samples, last 32 tail-windowed]
+      // (encoder.js:240-247,309-316)
+      {
+        const float pv = prev ? prev[size - 32 + lane] : 0.0f;
+        arr[lane] = prev ? rnd32(w_fwd * (double)pv) : 0.0;
+      }
+      for (int k = lane; k < size; k += 32) {
+        const double x = (double)cur[k];
+        arr[32 + k] = k >= size - 32 ? rnd32(x * w_rev) : x;  // k - (size - 32) == lane
       }
       __syncwarp();
-      mdct_warp(buf, n, band == 2 ? 7 : 6, band == 2 ? T->mdct_fwd512 : T->mdct_fwd256, T->fft_tw, re, im,
-                dst, band > 0, lane);
+      const int ws = band == 2 ? 112 : 48;  // constants.js:115-119
+      const int span = size + 32;
+      auto in = [&](int k) -> double {
+        const unsigned a = (unsigned)(k - ws);
+        return a < (unsigned)span ? arr[a] : 0.0;
+      };
+      const int r5 = brev_bits(lane, 5);
+      if (band < 2) {
+        const double *tab = T->mdct_fwd256;
+        Cplx a = mdct_pre(r5, 256, in, tab);
+        Cplx b = mdct_pre(32 + r5, 256, in, tab);
+        warp_fft_regs<5>(a, b, tw, lane);
+        mdct_post(a, lane, 256, tab, out + off, rev);
+        mdct_post(b, lane + 32, 256, tab, out + off, rev);
+      } else {
+        const double *tab = T->mdct_fwd512;
+        Cplx a0 = mdct_pre(2 * r5, 512, in, tab);
+        Cplx b0 = mdct_pre(64 + 2 * r5, 512, in, tab);
+        Cplx a1 = mdct_pre(2 * r5 + 1, 512, in, tab);
+        Cplx b1 = mdct_pre(64 + 2 * r5 + 1, 512, in, tab);
+        warp_fft128_regs(a0, b0, a1, b1, tw, lane);
+        mdct_post(a0, lane, 512, tab, out + off, rev);
+        mdct_post(b0, lane + 32, 512, tab, out + off, rev);
+        mdct_post(a1, lane + 64, 512, tab, out + off, rev);
+        mdct_post(b1, lane + 96, 512, tab, out + off, rev);
+      }
+      __syncwarp();
     } else {
+      // short blocks: block b transforms [WIN * previous block (32) | block * reversed WIN (32)]
+      // (encoder.js:279-304)
       const int blocks = size >> 5;
       for (int b = 0; b < blocks; b++) {
-        {
-          // lanes 0..31: overlap = WIN[i] * (previous 32-sample block); block = x * WIN[31-i]
-          const int i = lane;
-          float src_prev;
-          if (b == 0) src_prev = prev ? prev[size - 32 + i] : 0.0f;
-          else src_prev = cur[32 * (b - 1) + i];
-          // frame 0 / block 0 starts from the all-zero overlap buffer (buffers.js:60-65)
-          buf[i] = (b == 0 && !prev) ? 0.0f : (float)(win[i] * (double)src_prev);
-          buf[32 + i] = (float)((double)cur[32 * b + i] * win[31 - i]);
-        }
-        __syncwarp();
-        mdct_warp(buf, 64, 4, T->mdct_fwd64, T->fft_tw, re, im, dst + 32 * b, band > 0, lane);
+        float src_prev = 0.0f;
+        bool have_prev = true;
+        if (b == 0) { have_prev = prev != nullptr; if (prev) src_prev = prev[size - 32 + lane]; }
+        else src_prev = cur[32 * (b - 1) + lane];
+        arr[64 * b + lane] = have_prev ? rnd32(w_fwd * (double)src_prev) : 0.0;
+        arr[64 * b + 32 + lane] = rnd32((double)cur[32 * b + lane] * w_rev);
       }
+      __syncwarp();
+      const double *tab = T->mdct_fwd64;
+      const int g = lane & 7, r3 = brev_bits(g, 3);
+      for (int b0 = 0; b0 < blocks; b0 += 4) {
+        const int blk = b0 + (lane >> 3);
+        const double *ab = arr + 64 * blk;
+        auto in = [&](int k) -> double { return ab[k]; };
+        Cplx a = mdct_pre(r3, 64, in, tab);
+        Cplx b = mdct_pre(8 + r3, 64, in, tab);
+        warp_fft_regs<3>(a, b, tw, lane);
+        mdct_post(a, g, 64, tab, out + off + 32 * blk, rev);
+        mdct_post(b, g + 8, 64, tab, out + off + 32 * blk, rev);
+      }
+      __syncwarp();
     }
   }
+  __syncwarp();
+  float4 *dst = reinterpret_cast<float4 *>(coefs + (size_t)su * 512);
+  const float4 *src = reinterpret_cast<const float4 *>(out);
+#pragma unroll
+  for (int k = 0; k < 4; k++) dst[lane + 32 * k] = src[lane + 32 * k];
 }
 
 // ------------------------------------------------------------------------------------
@@ -767,7 +810,7 @@ size_t alloc_rec_bytes() { return sizeof(AllocRec) + sizeof(AllocCand); }
 
 const char *kernel_name(int id) {
   static const char *names[K_COUNT] = {"qmf_analysis", "band_mags", "transient_modes", "mdct",
-                                       "alloc", "quant_pack", "unpack_dequant", "imdct", "bands_time", "synth"};
+                                       "alloc", "quant_pack", "unpack_imdct", "bands_time", "synth"};
   return id >= 0 && id < K_COUNT ? names[id] : "?";
 }
 
@@ -800,7 +843,7 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
     prof->end(K_TRANSIENT_MODES, st);
   }
   prof->begin(K_MDCT, st);
-  mdct_kernel<<<(n_su + 3) / 4, 128, 0, st>>>(L.bands, L.modes, frames, n_su, L.tables, L.params, L.coefs);
+  mdct_kernel<<<(n_su + kMdctWarps - 1) / kMdctWarps, kMdctWarps * 32, 0, st>>>(L.bands, L.modes, frames, n_su, L.tables, L.params, L.coefs);
   prof->end(K_MDCT, st);
   const long long n_units = (long long)L.n_streams * L.n_out_frames;
   if (n_units > 0 && L.su_out) {

@@ -49,7 +49,7 @@ struct DecodeLaunch {
   int n_out_frames;
   const DevTables *tables;
   // scratch, [n_streams][frames_total][...]
-  float *coefs;             // 512 per unit
+  float *coefs_dbg;         // optional 512 per unit: dequantised coefficients (stage tap)
   uint8_t *modes;           // 4 per unit
   float *inv;               // 512 per unit: IMDCT output before overlap-add
   float *bands_dbg;         // optional 512 per unit: time-domain bands (stage tap)
@@ -63,7 +63,7 @@ struct DecodeLaunch {
 // Launch accounting and optional per-kernel CUDA-event timing (bench.py's roofline leg).
 enum KernelId {
   K_QMF_ANALYSIS = 0, K_BAND_MAGS, K_TRANSIENT_MODES, K_MDCT, K_ALLOC, K_QUANT_PACK,
-  K_UNPACK_DEQUANT, K_IMDCT, K_BANDS_TIME, K_SYNTH, K_COUNT
+  K_UNPACK_IMDCT, K_BANDS_TIME, K_SYNTH, K_COUNT
 };
 const char *kernel_name(int id);
 
@@ -91,5 +91,6 @@ cudaError_t upload_encode_constants(const double *even24, const double *odd24);
 cudaError_t upload_decode_constants(const double *even24, const double *odd24);
 cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof);
 cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, Prof *prof);
+cudaError_t launch_selftest(const DevTables *tables, unsigned long long *d_bad, cudaStream_t st);
 
 }  // namespace c1

@@ -162,6 +162,11 @@ int carta1_debug_encode_stages(carta1_ctx *ctx, const float *pcm, size_t n_sampl
 int carta1_debug_decode_stages(carta1_ctx *ctx, const uint8_t *su, size_t n_su, float *coefs,
                                float *bands, float *pcm);
 
+/* Device self-test of the kernels' exact arithmetic shortcuts (reciprocal-based division,
+ * in-FP64 rounding to binary32) against the IEEE operations they replace; *mismatches must
+ * come back 0. */
+int carta1_debug_selftest(carta1_ctx *ctx, uint64_t *mismatches);
+
 /* ---- AEA container (codec/io/serialization.js:190-253) --------------------------- */
 int carta1_aea_write_header(const char *title_utf8, uint32_t su_count, int n_ch,
                             uint8_t out[CARTA1_AEA_HEADER_BYTES]);

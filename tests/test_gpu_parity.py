@@ -201,6 +201,12 @@ def test_chunked_host_path(ctx, oracle, monkeypatch):
     assert np.array_equal(su, want)
 
 
+def test_arithmetic_shortcuts_selftest(ctx):
+    """Exhaustive device check: reciprocal division == IEEE division for every (q, R, SF);
+    in-FP64 rounding == cvt.rn.f32.f64 on 3e8 values around rounding ties."""
+    assert ctx.selftest() == 0
+
+
 def test_error_messages(ctx):
     with pytest.raises(TypeError, match="one or two Float32 channels"):
         ctx.encode_pcm([np.zeros(10, np.float32)] * 3)
