@@ -46,15 +46,16 @@ __device__ __forceinline__ double int_to_double(int q) {  // exact, no conversio
 }
 
 // mdct.js:161-170: pre-twiddle of FFT input i (natural order)
-template <typename In>
-__device__ __forceinline__ Cplx imdct_pre(int i, int n, const In &in, const double *__restrict__ tab) {
+template <typename In, typename R>
+__device__ __forceinline__ Cplx imdct_pre(int i, int n, const In &in, const double *__restrict__ tab,
+                                          const R &rnd) {
   const int i2 = 2 * i, half = n >> 1;
   const double r = -in(i2);
   const double m = -in(half - 1 - i2);
   const double c = __ldg(&tab[i2]), s = __ldg(&tab[i2 + 1]);
   Cplx z;
-  z.re = rnd32(m * s + r * c);
-  z.im = rnd32(m * c - r * s);
+  z.re = rnd(m * s + r * c);
+  z.im = rnd(m * c - r * s);
   return z;
 }
 
@@ -69,13 +70,65 @@ __device__ __forceinline__ void imdct_post(const Cplx z, int i, int n, const dou
   out[idx] = i1;             // output[n4 + idx]
 }
 
+// One band of one sound unit, by one warp: x (coefficients) -> y (IMDCT middle half).
+template <typename R>
+__device__ __forceinline__ void imdct_band(int band, bool is_long, const float *x, float *y,
+                                           const DevTables *__restrict__ T, int lane) {
+  R rnd;
+  const double2 *tw = T->fft_tw;
+  const int size = band == 2 ? 256 : 128;
+  const bool rev = band > 0;  // utils.js:42-48: un-reverse mid / high spectra
+  if (is_long) {
+    auto in = [&](int k) -> double { return (double)x[rev ? size - 1 - k : k]; };
+    const int r5 = brev_bits(lane, 5);
+    if (band < 2) {
+      const double *tab = T->mdct_inv256;
+      Cplx a = imdct_pre(r5, 256, in, tab, rnd);
+      Cplx b = imdct_pre(32 + r5, 256, in, tab, rnd);
+      warp_fft_regs<5>(a, b, tw, lane, rnd);
+      imdct_post(a, lane, 256, tab, y);
+      imdct_post(b, lane + 32, 256, tab, y);
+    } else {
+      const double *tab = T->mdct_inv512;
+      Cplx a0 = imdct_pre(2 * r5, 512, in, tab, rnd);
+      Cplx b0 = imdct_pre(64 + 2 * r5, 512, in, tab, rnd);
+      Cplx a1 = imdct_pre(2 * r5 + 1, 512, in, tab, rnd);
+      Cplx b1 = imdct_pre(64 + 2 * r5 + 1, 512, in, tab, rnd);
+      warp_fft128_regs(a0, b0, a1, b1, tw, lane, rnd);
+      imdct_post(a0, lane, 512, tab, y);
+      imdct_post(b0, lane + 32, 512, tab, y);
+      imdct_post(a1, lane + 64, 512, tab, y);
+      imdct_post(b1, lane + 96, 512, tab, y);
+    }
+  } else {
+    const double *tab = T->mdct_inv64;
+    const int g = lane & 7, r3 = brev_bits(g, 3);
+    for (int b0 = 0; b0 < (size >> 5); b0 += 4) {
+      const int blk = b0 + (lane >> 3);
+      const float *xb = x + 32 * blk;
+      auto in = [&](int k) -> double { return (double)xb[rev ? 31 - k : k]; };
+      Cplx a = imdct_pre(r3, 64, in, tab, rnd);
+      Cplx b = imdct_pre(8 + r3, 64, in, tab, rnd);
+      warp_fft_regs<3>(a, b, tw, lane, rnd);
+      imdct_post(a, g, 64, tab, y + 32 * blk);
+      imdct_post(b, g + 8, 64, tab, y + 32 * blk);
+    }
+  }
+}
+
+__device__ __noinline__ void imdct_band_exact(int band, bool is_long, const float *x, float *y,
+                                              const DevTables *__restrict__ T, int lane) {
+  imdct_band<ExactRound>(band, is_long, x, y, T, lane);
+}
+
 constexpr int kUiWarps = 8;
 
-__global__ void __launch_bounds__(kUiWarps * 32)
+__global__ void __launch_bounds__(kUiWarps * 32, 3)
 unpack_imdct_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_stream_stride,
                     long long n_su_valid, int frames, int n_units, const DevTables *__restrict__ T,
                     float *__restrict__ coefs_dbg, uint8_t *__restrict__ modes, float *__restrict__ inv) {
   __shared__ __align__(16) float s_row[kUiWarps][512];
+  __shared__ __align__(16) float s_inv[kUiWarps][512];
   __shared__ double s_rcp[kUiWarps][52];
   __shared__ uint32_t s_words[kUiWarps][56];
   __shared__ uint16_t s_base[kUiWarps][52];
@@ -158,54 +211,20 @@ unpack_imdct_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size
 #pragma unroll
     for (int k = 0; k < 4; k++) d[lane + 32 * k] = s4[lane + 32 * k];
   }
-  const double2 *tw = T->fft_tw;
+  float *y = s_inv[warp];
   for (int band = 0; band < 3; band++) {
-    const int size = band == 2 ? 256 : 128;
     const int off = band == 0 ? 0 : band == 1 ? 128 : 256;
-    float *x = row + off;
-    const bool rev = band > 0;  // utils.js:42-48: un-reverse mid / high spectra
-    if (!((short_mask >> band) & 1)) {
-      auto in = [&](int k) -> double { return (double)x[rev ? size - 1 - k : k]; };
-      if (band < 2) {
-        const double *tab = T->mdct_inv256;
-        const int r5 = brev_bits(lane, 5);
-        Cplx a = imdct_pre(r5, 256, in, tab);
-        Cplx b = imdct_pre(32 + r5, 256, in, tab);
-        __syncwarp();
-        warp_fft_regs<5>(a, b, tw, lane);
-        imdct_post(a, lane, 256, tab, x);
-        imdct_post(b, lane + 32, 256, tab, x);
-      } else {
-        const double *tab = T->mdct_inv512;
-        const int r5 = brev_bits(lane, 5);
-        Cplx a0 = imdct_pre(2 * r5, 512, in, tab);
-        Cplx b0 = imdct_pre(64 + 2 * r5, 512, in, tab);
-        Cplx a1 = imdct_pre(2 * r5 + 1, 512, in, tab);
-        Cplx b1 = imdct_pre(64 + 2 * r5 + 1, 512, in, tab);
-        __syncwarp();
-        warp_fft128_regs(a0, b0, a1, b1, tw, lane);
-        imdct_post(a0, lane, 512, tab, x);
-        imdct_post(b0, lane + 32, 512, tab, x);
-        imdct_post(a1, lane + 64, 512, tab, x);
-        imdct_post(b1, lane + 96, 512, tab, x);
-      }
-    } else {
-      const double *tab = T->mdct_inv64;
-      const int g = lane & 7, r3 = brev_bits(g, 3);
-      for (int b0 = 0; b0 < (size >> 5); b0 += 4) {
-        float *xb = x + 32 * (b0 + (lane >> 3));
-        auto in = [&](int k) -> double { return (double)xb[rev ? 31 - k : k]; };
-        Cplx a = imdct_pre(r3, 64, in, tab);
-        Cplx b = imdct_pre(8 + r3, 64, in, tab);
-        __syncwarp();
-        warp_fft_regs<3>(a, b, tw, lane);
-        imdct_post(a, g, 64, tab, xb);
-        imdct_post(b, g + 8, 64, tab, xb);
-      }
-    }
-    __syncwarp();
+    const bool is_long = !((short_mask >> band) & 1);
+    unsigned big = 0;
+    for (int k = lane; k < (band == 2 ? 256 : 128); k += 32) big = max(big, __float_as_uint(row[off + k]) & 0x7FFFFFFFu);
+    // 0x71800000 is 2^100 as binary32
+    if (__reduce_max_sync(0xffffffffu, big) < 0x71800000u)
+      imdct_band<FastRound>(band, is_long, row + off, y + off, T, lane);
+    else
+      imdct_band_exact(band, is_long, row + off, y + off, T, lane);
   }
-  const float4 *s4 = reinterpret_cast<const float4 *>(row);
+  __syncwarp();
+  const float4 *s4 = reinterpret_cast<const float4 *>(y);
 #pragma unroll
   for (int k = 0; k < 4; k++) dst4[lane + 32 * k] = s4[lane + 32 * k];
 }
@@ -397,7 +416,7 @@ constexpr size_t kSynSmemBytes =
 
 // ------------------------------------------------------------------------------------
 // Self-test of the two arithmetic shortcuts against the IEEE operations they replace:
-// div_by_range vs '/', for every (word length, quantised value, scale factor); rnd32 vs the
+// div_by_range vs '/', for every (word length, quantised value, scale factor); FastRound vs the
 // cvt round trip on values at and around f32 rounding ties in every binade.
 // ------------------------------------------------------------------------------------
 __global__ void selftest_kernel(const DevTables *__restrict__ T, unsigned long long *bad) {
@@ -430,8 +449,10 @@ __global__ void selftest_kernel(const DevTables *__restrict__ T, unsigned long l
     for (int j = -9; j <= 9; j++) {
       const double v = d + ulp * (0.125 * j) + ((j & 1) ? ulp * 1e-9 : 0.0);
       const double want = (double)(float)v;
-      const double got = rnd32(v);
-      if (__double_as_longlong(want) != __double_as_longlong(got)) local++;
+      FastRound fr;
+      const double got = fr(v);
+      // exact for everything below 2^127, zeros and f32 subnormals included
+      if (abs_hi_word(v) < 0x47E00000u && __double_as_longlong(want) != __double_as_longlong(got)) local++;
     }
   }
   if (local) atomicAdd(bad, local);

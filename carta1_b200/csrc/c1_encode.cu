@@ -290,8 +290,9 @@ transient_modes_kernel(const float *__restrict__ mags, int frames, int n_su,
 // (c1_fft.cuh); the only f64->f32 conversions are the final coefficient stores.
 // ------------------------------------------------------------------------------------
 // mdct.js:76-105: pre-twiddle of FFT input q (natural order) of an N-point MDCT
-template <typename In>
-__device__ __forceinline__ Cplx mdct_pre(int q, int n, const In &in, const double *__restrict__ tab) {
+template <typename In, typename R>
+__device__ __forceinline__ Cplx mdct_pre(int q, int n, const In &in, const double *__restrict__ tab,
+                                         const R &rnd) {
   const int i = 2 * q, n4 = n >> 2, n34 = 3 * n4;
   double r, m;
   if (i < n4) {
@@ -303,8 +304,8 @@ __device__ __forceinline__ Cplx mdct_pre(int q, int n, const In &in, const doubl
   }
   const double c = __ldg(&tab[i]), s = __ldg(&tab[i + 1]);
   Cplx z;
-  z.re = rnd32(r * c + m * s);
-  z.im = rnd32(m * c - r * s);
+  z.re = rnd(r * c + m * s);
+  z.im = rnd(m * c - r * s);
   return z;
 }
 
@@ -314,17 +315,76 @@ __device__ __forceinline__ void mdct_post(const Cplx z, int i, int n, const doub
                                           float *out, bool reverse) {
   const int half = n >> 1;
   const double c = __ldg(&tab[2 * i]), s = __ldg(&tab[2 * i + 1]);
-  const double o0 = rnd32(-z.re * c - z.im * s);
-  const double o1 = rnd32(-z.re * s + z.im * c);
+  const float o0 = (float)(-z.re * c - z.im * s);
+  const float o1 = (float)(-z.re * s + z.im * c);
   int i0 = 2 * i, i1 = half - 1 - 2 * i;
   if (reverse) { i0 = half - 1 - i0; i1 = half - 1 - i1; }
-  out[i0] = (float)o0;
-  out[i1] = (float)o1;
+  out[i0] = o0;
+  out[i1] = o1;
+}
+
+// One band of one sound unit, by one warp.  arr holds the windowed transform input (see
+// mdct_kernel).
+template <typename R>
+__device__ __forceinline__ void mdct_band(int band, bool is_long, const double *arr, float *out,
+                                          const DevTables *__restrict__ T, int lane) {
+  R rnd;
+  const double2 *tw = T->fft_tw;
+  const int size = band == 2 ? 256 : 128;
+  const bool rev = band > 0;
+  if (is_long) {
+    const int ws = band == 2 ? 112 : 48;  // constants.js:115-119
+    const int span = size + 32;
+    auto in = [&](int k) -> double {
+      const unsigned a = (unsigned)(k - ws);
+      return a < (unsigned)span ? arr[a] : 0.0;
+    };
+    const int r5 = brev_bits(lane, 5);
+    if (band < 2) {
+      const double *tab = T->mdct_fwd256;
+      Cplx a = mdct_pre(r5, 256, in, tab, rnd);
+      Cplx b = mdct_pre(32 + r5, 256, in, tab, rnd);
+      warp_fft_regs<5>(a, b, tw, lane, rnd);
+      mdct_post(a, lane, 256, tab, out, rev);
+      mdct_post(b, lane + 32, 256, tab, out, rev);
+    } else {
+      const double *tab = T->mdct_fwd512;
+      Cplx a0 = mdct_pre(2 * r5, 512, in, tab, rnd);
+      Cplx b0 = mdct_pre(64 + 2 * r5, 512, in, tab, rnd);
+      Cplx a1 = mdct_pre(2 * r5 + 1, 512, in, tab, rnd);
+      Cplx b1 = mdct_pre(64 + 2 * r5 + 1, 512, in, tab, rnd);
+      warp_fft128_regs(a0, b0, a1, b1, tw, lane, rnd);
+      mdct_post(a0, lane, 512, tab, out, rev);
+      mdct_post(b0, lane + 32, 512, tab, out, rev);
+      mdct_post(a1, lane + 64, 512, tab, out, rev);
+      mdct_post(b1, lane + 96, 512, tab, out, rev);
+    }
+  } else {
+    const double *tab = T->mdct_fwd64;
+    const int g = lane & 7, r3 = brev_bits(g, 3);
+    for (int b0 = 0; b0 < (size >> 5); b0 += 4) {
+      const int blk = b0 + (lane >> 3);
+      const double *ab = arr + 64 * blk;
+      auto in = [&](int k) -> double { return ab[k]; };
+      Cplx a = mdct_pre(r3, 64, in, tab, rnd);
+      Cplx b = mdct_pre(8 + r3, 64, in, tab, rnd);
+      warp_fft_regs<3>(a, b, tw, lane, rnd);
+      mdct_post(a, g, 64, tab, out + 32 * blk, rev);
+      mdct_post(b, g + 8, 64, tab, out + 32 * blk, rev);
+    }
+  }
+}
+
+// Conversion-based rounding for inputs beyond kFastRoundInputLimit; out of line to keep the
+// hot path small.
+__device__ __noinline__ void mdct_band_exact(int band, bool is_long, const double *arr, float *out,
+                                             const DevTables *__restrict__ T, int lane) {
+  mdct_band<ExactRound>(band, is_long, arr, out, T, lane);
 }
 
 constexpr int kMdctWarps = 8;
 
-__global__ void __launch_bounds__(kMdctWarps * 32)
+__global__ void __launch_bounds__(kMdctWarps * 32, 3)
 mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, int frames, int n_su,
             const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
             float *__restrict__ coefs) {
@@ -337,82 +397,47 @@ mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, 
   const int frame = su % frames;
   double *arr = s_arr[warp];
   float *out = s_out[warp];
-  const double2 *tw = T->fft_tw;
+  ExactRound xr;
   for (int band = 0; band < 3; band++) {
     const int size = band == 2 ? 256 : 128;
     const int off = band == 0 ? 0 : band == 1 ? 128 : 256;
     const float *cur = bands + (size_t)su * 512 + off;
     const float *prev = frame > 0 ? cur - 512 : nullptr;
     const int mode = P->use_fixed ? P->fixed[band] : (int)modes[(size_t)su * 4 + band];
-    const bool rev = band > 0;
+    unsigned big = 0;  // largest |input| (high word) of this band's transform
     if (mode == 0) {
       // arr = [overlap saved by the previous frame (32) | samples, last 32 tail-windowed]
       // (encoder.js:240-247,309-316)
       {
         const float pv = prev ? prev[size - 32 + lane] : 0.0f;
-        arr[lane] = prev ? rnd32(w_fwd * (double)pv) : 0.0;
+        arr[lane] = prev ? xr(w_fwd * (double)pv) : 0.0;
+        big = abs_hi_word((double)pv);
       }
       for (int k = lane; k < size; k += 32) {
         const double x = (double)cur[k];
-        arr[32 + k] = k >= size - 32 ? rnd32(x * w_rev) : x;  // k - (size - 32) == lane
+        big = max(big, abs_hi_word(x));
+        arr[32 + k] = k >= size - 32 ? xr(x * w_rev) : x;  // k - (size - 32) == lane
       }
-      __syncwarp();
-      const int ws = band == 2 ? 112 : 48;  // constants.js:115-119
-      const int span = size + 32;
-      auto in = [&](int k) -> double {
-        const unsigned a = (unsigned)(k - ws);
-        return a < (unsigned)span ? arr[a] : 0.0;
-      };
-      const int r5 = brev_bits(lane, 5);
-      if (band < 2) {
-        const double *tab = T->mdct_fwd256;
-        Cplx a = mdct_pre(r5, 256, in, tab);
-        Cplx b = mdct_pre(32 + r5, 256, in, tab);
-        warp_fft_regs<5>(a, b, tw, lane);
-        mdct_post(a, lane, 256, tab, out + off, rev);
-        mdct_post(b, lane + 32, 256, tab, out + off, rev);
-      } else {
-        const double *tab = T->mdct_fwd512;
-        Cplx a0 = mdct_pre(2 * r5, 512, in, tab);
-        Cplx b0 = mdct_pre(64 + 2 * r5, 512, in, tab);
-        Cplx a1 = mdct_pre(2 * r5 + 1, 512, in, tab);
-        Cplx b1 = mdct_pre(64 + 2 * r5 + 1, 512, in, tab);
-        warp_fft128_regs(a0, b0, a1, b1, tw, lane);
-        mdct_post(a0, lane, 512, tab, out + off, rev);
-        mdct_post(b0, lane + 32, 512, tab, out + off, rev);
-        mdct_post(a1, lane + 64, 512, tab, out + off, rev);
-        mdct_post(b1, lane + 96, 512, tab, out + off, rev);
-      }
-      __syncwarp();
     } else {
       // short blocks: block b transforms [WIN * previous block (32) | block * reversed WIN (32)]
       // (encoder.js:279-304)
-      const int blocks = size >> 5;
-      for (int b = 0; b < blocks; b++) {
+      for (int b = 0; b < (size >> 5); b++) {
         float src_prev = 0.0f;
         bool have_prev = true;
         if (b == 0) { have_prev = prev != nullptr; if (prev) src_prev = prev[size - 32 + lane]; }
         else src_prev = cur[32 * (b - 1) + lane];
-        arr[64 * b + lane] = have_prev ? rnd32(w_fwd * (double)src_prev) : 0.0;
-        arr[64 * b + 32 + lane] = rnd32((double)cur[32 * b + lane] * w_rev);
+        arr[64 * b + lane] = have_prev ? xr(w_fwd * (double)src_prev) : 0.0;
+        arr[64 * b + 32 + lane] = xr((double)cur[32 * b + lane] * w_rev);
+        big = max(big, max(abs_hi_word((double)src_prev), abs_hi_word((double)cur[32 * b + lane])));
       }
-      __syncwarp();
-      const double *tab = T->mdct_fwd64;
-      const int g = lane & 7, r3 = brev_bits(g, 3);
-      for (int b0 = 0; b0 < blocks; b0 += 4) {
-        const int blk = b0 + (lane >> 3);
-        const double *ab = arr + 64 * blk;
-        auto in = [&](int k) -> double { return ab[k]; };
-        Cplx a = mdct_pre(r3, 64, in, tab);
-        Cplx b = mdct_pre(8 + r3, 64, in, tab);
-        warp_fft_regs<3>(a, b, tw, lane);
-        mdct_post(a, g, 64, tab, out + off + 32 * blk, rev);
-        mdct_post(b, g + 8, 64, tab, out + off + 32 * blk, rev);
-      }
-      __syncwarp();
     }
+    __syncwarp();
+    if (__reduce_max_sync(0xffffffffu, big) < kFastRoundInputLimit)
+      mdct_band<FastRound>(band, mode == 0, arr, out + off, T, lane);
+    else
+      mdct_band_exact(band, mode == 0, arr, out + off, T, lane);
+    __syncwarp();
   }
-  __syncwarp();
   float4 *dst = reinterpret_cast<float4 *>(coefs + (size_t)su * 512);
   const float4 *src = reinterpret_cast<const float4 *>(out);
 #pragma unroll
