@@ -224,26 +224,51 @@ unpack_imdct_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size
       imdct_band_exact(band, is_long, row + off, y + off, T, lane);
   }
   __syncwarp();
-  const float4 *s4 = reinterpret_cast<const float4 *>(y);
+  // Band record (what K7 reads): per band [head16 | tail16 | time-domain samples 32..size).
+  // Samples >= 32 depend on this unit only (decoder.js:203-226,244-300): a copy of the IMDCT
+  // half in long mode, the block-to-block overlap-add in short mode.  The first 32 samples
+  // also need the previous unit's tail16 and are finished in K7.
+  for (int band = 0; band < 3; band++) {
+    const int size = band == 2 ? 256 : 128;
+    const int off = band == 0 ? 0 : band == 1 ? 128 : 256;
+    const bool is_long = !((short_mask >> band) & 1);
+    const float *v = y + off;
+    float *z = row + off;
+    if (lane < 16) z[lane] = v[lane];
+    else z[lane] = v[size - 32 + lane];
+    for (int p = 32 + lane; p < size; p += 32) {
+      float o;
+      if (is_long) {
+        o = v[p - 16];
+      } else {  // mdct.js:230-245 with prev = second half of the previous block
+        const int q = p & 31, blk = p - q;
+        const int i = q < 16 ? q : 31 - q;
+        const double pv = (double)v[blk - 16 + i], cv = (double)v[blk + 15 - i];
+        const double w1 = __ldg(&T->win[i]), w2 = __ldg(&T->win[31 - i]);
+        o = q < 16 ? (float)(pv * w2 - cv * w1) : (float)(pv * w1 + cv * w2);
+      }
+      z[p] = o;
+    }
+  }
+  __syncwarp();
+  const float4 *s4 = reinterpret_cast<const float4 *>(row);
 #pragma unroll
   for (int k = 0; k < 4; k++) dst4[lane + 32 * k] = s4[lane + 32 * k];
 }
 
 // ------------------------------------------------------------------------------------
-// Overlap-add as a pure function of the IMDCT halves (decoder.js:175-306, mdct.js:230-245).
-// inv_f / inv_prev: this / the previous frame's band slice of `inv`; p: position in band.
+// Time-domain band sample p from the band records of this and the previous unit
+// (decoder.js:196-206,255-263; mdct.js:230-245): rec = [head16 | tail16 | samples 32..size).
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ float band_sample(const float *__restrict__ inv_f, const float *__restrict__ inv_prev,
-                                             int size, bool is_long, int p, const double *__restrict__ win) {
-  if (is_long && p >= 32) return inv_f[p - 16];
-  const int q = is_long ? p : (p & 31);
-  const int blk = p - q;
-  const int i = q < 16 ? q : 31 - q;
-  const float pv = blk == 0 ? (inv_prev ? inv_prev[size - 16 + i] : 0.0f) : inv_f[blk - 16 + i];
-  const float cv = inv_f[blk + 15 - i];
+__device__ __forceinline__ float band_sample(const float *__restrict__ rec, const float *__restrict__ rec_prev,
+                                             int p, const double *__restrict__ win) {
+  if (p >= 32) return rec[p];
+  const int i = p < 16 ? p : 31 - p;
+  const double pv = rec_prev ? (double)rec_prev[16 + i] : 0.0;
+  const double cv = (double)rec[15 - i];
   const double w1 = win[i], w2 = win[31 - i];
-  if (q < 16) return (float)((double)pv * w2 - (double)cv * w1);
-  return (float)((double)pv * w1 + (double)cv * w2);
+  if (p < 16) return (float)(pv * w2 - cv * w1);
+  return (float)(pv * w1 + cv * w2);
 }
 
 __global__ void __launch_bounds__(256)
@@ -258,7 +283,7 @@ bands_time_kernel(const float *__restrict__ inv, const uint8_t *__restrict__ mod
     const int size = band == 2 ? 256 : 128;
     const float *f = inv + (size_t)unit * 512 + off;
     bands[(size_t)unit * 512 + c] =
-        band_sample(f, frame > 0 ? f - 512 : nullptr, size, modes[(size_t)unit * 4 + band] == 0, c - off, T->win);
+        band_sample(f, frame > 0 ? f - 512 : nullptr, c - off, T->win);
   }
 }
 
@@ -272,11 +297,13 @@ bands_time_kernel(const float *__restrict__ inv, const uint8_t *__restrict__ mod
 // shared memory as binary64, row kk&7 / column kk>>3, and every thread produces 8 outputs
 // of each polyphase from a 31-value register window.
 // ------------------------------------------------------------------------------------
-constexpr int kSynTile = 8;
-constexpr int kSynThreads = 256;
+constexpr int kSynTile = 4;
+constexpr int kSynThreads = 32 * kSynTile;
 constexpr int kSynS2Threads = 16 * kSynTile + 2;
-constexpr int kSynStrideA = 146;  // >= (8*kSynS2Threads + 31)/8 + 1, == 2 mod 16
-constexpr int kSynStrideB = 274;  // >= (8*32*kSynTile + 31)/8 + 1,   == 2 mod 16
+constexpr int kSynStrideA = 82;   // >= (8*kSynS2Threads + 31)/8 + 1, == 2 mod 16
+constexpr int kSynStrideB = 146;  // >= (8*32*kSynTile + 31)/8 + 1,   == 2 mod 16
+static_assert((8 * kSynS2Threads + 31) / 8 + 1 <= kSynStrideA && kSynStrideA % 16 == 2, "stride A");
+static_assert((8 * 32 * kSynTile + 31) / 8 + 1 <= kSynStrideB && kSynStrideB % 16 == 2, "stride B");
 constexpr int kSynHd = 256 * kSynTile + 24;
 
 __constant__ double c_syn_even[24];
@@ -306,7 +333,7 @@ __device__ __forceinline__ void fir8_synthesis(const double *__restrict__ seq, i
 }
 
 template <int kFmt>  // 0: f32 planar rows, 1: s16 interleaved (processor.js:382-389)
-__global__ void __launch_bounds__(kSynThreads)
+__global__ void __launch_bounds__(kSynThreads, 8)
 synth_kernel(const float *__restrict__ inv, const uint8_t *__restrict__ modes, int frames, int halo,
              const DevTables *__restrict__ T, void *__restrict__ pcm_v, size_t row_stride, int n_ch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -320,19 +347,22 @@ synth_kernel(const float *__restrict__ inv, const uint8_t *__restrict__ modes, i
   if (tid < 32) win[tid] = T->win[tid];
   __syncthreads();
   const float *inv_row = inv + (size_t)stream * frames * 512;
-  const uint8_t *mode_row = modes + (size_t)stream * frames * 4;
   const int f_end = min(f0 + kSynTile, frames);
 
   // merged low/mid pairs: kk -> m = 128*f0 - 40 + kk
   const int m_lo = 128 * f0 - 40;
-  for (int kk = tid; kk < 8 * kSynS2Threads + 32; kk += kSynThreads) {
+  constexpr int kFillA = 8 * kSynS2Threads + 32;
+#pragma unroll
+  for (int it = 0; it < (kFillA + kSynThreads - 1) / kSynThreads; it++) {
+    const int kk = tid + it * kSynThreads;
+    if (kk >= kFillA) break;
     const int m = m_lo + kk;
     float sum = 0.0f, dif = 0.0f;
     if (m >= 0 && m < 128 * f_end) {
       const int fr = m >> 7, p = m & 127;
       const float *fl = inv_row + (size_t)fr * 512;
-      const float l = band_sample(fl, fr > 0 ? fl - 512 : nullptr, 128, mode_row[fr * 4 + 0] == 0, p, win);
-      const float h = band_sample(fl + 128, fr > 0 ? fl - 384 : nullptr, 128, mode_row[fr * 4 + 1] == 0, p, win);
+      const float l = band_sample(fl, fr > 0 ? fl - 512 : nullptr, p, win);
+      const float h = band_sample(fl + 128, fr > 0 ? fl - 384 : nullptr, p, win);
       sum = (float)(0.5 * ((double)l + (double)h));
       dif = (float)(0.5 * ((double)l - (double)h));
     }
@@ -341,13 +371,16 @@ synth_kernel(const float *__restrict__ inv, const uint8_t *__restrict__ modes, i
     sa[8 * kSynStrideA + at] = (double)sum;
   }
   // delayed high band: hd[q] = H[n - 39], n = 256*f0 - 24 + q
-  for (int q = tid; q < kSynHd; q += kSynThreads) {
+#pragma unroll
+  for (int it = 0; it < (kSynHd + kSynThreads - 1) / kSynThreads; it++) {
+    const int q = tid + it * kSynThreads;
+    if (q >= kSynHd) break;
     const int g = 256 * f0 - 24 + q - 39;
     float h = 0.0f;
     if (g >= 0 && g < 256 * f_end) {
       const int fr = g >> 8, p = g & 255;
       const float *fh = inv_row + (size_t)fr * 512 + 256;
-      h = band_sample(fh, fr > 0 ? fh - 512 : nullptr, 256, mode_row[fr * 4 + 2] == 0, p, win);
+      h = band_sample(fh, fr > 0 ? fh - 512 : nullptr, p, win);
     }
     hd[q] = h;
   }

@@ -55,11 +55,14 @@ __device__ __forceinline__ int bitrev(int x, int log2n) { return (int)(__brev((u
 // kk of a sequence lives at row kk&7, column kk>>3 (row stride == 2 mod 16 doubles): a warp's
 // window reads and the tile fill are both bank-conflict free.
 // ------------------------------------------------------------------------------------
-constexpr int kQmfTile = 8;                       // frames per CTA
+constexpr int kQmfTile = 4;                       // frames per CTA
 constexpr int kQmfS1Threads = 32 * kQmfTile + 6;  // stage-1 work items (8 outputs each)
-constexpr int kQmfThreads = 288;
-constexpr int kQmfStride1 = 274;                  // >= (8*kQmfS1Threads + 31)/8 + 1, == 2 mod 16
-constexpr int kQmfStride2 = 146;                  // >= (8*16*kQmfTile + 31)/8 + 1,   == 2 mod 16
+constexpr int kQmfThreads = 160;
+constexpr int kQmfStride1 = 146;                  // >= (8*kQmfS1Threads + 31)/8 + 1, == 2 mod 16
+constexpr int kQmfStride2 = 82;                   // >= (8*16*kQmfTile + 31)/8 + 1,   == 2 mod 16
+constexpr int kQmfFill = 2 * (8 * kQmfS1Threads + 32);
+static_assert((8 * kQmfS1Threads + 31) / 8 + 1 <= kQmfStride1 && kQmfStride1 % 16 == 2, "stride 1");
+static_assert((8 * 16 * kQmfTile + 31) / 8 + 1 <= kQmfStride2 && kQmfStride2 % 16 == 2, "stride 2");
 static_assert(kQmfS1Threads <= kQmfThreads, "stage 1 must fit the block");
 
 __constant__ double c_qmf_even[24];
@@ -89,7 +92,7 @@ __device__ __forceinline__ void fir8_analysis(const double *__restrict__ seq, in
 }
 
 template <int kFmt>  // 0: f32 planar rows, 1: s16 interleaved
-__global__ void __launch_bounds__(kQmfThreads)
+__global__ void __launch_bounds__(kQmfThreads, 5)
 qmf_analysis_kernel(const void *__restrict__ pcm_v, size_t row_stride, int n_ch, long long valid_samples,
                     int frames, float *__restrict__ bands) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -100,20 +103,31 @@ qmf_analysis_kernel(const void *__restrict__ pcm_v, size_t row_stride, int n_ch,
   const int stream = blockIdx.y;
   const int nb = 256 * f0 - 48;  // first stage-1 output of the tile
   const int kb = nb - 24;        // polyphase index of kk == 0
-  // fill: kk in [0, 8*kQmfS1Threads + 32), both polyphases
-  for (int idx = tid; idx < 2 * (8 * kQmfS1Threads + 32); idx += kQmfThreads) {
-    const int kk = idx >> 1, par = idx & 1;
-    const long long g = 2ll * (kb + kk) + par;
-    float v = 0.0f;
-    if (g >= 0 && g < valid_samples) {
-      if (kFmt == 0) {
-        v = static_cast<const float *>(pcm_v)[(size_t)stream * row_stride + (size_t)g];
-      } else {  // bin/cli.js:395  readInt16LE / 32768.0 -> Float32Array
-        const short sv = static_cast<const short *>(pcm_v)[(size_t)g * n_ch + stream];
-        v = (float)((double)sv / 32768.0);
+  // fill: kk in [0, 8*kQmfS1Threads + 32), both polyphases; all loads are issued before the
+  // first conversion so one round trip to memory covers the whole tile
+  {
+    constexpr int kPer = (kQmfFill + kQmfThreads - 1) / kQmfThreads;
+    float v[kPer];
+#pragma unroll
+    for (int it = 0; it < kPer; it++) {
+      const int idx = tid + it * kQmfThreads;
+      const long long g = 2ll * kb + idx;  // == 2*(kb + kk) + par
+      v[it] = 0.0f;
+      if (idx < kQmfFill && g >= 0 && g < valid_samples) {
+        if (kFmt == 0) {
+          v[it] = __ldg(static_cast<const float *>(pcm_v) + (size_t)stream * row_stride + (size_t)g);
+        } else {  // bin/cli.js:395  readInt16LE / 32768.0 -> Float32Array
+          const short sv = __ldg(static_cast<const short *>(pcm_v) + (size_t)g * n_ch + stream);
+          v[it] = (float)((double)sv / 32768.0);
+        }
       }
     }
-    x1[(par ? 0 : 8 * kQmfStride1) + (kk & 7) * kQmfStride1 + (kk >> 3)] = (double)v;
+#pragma unroll
+    for (int it = 0; it < kPer; it++) {
+      const int idx = tid + it * kQmfThreads;
+      const int kk = idx >> 1, par = idx & 1;
+      if (idx < kQmfFill) x1[(par ? 0 : 8 * kQmfStride1) + (kk & 7) * kQmfStride1 + (kk >> 3)] = (double)v[it];
+    }
   }
   __syncthreads();
   float *out = bands + ((size_t)stream * frames) * 512;
