@@ -53,6 +53,7 @@ EXPORTED_SYMBOLS = [
     "carta1_encode_pcm", "carta1_decode_su", "carta1_encode_pcm_s16", "carta1_decode_su_s16",
     "carta1_enc_create", "carta1_enc_destroy", "carta1_enc_reset", "carta1_enc_frames",
     "carta1_dec_create", "carta1_dec_destroy", "carta1_dec_reset", "carta1_dec_frames",
+    "carta1_dec_frames_expanded",
     "carta1_encode_device", "carta1_decode_device", "carta1_ctx_sync", "carta1_ctx_stream",
     "carta1_ctx_launch_count", "carta1_debug_encode_stages", "carta1_debug_decode_stages",
     "carta1_aea_write_header", "carta1_aea_parse_header", "carta1_kernel_count", "carta1_kernel_name",
@@ -101,6 +102,7 @@ def load():
     L.carta1_dec_destroy.restype = None
     L.carta1_dec_reset.argtypes = [vp]
     L.carta1_dec_frames.argtypes = [vp, vp, C.c_int, vp]
+    L.carta1_dec_frames_expanded.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
     L.carta1_encode_device.argtypes = [vp, vp, sz, C.c_int, sz, sz, sz, C.POINTER(EncOpts), vp, sz, sz, C.c_int]
     L.carta1_decode_device.argtypes = [vp, vp, sz, sz, sz, C.c_int, sz, sz, vp, sz, C.c_int]
     L.carta1_ctx_sync.argtypes = [vp]
@@ -345,6 +347,18 @@ class StreamDecoder:
         nf = su.shape[1]
         pcm = np.zeros((self.n_streams, nf, FRAME), np.float32)
         self.ctx._check(self.ctx.L.carta1_dec_frames(self.h, _ptr(su), nf, _ptr(pcm)))
+        return pcm
+
+    def frames_expanded(self, q: np.ndarray, sfi: np.ndarray, bits: np.ndarray, modes: np.ndarray) -> np.ndarray:
+        """Frame objects in position-expanded form (carta1_dec_frames_expanded)."""
+        q = np.ascontiguousarray(q, np.int32).reshape(self.n_streams, -1, FRAME)
+        nf = q.shape[1]
+        sfi = np.ascontiguousarray(sfi, np.uint8).reshape(self.n_streams, nf, FRAME)
+        bits = np.ascontiguousarray(bits, np.uint8).reshape(self.n_streams, nf, FRAME)
+        modes = np.ascontiguousarray(modes, np.int32).reshape(self.n_streams, nf, 3)
+        pcm = np.zeros((self.n_streams, nf, FRAME), np.float32)
+        self.ctx._check(self.ctx.L.carta1_dec_frames_expanded(self.h, _ptr(q), _ptr(sfi), _ptr(bits), _ptr(modes),
+                                                              nf, _ptr(pcm)))
         return pcm
 
     def reset(self):

@@ -229,7 +229,7 @@ struct carta1_decoder {
   carta1_ctx *ctx;
   int n_streams;
   bool has_prev = false;
-  uint8_t *d_prev = nullptr;  // [n_streams][212]: the previous sound unit per stream
+  float *d_rec = nullptr;  // [n_streams][512]: band record (IMDCT output) of the previous unit
   DevBuf work, pcm;
 };
 
@@ -449,7 +449,9 @@ static int encode_device_impl(carta1_ctx *ctx, const void *d_pcm, int pcm_fmt, s
 static int decode_device_impl(carta1_ctx *ctx, const uint8_t *d_su, size_t su_frame_stride,
                               size_t su_stream_stride, size_t n_su_valid, int n_streams, size_t halo_frames,
                               size_t n_frames, void *d_pcm, int pcm_fmt, size_t row_stride, int n_ch_interleave,
-                              float *dbg_coefs, float *dbg_bands) {
+                              float *dbg_coefs, float *dbg_bands, const float *prev_rec = nullptr,
+                              const int32_t *x_q = nullptr, const uint8_t *x_sfi = nullptr,
+                              const uint8_t *x_bits = nullptr, const uint8_t *x_modes = nullptr) {
   const size_t frames_total = halo_frames + n_frames;
   const size_t units = frames_total * (size_t)n_streams;
   if (units == 0) return CARTA1_OK;
@@ -465,6 +467,8 @@ static int decode_device_impl(carta1_ctx *ctx, const uint8_t *d_su, size_t su_fr
   L.modes = (uint8_t *)ctx->modes.p;
   L.inv = (float *)ctx->inv.p;
   L.bands_dbg = dbg_bands;
+  L.prev_rec = prev_rec;
+  L.x_q = x_q; L.x_sfi = x_sfi; L.x_bits = x_bits; L.x_modes = x_modes;
   L.pcm = d_pcm; L.pcm_fmt = pcm_fmt; L.row_stride = row_stride; L.n_ch_interleave = n_ch_interleave;
   CU(ctx, launch_decode(L, ctx->stream, &ctx->prof));
   return CARTA1_OK;
@@ -702,7 +706,7 @@ int carta1_dec_create(carta1_ctx *ctx, int n_streams, carta1_decoder **out) {
   carta1_decoder *d = new carta1_decoder();
   d->ctx = ctx;
   d->n_streams = n_streams;
-  cudaError_t ce = cudaMalloc(&d->d_prev, (size_t)n_streams * CARTA1_SU_BYTES);
+  cudaError_t ce = cudaMalloc(&d->d_rec, (size_t)n_streams * 512 * sizeof(float));
   if (ce != cudaSuccess) { delete d; return cuda_fail(ctx, ce, "carta1_dec_create"); }
   *out = d;
   return CARTA1_OK;
@@ -712,7 +716,7 @@ void carta1_dec_destroy(carta1_decoder *d) {
   if (!d) return;
   cudaSetDevice(d->ctx->device);
   cudaStreamSynchronize(d->ctx->stream);
-  if (d->d_prev) cudaFree(d->d_prev);
+  if (d->d_rec) cudaFree(d->d_rec);
   d->work.release(); d->pcm.release();
   delete d;
 }
@@ -723,36 +727,70 @@ int carta1_dec_reset(carta1_decoder *d) {
   return CARTA1_OK;
 }
 
-// The decoder's carried state (QMF delays, IMDCT tails) is a function of the previous
-// sound unit alone, so the handle keeps that unit per stream.
-int carta1_dec_frames(carta1_decoder *d, const uint8_t *su, int n_frames, float *pcm_out) {
-  if (!d) return CARTA1_ERR_ARG;
+// The decoder's carried state (QMF delays, IMDCT tails) is a function of the previous sound
+// unit alone; the handle keeps that unit's band record (its IMDCT
+// output, 512 floats per stream), which is all the synthesis kernel reads of it.
+static int dec_frames_impl(carta1_decoder *d, const uint8_t *su, const int32_t *x_q, const uint8_t *x_sfi,
+                           const uint8_t *x_bits, const int32_t *x_modes, int n_frames, float *pcm_out) {
   carta1_ctx *ctx = d->ctx;
-  if (n_frames < 0 || (n_frames && (!su || !pcm_out))) return fail(ctx, CARTA1_ERR_ARG, "carta1_dec_frames: bad argument");
-  if (n_frames == 0) return CARTA1_OK;
   CU(ctx, cudaSetDevice(ctx->device));
   const size_t ns = (size_t)d->n_streams;
+  const size_t nf = (size_t)n_frames;
   const size_t halo = d->has_prev ? 1 : 0;
-  const size_t fr = (size_t)n_frames + halo;
-  CU(ctx, d->work.ensure(ns * fr * CARTA1_SU_BYTES));
-  CU(ctx, d->pcm.ensure(ns * (size_t)n_frames * 512 * sizeof(float)));
-  uint8_t *w = (uint8_t *)d->work.p;  // [stream][frame][212]
-  if (halo)
-    CU(ctx, cudaMemcpy2DAsync(w, fr * CARTA1_SU_BYTES, d->d_prev, CARTA1_SU_BYTES, CARTA1_SU_BYTES, ns,
-                              cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(ctx, cudaMemcpy2DAsync(w + halo * CARTA1_SU_BYTES, fr * CARTA1_SU_BYTES, su,
-                            (size_t)n_frames * CARTA1_SU_BYTES, (size_t)n_frames * CARTA1_SU_BYTES, ns,
-                            cudaMemcpyHostToDevice, ctx->stream));
-  int rc = decode_device_impl(ctx, w, 1, fr, ns * fr, d->n_streams, halo, (size_t)n_frames, d->pcm.p, 0,
-                              (size_t)n_frames * 512, 1, nullptr, nullptr);
+  const size_t fr = nf + halo;
+  CU(ctx, d->pcm.ensure(ns * nf * 512 * sizeof(float)));
+  const uint8_t *d_su = nullptr;
+  const int32_t *dq = nullptr;
+  const uint8_t *dsfi = nullptr, *dbits = nullptr, *dmodes = nullptr;
+  if (su) {
+    CU(ctx, d->work.ensure(ns * nf * CARTA1_SU_BYTES));
+    CU(ctx, cudaMemcpyAsync(d->work.p, su, ns * nf * CARTA1_SU_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    d_su = (const uint8_t *)d->work.p;  // [stream][frame][212]
+  } else {
+    const size_t n = ns * nf;
+    CU(ctx, d->work.ensure(n * 512 * 6 + n * 4 + 64));
+    uint8_t *w = (uint8_t *)d->work.p;
+    std::vector<uint8_t> m(n * 4, 0);
+    for (size_t i = 0; i < n; i++)
+      for (int b = 0; b < 3; b++) m[i * 4 + b] = x_modes[i * 3 + b] != 0;
+    CU(ctx, cudaMemcpyAsync(w, x_q, n * 512 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(w + n * 2048, x_sfi, n * 512, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(w + n * 2560, x_bits, n * 512, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(w + n * 3072, m.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));  // m lives on this stack frame
+    dq = (const int32_t *)w; dsfi = w + n * 2048; dbits = w + n * 2560; dmodes = w + n * 3072;
+  }
+  int rc = decode_device_impl(ctx, d_su, 1, nf, ns * nf, d->n_streams, halo, nf, d->pcm.p, 0, nf * 512, 1,
+                              nullptr, nullptr, halo ? d->d_rec : nullptr, dq, dsfi, dbits, dmodes);
   if (rc) return rc;
-  CU(ctx, cudaMemcpy2DAsync(d->d_prev, CARTA1_SU_BYTES, w + (fr - 1) * CARTA1_SU_BYTES, fr * CARTA1_SU_BYTES,
-                            CARTA1_SU_BYTES, ns, cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(ctx, cudaMemcpyAsync(pcm_out, d->pcm.p, ns * (size_t)n_frames * 512 * sizeof(float), cudaMemcpyDeviceToHost,
-                          ctx->stream));
+  CU(ctx, cudaMemcpy2DAsync(d->d_rec, 512 * sizeof(float), (const float *)ctx->inv.p + (fr - 1) * 512,
+                            fr * 512 * sizeof(float), 512 * sizeof(float), ns, cudaMemcpyDeviceToDevice,
+                            ctx->stream));
+  CU(ctx, cudaMemcpyAsync(pcm_out, d->pcm.p, ns * nf * 512 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   d->has_prev = true;
   return CARTA1_OK;
+}
+
+int carta1_dec_frames(carta1_decoder *d, const uint8_t *su, int n_frames, float *pcm_out) {
+  if (!d) return CARTA1_ERR_ARG;
+  if (n_frames < 0 || (n_frames && (!su || !pcm_out)))
+    return fail(d->ctx, CARTA1_ERR_ARG, "carta1_dec_frames: bad argument");
+  if (n_frames == 0) return CARTA1_OK;
+  return dec_frames_impl(d, su, nullptr, nullptr, nullptr, nullptr, n_frames, pcm_out);
+}
+
+int carta1_dec_frames_expanded(carta1_decoder *d, const int32_t *q, const uint8_t *sfi, const uint8_t *bits,
+                               const int32_t *modes, int n_frames, float *pcm_out) {
+  if (!d) return CARTA1_ERR_ARG;
+  if (n_frames < 0 || (n_frames && (!q || !sfi || !bits || !modes || !pcm_out)))
+    return fail(d->ctx, CARTA1_ERR_ARG, "carta1_dec_frames_expanded: bad argument");
+  if (n_frames == 0) return CARTA1_OK;
+  const size_t n = (size_t)d->n_streams * (size_t)n_frames * 512;
+  for (size_t i = 0; i < n; i++)
+    if (sfi[i] > 63 || bits[i] == 1 || bits[i] > 16)
+      return fail(d->ctx, CARTA1_ERR_ARG, "carta1_dec_frames_expanded: scale-factor index or bit width out of range");
+  return dec_frames_impl(d, nullptr, q, sfi, bits, modes, n_frames, pcm_out);
 }
 
 // ------------------------------------------------------------------ stage taps

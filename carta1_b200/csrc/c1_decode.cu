@@ -45,6 +45,17 @@ __device__ __forceinline__ double int_to_double(int q) {  // exact, no conversio
   return __hiloint2double(0x43300000, (int)((unsigned)q ^ 0x80000000u)) - 4503601774854144.0;
 }
 
+// Frame objects the 212-byte layout cannot hold (decode() accepts any object with the frame
+// keys, e.g. tests/decoder.test.js:70-84): the host replays dequantizationStage's
+// `coefficients.set(dequantized, position)` sequence (decoder.js:73-94) into per-position
+// arrays, [unit][512] each, and the kernel dequantises per position.  bits == 0: position
+// never written (stays +0).
+struct ExpandedFrames {
+  const int32_t *q;
+  const uint8_t *sfi, *bits;
+  const uint8_t *modes;  // [unit][4]
+};
+
 // mdct.js:161-170: pre-twiddle of FFT input i (natural order)
 template <typename In, typename R>
 __device__ __forceinline__ Cplx imdct_pre(int i, int n, const In &in, const double *__restrict__ tab,
@@ -126,7 +137,8 @@ constexpr int kUiWarps = 8;
 __global__ void __launch_bounds__(kUiWarps * 32, 3)
 unpack_imdct_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_stream_stride,
                     long long n_su_valid, int frames, int n_units, const DevTables *__restrict__ T,
-                    float *__restrict__ coefs_dbg, uint8_t *__restrict__ modes, float *__restrict__ inv) {
+                    float *__restrict__ coefs_dbg, uint8_t *__restrict__ modes, float *__restrict__ inv,
+                    const float *__restrict__ prev_rec, ExpandedFrames xf) {
   __shared__ __align__(16) float s_row[kUiWarps][512];
   __shared__ __align__(16) float s_inv[kUiWarps][512];
   __shared__ double s_rcp[kUiWarps][52];
@@ -137,12 +149,37 @@ unpack_imdct_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size
   const int unit = blockIdx.x * kUiWarps + warp;
   if (unit >= n_units) return;
   const int stream = unit / frames, frame = unit - stream * frames;
-  const long long lin = (long long)frame * (long long)su_frame_stride + (long long)stream * (long long)su_stream_stride;
   const FormatTables &F = T->fmt;
   float *row = s_row[warp];
   float4 *dst4 = reinterpret_cast<float4 *>(inv + (size_t)unit * 512);
+  // stateful handles: frame 0 of every row is the band record kept from the previous call
+  const int su_skip = prev_rec ? 1 : 0;
+  if (prev_rec && frame == 0) {
+    const float4 *s4 = reinterpret_cast<const float4 *>(prev_rec + (size_t)stream * 512);
+#pragma unroll
+    for (int k = 0; k < 4; k++) dst4[lane + 32 * k] = s4[lane + 32 * k];
+    return;
+  }
+  const long long lin = (long long)(frame - su_skip) * (long long)su_frame_stride +
+                        (long long)stream * (long long)su_stream_stride;
   int short_mask = 0;  // bit b: band b uses short blocks (any non-zero mode, decoder.js:82-83)
-  if (lin >= n_su_valid) {  // dummy frame {nBfu: 0, blockModes: [0,0,0]} (processor.js:299-307)
+  if (xf.q) {
+    // frame objects in position-expanded form (see ExpandedFrames): the general decode() input
+    const size_t xu = (size_t)stream * (frames - su_skip) + (frame - su_skip);
+    const int m0 = xf.modes[xu * 4], m1 = xf.modes[xu * 4 + 1], m2 = xf.modes[xu * 4 + 2];
+    short_mask = (m0 != 0) | ((m1 != 0) << 1) | ((m2 != 0) << 2);
+    if (lane < 4) modes[(size_t)unit * 4 + lane] = (uint8_t)((short_mask >> lane) & 1);
+    for (int k = 0; k < 16; k++) {
+      const int c = lane + 32 * k;
+      const int bits = xf.bits[xu * 512 + c], sfi = xf.sfi[xu * 512 + c];
+      float val = 0.0f;
+      if (bits > 0 && sfi > 0) {  // quantization.js:65-78, the IEEE division itself
+        const double range = (double)((1 << (bits - 1)) - 1);
+        val = (float)(((double)xf.q[xu * 512 + c] * T->sf[sfi]) / range);
+      }
+      row[c] = val;
+    }
+  } else if (lin >= n_su_valid) {  // dummy frame {nBfu: 0, blockModes: [0,0,0]} (processor.js:299-307)
     // all-zero coefficients: every IMDCT output is +0 or -0; run the transform for the signs
     for (int k = 0; k < 16; k++) row[lane + 32 * k] = 0.0f;
     if (lane < 4) modes[(size_t)unit * 4 + lane] = 0;
@@ -502,7 +539,7 @@ cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, Prof *prof) {
   prof->begin(K_UNPACK_IMDCT, st);
   unpack_imdct_kernel<<<(n_units + kUiWarps - 1) / kUiWarps, kUiWarps * 32, 0, st>>>(
       L.su, L.su_frame_stride, L.su_stream_stride, L.n_su_valid, L.frames_total, n_units, L.tables, L.coefs_dbg,
-      L.modes, L.inv);
+      L.modes, L.inv, L.prev_rec, ExpandedFrames{L.x_q, L.x_sfi, L.x_bits, L.x_modes});
   prof->end(K_UNPACK_IMDCT, st);
   if (L.bands_dbg) {
     prof->begin(K_BANDS_TIME, st);

@@ -43,6 +43,12 @@ struct DecodeLaunch {
   const uint8_t *su;        // unit (f, s) at su + (f*su_frame_stride + s*su_stream_stride)*212
   size_t su_frame_stride, su_stream_stride;
   long long n_su_valid;     // linear unit indices >= this decode as the dummy frame
+  // alternative input: position-expanded frame objects, [n_streams][n_out_frames][512] (su unused)
+  const int32_t *x_q;
+  const uint8_t *x_sfi, *x_bits, *x_modes;
+  // stateful handles: [n_streams][512] band records of the unit before the call; when set,
+  // frame 0 of every row is that record and the su / expanded arrays start at frame 1
+  const float *prev_rec;
   int n_streams;
   int frames_total;         // halo_frames + n_out_frames
   int halo_frames;

@@ -114,6 +114,16 @@ int carta1_dec_create(carta1_ctx *ctx, int n_streams, carta1_decoder **out);
 void carta1_dec_destroy(carta1_decoder *dec);
 int carta1_dec_reset(carta1_decoder *dec);
 int carta1_dec_frames(carta1_decoder *dec, const uint8_t *su, int n_frames, float *pcm_out);
+/* The same closures fed with frame OBJECTS that the 212-byte layout cannot hold: decode()
+ * accepts any object with the frame keys (tests/decoder.test.js:70-98: nBfu 0, arbitrary
+ * quantizedCoefficients lengths).  The host replays dequantizationStage's
+ * `coefficients.set(dequantized, position)` sequence (codec/pipeline/decoder.js:73-94) into
+ * per-position arrays [n_streams][n_frames][512]: q (quantised value), sfi (scale-factor index,
+ * 0..63), bits (WORD_LENGTH_BITS value 0 or 2..16; 0 = position never written); modes is
+ * [n_streams][n_frames][3] (any non-zero = short blocks, decoder.js:82-83). */
+int carta1_dec_frames_expanded(carta1_decoder *dec, const int32_t *q, const uint8_t *sfi,
+                               const uint8_t *bits, const int32_t *modes, int n_frames,
+                               float *pcm_out);
 
 /* ---- device-resident entry points (bench `value`, multi-GPU shards) ---------------
  * All pointers are device pointers on the context's GPU; work is enqueued on the
