@@ -58,6 +58,7 @@ EXPORTED_SYMBOLS = [
     "carta1_ctx_launch_count", "carta1_debug_encode_stages", "carta1_debug_decode_stages",
     "carta1_aea_write_header", "carta1_aea_parse_header", "carta1_kernel_count", "carta1_kernel_name",
     "carta1_ctx_profile", "carta1_ctx_profile_read", "carta1_debug_selftest",
+    "carta1_ctx_set_max_units_per_pass",
 ]
 
 _lib = None
@@ -116,6 +117,7 @@ def load():
     L.carta1_ctx_profile.argtypes = [vp, C.c_int]
     L.carta1_ctx_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
     L.carta1_debug_selftest.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.carta1_ctx_set_max_units_per_pass.argtypes = [vp, sz]
     L.carta1_debug_encode_stages.argtypes = [vp, vp, sz, C.POINTER(EncOpts), vp, vp, vp, vp, vp]
     L.carta1_debug_decode_stages.argtypes = [vp, vp, sz, vp, vp, vp]
     L.carta1_aea_write_header.argtypes = [C.c_char_p, C.c_uint32, C.c_int, vp]
@@ -240,6 +242,9 @@ class Context:
 
     def sync(self):
         self._check(self.L.carta1_ctx_sync(self.h))
+
+    def set_max_units_per_pass(self, units: int):
+        self._check(self.L.carta1_ctx_set_max_units_per_pass(self.h, int(units)))
 
     @property
     def stream(self) -> int:

@@ -213,6 +213,7 @@ struct carta1_ctx {
   carta1_enc_opts params_opts;
   double params_bsf[64];
   DevBuf bands, mags, modes, coefs, inv, scores, stage_pcm, stage_su, dbg, recs;
+  size_t max_units_per_pass = 1u << 19;  // frames*channels per pass of the chunked host entry points
 };
 
 struct carta1_encoder {
@@ -286,9 +287,6 @@ int ensure_decode_scratch(carta1_ctx *ctx, size_t units) {
   CU(ctx, ctx->modes.ensure(units * 4));
   return CARTA1_OK;
 }
-
-// Frames per pass for the chunked host entry points (bounds scratch and staging memory).
-const size_t kMaxUnitsPerPass = 1u << 19;
 
 }  // namespace
 
@@ -415,6 +413,12 @@ int carta1_ctx_profile_read(carta1_ctx *ctx, double *ms_out, uint64_t *count_out
 }
 size_t carta1_frame_count(size_t n_samples) { return (n_samples + 511) / 512; }
 
+int carta1_ctx_set_max_units_per_pass(carta1_ctx *ctx, size_t units) {
+  if (!ctx) return CARTA1_ERR_ARG;
+  ctx->max_units_per_pass = units ? units : (size_t)1 << 19;
+  return CARTA1_OK;
+}
+
 // ------------------------------------------------------------------ device-resident
 static int encode_device_impl(carta1_ctx *ctx, const void *d_pcm, int pcm_fmt, size_t row_stride,
                               int n_ch_interleave, int n_streams, size_t valid_samples, size_t halo_frames,
@@ -528,7 +532,7 @@ static int encode_host_impl(carta1_ctx *ctx, const float *const *channels, const
   int rc = upload_params(ctx, opts, ctx->d_params);
   if (rc) return rc;
   const bool fixed = opts && opts->use_fixed_block_modes;
-  const size_t chunk = std::max<size_t>(16, kMaxUnitsPerPass / (size_t)n_ch);
+  const size_t chunk = std::max<size_t>(2, ctx->max_units_per_pass / (size_t)n_ch);
   for (size_t a = 0; a < frames; a += chunk) {
     const size_t b = std::min(frames, a + chunk);
     const size_t halo = a >= 2 ? 2 : 0;  // a is 0 or >= chunk
@@ -586,7 +590,7 @@ static int decode_host_impl(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int
   const size_t frames = (n_su + (size_t)n_ch - 1) / (size_t)n_ch;
   if (frames == 0) return CARTA1_OK;
   CU(ctx, cudaSetDevice(ctx->device));
-  const size_t chunk = std::max<size_t>(16, kMaxUnitsPerPass / (size_t)n_ch);
+  const size_t chunk = std::max<size_t>(2, ctx->max_units_per_pass / (size_t)n_ch);
   for (size_t a = 0; a < frames; a += chunk) {
     const size_t b = std::min(frames, a + chunk);
     const size_t halo = a >= 1 ? 1 : 0;

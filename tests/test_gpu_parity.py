@@ -193,12 +193,72 @@ def test_stateful_streams_match_whole_buffer(ctx, oracle):
         dec.close()
 
 
-def test_chunked_host_path(ctx, oracle, monkeypatch):
-    """More frames than one pass holds: the halo logic of the chunked entry points."""
-    chans = S.cfg3_transients(3.0, n_ch=2)
-    su = ctx.encode_pcm(chans)
+@pytest.mark.parametrize("units", [4, 14, 250])
+def test_chunked_host_path(ctx, oracle, units):
+    """More frames than one pass holds: the halo logic of the chunked entry points
+    (2 frames of PCM for encode, 1 sound unit for decode, at every pass boundary)."""
+    chans = S.cfg3_transients(1.5, n_ch=2)
     want = oracle.encode_pcm(chans, threads=8, chunk_frames=32)
-    assert np.array_equal(su, want)
+    ref = oracle.decode_su(want, 2, threads=8, chunk_frames=32)
+    ctx.set_max_units_per_pass(units)
+    try:
+        su = ctx.encode_pcm(chans)
+        assert np.array_equal(su, want)
+        pcm = ctx.decode_su(su, 2)
+        for x, y in zip(pcm, ref):
+            assert np.array_equal(bits(x), bits(y))
+        s16 = ctx.decode_su_s16(su, 2).reshape(-1, 2)
+        for c in range(2):
+            assert np.array_equal(s16[:, c], oracle.pcm_to_int16(ref[c]))
+        x16 = np.stack([oracle.pcm_to_int16(c) for c in chans], axis=1)
+        back = [oracle.int16_to_pcm(x16[:, c].copy()) for c in range(2)]
+        assert np.array_equal(ctx.encode_pcm_s16(x16, 2), oracle.encode_pcm(back, threads=8, chunk_frames=32))
+    finally:
+        ctx.set_max_units_per_pass(0)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_device_path(ctx, oracle, world):
+    """Config 5's shape at test size: (stream, frame-range) shards with halos through the
+    device-resident entry points; every shard only sees its own slice (+halo) of the input and
+    writes a disjoint slice of the output.  All shards run on this one GPU, one after another."""
+    import torch
+
+    from carta1_b200 import sharding
+
+    streams = [S.cfg3_transients(sec, seed=40 + i, n_ch=2) for i, sec in enumerate((0.45, 0.2, 0.33))]
+    frames = [oracle.frame_count(len(ch[0])) for ch in streams]
+    plan = sharding.plan(frames, world)
+    sharding.check_plan(plan, frames)
+    su_out = [np.zeros((f * 2, 212), np.uint8) for f in frames]
+    pcm_out = [np.zeros((2, f * 512), np.float32) for f in frames]
+    wants = [oracle.encode_pcm(ch) for ch in streams]
+    for shards in plan:
+        for sh in shards:
+            ch = streams[sh.stream]
+            first, last = sh.pcm_span()
+            n = last - first
+            host = np.zeros((2, n), np.float32)
+            for c in range(2):
+                part = ch[c][first:last]
+                host[c, :len(part)] = part
+            d_pcm = torch.from_numpy(host).cuda()
+            d_su = torch.zeros(sh.frames * 2 * 212, dtype=torch.uint8, device="cuda")
+            ctx.encode_device(d_pcm.data_ptr(), n, 2, n, sh.enc_halo, sh.frames, None, d_su.data_ptr(), 2, 1, sync=True)
+            su_out[sh.stream][sh.begin * 2:sh.end * 2] = d_su.cpu().numpy().reshape(-1, 212)
+    for i in range(len(streams)):
+        assert np.array_equal(su_out[i], wants[i]), i
+    for shards in plan:
+        for sh in shards:
+            ua, ub = sh.unit_span(2)
+            d_su = torch.from_numpy(np.ascontiguousarray(wants[sh.stream][ua:ub]).reshape(-1)).cuda()
+            d_pcm = torch.zeros((2, sh.frames * 512), dtype=torch.float32, device="cuda")
+            ctx.decode_device(d_su.data_ptr(), 2, 1, ub - ua, 2, sh.dec_halo, sh.frames, d_pcm.data_ptr(), sh.frames * 512, sync=True)
+            pcm_out[sh.stream][:, sh.begin * 512:sh.end * 512] = d_pcm.cpu().numpy()
+    for i in range(len(streams)):
+        ref = oracle.decode_su(wants[i], 2)
+        for c in range(2):
+            assert np.array_equal(bits(pcm_out[i][c]), bits(ref[c])), (i, c)
 
 
 def test_arithmetic_shortcuts_selftest(ctx):
