@@ -346,8 +346,8 @@ int carta1_ctx_create(int device, const carta1_tables *tables, carta1_ctx **out)
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_tables, sizeof(DevTables));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_params, sizeof(DevEncParams));
   if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tables, ht, sizeof(DevTables), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = upload_encode_constants(ht->qmf_even, ht->qmf_odd);
-  if (e == cudaSuccess) e = upload_decode_constants(ht->qmf_even, ht->qmf_odd);
+  if (e == cudaSuccess) e = upload_encode_constants(ht);
+  if (e == cudaSuccess) e = upload_decode_constants(ht);
   delete ht;
   if (e != cudaSuccess) {
     cuda_fail(nullptr, e, "carta1_ctx_create");

@@ -346,10 +346,11 @@ constexpr int kSynHd = 256 * kSynTile + 24;
 __constant__ double c_syn_even[24];
 __constant__ double c_syn_odd[24];
 
-cudaError_t upload_decode_constants(const double *even24, const double *odd24) {
-  cudaError_t e = cudaMemcpyToSymbol(c_syn_even, even24, 24 * sizeof(double));
-  if (e != cudaSuccess) return e;
-  return cudaMemcpyToSymbol(c_syn_odd, odd24, 24 * sizeof(double));
+cudaError_t upload_decode_constants(const DevTables *host_tables) {
+  cudaError_t e = cudaMemcpyToSymbol(c_syn_even, host_tables->qmf_even, 24 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_syn_odd, host_tables->qmf_odd, 24 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_fft_tw, host_tables->fft_tw, sizeof(host_tables->fft_tw));
+  return e;
 }
 
 // acc[r] = sum_j w[8t + 1 + r + j] * taps[j], j ascending, for r = 0..7 (thread t)

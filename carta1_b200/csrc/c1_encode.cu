@@ -68,10 +68,11 @@ static_assert(kQmfS1Threads <= kQmfThreads, "stage 1 must fit the block");
 __constant__ double c_qmf_even[24];
 __constant__ double c_qmf_odd[24];
 
-cudaError_t upload_encode_constants(const double *even24, const double *odd24) {
-  cudaError_t e = cudaMemcpyToSymbol(c_qmf_even, even24, 24 * sizeof(double));
-  if (e != cudaSuccess) return e;
-  return cudaMemcpyToSymbol(c_qmf_odd, odd24, 24 * sizeof(double));
+cudaError_t upload_encode_constants(const DevTables *host_tables) {
+  cudaError_t e = cudaMemcpyToSymbol(c_qmf_even, host_tables->qmf_even, 24 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_qmf_odd, host_tables->qmf_odd, 24 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_fft_tw, host_tables->fft_tw, sizeof(host_tables->fft_tw));
+  return e;
 }
 
 // acc[r] = sum_j w[8t + 24 + r - j] * taps[j], j ascending, for r = 0..7 (thread t)
@@ -396,60 +397,158 @@ __device__ __noinline__ void mdct_band_exact(int band, bool is_long, const doubl
   mdct_band<ExactRound>(band, is_long, arr, out, T, lane);
 }
 
+// ---- long blocks, all three bands of a sound unit at once (c1_fft.cuh, in-thread passes) ----
+constexpr int kArrLow = 0, kArrMid = 160, kArrHigh = 320, kArrDoubles = 608;  // [overlap 32 | samples] per band
+
+// mdct.js:76-105 with the loop a value belongs to known at compile time (first: i < N/4)
+template <bool kFirst, typename In, typename R>
+__device__ __forceinline__ Cplx mdct_pre_long(int q, int n, const In &in, const double *__restrict__ tab, const R &rnd) {
+  const int i = 2 * q, n4 = n >> 2, n34 = 3 * n4;
+  double r, m;
+  if (kFirst) {
+    r = in(n34 - 1 - i) + in(n34 + i);
+    m = in(n4 + i) - in(n4 - 1 - i);
+  } else {
+    r = in(n34 - 1 - i) - in(i - n4);
+    m = in(n4 + i) + in(5 * n4 - 1 - i);
+  }
+  const double2 cs = __ldg(reinterpret_cast<const double2 *>(tab + i));
+  Cplx z;
+  z.re = rnd(r * cs.x + m * cs.y);
+  z.im = rnd(m * cs.x - r * cs.y);
+  return z;
+}
+
+template <typename R>
+__device__ __forceinline__ void mdct_long3(unsigned long_mask, double *arr, float *out,
+                                           const DevTables *__restrict__ T, int lane) {
+  R rnd;
+  const LongLanes G(lane);
+  const bool active = (long_mask >> G.band) & 1;
+  const int n = G.band == 2 ? 512 : 256;
+  const int ws = G.band == 2 ? 112 : 48;          // constants.js:115-119
+  const int span = (G.band == 2 ? 256 : 128) + 32;
+  const double *a = arr + (G.band == 0 ? kArrLow : G.band == 1 ? kArrMid : kArrHigh);
+  const double *tab = G.band == 2 ? T->mdct_fwd512 : T->mdct_fwd256;
+  auto in = [&](int k) -> double {
+    const unsigned at = (unsigned)(k - ws);
+    return at < (unsigned)span ? a[at] : 0.0;
+  };
+  Cplx v[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    v[j].re = 0.0;
+    v[j].im = 0.0;
+    if (active) {
+      // position 8t + j holds natural index q; q < N/8 exactly when j is even
+      if ((j & 1) == 0) v[j] = mdct_pre_long<true>(G.q_of(j), n, in, tab, rnd);
+      else v[j] = mdct_pre_long<false>(G.q_of(j), n, in, tab, rnd);
+    }
+  }
+  double2 *xbuf = reinterpret_cast<double2 *>(arr) + (G.band == 0 ? 0 : G.band == 1 ? kXposeSlots64 : 2 * kXposeSlots64);
+  fft_long_inthread(v, G, xbuf, T->fft_tw, active, rnd);
+  if (active) {
+    float *o = out + (G.band == 0 ? 0 : G.band == 1 ? 128 : 256);
+#pragma unroll
+    for (int k = 0; k < 8; k++) mdct_post(v[k], long_out_index(G, k), n, tab, o, G.band > 0);
+  }
+}
+static_assert(2 * kXposeSlots64 + kXposeSlots128 <= kArrDoubles / 2, "transpose buffers alias the input buffer");
+
+__device__ __noinline__ void mdct_long3_exact(unsigned long_mask, double *arr, float *out,
+                                              const DevTables *__restrict__ T, int lane) {
+  mdct_long3<ExactRound>(long_mask, arr, out, T, lane);
+}
+
 constexpr int kMdctWarps = 8;
+struct MdctWarpSmem {
+  double arr[kArrDoubles];
+  float out[512];
+};
+constexpr size_t kMdctSmemBytes = sizeof(MdctWarpSmem) * kMdctWarps;
 
 __global__ void __launch_bounds__(kMdctWarps * 32, 3)
 mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, int frames, int n_su,
             const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
             float *__restrict__ coefs) {
-  __shared__ double s_arr[kMdctWarps][512];
-  __shared__ __align__(16) float s_out[kMdctWarps][512];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int su = blockIdx.x * kMdctWarps + warp;
   if (su >= n_su) return;
+  MdctWarpSmem &S = reinterpret_cast<MdctWarpSmem *>(smem_raw)[warp];
+  double *arr = S.arr;
+  float *out = S.out;
   const double w_fwd = T->win[lane], w_rev = T->win[31 - lane];  // WINDOW_SHORT[i], [31 - i]
   const int frame = su % frames;
-  double *arr = s_arr[warp];
-  float *out = s_out[warp];
+  const float *cur = bands + (size_t)su * 512;
+  const float *prev = frame > 0 ? cur - 512 : nullptr;
+  int mode[3];
+  unsigned long_mask = 0;
+#pragma unroll
+  for (int b = 0; b < 3; b++) {
+    mode[b] = P->use_fixed ? P->fixed[b] : (int)modes[(size_t)su * 4 + b];
+    long_mask |= (mode[b] == 0 ? 1u : 0u) << b;
+  }
   ExactRound xr;
-  for (int band = 0; band < 3; band++) {
-    const int size = band == 2 ? 256 : 128;
-    const int off = band == 0 ? 0 : band == 1 ? 128 : 256;
-    const float *cur = bands + (size_t)su * 512 + off;
-    const float *prev = frame > 0 ? cur - 512 : nullptr;
-    const int mode = P->use_fixed ? P->fixed[band] : (int)modes[(size_t)su * 4 + band];
-    unsigned big = 0;  // largest |input| (high word) of this band's transform
-    if (mode == 0) {
-      // arr = [overlap saved by the previous frame (32) | samples, last 32 tail-windowed]
-      // (encoder.js:240-247,309-316)
-      {
-        const float pv = prev ? prev[size - 32 + lane] : 0.0f;
-        arr[lane] = prev ? xr(w_fwd * (double)pv) : 0.0;
-        big = abs_hi_word((double)pv);
-      }
-      for (int k = lane; k < size; k += 32) {
-        const double x = (double)cur[k];
-        big = max(big, abs_hi_word(x));
-        arr[32 + k] = k >= size - 32 ? xr(x * w_rev) : x;  // k - (size - 32) == lane
-      }
-    } else {
-      // short blocks: block b transforms [WIN * previous block (32) | block * reversed WIN (32)]
-      // (encoder.js:279-304)
-      for (int b = 0; b < (size >> 5); b++) {
-        float src_prev = 0.0f;
-        bool have_prev = true;
-        if (b == 0) { have_prev = prev != nullptr; if (prev) src_prev = prev[size - 32 + lane]; }
-        else src_prev = cur[32 * (b - 1) + lane];
-        arr[64 * b + lane] = have_prev ? xr(w_fwd * (double)src_prev) : 0.0;
-        arr[64 * b + 32 + lane] = xr((double)cur[32 * b + lane] * w_rev);
-        big = max(big, max(abs_hi_word((double)src_prev), abs_hi_word((double)cur[32 * b + lane])));
-      }
+  unsigned big = 0;  // largest |input| (binary32 bits) of this unit's transforms
+  // ---- long-block input buffers: [overlap saved by the previous frame (32) | samples, last 32
+  // tail-windowed] per band (encoder.js:240-247,309-316)
+  {
+    const float4 *cur4 = reinterpret_cast<const float4 *>(cur);
+    float4 x[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) x[k] = __ldg(cur4 + lane + 32 * k);
+    float pv[3];
+#pragma unroll
+    for (int b = 0; b < 3; b++) pv[b] = prev ? __ldg(prev + (b == 0 ? 96 : b == 1 ? 224 : 480) + lane) : 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      // element 4*(lane + 32k): k = 0 low, 1 mid, 2..3 high
+      const int at = (k == 0 ? kArrLow + 32 : k == 1 ? kArrMid + 32 : kArrHigh + 32 + 128 * (k - 2)) + 4 * lane;
+      double2 *d = reinterpret_cast<double2 *>(arr + at);
+      d[0] = make_double2((double)x[k].x, (double)x[k].y);
+      d[1] = make_double2((double)x[k].z, (double)x[k].w);
+      big = max(big, max(max(__float_as_uint(x[k].x) & 0x7FFFFFFFu, __float_as_uint(x[k].y) & 0x7FFFFFFFu),
+                         max(__float_as_uint(x[k].z) & 0x7FFFFFFFu, __float_as_uint(x[k].w) & 0x7FFFFFFFu)));
     }
     __syncwarp();
-    if (__reduce_max_sync(0xffffffffu, big) < kFastRoundInputLimit)
-      mdct_band<FastRound>(band, mode == 0, arr, out + off, T, lane);
-    else
-      mdct_band_exact(band, mode == 0, arr, out + off, T, lane);
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      const int base = b == 0 ? kArrLow : b == 1 ? kArrMid : kArrHigh;
+      const int size = b == 2 ? 256 : 128;
+      arr[base + lane] = prev ? xr(w_fwd * (double)pv[b]) : 0.0;
+      arr[base + size + lane] = xr(arr[base + size + lane] * w_rev);
+      big = max(big, __float_as_uint(pv[b]) & 0x7FFFFFFFu);
+    }
+    __syncwarp();
+  }
+  // 0x71800000 is 2^100 as binary32: below it no transform value can reach the binary32 overflow
+  // threshold, the one case FastRound cannot round
+  const bool fast = __reduce_max_sync(0xffffffffu, big) < 0x71800000u;
+  if (long_mask) {
+    if (fast) mdct_long3<FastRound>(long_mask, arr, out, T, lane);
+    else mdct_long3_exact(long_mask, arr, out, T, lane);
+    __syncwarp();
+  }
+  // ---- short blocks, one band at a time: block b transforms
+  // [WIN * previous block (32) | block * reversed WIN (32)] (encoder.js:279-304)
+  for (int band = 0; band < 3; band++) {
+    if (mode[band] == 0) continue;
+    const int size = band == 2 ? 256 : 128;
+    const int off = band == 0 ? 0 : band == 1 ? 128 : 256;
+    const float *c = cur + off;
+    const float *p = prev ? prev + off : nullptr;
+    for (int b = 0; b < (size >> 5); b++) {
+      float src_prev = 0.0f;
+      bool have_prev = true;
+      if (b == 0) { have_prev = p != nullptr; if (p) src_prev = p[size - 32 + lane]; }
+      else src_prev = c[32 * (b - 1) + lane];
+      arr[64 * b + lane] = have_prev ? xr(w_fwd * (double)src_prev) : 0.0;
+      arr[64 * b + 32 + lane] = xr((double)c[32 * b + lane] * w_rev);
+    }
+    __syncwarp();
+    if (fast) mdct_band<FastRound>(band, false, arr, out + off, T, lane);
+    else mdct_band_exact(band, false, arr, out + off, T, lane);
     __syncwarp();
   }
   float4 *dst = reinterpret_cast<float4 *>(coefs + (size_t)su * 512);
@@ -882,7 +981,11 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
     prof->end(K_TRANSIENT_MODES, st);
   }
   prof->begin(K_MDCT, st);
-  mdct_kernel<<<(n_su + kMdctWarps - 1) / kMdctWarps, kMdctWarps * 32, 0, st>>>(L.bands, L.modes, frames, n_su, L.tables, L.params, L.coefs);
+  {
+    cudaError_t e1 = cudaFuncSetAttribute(mdct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMdctSmemBytes);
+    if (e1 != cudaSuccess) return e1;
+  }
+  mdct_kernel<<<(n_su + kMdctWarps - 1) / kMdctWarps, kMdctWarps * 32, kMdctSmemBytes, st>>>(L.bands, L.modes, frames, n_su, L.tables, L.params, L.coefs);
   prof->end(K_MDCT, st);
   const long long n_units = (long long)L.n_streams * L.n_out_frames;
   if (n_units > 0 && L.su_out) {

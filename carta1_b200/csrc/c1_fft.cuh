@@ -30,12 +30,12 @@ namespace c1 {
 // conversions", which is the cost this avoids.
 struct FastRound {
   __device__ __forceinline__ double operator()(double v) const {
-    const unsigned h = (unsigned)__double2hiint(v);
-    const unsigned a = h & 0x7FFFFFFFu;
-    const unsigned ce = (max(a, 0x38100000u) & 0x7FF00000u) + 0x01D00000u;
+    const int h = __double2hiint(v);
+    // exponent field of C: max(e, -126) + 29; the low word of C is zero
+    const unsigned ce = max((unsigned)h & 0x7FF00000u, 0x38100000u) + 0x01D00000u;
     const double c = __hiloint2double((int)ce, 0);
-    const double r = (__hiloint2double((int)a, __double2loint(v)) + c) - c;
-    return __hiloint2double((int)((unsigned)__double2hiint(r) | (h & 0x80000000u)), __double2loint(r));
+    const double r = (fabs(v) + c) - c;  // r >= +0: its sign bit is clear
+    return __hiloint2double(__double2hiint(r) | (h & (int)0x80000000u), __double2loint(r));
   }
 };
 struct ExactRound {
@@ -109,5 +109,127 @@ __device__ __forceinline__ void warp_fft128_regs(Cplx &a0, Cplx &b0, Cplx &a1, C
 }
 
 __device__ __forceinline__ int brev_bits(int x, int bits) { return (int)(__brev((unsigned)x) >> (32 - bits)); }
+
+// ------------------------------------------------------------------------------------
+// In-thread formulation for the long blocks (FFT64 / FFT128): every thread owns 8 complex
+// values and runs three radix-2 stages on them without talking to anybody; between such
+// passes the values are transposed through shared memory.  The butterflies, their inputs
+// and their order of roundings are exactly the reference's (fft.js:35-66) -- only which
+// thread executes which butterfly changes.
+//
+//   pass A: thread t owns array positions 8t + j           -> stages 0,1,2 (twiddles are
+//           compile-time entries of the recurrence table: constant-bank operands)
+//   pass B: thread (b6, u) owns positions 64 b6 + 8m + u   -> stages 3,4,5
+//   pass C: (FFT128 only) thread (u, h) owns positions 8m + u and 64 + 8m + u, m in 4h..4h+3
+//           -> stage 6
+// FFT64 uses 8 threads, FFT128 16: one warp transforms the low, mid and high band of a
+// sound unit at once (lanes 0-7, 8-15, 16-31).
+//
+// Transpose buffer: complex position p lives at 16-byte slot p + (p >> 3); every quarter-warp
+// access of the three layouts above then touches 8 distinct 16-byte bank groups.
+// ------------------------------------------------------------------------------------
+static __constant__ double2 c_fft_tw[255];  // DevTables::fft_tw, one copy per translation unit
+
+constexpr int kXposeSlots64 = 64 + 8, kXposeSlots128 = 128 + 16;
+__device__ __forceinline__ int xpose_slot(int p) { return p + (p >> 3); }
+
+template <typename R>
+__device__ __forceinline__ void fft8_pass_a(Cplx (&v)[8], const R &rnd) {
+#pragma unroll
+  for (int s = 0; s < 3; s++) {
+    const int d = 1 << s;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (!(j & d)) butterfly(v[j], v[j + d], c_fft_tw[d - 1 + (j & (d - 1))], rnd);
+  }
+}
+
+// v[m] = position base + 8m + u; stage 3 + ls pairs m with m + 2^ls, twiddle index
+// (pos & (half - 1)) = 8 (m & (2^ls - 1)) + u with half = 8 * 2^ls
+template <typename R>
+__device__ __forceinline__ void fft8_pass_b(Cplx (&v)[8], int u, const double2 *__restrict__ tw, const R &rnd) {
+#pragma unroll
+  for (int ls = 0; ls < 3; ls++) {
+    const int d = 1 << ls, half = 8 << ls;
+#pragma unroll
+    for (int m = 0; m < 8; m++)
+      if (!(m & d)) butterfly(v[m], v[m + d], __ldg(&tw[half - 1 + 8 * (m & (d - 1)) + u]), rnd);
+  }
+}
+
+// v[k] = position 8 (4h + k) + u, v[4 + k] = that + 64: stage 6, twiddle index 8 (4h + k) + u
+template <typename R>
+__device__ __forceinline__ void fft8_pass_c(Cplx (&v)[8], int u, int h, const double2 *__restrict__ tw, const R &rnd) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) butterfly(v[k], v[4 + k], __ldg(&tw[63 + 8 * (4 * h + k) + u]), rnd);
+}
+
+__device__ __forceinline__ void xpose_put(double2 *buf, int p, const Cplx &z) { buf[xpose_slot(p)] = make_double2(z.re, z.im); }
+__device__ __forceinline__ Cplx xpose_get(const double2 *buf, int p) {
+  const double2 t = buf[xpose_slot(p)];
+  Cplx z;
+  z.re = t.x;
+  z.im = t.y;
+  return z;
+}
+
+// Lane geometry of the three concurrent long-block transforms of one sound unit.
+struct LongLanes {
+  int band;      // 0 low, 1 mid, 2 high
+  int t;         // thread index inside the band's transform (0..7 or 0..15)
+  int nl;        // threads of the transform = FFT size / 8
+  int rev_t;     // bit reversal of t over log2(nl) bits
+  int u, b6;     // pass B: positions 64 b6 + 8m + u
+  __device__ __forceinline__ explicit LongLanes(int lane) {
+    band = lane < 8 ? 0 : (lane < 16 ? 1 : 2);
+    t = band == 2 ? lane - 16 : (lane & 7);
+    nl = band == 2 ? 16 : 8;
+    rev_t = band == 2 ? brev_bits(t, 4) : brev_bits(t, 3);
+    u = t & 7;
+    b6 = t >> 3;
+  }
+  // natural FFT-input index held at array position 8t + j (bit-reversed order, fft.js:21-32)
+  __device__ __forceinline__ int q_of(int j) const { return (int)(__brev((unsigned)j) >> 29) * nl + rev_t; }
+};
+
+// Runs passes A..C on v (pass-A layout on entry: v[j] = position 8t + j); on exit v[k] holds the
+// natural-order output whose index is out_index(k).  xbuf: this transform's transpose buffer.
+template <typename R>
+__device__ __forceinline__ void fft_long_inthread(Cplx (&v)[8], const LongLanes &G, double2 *xbuf,
+                                                  const double2 *__restrict__ tw, bool active, const R &rnd) {
+  fft8_pass_a(v, rnd);
+  __syncwarp();
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) xpose_put(xbuf, 8 * G.t + j, v[j]);
+  }
+  __syncwarp();
+  if (active) {
+#pragma unroll
+    for (int m = 0; m < 8; m++) v[m] = xpose_get(xbuf, 64 * G.b6 + 8 * m + G.u);
+  }
+  fft8_pass_b(v, G.u, tw, rnd);
+  if (G.band == 2) {  // lanes 16-31: one more stage
+    __syncwarp(0xffff0000u);
+    if (active) {
+#pragma unroll
+      for (int m = 0; m < 8; m++) xpose_put(xbuf, 64 * G.b6 + 8 * m + G.u, v[m]);
+    }
+    __syncwarp(0xffff0000u);
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        v[k] = xpose_get(xbuf, 8 * (4 * G.b6 + k) + G.u);
+        v[4 + k] = xpose_get(xbuf, 64 + 8 * (4 * G.b6 + k) + G.u);
+      }
+    }
+    fft8_pass_c(v, G.u, G.b6, tw, rnd);
+  }
+}
+// natural-order output index of v[k] after fft_long_inthread
+__device__ __forceinline__ int long_out_index(const LongLanes &G, int k) {
+  if (G.band == 2) return 8 * (4 * G.b6 + (k & 3)) + G.u + 64 * (k >> 2);
+  return 8 * k + G.u;
+}
 
 }  // namespace c1

@@ -92,9 +92,9 @@ struct Prof {
 };
 
 size_t alloc_rec_bytes();
-// QMF taps go to __constant__ memory of the current device (call once per context).
-cudaError_t upload_encode_constants(const double *even24, const double *odd24);
-cudaError_t upload_decode_constants(const double *even24, const double *odd24);
+// QMF taps and FFT twiddles go to __constant__ memory of the current device (once per context).
+cudaError_t upload_encode_constants(const DevTables *host_tables);
+cudaError_t upload_decode_constants(const DevTables *host_tables);
 cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof);
 cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, Prof *prof);
 cudaError_t launch_selftest(const DevTables *tables, unsigned long long *d_bad, cudaStream_t st);
