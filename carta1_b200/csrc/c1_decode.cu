@@ -132,25 +132,72 @@ __device__ __noinline__ void imdct_band_exact(int band, bool is_long, const floa
   imdct_band<ExactRound>(band, is_long, x, y, T, lane);
 }
 
+// ---- long blocks, all three bands of a sound unit at once (c1_fft.cuh, in-thread passes) ----
+template <typename R>
+__device__ __forceinline__ void imdct_long3(unsigned long_mask, const float *x, float *y, double2 *xbuf_all,
+                                            const DevTables *__restrict__ T, int lane) {
+  R rnd;
+  const LongLanes G(lane);
+  const bool active = (long_mask >> G.band) & 1;
+  const int n = G.band == 2 ? 512 : 256;
+  const int size = n >> 1;
+  const int off = G.band == 0 ? 0 : G.band == 1 ? 128 : 256;
+  const float *xb = x + off;
+  const bool rev = G.band > 0;  // utils.js:42-48: un-reverse mid / high spectra
+  const double *tab = G.band == 2 ? T->mdct_inv512 : T->mdct_inv256;
+  Cplx v[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    v[j].re = 0.0;
+    v[j].im = 0.0;
+    if (active) {  // mdct.js:161-170
+      const int i2 = 2 * G.q_of(j);
+      const int ka = rev ? size - 1 - i2 : i2, kb = rev ? i2 : size - 1 - i2;
+      const double r = -(double)xb[ka];
+      const double m = -(double)xb[kb];
+      const double2 cs = __ldg(reinterpret_cast<const double2 *>(tab + i2));
+      v[j].re = rnd(m * cs.y + r * cs.x);
+      v[j].im = rnd(m * cs.x - r * cs.y);
+    }
+  }
+  double2 *xbuf = xbuf_all + (G.band == 0 ? 0 : G.band == 1 ? kXposeSlots64 : 2 * kXposeSlots64);
+  fft_long_inthread(v, G, xbuf, T->fft_tw, active, rnd);
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) imdct_post(v[k], long_out_index(G, k), n, tab, y + off);
+  }
+}
+
+__device__ __noinline__ void imdct_long3_exact(unsigned long_mask, const float *x, float *y, double2 *xbuf_all,
+                                               const DevTables *__restrict__ T, int lane) {
+  imdct_long3<ExactRound>(long_mask, x, y, xbuf_all, T, lane);
+}
+
 constexpr int kUiWarps = 8;
+struct UiWarpSmem {
+  double2 xbuf[2 * kXposeSlots64 + kXposeSlots128];  // transposes of the long-block FFTs
+  float row[512];   // dequantised coefficients, later the band record being assembled
+  float inv[512];   // IMDCT middle halves
+  double rcp[52];
+  uint32_t words[56];
+  uint16_t base[52];
+  uint8_t wl[52], sfi[52];
+};
+constexpr size_t kUiSmemBytes = sizeof(UiWarpSmem) * kUiWarps;
 
 __global__ void __launch_bounds__(kUiWarps * 32, 3)
 unpack_imdct_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_stream_stride,
                     long long n_su_valid, int frames, int n_units, const DevTables *__restrict__ T,
                     float *__restrict__ coefs_dbg, uint8_t *__restrict__ modes, float *__restrict__ inv,
                     const float *__restrict__ prev_rec, ExpandedFrames xf) {
-  __shared__ __align__(16) float s_row[kUiWarps][512];
-  __shared__ __align__(16) float s_inv[kUiWarps][512];
-  __shared__ double s_rcp[kUiWarps][52];
-  __shared__ uint32_t s_words[kUiWarps][56];
-  __shared__ uint16_t s_base[kUiWarps][52];
-  __shared__ uint8_t s_wl[kUiWarps][52], s_sfi[kUiWarps][52];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x * kUiWarps + warp;
   if (unit >= n_units) return;
+  UiWarpSmem &S = reinterpret_cast<UiWarpSmem *>(smem_raw)[warp];
   const int stream = unit / frames, frame = unit - stream * frames;
   const FormatTables &F = T->fmt;
-  float *row = s_row[warp];
+  float *row = S.row;
   float4 *dst4 = reinterpret_cast<float4 *>(inv + (size_t)unit * 512);
   // stateful handles: frame 0 of every row is the band record kept from the previous call
   const int su_skip = prev_rec ? 1 : 0;
@@ -184,7 +231,7 @@ unpack_imdct_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size
     for (int k = 0; k < 16; k++) row[lane + 32 * k] = 0.0f;
     if (lane < 4) modes[(size_t)unit * 4 + lane] = 0;
   } else {
-    uint32_t *words = s_words[warp];
+    uint32_t *words = S.words;
     const uint32_t *src = reinterpret_cast<const uint32_t *>(su + (size_t)lin * kSuBytes);
     for (int i = lane; i < 56; i += 32) words[i] = i < kSuWords ? __byte_perm(src[i], 0, 0x0123) : 0u;
     __syncwarp();
@@ -211,10 +258,10 @@ unpack_imdct_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size
         if (lane >= d) incl += t;
       }
       if (b < 52) {
-        s_wl[warp][b] = (uint8_t)(b < n ? wl : 0);
-        s_sfi[warp][b] = (uint8_t)sfi;
-        s_base[warp][b] = (uint16_t)(run + incl - cost);
-        s_rcp[warp][b] = bits > 0 ? 1.0 / (double)((1 << (bits - 1)) - 1) : 0.0;
+        S.wl[b] = (uint8_t)(b < n ? wl : 0);
+        S.sfi[b] = (uint8_t)sfi;
+        S.base[b] = (uint16_t)(run + incl - cost);
+        S.rcp[b] = bits > 0 ? 1.0 / (double)((1 << (bits - 1)) - 1) : 0.0;
       }
       run += __shfl_sync(0xffffffffu, incl, 31);
     }
@@ -227,15 +274,15 @@ unpack_imdct_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size
       const int mode = k < 4 ? m0 : (k < 8 ? m1 : m2);
       const int b = mode == 0 ? F.bfu_of_long[c] : F.bfu_of_short[c];
       float val = 0.0f;
-      const int bits = wl_bits(s_wl[warp][b]);  // 0 for b >= n
+      const int bits = wl_bits(S.wl[b]);  // 0 for b >= n
       if (bits > 0) {
         const int j = c - (mode == 0 ? F.start_long[b] : F.start_short[b]);
-        const int v = (int)get_bits(words, (int)s_base[warp][b] + j * bits, bits);
+        const int v = (int)get_bits(words, (int)S.base[b] + j * bits, bits);
         const int q = v >= (1 << (bits - 1)) ? v - (1 << bits) : v;  // bitstream.js:78-82
-        const int sfi = s_sfi[warp][b];
+        const int sfi = S.sfi[b];
         if (sfi != 0) {
           const double range = (double)((1 << (bits - 1)) - 1);
-          val = (float)div_by_range(int_to_double(q) * T->sf[sfi], range, s_rcp[warp][b]);
+          val = (float)div_by_range(int_to_double(q) * T->sf[sfi], range, S.rcp[b]);
         }
       }
       row[c] = val;
@@ -248,17 +295,22 @@ unpack_imdct_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size
 #pragma unroll
     for (int k = 0; k < 4; k++) d[lane + 32 * k] = s4[lane + 32 * k];
   }
-  float *y = s_inv[warp];
+  float *y = S.inv;
+  // 0x71800000 is 2^100 as binary32: below it FastRound is exact for every transform value
+  unsigned big = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) big = max(big, __float_as_uint(row[lane + 32 * k]) & 0x7FFFFFFFu);
+  const bool fast = __reduce_max_sync(0xffffffffu, big) < 0x71800000u;
+  const unsigned long_mask = ~(unsigned)short_mask & 7u;
+  if (long_mask) {
+    if (fast) imdct_long3<FastRound>(long_mask, row, y, S.xbuf, T, lane);
+    else imdct_long3_exact(long_mask, row, y, S.xbuf, T, lane);
+  }
   for (int band = 0; band < 3; band++) {
+    if (!((short_mask >> band) & 1)) continue;
     const int off = band == 0 ? 0 : band == 1 ? 128 : 256;
-    const bool is_long = !((short_mask >> band) & 1);
-    unsigned big = 0;
-    for (int k = lane; k < (band == 2 ? 256 : 128); k += 32) big = max(big, __float_as_uint(row[off + k]) & 0x7FFFFFFFu);
-    // 0x71800000 is 2^100 as binary32
-    if (__reduce_max_sync(0xffffffffu, big) < 0x71800000u)
-      imdct_band<FastRound>(band, is_long, row + off, y + off, T, lane);
-    else
-      imdct_band_exact(band, is_long, row + off, y + off, T, lane);
+    if (fast) imdct_band<FastRound>(band, false, row + off, y + off, T, lane);
+    else imdct_band_exact(band, false, row + off, y + off, T, lane);
   }
   __syncwarp();
   // Band record (what K7 reads): per band [head16 | tail16 | time-domain samples 32..size).
@@ -538,7 +590,11 @@ cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, Prof *prof) {
   const int n_units = L.n_streams * L.frames_total;
   if (n_units == 0) return cudaSuccess;
   prof->begin(K_UNPACK_IMDCT, st);
-  unpack_imdct_kernel<<<(n_units + kUiWarps - 1) / kUiWarps, kUiWarps * 32, 0, st>>>(
+  {
+    cudaError_t e1 = cudaFuncSetAttribute(unpack_imdct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUiSmemBytes);
+    if (e1 != cudaSuccess) return e1;
+  }
+  unpack_imdct_kernel<<<(n_units + kUiWarps - 1) / kUiWarps, kUiWarps * 32, kUiSmemBytes, st>>>(
       L.su, L.su_frame_stride, L.su_stream_stride, L.n_su_valid, L.frames_total, n_units, L.tables, L.coefs_dbg,
       L.modes, L.inv, L.prev_rec, ExpandedFrames{L.x_q, L.x_sfi, L.x_bits, L.x_modes});
   prof->end(K_UNPACK_IMDCT, st);
