@@ -284,6 +284,7 @@ int ensure_encode_scratch(carta1_ctx *ctx, size_t units, bool auto_modes) {
 }
 int ensure_decode_scratch(carta1_ctx *ctx, size_t units) {
   CU(ctx, ctx->inv.ensure(units * 512 * sizeof(float)));
+  CU(ctx, ctx->coefs.ensure(units * 512 * sizeof(float)));
   CU(ctx, ctx->modes.ensure(units * 4));
   return CARTA1_OK;
 }
@@ -467,7 +468,7 @@ static int decode_device_impl(carta1_ctx *ctx, const uint8_t *d_su, size_t su_fr
   L.su = d_su; L.su_frame_stride = su_frame_stride; L.su_stream_stride = su_stream_stride;
   L.n_su_valid = (long long)n_su_valid; L.n_streams = n_streams; L.frames_total = (int)frames_total;
   L.halo_frames = (int)halo_frames; L.n_out_frames = (int)n_frames; L.tables = ctx->d_tables;
-  L.coefs_dbg = dbg_coefs;
+  L.coefs = dbg_coefs ? dbg_coefs : (float *)ctx->coefs.p;
   L.modes = (uint8_t *)ctx->modes.p;
   L.inv = (float *)ctx->inv.p;
   L.bands_dbg = dbg_bands;

@@ -12,6 +12,8 @@
 #include "c1_fft.cuh"
 #include "c1_launch.h"
 
+#include <algorithm>
+
 namespace c1 {
 
 // ------------------------------------------------------------------------------------
@@ -59,21 +61,22 @@ struct ExpandedFrames {
 // mdct.js:161-170: pre-twiddle of FFT input i (natural order)
 template <typename In, typename R>
 __device__ __forceinline__ Cplx imdct_pre(int i, int n, const In &in, const double *__restrict__ tab,
-                                          const R &rnd) {
+                                          R &rnd) {
   const int i2 = 2 * i, half = n >> 1;
   const double r = -in(i2);
   const double m = -in(half - 1 - i2);
   const double c = __ldg(&tab[i2]), s = __ldg(&tab[i2 + 1]);
   Cplx z;
-  z.re = rnd(m * s + r * c);
-  z.im = rnd(m * c - r * s);
+  z.re = rnd.r0(m * s + r * c);
+  z.im = rnd.r1(m * c - r * s);
   return z;
 }
 
 // mdct.js:177-208 restricted to output[n4 .. 3*n4): out[] is that middle half
 __device__ __forceinline__ void imdct_post(const Cplx z, int i, int n, const double *__restrict__ tab, float *out) {
   const int half = n >> 1, n4 = n >> 2, fft_n = n >> 2;
-  const double c = __ldg(&tab[2 * i]), s = __ldg(&tab[2 * i + 1]);
+  const double2 cs = __ldg(reinterpret_cast<const double2 *>(tab + 2 * i));
+  const double c = cs.x, s = cs.y;
   const float r1 = (float)(z.re * c + z.im * s);
   const float i1 = (float)(z.re * s - z.im * c);
   const int idx = i < (fft_n >> 1) ? 2 * i : (i - (fft_n >> 1)) * 2 + n4;
@@ -121,6 +124,7 @@ __device__ __forceinline__ void imdct_band(int band, bool is_long, const float *
       Cplx a = imdct_pre(r3, 64, in, tab, rnd);
       Cplx b = imdct_pre(8 + r3, 64, in, tab, rnd);
       warp_fft_regs<3>(a, b, tw, lane, rnd);
+      __syncwarp();  // y may alias x: every coefficient of these blocks is read by now
       imdct_post(a, g, 64, tab, y + 32 * blk);
       imdct_post(b, g + 8, 64, tab, y + 32 * blk);
     }
@@ -132,217 +136,292 @@ __device__ __noinline__ void imdct_band_exact(int band, bool is_long, const floa
   imdct_band<ExactRound>(band, is_long, x, y, T, lane);
 }
 
-// ---- long blocks, all three bands of a sound unit at once (c1_fft.cuh, in-thread passes) ----
-template <typename R>
-__device__ __forceinline__ void imdct_long3(unsigned long_mask, const float *x, float *y, double2 *xbuf_all,
-                                            const DevTables *__restrict__ T, int lane) {
-  R rnd;
-  const LongLanes G(lane);
-  const bool active = (long_mask >> G.band) & 1;
-  const int n = G.band == 2 ? 512 : 256;
-  const int size = n >> 1;
-  const int off = G.band == 0 ? 0 : G.band == 1 ? 128 : 256;
-  const float *xb = x + off;
-  const bool rev = G.band > 0;  // utils.js:42-48: un-reverse mid / high spectra
-  const double *tab = G.band == 2 ? T->mdct_inv512 : T->mdct_inv256;
-  Cplx v[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    v[j].re = 0.0;
-    v[j].im = 0.0;
-    if (active) {  // mdct.js:161-170
-      const int i2 = 2 * G.q_of(j);
-      const int ka = rev ? size - 1 - i2 : i2, kb = rev ? i2 : size - 1 - i2;
-      const double r = -(double)xb[ka];
-      const double m = -(double)xb[kb];
-      const double2 cs = __ldg(reinterpret_cast<const double2 *>(tab + i2));
-      v[j].re = rnd(m * cs.y + r * cs.x);
-      v[j].im = rnd(m * cs.x - r * cs.y);
-    }
-  }
-  double2 *xbuf = xbuf_all + (G.band == 0 ? 0 : G.band == 1 ? kXposeSlots64 : 2 * kXposeSlots64);
-  fft_long_inthread(v, G, xbuf, T->fft_tw, active, rnd);
-  if (active) {
-#pragma unroll
-    for (int k = 0; k < 8; k++) imdct_post(v[k], long_out_index(G, k), n, tab, y + off);
-  }
-}
-
-__device__ __noinline__ void imdct_long3_exact(unsigned long_mask, const float *x, float *y, double2 *xbuf_all,
-                                               const DevTables *__restrict__ T, int lane) {
-  imdct_long3<ExactRound>(long_mask, x, y, xbuf_all, T, lane);
-}
-
-constexpr int kUiWarps = 8;
-struct UiWarpSmem {
-  double2 xbuf[2 * kXposeSlots64 + kXposeSlots128];  // transposes of the long-block FFTs
-  float row[512];   // dequantised coefficients, later the band record being assembled
-  float inv[512];   // IMDCT middle halves
+// ------------------------------------------------------------------------------------
+// K5: unpack + dequantise, one warp per sound unit -> 512 coefficients + block modes.
+// ------------------------------------------------------------------------------------
+constexpr int kUnpackWarps = 8;
+struct UnpackWarpSmem {
+  float row[512];
   double rcp[52];
   uint32_t words[56];
   uint16_t base[52];
   uint8_t wl[52], sfi[52];
 };
-constexpr size_t kUiSmemBytes = sizeof(UiWarpSmem) * kUiWarps;
 
-__global__ void __launch_bounds__(kUiWarps * 32, 3)
-unpack_imdct_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_stream_stride,
-                    long long n_su_valid, int frames, int n_units, const DevTables *__restrict__ T,
-                    float *__restrict__ coefs_dbg, uint8_t *__restrict__ modes, float *__restrict__ inv,
-                    const float *__restrict__ prev_rec, ExpandedFrames xf) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// modes[unit * 4 + 0..2]: 1 = short blocks; modes[unit * 4 + 3]: 1 = the unit's band record is
+// already in place (stateful handles: frame 0 of every row is the record kept from the
+// previous call), the IMDCT kernels skip it.
+__global__ void __launch_bounds__(kUnpackWarps * 32)
+unpack_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_stream_stride,
+              long long n_su_valid, int frames, int n_units, const DevTables *__restrict__ T,
+              float *__restrict__ coefs, uint8_t *__restrict__ modes, float *__restrict__ inv,
+              const float *__restrict__ prev_rec, ExpandedFrames xf) {
+  __shared__ __align__(16) UnpackWarpSmem s_all[kUnpackWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * kUiWarps + warp;
-  if (unit >= n_units) return;
-  UiWarpSmem &S = reinterpret_cast<UiWarpSmem *>(smem_raw)[warp];
-  const int stream = unit / frames, frame = unit - stream * frames;
+  UnpackWarpSmem &S = s_all[warp];
   const FormatTables &F = T->fmt;
-  float *row = S.row;
-  float4 *dst4 = reinterpret_cast<float4 *>(inv + (size_t)unit * 512);
-  // stateful handles: frame 0 of every row is the band record kept from the previous call
   const int su_skip = prev_rec ? 1 : 0;
-  if (prev_rec && frame == 0) {
-    const float4 *s4 = reinterpret_cast<const float4 *>(prev_rec + (size_t)stream * 512);
-#pragma unroll
-    for (int k = 0; k < 4; k++) dst4[lane + 32 * k] = s4[lane + 32 * k];
-    return;
-  }
-  const long long lin = (long long)(frame - su_skip) * (long long)su_frame_stride +
-                        (long long)stream * (long long)su_stream_stride;
-  int short_mask = 0;  // bit b: band b uses short blocks (any non-zero mode, decoder.js:82-83)
-  if (xf.q) {
-    // frame objects in position-expanded form (see ExpandedFrames): the general decode() input
-    const size_t xu = (size_t)stream * (frames - su_skip) + (frame - su_skip);
-    const int m0 = xf.modes[xu * 4], m1 = xf.modes[xu * 4 + 1], m2 = xf.modes[xu * 4 + 2];
-    short_mask = (m0 != 0) | ((m1 != 0) << 1) | ((m2 != 0) << 2);
-    if (lane < 4) modes[(size_t)unit * 4 + lane] = (uint8_t)((short_mask >> lane) & 1);
-    for (int k = 0; k < 16; k++) {
-      const int c = lane + 32 * k;
-      const int bits = xf.bits[xu * 512 + c], sfi = xf.sfi[xu * 512 + c];
-      float val = 0.0f;
-      if (bits > 0 && sfi > 0) {  // quantization.js:65-78, the IEEE division itself
-        const double range = (double)((1 << (bits - 1)) - 1);
-        val = (float)(((double)xf.q[xu * 512 + c] * T->sf[sfi]) / range);
-      }
-      row[c] = val;
-    }
-  } else if (lin >= n_su_valid) {  // dummy frame {nBfu: 0, blockModes: [0,0,0]} (processor.js:299-307)
-    // all-zero coefficients: every IMDCT output is +0 or -0; run the transform for the signs
-    for (int k = 0; k < 16; k++) row[lane + 32 * k] = 0.0f;
-    if (lane < 4) modes[(size_t)unit * 4 + lane] = 0;
-  } else {
-    uint32_t *words = S.words;
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(su + (size_t)lin * kSuBytes);
-    for (int i = lane; i < 56; i += 32) words[i] = i < kSuWords ? __byte_perm(src[i], 0, 0x0123) : 0u;
+  float *row = S.row;
+  for (int unit = blockIdx.x * kUnpackWarps + warp; unit < n_units; unit += gridDim.x * kUnpackWarps) {
     __syncwarp();
-    const uint32_t header = words[0] >> 16;  // serialization.js:118-126
-    const int m0 = 2 - (int)((header >> 14) & 3), m1 = 2 - (int)((header >> 12) & 3),
-              m2 = 3 - (int)((header >> 10) & 3);
-    const int idx = (header >> 5) & 7;
-    const int n = idx == 0 ? 20 : 24 + 4 * idx;  // BFU_AMOUNTS
-    int run = 16 + 10 * n;
+    const int stream = unit / frames, frame = unit - stream * frames;
+    if (prev_rec && frame == 0) {
+      const float4 *s4 = reinterpret_cast<const float4 *>(prev_rec + (size_t)stream * 512);
+      float4 *dst4 = reinterpret_cast<float4 *>(inv + (size_t)unit * 512);
 #pragma unroll
-    for (int h = 0; h < 2; h++) {  // word lengths, scale factors, bit offsets (exclusive scan)
-      const int b = lane + 32 * h;
-      int wl = 0, sfi = 0;
-      if (b < n) {
-        wl = (int)get_bits(words, 16 + 4 * b, 4);
-        sfi = (int)get_bits(words, 16 + 4 * n + 6 * b, 6);
-      }
-      const int bits = wl_bits(wl);
-      const int cost = b < n ? bits * (int)F.specs[b < 52 ? b : 0] : 0;
-      int incl = cost;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-      }
-      if (b < 52) {
-        S.wl[b] = (uint8_t)(b < n ? wl : 0);
-        S.sfi[b] = (uint8_t)sfi;
-        S.base[b] = (uint16_t)(run + incl - cost);
-        S.rcp[b] = bits > 0 ? 1.0 / (double)((1 << (bits - 1)) - 1) : 0.0;
-      }
-      run += __shfl_sync(0xffffffffu, incl, 31);
+      for (int k = 0; k < 4; k++) dst4[lane + 32 * k] = s4[lane + 32 * k];
+      if (lane < 4) modes[(size_t)unit * 4 + lane] = lane == 3 ? 1 : 0;
+      continue;
     }
-    __syncwarp();
-    short_mask = (m0 != 0) | ((m1 != 0) << 1) | ((m2 != 0) << 2);
-    if (lane < 4) modes[(size_t)unit * 4 + lane] = (uint8_t)((short_mask >> lane) & 1);
-#pragma unroll 4
-    for (int k = 0; k < 16; k++) {  // serialization.js:153-166 + decoder.js:65-94
-      const int c = lane + 32 * k;
-      const int mode = k < 4 ? m0 : (k < 8 ? m1 : m2);
-      const int b = mode == 0 ? F.bfu_of_long[c] : F.bfu_of_short[c];
-      float val = 0.0f;
-      const int bits = wl_bits(S.wl[b]);  // 0 for b >= n
-      if (bits > 0) {
-        const int j = c - (mode == 0 ? F.start_long[b] : F.start_short[b]);
-        const int v = (int)get_bits(words, (int)S.base[b] + j * bits, bits);
-        const int q = v >= (1 << (bits - 1)) ? v - (1 << bits) : v;  // bitstream.js:78-82
-        const int sfi = S.sfi[b];
-        if (sfi != 0) {
+    const long long lin = (long long)(frame - su_skip) * (long long)su_frame_stride +
+                          (long long)stream * (long long)su_stream_stride;
+    int short_mask = 0;  // bit b: band b uses short blocks (any non-zero mode, decoder.js:82-83)
+    if (xf.q) {
+      // frame objects in position-expanded form (see ExpandedFrames): the general decode() input
+      const size_t xu = (size_t)stream * (frames - su_skip) + (frame - su_skip);
+      const int m0 = xf.modes[xu * 4], m1 = xf.modes[xu * 4 + 1], m2 = xf.modes[xu * 4 + 2];
+      short_mask = (m0 != 0) | ((m1 != 0) << 1) | ((m2 != 0) << 2);
+      for (int k = 0; k < 16; k++) {
+        const int c = lane + 32 * k;
+        const int bits = xf.bits[xu * 512 + c], sfi = xf.sfi[xu * 512 + c];
+        float val = 0.0f;
+        if (bits > 0 && sfi > 0) {  // quantization.js:65-78, the IEEE division itself
           const double range = (double)((1 << (bits - 1)) - 1);
-          val = (float)div_by_range(int_to_double(q) * T->sf[sfi], range, S.rcp[b]);
+          val = (float)(((double)xf.q[xu * 512 + c] * T->sf[sfi]) / range);
         }
+        row[c] = val;
       }
-      row[c] = val;
+    } else if (lin >= n_su_valid) {  // dummy frame {nBfu: 0, blockModes: [0,0,0]} (processor.js:299-307)
+      // all-zero coefficients: every IMDCT output is +0 or -0; the transform runs for the signs
+      for (int k = 0; k < 16; k++) row[lane + 32 * k] = 0.0f;
+    } else {
+      uint32_t *words = S.words;
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(su + (size_t)lin * kSuBytes);
+      for (int i = lane; i < 56; i += 32) words[i] = i < kSuWords ? __byte_perm(__ldg(src + i), 0, 0x0123) : 0u;
+      __syncwarp();
+      const uint32_t header = words[0] >> 16;  // serialization.js:118-126
+      const int m0 = 2 - (int)((header >> 14) & 3), m1 = 2 - (int)((header >> 12) & 3),
+                m2 = 3 - (int)((header >> 10) & 3);
+      const int idx = (header >> 5) & 7;
+      const int n = idx == 0 ? 20 : 24 + 4 * idx;  // BFU_AMOUNTS
+      int run = 16 + 10 * n;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {  // word lengths, scale factors, bit offsets (exclusive scan)
+        const int b = lane + 32 * h;
+        int wl = 0, sfi = 0;
+        if (b < n) {
+          wl = (int)get_bits(words, 16 + 4 * b, 4);
+          sfi = (int)get_bits(words, 16 + 4 * n + 6 * b, 6);
+        }
+        const int bits = wl_bits(wl);
+        const int cost = b < n ? bits * (int)F.specs[b < 52 ? b : 0] : 0;
+        int incl = cost;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += t;
+        }
+        if (b < 52) {
+          S.wl[b] = (uint8_t)(b < n ? wl : 0);
+          S.sfi[b] = (uint8_t)sfi;
+          S.base[b] = (uint16_t)(run + incl - cost);
+          S.rcp[b] = bits > 0 ? 1.0 / (double)((1 << (bits - 1)) - 1) : 0.0;
+        }
+        run += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      __syncwarp();
+      short_mask = (m0 != 0) | ((m1 != 0) << 1) | ((m2 != 0) << 2);
+#pragma unroll 4
+      for (int k = 0; k < 16; k++) {  // serialization.js:153-166 + decoder.js:65-94
+        const int c = lane + 32 * k;
+        const int mode = k < 4 ? m0 : (k < 8 ? m1 : m2);
+        const int b = mode == 0 ? F.bfu_of_long[c] : F.bfu_of_short[c];
+        float val = 0.0f;
+        const int bits = wl_bits(S.wl[b]);  // 0 for b >= n
+        if (bits > 0) {
+          const int j = c - (mode == 0 ? F.start_long[b] : F.start_short[b]);
+          const int v = (int)get_bits(words, (int)S.base[b] + j * bits, bits);
+          const int q = v >= (1 << (bits - 1)) ? v - (1 << bits) : v;  // bitstream.js:78-82
+          const int sfi = S.sfi[b];
+          if (sfi != 0) {
+            const double range = (double)((1 << (bits - 1)) - 1);
+            val = (float)div_by_range(int_to_double(q) * T->sf[sfi], range, S.rcp[b]);
+          }
+        }
+        row[c] = val;
+      }
     }
-  }
-  __syncwarp();
-  if (coefs_dbg) {
-    float4 *d = reinterpret_cast<float4 *>(coefs_dbg + (size_t)unit * 512);
+    __syncwarp();
+    if (lane < 4) modes[(size_t)unit * 4 + lane] = lane == 3 ? 0 : (uint8_t)((short_mask >> lane) & 1);
+    float4 *d = reinterpret_cast<float4 *>(coefs + (size_t)unit * 512);
     const float4 *s4 = reinterpret_cast<const float4 *>(row);
 #pragma unroll
     for (int k = 0; k < 4; k++) d[lane + 32 * k] = s4[lane + 32 * k];
   }
-  float *y = S.inv;
-  // 0x71800000 is 2^100 as binary32: below it FastRound is exact for every transform value
-  unsigned big = 0;
+}
+
+// ------------------------------------------------------------------------------------
+// K6: IMDCT.  Long blocks use the in-thread passes of c1_fft.cuh.  A warp task is a pair of
+// consecutive sound units and a ROLE: role 0 transforms the low and mid bands of both units
+// (4 x IMDCT256), role 1 their high bands (2 x IMDCT512); rows holds the task's coefficients,
+// [transform][kSize].
+//
+// The output goes straight into the band record K7 reads, per band
+//   [head16 | tail16 | time-domain samples 32..size)
+// Samples >= 32 depend on this unit only (decoder.js:203-226,244-300): in long mode they are the
+// IMDCT middle half y shifted by 16 (record[p] = y[p - 16]), head16 = y[0..16) and
+// tail16 = y[size-16..size) feed the overlap-add that K7 finishes with the previous unit's tail.
+// The record overwrites the coefficients of the same band (every coefficient is read before
+// the first transpose, every output written after the last).  Transforms whose bit in
+// long_mask is clear run the same instructions and do not store.
+// ------------------------------------------------------------------------------------
+template <int kRole, typename R>
+__device__ __forceinline__ void imdct_long_task(unsigned long_mask, float *rows, double2 *xbuf_all,
+                                                const DevTables *__restrict__ T, int lane) {
+  using G = LongGeom<kRole>;
+  constexpr int kSize = G::kSize;
+  R rnd;
+  const G g(lane);
+  float *xb = rows + g.x * kSize;
+  const bool rev = kRole == 1 || (g.x & 1);  // utils.js:42-48: un-reverse mid / high spectra
+  const double *tab = kRole == 0 ? T->mdct_inv256 : T->mdct_inv512;
+  const float *pa = xb + 2 * g.rev_t, *pb = xb + (kSize - 1) - 2 * g.rev_t;
+  const double *ptab = tab + 2 * g.rev_t;
+  Cplx v[8];
 #pragma unroll
-  for (int k = 0; k < 16; k++) big = max(big, __float_as_uint(row[lane + 32 * k]) & 0x7FFFFFFFu);
-  const bool fast = __reduce_max_sync(0xffffffffu, big) < 0x71800000u;
-  const unsigned long_mask = ~(unsigned)short_mask & 7u;
-  if (long_mask) {
-    if (fast) imdct_long3<FastRound>(long_mask, row, y, S.xbuf, T, lane);
-    else imdct_long3_exact(long_mask, row, y, S.xbuf, T, lane);
+  for (int j = 0; j < 8; j++) {  // mdct.js:161-170 for FFT input q = q_step(j) + rev_t
+    const int i0 = 2 * G::q_step(j);
+    const float fa = pa[i0], fb = pb[-i0];  // x[2q], x[size - 1 - 2q]
+    const double r = -(double)(rev ? fb : fa);
+    const double m = -(double)(rev ? fa : fb);
+    const double2 cs = __ldg(reinterpret_cast<const double2 *>(ptab + i0));
+    v[j].re = rnd.r0(m * cs.y + r * cs.x);
+    v[j].im = rnd.r1(m * cs.x - r * cs.y);
   }
-  for (int band = 0; band < 3; band++) {
-    if (!((short_mask >> band) & 1)) continue;
-    const int off = band == 0 ? 0 : band == 1 ? 128 : 256;
-    if (fast) imdct_band<FastRound>(band, false, row + off, y + off, T, lane);
-    else imdct_band_exact(band, false, row + off, y + off, T, lane);
-  }
-  __syncwarp();
-  // Band record (what K7 reads): per band [head16 | tail16 | time-domain samples 32..size).
-  // Samples >= 32 depend on this unit only (decoder.js:203-226,244-300): a copy of the IMDCT
-  // half in long mode, the block-to-block overlap-add in short mode.  The first 32 samples
-  // also need the previous unit's tail16 and are finished in K7.
-  for (int band = 0; band < 3; band++) {
-    const int size = band == 2 ? 256 : 128;
-    const int off = band == 0 ? 0 : band == 1 ? 128 : 256;
-    const bool is_long = !((short_mask >> band) & 1);
-    const float *v = y + off;
-    float *z = row + off;
-    if (lane < 16) z[lane] = v[lane];
-    else z[lane] = v[size - 32 + lane];
-    for (int p = 32 + lane; p < size; p += 32) {
-      float o;
-      if (is_long) {
-        o = v[p - 16];
-      } else {  // mdct.js:230-245 with prev = second half of the previous block
-        const int q = p & 31, blk = p - q;
-        const int i = q < 16 ? q : 31 - q;
-        const double pv = (double)v[blk - 16 + i], cv = (double)v[blk + 15 - i];
-        const double w1 = __ldg(&T->win[i]), w2 = __ldg(&T->win[31 - i]);
-        o = q < 16 ? (float)(pv * w2 - cv * w1) : (float)(pv * w1 + cv * w2);
-      }
-      z[p] = o;
+  fft_long_inthread<kRole>(v, g, xbuf_all + g.x * G::kSlots, T->fft_tw, rnd);
+  if ((long_mask >> g.x) & 1) {
+    // mdct.js:177-208 restricted to output[n/4 .. 3n/4): FFT output i gives y[2i] and y[size-1-2i].
+    // Record position of y[q]: q + 16, except q < 16 -> q (head) and q >= size - 16 -> q - size + 32
+    // (tail).  2i < 16 only for k == 0 and 2i >= size - 16 only for k == 7 (role 1: on the lanes
+    // with b6 == 0 / b6 == 1 respectively).
+    const int ib = g.out_base();
+    const double2 *pt = reinterpret_cast<const double2 *>(tab) + ib;
+    float *o0 = xb + 2 * ib + 16, *o1 = xb + (kSize - 1) - 2 * ib + 16;
+    const bool first = kRole == 0 || g.b6 == 0, last = kRole == 0 || g.b6 == 1;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int st = G::out_step(k);
+      const double2 cs = __ldg(pt + st);
+      const float y1 = (float)(v[k].re * cs.x + v[k].im * cs.y);  // y[size - 1 - 2i]
+      const float y0 = (float)(v[k].re * cs.y - v[k].im * cs.x);  // y[2i]
+      int d0 = 2 * st, d1 = -2 * st;
+      if (k == 0 && first) { d0 -= 16; d1 += 16 - kSize; }  // y[2i] is head, y[size-1-2i] is tail
+      if (k == 7 && last) { d0 += 16 - kSize; d1 -= 16; }   // y[2i] is tail, y[size-1-2i] is head
+      o0[d0] = y0;
+      o1[d1] = y1;
     }
   }
+}
+
+template <int kRole>
+__device__ __noinline__ void imdct_long_task_exact(unsigned long_mask, float *rows, double2 *xbuf_all,
+                                                   const DevTables *__restrict__ T, int lane) {
+  imdct_long_task<kRole, ExactRound>(long_mask, rows, xbuf_all, T, lane);
+}
+
+// Short blocks of one band (rare: out of line): transform in place, then assemble the record
+// through `stage` (block-to-block overlap-add, mdct.js:230-245 with prev = second half of the
+// previous block).
+__device__ __noinline__ void imdct_short_band(int band, float *x, float *stage, bool fast,
+                                              const DevTables *__restrict__ T, int lane) {
+  const int size = band == 2 ? 256 : 128;
+  if (fast) imdct_band<FastRound>(band, false, x, x, T, lane);
+  else imdct_band<ExactRound>(band, false, x, x, T, lane);
   __syncwarp();
-  const float4 *s4 = reinterpret_cast<const float4 *>(row);
+  const float *v = x;
+  if (lane < 16) stage[lane] = v[lane];
+  else stage[lane] = v[size - 32 + lane];
+  for (int p = 32 + lane; p < size; p += 32) {
+    const int q = p & 31, blk = p - q;
+    const int i = q < 16 ? q : 31 - q;
+    const double pv = (double)v[blk - 16 + i], cv = (double)v[blk + 15 - i];
+    const double w1 = __ldg(&T->win[i]), w2 = __ldg(&T->win[31 - i]);
+    stage[p] = q < 16 ? (float)(pv * w2 - cv * w1) : (float)(pv * w1 + cv * w2);
+  }
+  __syncwarp();
+  for (int p = lane; p < size; p += 32) x[p] = stage[p];
+  __syncwarp();
+}
+
+constexpr int kImdctWarps = 8, kImdctCtasPerSm = 3;
+struct ImdctWarpSmem {
+  double2 xbuf[4 * LongGeom<0>::kSlots];  // transposes of the long-block FFTs (also the short-block stage)
+  float rows[512];                         // role 0: 4 x 128, role 1: 2 x 256
+};
+static_assert(4 * LongGeom<0>::kSlots == 2 * LongGeom<1>::kSlots, "xbuf");
+constexpr size_t kImdctSmemBytes = sizeof(ImdctWarpSmem) * kImdctWarps;
+
+// One kernel per role (see mdct_kernel): the hot loop stays inside the instruction cache.
+template <int kRole>
+__global__ void __launch_bounds__(kImdctWarps * 32, kImdctCtasPerSm)
+imdct_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes, int n_units,
+             const DevTables *__restrict__ T, float *__restrict__ inv) {
+  using G = LongGeom<kRole>;
+  constexpr int kSize = G::kSize, kPer = G::kPerWarp / 2;  // transforms per unit
+  constexpr int kOff = kRole == 0 ? 0 : 256;              // first coefficient of the role
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ImdctWarpSmem &S = reinterpret_cast<ImdctWarpSmem *>(smem_raw)[warp];
+  const int n_pairs = (n_units + 1) >> 1;
+  for (int pair = blockIdx.x * kImdctWarps + warp; pair < n_pairs; pair += gridDim.x * kImdctWarps) {
+    __syncwarp();
+    const int u0 = 2 * pair;
+    bool live[2];
+    unsigned long_mask = 0, short_mask = 0;
 #pragma unroll
-  for (int k = 0; k < 4; k++) dst4[lane + 32 * k] = s4[lane + 32 * k];
+    for (int s = 0; s < 2; s++) {
+      live[s] = u0 + s < n_units;
+      if (live[s]) {
+        const uchar4 m = *reinterpret_cast<const uchar4 *>(modes + (size_t)(u0 + s) * 4);
+        live[s] = m.w == 0;
+        const unsigned sm = kRole == 0 ? (unsigned)(m.x != 0) | ((unsigned)(m.y != 0) << 1) : (unsigned)(m.z != 0);
+        if (live[s]) {
+          short_mask |= sm << (s * kPer);
+          long_mask |= (~sm & ((1u << kPer) - 1u)) << (s * kPer);
+        }
+      }
+    }
+    if (!live[0] && !live[1]) continue;
+    // 256 coefficients of the role per unit = 2 float4 per lane and unit
+    unsigned big = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float4 x = live[k >> 1]
+                           ? __ldg(reinterpret_cast<const float4 *>(coefs + (size_t)(u0 + (k >> 1)) * 512 + kOff) + lane + 32 * (k & 1))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      reinterpret_cast<float4 *>(S.rows)[lane + 32 * k] = x;
+      big = max(big, max(max(__float_as_uint(x.x) & 0x7FFFFFFFu, __float_as_uint(x.y) & 0x7FFFFFFFu),
+                         max(__float_as_uint(x.z) & 0x7FFFFFFFu, __float_as_uint(x.w) & 0x7FFFFFFFu)));
+    }
+    __syncwarp();
+    // 0x71800000 is 2^100 as binary32: below it FastRound is exact for every transform value
+    const bool fast = __reduce_max_sync(0xffffffffu, big) < 0x71800000u;
+    if (long_mask) {
+      if (fast) imdct_long_task<kRole, FastRound>(long_mask, S.rows, S.xbuf, T, lane);
+      else imdct_long_task_exact<kRole>(long_mask, S.rows, S.xbuf, T, lane);
+      __syncwarp();
+    }
+    if (short_mask) {
+      for (int x = 0; x < G::kPerWarp; x++)
+        if ((short_mask >> x) & 1)
+          imdct_short_band(kRole == 0 ? x % kPer : 2, S.rows + x * kSize, reinterpret_cast<float *>(S.xbuf), fast, T, lane);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (live[k >> 1])
+        reinterpret_cast<float4 *>(inv + (size_t)(u0 + (k >> 1)) * 512 + kOff)[lane + 32 * (k & 1)] =
+            reinterpret_cast<const float4 *>(S.rows)[lane + 32 * k];
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -573,7 +652,7 @@ __global__ void selftest_kernel(const DevTables *__restrict__ T, unsigned long l
       const double v = d + ulp * (0.125 * j) + ((j & 1) ? ulp * 1e-9 : 0.0);
       const double want = (double)(float)v;
       FastRound fr;
-      const double got = fr(v);
+      const double got = fr.r0(v);
       // exact for everything below 2^127, zeros and f32 subnormals included
       if (abs_hi_word(v) < 0x47E00000u && __double_as_longlong(want) != __double_as_longlong(got)) local++;
     }
@@ -589,15 +668,24 @@ cudaError_t launch_selftest(const DevTables *tables, unsigned long long *d_bad, 
 cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, Prof *prof) {
   const int n_units = L.n_streams * L.frames_total;
   if (n_units == 0) return cudaSuccess;
-  prof->begin(K_UNPACK_IMDCT, st);
-  {
-    cudaError_t e1 = cudaFuncSetAttribute(unpack_imdct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUiSmemBytes);
-    if (e1 != cudaSuccess) return e1;
-  }
-  unpack_imdct_kernel<<<(n_units + kUiWarps - 1) / kUiWarps, kUiWarps * 32, kUiSmemBytes, st>>>(
-      L.su, L.su_frame_stride, L.su_stream_stride, L.n_su_valid, L.frames_total, n_units, L.tables, L.coefs_dbg,
+  prof->begin(K_UNPACK, st);
+  unpack_kernel<<<std::min((n_units + kUnpackWarps - 1) / kUnpackWarps, persistent_ctas(6)), kUnpackWarps * 32, 0, st>>>(
+      L.su, L.su_frame_stride, L.su_stream_stride, L.n_su_valid, L.frames_total, n_units, L.tables, L.coefs,
       L.modes, L.inv, L.prev_rec, ExpandedFrames{L.x_q, L.x_sfi, L.x_bits, L.x_modes});
-  prof->end(K_UNPACK_IMDCT, st);
+  prof->end(K_UNPACK, st);
+  {
+    cudaError_t e1 = cudaFuncSetAttribute(imdct_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kImdctSmemBytes);
+    if (e1 == cudaSuccess)
+      e1 = cudaFuncSetAttribute(imdct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kImdctSmemBytes);
+    if (e1 != cudaSuccess) return e1;
+    const int n_pairs = (n_units + 1) / 2;
+    const int grid = std::min((n_pairs + kImdctWarps - 1) / kImdctWarps, persistent_ctas(kImdctCtasPerSm));
+    prof->begin(K_IMDCT, st);
+    imdct_kernel<0><<<grid, kImdctWarps * 32, kImdctSmemBytes, st>>>(L.coefs, L.modes, n_units, L.tables, L.inv);
+    imdct_kernel<1><<<grid, kImdctWarps * 32, kImdctSmemBytes, st>>>(L.coefs, L.modes, n_units, L.tables, L.inv);
+    prof->launches++;
+    prof->end(K_IMDCT, st);
+  }
   if (L.bands_dbg) {
     prof->begin(K_BANDS_TIME, st);
     bands_time_kernel<<<n_units, 256, 0, st>>>(L.inv, L.modes, L.frames_total, n_units, L.tables, L.bands_dbg);

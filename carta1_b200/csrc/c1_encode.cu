@@ -14,6 +14,8 @@
 #include "c1_fft.cuh"
 #include "c1_launch.h"
 
+#include <algorithm>
+
 namespace c1 {
 
 // ------------------------------------------------------------------------------------
@@ -307,7 +309,7 @@ transient_modes_kernel(const float *__restrict__ mags, int frames, int n_su,
 // mdct.js:76-105: pre-twiddle of FFT input q (natural order) of an N-point MDCT
 template <typename In, typename R>
 __device__ __forceinline__ Cplx mdct_pre(int q, int n, const In &in, const double *__restrict__ tab,
-                                         const R &rnd) {
+                                         R &rnd) {
   const int i = 2 * q, n4 = n >> 2, n34 = 3 * n4;
   double r, m;
   if (i < n4) {
@@ -319,8 +321,8 @@ __device__ __forceinline__ Cplx mdct_pre(int q, int n, const In &in, const doubl
   }
   const double c = __ldg(&tab[i]), s = __ldg(&tab[i + 1]);
   Cplx z;
-  z.re = rnd(r * c + m * s);
-  z.im = rnd(m * c - r * s);
+  z.re = rnd.r0(r * c + m * s);
+  z.im = rnd.r1(m * c - r * s);
   return z;
 }
 
@@ -397,114 +399,179 @@ __device__ __noinline__ void mdct_band_exact(int band, bool is_long, const doubl
   mdct_band<ExactRound>(band, is_long, arr, out, T, lane);
 }
 
-// ---- long blocks, all three bands of a sound unit at once (c1_fft.cuh, in-thread passes) ----
-constexpr int kArrLow = 0, kArrMid = 160, kArrHigh = 320, kArrDoubles = 608;  // [overlap 32 | samples] per band
-
-// mdct.js:76-105 with the loop a value belongs to known at compile time (first: i < N/4)
-template <bool kFirst, typename In, typename R>
-__device__ __forceinline__ Cplx mdct_pre_long(int q, int n, const In &in, const double *__restrict__ tab, const R &rnd) {
-  const int i = 2 * q, n4 = n >> 2, n34 = 3 * n4;
-  double r, m;
-  if (kFirst) {
-    r = in(n34 - 1 - i) + in(n34 + i);
-    m = in(n4 + i) - in(n4 - 1 - i);
+// ---- long blocks (c1_fft.cuh, in-thread passes) --------------------------------------------
+// A warp task is a pair of consecutive sound units and a ROLE: role 0 transforms the low and
+// mid bands of both units (4 x MDCT256), role 1 their high bands (2 x MDCT512).
+//
+// mdct.js:76-105 for FFT input q (natural order).  The transform buffer is zero outside
+// [windowStart, windowStart + size + 32) (encoder.js:240-247), so of the four taps of a
+// pre-twiddle two are always inside; the other two are inside only for the first 8 values of
+// the first loop (q < 8) and the last 8 of the second (q >= N/4 - 8).  Position 8t + j of the
+// bit-reversed array holds q = brev3(j) * kLanes + brev(t): first loop for even j, second for
+// odd j, edge values only for j == 0 / j == 7 (every lane of FFT64; even t / odd t of FFT128).
+// Adding the +0 of an outside tap is kept where it can turn a -0 into +0 (x + 0), dropped
+// where it cannot (x - 0).
+//   pr = &a[n34 - 1 - ws - 2 rev_t], pm = &a[n4 - ws + 2 rev_t]  (a: buffer, index 0 == windowStart)
+template <int kRole, int kJ, typename R>
+__device__ __forceinline__ Cplx mdct_pre_long(const double *pr, const double *pm, const double *ptab, bool edge,
+                                              R &rnd) {
+  using G = LongGeom<kRole>;
+  constexpr int i0 = 2 * G::q_step(kJ);  // i = i0 + 2 rev_t
+  constexpr int n4 = G::kN / 4;
+  double r = pr[-i0], m = pm[i0];
+  if (kJ == 0) {         // r = in(n34-1-i) + in(n34+i), m = in(n4+i) - in(n4-1-i): taps n34+i, n4-1-i
+    const double r1 = edge ? pm[i0 + 2 * n4] : 0.0, m1 = edge ? pr[-i0 - 2 * n4] : 0.0;
+    r = r + r1;
+    m = m - m1;
+  } else if (kJ == 7) {  // r = in(n34-1-i) - in(i-n4), m = in(n4+i) + in(5*n4-1-i): taps i-n4, 5*n4-1-i
+    const double r1 = edge ? pm[i0 - 2 * n4] : 0.0, m1 = edge ? pr[-i0 + 2 * n4] : 0.0;
+    r = r - r1;
+    m = m + m1;
+  } else if ((kJ & 1) == 0) {
+    r = r + 0.0;
   } else {
-    r = in(n34 - 1 - i) - in(i - n4);
-    m = in(n4 + i) + in(5 * n4 - 1 - i);
+    m = m + 0.0;
   }
-  const double2 cs = __ldg(reinterpret_cast<const double2 *>(tab + i));
+  const double2 cs = __ldg(reinterpret_cast<const double2 *>(ptab + i0));
   Cplx z;
-  z.re = rnd(r * cs.x + m * cs.y);
-  z.im = rnd(m * cs.x - r * cs.y);
+  z.re = rnd.r0(r * cs.x + m * cs.y);
+  z.im = rnd.r1(m * cs.x - r * cs.y);
   return z;
 }
 
-template <typename R>
-__device__ __forceinline__ void mdct_long3(unsigned long_mask, double *arr, float *out,
-                                           const DevTables *__restrict__ T, int lane) {
+template <int kRole, int kJ, typename R>
+__device__ __forceinline__ void mdct_pre_all(Cplx (&v)[8], const double *pr, const double *pm, const double *ptab,
+                                             int t, R &rnd) {
+  if constexpr (kJ < 8) {
+    // FFT128: q < 8 needs brev4(t) < 8 (t even), q >= 120 needs t odd
+    const bool edge = kRole == 0 || ((t & 1) == (kJ == 7 ? 1 : 0));
+    v[kJ] = mdct_pre_long<kRole, kJ>(pr, pm, ptab, edge, rnd);
+    mdct_pre_all<kRole, kJ + 1>(v, pr, pm, ptab, t, rnd);
+  }
+}
+
+// The transforms of one warp task.  arr: kPerWarp buffers of [overlap 32 | samples kSize] doubles
+// (each doubles as its transform's transpose buffer once the pre-twiddle has read it); out:
+// kPerWarp x kSize coefficients.  Transforms whose bit in long_mask is clear (short mode) run the
+// same instructions on whatever their buffer holds and do not store.
+template <int kRole, typename R>
+__device__ __forceinline__ void mdct_long_task(unsigned long_mask, double *arr, float *out,
+                                               const DevTables *__restrict__ T, int lane) {
+  using G = LongGeom<kRole>;
+  constexpr int kWs = kRole == 0 ? 48 : 112;  // constants.js:115-119
+  constexpr int kN = G::kN, kBuf = G::kSize + 32;
   R rnd;
-  const LongLanes G(lane);
-  const bool active = (long_mask >> G.band) & 1;
-  const int n = G.band == 2 ? 512 : 256;
-  const int ws = G.band == 2 ? 112 : 48;          // constants.js:115-119
-  const int span = (G.band == 2 ? 256 : 128) + 32;
-  const double *a = arr + (G.band == 0 ? kArrLow : G.band == 1 ? kArrMid : kArrHigh);
-  const double *tab = G.band == 2 ? T->mdct_fwd512 : T->mdct_fwd256;
-  auto in = [&](int k) -> double {
-    const unsigned at = (unsigned)(k - ws);
-    return at < (unsigned)span ? a[at] : 0.0;
-  };
+  const G g(lane);
+  double *a = arr + g.x * kBuf;
+  const double *tab = kRole == 0 ? T->mdct_fwd256 : T->mdct_fwd512;
   Cplx v[8];
+  mdct_pre_all<kRole, 0>(v, a + (3 * kN / 4 - 1 - kWs) - 2 * g.rev_t, a + (kN / 4 - kWs) + 2 * g.rev_t,
+                         tab + 2 * g.rev_t, g.t, rnd);
+  fft_long_inthread<kRole>(v, g, reinterpret_cast<double2 *>(a), T->fft_tw, rnd);
+  if ((long_mask >> g.x) & 1) {
+    // mdct.js:111-119; spectrum reversed for the mid and high bands (utils.js:42-48)
+    const bool reverse = kRole == 1 || (g.x & 1);
+    const int ib = g.out_base();
+    float *o = out + g.x * G::kSize;
+    const double2 *pt = reinterpret_cast<const double2 *>(tab) + ib;
+    float *o0 = reverse ? o + (G::kSize - 1 - 2 * ib) : o + 2 * ib;
+    float *o1 = reverse ? o + 2 * ib : o + (G::kSize - 1 - 2 * ib);
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
-    v[j].re = 0.0;
-    v[j].im = 0.0;
-    if (active) {
-      // position 8t + j holds natural index q; q < N/8 exactly when j is even
-      if ((j & 1) == 0) v[j] = mdct_pre_long<true>(G.q_of(j), n, in, tab, rnd);
-      else v[j] = mdct_pre_long<false>(G.q_of(j), n, in, tab, rnd);
+    for (int k = 0; k < 8; k++) {
+      const int st = G::out_step(k);
+      const double2 cs = __ldg(pt + st);
+      const float c0 = (float)(-v[k].re * cs.x - v[k].im * cs.y);
+      const float c1 = (float)(-v[k].re * cs.y + v[k].im * cs.x);
+      if (reverse) { o0[-2 * st] = c0; o1[2 * st] = c1; }
+      else { o0[2 * st] = c0; o1[-2 * st] = c1; }
     }
   }
-  double2 *xbuf = reinterpret_cast<double2 *>(arr) + (G.band == 0 ? 0 : G.band == 1 ? kXposeSlots64 : 2 * kXposeSlots64);
-  fft_long_inthread(v, G, xbuf, T->fft_tw, active, rnd);
-  if (active) {
-    float *o = out + (G.band == 0 ? 0 : G.band == 1 ? 128 : 256);
-#pragma unroll
-    for (int k = 0; k < 8; k++) mdct_post(v[k], long_out_index(G, k), n, tab, o, G.band > 0);
-  }
 }
-static_assert(2 * kXposeSlots64 + kXposeSlots128 <= kArrDoubles / 2, "transpose buffers alias the input buffer");
+static_assert(LongGeom<0>::kSlots * 2 <= 160 && LongGeom<1>::kSlots * 2 <= 288, "transpose buffers alias the input buffers");
 
-__device__ __noinline__ void mdct_long3_exact(unsigned long_mask, double *arr, float *out,
-                                              const DevTables *__restrict__ T, int lane) {
-  mdct_long3<ExactRound>(long_mask, arr, out, T, lane);
+template <int kRole>
+__device__ __noinline__ void mdct_long_task_exact(unsigned long_mask, double *arr, float *out,
+                                                  const DevTables *__restrict__ T, int lane) {
+  mdct_long_task<kRole, ExactRound>(long_mask, arr, out, T, lane);
 }
 
-constexpr int kMdctWarps = 8;
+constexpr int kMdctWarps = 8, kMdctCtasPerSm = 3;
 struct MdctWarpSmem {
-  double arr[kArrDoubles];
-  float out[512];
+  double guard[16]; // the two edge taps of mdct_pre_long are loaded (and discarded) up to 16 doubles
+                    // outside a buffer on lanes where they fall into the zero padding
+  double arr[640];  // role 0: 4 x 160, role 1: 2 x 288; short blocks: up to 512
+  float out[512];   // role 0: 4 x 128, role 1: 2 x 256 (also absorbs the overshoot past arr)
 };
 constexpr size_t kMdctSmemBytes = sizeof(MdctWarpSmem) * kMdctWarps;
 
-__global__ void __launch_bounds__(kMdctWarps * 32, 3)
-mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, int frames, int n_su,
-            const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
-            float *__restrict__ coefs) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int su = blockIdx.x * kMdctWarps + warp;
-  if (su >= n_su) return;
-  MdctWarpSmem &S = reinterpret_cast<MdctWarpSmem *>(smem_raw)[warp];
+// Short blocks of one band (encoder.js:279-304): block b transforms
+// [WIN * previous block (32) | block * reversed WIN (32)].  c: the band's samples of this frame
+// (c - 512: the previous frame's).
+__device__ __noinline__ void mdct_short_band(int band, const float *__restrict__ c, bool has_prev, bool fast,
+                                             double *arr, float *out, const DevTables *__restrict__ T, int lane,
+                                             double w_fwd, double w_rev) {
+  ExactRound xr;
+  const int size = band == 2 ? 256 : 128;
+  for (int b = 0; b < (size >> 5); b++) {
+    float src_prev = 0.0f;
+    bool have_prev = true;
+    if (b == 0) { have_prev = has_prev; if (has_prev) src_prev = c[-512 + size - 32 + lane]; }
+    else src_prev = c[32 * (b - 1) + lane];
+    arr[64 * b + lane] = have_prev ? xr(w_fwd * (double)src_prev) : 0.0;
+    arr[64 * b + 32 + lane] = xr((double)c[32 * b + lane] * w_rev);
+  }
+  __syncwarp();
+  if (fast) mdct_band<FastRound>(band, false, arr, out, T, lane);
+  else mdct_band<ExactRound>(band, false, arr, out, T, lane);
+  __syncwarp();
+}
+
+// One warp task: sound units su0 = 2 * pair and su0 + 1 (consecutive frames of a row, unless
+// the row ends in between).
+template <int kRole>
+__device__ __forceinline__ void mdct_warp_task(int pair, const float *__restrict__ bands,
+                                               const uint8_t *__restrict__ modes, int frames, int n_su,
+                                               const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
+                                               float *__restrict__ coefs, MdctWarpSmem &S, int lane, double w_fwd,
+                                               double w_rev) {
+  using G = LongGeom<kRole>;
+  constexpr int kSize = G::kSize, kBuf = kSize + 32, kPer = G::kPerWarp / 2;  // transforms per unit
+  constexpr int kOff = kRole == 0 ? 0 : 256;                                // first band sample of the role
   double *arr = S.arr;
   float *out = S.out;
-  const double w_fwd = T->win[lane], w_rev = T->win[31 - lane];  // WINDOW_SHORT[i], [31 - i]
-  const int frame = su % frames;
-  const float *cur = bands + (size_t)su * 512;
-  const float *prev = frame > 0 ? cur - 512 : nullptr;
-  int mode[3];
+  const int su0 = 2 * pair;
+  const bool have1 = su0 + 1 < n_su;
+  const int frame0 = su0 % frames;
+  const bool cont1 = have1 && frame0 + 1 < frames;  // unit 1 continues unit 0's row
+  const float *cur0 = bands + (size_t)su0 * 512 + kOff;
+  ExactRound xr;
+  // block modes of this role's bands: transform x = unit * kPer + band
+  int mode[G::kPerWarp];
   unsigned long_mask = 0;
 #pragma unroll
-  for (int b = 0; b < 3; b++) {
-    mode[b] = P->use_fixed ? P->fixed[b] : (int)modes[(size_t)su * 4 + b];
-    long_mask |= (mode[b] == 0 ? 1u : 0u) << b;
+  for (int x = 0; x < G::kPerWarp; x++) {
+    const int unit = x / kPer, band = kRole == 0 ? x % kPer : 2;
+    mode[x] = 1;
+    if (unit == 0 || have1) mode[x] = P->use_fixed ? P->fixed[band] : (int)modes[(size_t)(su0 + unit) * 4 + band];
+    long_mask |= (mode[x] == 0 ? 1u : 0u) << x;
   }
-  ExactRound xr;
-  unsigned big = 0;  // largest |input| (binary32 bits) of this unit's transforms
-  // ---- long-block input buffers: [overlap saved by the previous frame (32) | samples, last 32
-  // tail-windowed] per band (encoder.js:240-247,309-316)
+  unsigned big = 0;  // largest |input| (binary32 bits) of this task's transforms
   {
-    const float4 *cur4 = reinterpret_cast<const float4 *>(cur);
+    // 256 samples of the role per unit = 64 float4 = 2 per lane and unit
     float4 x[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) x[k] = __ldg(cur4 + lane + 32 * k);
-    float pv[3];
+    for (int k = 0; k < 4; k++) {
+      const bool ok = k < 2 || have1;
+      x[k] = ok ? __ldg(reinterpret_cast<const float4 *>(cur0 + 512 * (k >> 1)) + lane + 32 * (k & 1))
+                : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float pv[kPer];  // tails of the frame before unit 0
 #pragma unroll
-    for (int b = 0; b < 3; b++) pv[b] = prev ? __ldg(prev + (b == 0 ? 96 : b == 1 ? 224 : 480) + lane) : 0.0f;
+    for (int b = 0; b < kPer; b++) pv[b] = frame0 > 0 ? __ldg(cur0 - 512 + b * kSize + kSize - 32 + lane) : 0.0f;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      // element 4*(lane + 32k): k = 0 low, 1 mid, 2..3 high
-      const int at = (k == 0 ? kArrLow + 32 : k == 1 ? kArrMid + 32 : kArrHigh + 32 + 128 * (k - 2)) + 4 * lane;
+      // role 0: k = transform (unit k>>1, band k&1), sample 4*lane; role 1: transform k>>1, sample 128*(k&1) + 4*lane
+      const int at = kRole == 0 ? k * kBuf + 32 + 4 * lane : (k >> 1) * kBuf + 32 + 128 * (k & 1) + 4 * lane;
       double2 *d = reinterpret_cast<double2 *>(arr + at);
       d[0] = make_double2((double)x[k].x, (double)x[k].y);
       d[1] = make_double2((double)x[k].z, (double)x[k].w);
@@ -512,12 +579,16 @@ mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, 
                          max(__float_as_uint(x[k].z) & 0x7FFFFFFFu, __float_as_uint(x[k].w) & 0x7FFFFFFFu)));
     }
     __syncwarp();
+    // tail windowing (encoder.js:309-316): the last 32 samples v of a frame become v * WIN[31-i] in
+    // this frame's buffer and WIN[i] * v in the overlap slot of the next frame's
 #pragma unroll
-    for (int b = 0; b < 3; b++) {
-      const int base = b == 0 ? kArrLow : b == 1 ? kArrMid : kArrHigh;
-      const int size = b == 2 ? 256 : 128;
-      arr[base + lane] = prev ? xr(w_fwd * (double)pv[b]) : 0.0;
-      arr[base + size + lane] = xr(arr[base + size + lane] * w_rev);
+    for (int b = 0; b < kPer; b++) {
+      double *a0 = arr + b * kBuf, *a1 = arr + (kPer + b) * kBuf;
+      const double v0 = a0[kSize + lane], v1 = a1[kSize + lane];
+      a0[lane] = frame0 > 0 ? xr(w_fwd * (double)pv[b]) : 0.0;
+      a0[kSize + lane] = xr(v0 * w_rev);
+      a1[lane] = cont1 ? xr(w_fwd * v0) : 0.0;
+      a1[kSize + lane] = xr(v1 * w_rev);
       big = max(big, __float_as_uint(pv[b]) & 0x7FFFFFFFu);
     }
     __syncwarp();
@@ -526,35 +597,44 @@ mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, 
   // threshold, the one case FastRound cannot round
   const bool fast = __reduce_max_sync(0xffffffffu, big) < 0x71800000u;
   if (long_mask) {
-    if (fast) mdct_long3<FastRound>(long_mask, arr, out, T, lane);
-    else mdct_long3_exact(long_mask, arr, out, T, lane);
+    if (fast) mdct_long_task<kRole, FastRound>(long_mask, arr, out, T, lane);
+    else mdct_long_task_exact<kRole>(long_mask, arr, out, T, lane);
     __syncwarp();
   }
-  // ---- short blocks, one band at a time: block b transforms
-  // [WIN * previous block (32) | block * reversed WIN (32)] (encoder.js:279-304)
-  for (int band = 0; band < 3; band++) {
-    if (mode[band] == 0) continue;
-    const int size = band == 2 ? 256 : 128;
-    const int off = band == 0 ? 0 : band == 1 ? 128 : 256;
-    const float *c = cur + off;
-    const float *p = prev ? prev + off : nullptr;
-    for (int b = 0; b < (size >> 5); b++) {
-      float src_prev = 0.0f;
-      bool have_prev = true;
-      if (b == 0) { have_prev = p != nullptr; if (p) src_prev = p[size - 32 + lane]; }
-      else src_prev = c[32 * (b - 1) + lane];
-      arr[64 * b + lane] = have_prev ? xr(w_fwd * (double)src_prev) : 0.0;
-      arr[64 * b + 32 + lane] = xr((double)c[32 * b + lane] * w_rev);
+  // ---- short blocks, one band at a time (rare: out of line)
+  if (long_mask != (have1 ? (1u << G::kPerWarp) - 1u : (1u << kPer) - 1u)) {
+    for (int x = 0; x < G::kPerWarp; x++) {
+      const int unit = x / kPer, bsel = x % kPer;
+      if (((long_mask >> x) & 1) || (unit == 1 && !have1)) continue;
+      mdct_short_band(kRole == 0 ? bsel : 2, cur0 + 512 * unit + bsel * kSize, unit == 0 ? frame0 > 0 : cont1, fast,
+                      arr, out + x * kSize, T, lane, w_fwd, w_rev);
     }
-    __syncwarp();
-    if (fast) mdct_band<FastRound>(band, false, arr, out + off, T, lane);
-    else mdct_band_exact(band, false, arr, out + off, T, lane);
-    __syncwarp();
   }
-  float4 *dst = reinterpret_cast<float4 *>(coefs + (size_t)su * 512);
+  // 256 coefficients of the role per unit
   const float4 *src = reinterpret_cast<const float4 *>(out);
 #pragma unroll
-  for (int k = 0; k < 4; k++) dst[lane + 32 * k] = src[lane + 32 * k];
+  for (int k = 0; k < 4; k++) {
+    if (k < 2 || have1)
+      reinterpret_cast<float4 *>(coefs + (size_t)(su0 + (k >> 1)) * 512 + kOff)[lane + 32 * (k & 1)] = src[lane + 32 * k];
+  }
+  __syncwarp();
+}
+
+// One kernel per role: the fully unrolled transforms of one role are ~30 KB of code; keeping a
+// single role per launch keeps the hot loop inside the instruction cache.
+template <int kRole>
+__global__ void __launch_bounds__(kMdctWarps * 32, kMdctCtasPerSm)
+mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, int frames, int n_su,
+            const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
+            float *__restrict__ coefs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  MdctWarpSmem &S = reinterpret_cast<MdctWarpSmem *>(smem_raw)[warp];
+  const double w_fwd = T->win[lane], w_rev = T->win[31 - lane];  // WINDOW_SHORT[i], [31 - i]
+  const int n_pairs = (n_su + 1) >> 1;
+  // persistent warps: the grid is sized to the machine and every warp walks the unit pairs
+  for (int pair = blockIdx.x * kMdctWarps + warp; pair < n_pairs; pair += gridDim.x * kMdctWarps)
+    mdct_warp_task<kRole>(pair, bands, modes, frames, n_su, T, P, coefs, S, lane, w_fwd, w_rev);
 }
 
 // ------------------------------------------------------------------------------------
@@ -948,8 +1028,19 @@ size_t alloc_rec_bytes() { return sizeof(AllocRec) + sizeof(AllocCand); }
 
 const char *kernel_name(int id) {
   static const char *names[K_COUNT] = {"qmf_analysis", "band_mags", "transient_modes", "mdct",
-                                       "alloc", "quant_pack", "unpack_imdct", "bands_time", "synth"};
+                                       "alloc", "quant_pack", "unpack_dequant", "imdct", "bands_time", "synth"};
   return id >= 0 && id < K_COUNT ? names[id] : "?";
+}
+
+// CTAs of a persistent kernel: every SM filled to `per_sm` resident CTAs.
+int persistent_ctas(int per_sm) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms * per_sm;
 }
 
 cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
@@ -982,10 +1073,16 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
   }
   prof->begin(K_MDCT, st);
   {
-    cudaError_t e1 = cudaFuncSetAttribute(mdct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMdctSmemBytes);
+    cudaError_t e1 = cudaFuncSetAttribute(mdct_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMdctSmemBytes);
+    if (e1 == cudaSuccess)
+      e1 = cudaFuncSetAttribute(mdct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMdctSmemBytes);
     if (e1 != cudaSuccess) return e1;
+    const int n_pairs = (n_su + 1) / 2;
+    const int grid = std::min((n_pairs + kMdctWarps - 1) / kMdctWarps, persistent_ctas(kMdctCtasPerSm));
+    mdct_kernel<0><<<grid, kMdctWarps * 32, kMdctSmemBytes, st>>>(L.bands, L.modes, frames, n_su, L.tables, L.params, L.coefs);
+    mdct_kernel<1><<<grid, kMdctWarps * 32, kMdctSmemBytes, st>>>(L.bands, L.modes, frames, n_su, L.tables, L.params, L.coefs);
+    prof->launches++;
   }
-  mdct_kernel<<<(n_su + kMdctWarps - 1) / kMdctWarps, kMdctWarps * 32, kMdctSmemBytes, st>>>(L.bands, L.modes, frames, n_su, L.tables, L.params, L.coefs);
   prof->end(K_MDCT, st);
   const long long n_units = (long long)L.n_streams * L.n_out_frames;
   if (n_units > 0 && L.su_out) {

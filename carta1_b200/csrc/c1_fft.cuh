@@ -29,17 +29,30 @@ namespace c1 {
 // otherwise.  A per-value branch would be if-converted by ptxas into "always pay both
 // conversions", which is the cost this avoids.
 struct FastRound {
-  __device__ __forceinline__ double operator()(double v) const {
+  // Carriers for C: 64-bit registers whose low word stays zero for the whole kernel; a rounding
+  // only rewrites the high word (no per-rounding move to zero a fresh low word).  Four of them so
+  // that the four roundings of a butterfly do not serialise on one register.
+  double cz0 = 0.0, cz1 = 0.0, cz2 = 0.0, cz3 = 0.0;
+  int clamp;  // exponent field of 2^(-126 + 29), kept in a register so add + max fuse (VIADDMNMX)
+  __device__ __forceinline__ FastRound() { asm("mov.u32 %0, 0x39E00000;" : "=r"(clamp)); }
+  __device__ __forceinline__ double round_with(double v, double &cz) const {
     const int h = __double2hiint(v);
-    // exponent field of C: max(e, -126) + 29; the low word of C is zero
-    const unsigned ce = max((unsigned)h & 0x7FF00000u, 0x38100000u) + 0x01D00000u;
-    const double c = __hiloint2double((int)ce, 0);
-    const double r = (fabs(v) + c) - c;  // r >= +0: its sign bit is clear
-    return __hiloint2double(__double2hiint(r) | (h & (int)0x80000000u), __double2loint(r));
+    const int ce = max((h & 0x7FF00000) + 0x01D00000, clamp);  // exponent field of C: max(e, -126) + 29
+    asm("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tmov.b64 %0, {lo, %1};\n\t}" : "+d"(cz) : "r"(ce));
+    const double r = (fabs(v) + cz) - cz;  // r >= +0
+    return copysign(r, v);
   }
+  __device__ __forceinline__ double r0(double v) { return round_with(v, cz0); }
+  __device__ __forceinline__ double r1(double v) { return round_with(v, cz1); }
+  __device__ __forceinline__ double r2(double v) { return round_with(v, cz2); }
+  __device__ __forceinline__ double r3(double v) { return round_with(v, cz3); }
 };
 struct ExactRound {
   __device__ __forceinline__ double operator()(double v) const { return (double)(float)v; }
+  __device__ __forceinline__ double r0(double v) const { return (double)(float)v; }
+  __device__ __forceinline__ double r1(double v) const { return (double)(float)v; }
+  __device__ __forceinline__ double r2(double v) const { return (double)(float)v; }
+  __device__ __forceinline__ double r3(double v) const { return (double)(float)v; }
 };
 // high word of 2^100: transforms whose inputs stay below it cannot reach 2^127 internally
 constexpr unsigned kFastRoundInputLimit = 0x46300000u;
@@ -51,14 +64,14 @@ struct Cplx {
 
 // fft.js:46-60 on (even, odd) = (a, b) with twiddle w
 template <typename R>
-__device__ __forceinline__ void butterfly(Cplx &a, Cplx &b, const double2 w, const R &rnd) {
+__device__ __forceinline__ void butterfly(Cplx &a, Cplx &b, const double2 w, R &rnd) {
   const double tr = b.re * w.x - b.im * w.y;
   const double ti = b.re * w.y + b.im * w.x;
   const double er = a.re, ei = a.im;
-  a.re = rnd(er + tr);
-  a.im = rnd(ei + ti);
-  b.re = rnd(er - tr);
-  b.im = rnd(ei - ti);
+  a.re = rnd.r0(er + tr);
+  a.im = rnd.r1(ei + ti);
+  b.re = rnd.r2(er - tr);
+  b.im = rnd.r3(ei - ti);
 }
 
 // Lanes l and l ^ h re-pair their values: the lane with bit h clear keeps a and receives the
@@ -80,7 +93,7 @@ __device__ __forceinline__ void repair(Cplx &a, Cplx &b, int h, int lane) {
 // b hold natural output indices g and g + N/2.
 template <int kLaneBits, typename R>
 __device__ __forceinline__ void warp_fft_regs(Cplx &a, Cplx &b, const double2 *__restrict__ tw, int lane,
-                                              const R &rnd) {
+                                              R &rnd) {
   const int g = lane & ((1 << kLaneBits) - 1);
 #pragma unroll
   for (int s = 0; s <= kLaneBits; s++) {
@@ -95,7 +108,7 @@ __device__ __forceinline__ void warp_fft_regs(Cplx &a, Cplx &b, const double2 *_
 // On exit a0, b0, a1, b1 hold natural outputs l, l+32, l+64, l+96.
 template <typename R>
 __device__ __forceinline__ void warp_fft128_regs(Cplx &a0, Cplx &b0, Cplx &a1, Cplx &b1,
-                                                 const double2 *__restrict__ tw, int lane, const R &rnd) {
+                                                 const double2 *__restrict__ tw, int lane, R &rnd) {
 #pragma unroll
   for (int s = 0; s <= 5; s++) {
     const int h = 1 << s;
@@ -122,19 +135,19 @@ __device__ __forceinline__ int brev_bits(int x, int bits) { return (int)(__brev(
 //   pass B: thread (b6, u) owns positions 64 b6 + 8m + u   -> stages 3,4,5
 //   pass C: (FFT128 only) thread (u, h) owns positions 8m + u and 64 + 8m + u, m in 4h..4h+3
 //           -> stage 6
-// FFT64 uses 8 threads, FFT128 16: one warp transforms the low, mid and high band of a
-// sound unit at once (lanes 0-7, 8-15, 16-31).
+// A warp is specialised by ROLE so that all of this geometry is compile-time and every
+// address is one per-lane base plus an immediate:
+//   role 0 (kFft = 64):  8 threads per transform, 4 transforms per warp (low and mid band of two
+//                        consecutive sound units)
+//   role 1 (kFft = 128): 16 threads per transform, 2 transforms per warp (high band of the two)
 //
 // Transpose buffer: complex position p lives at 16-byte slot p + (p >> 3); every quarter-warp
 // access of the three layouts above then touches 8 distinct 16-byte bank groups.
 // ------------------------------------------------------------------------------------
 static __constant__ double2 c_fft_tw[255];  // DevTables::fft_tw, one copy per translation unit
 
-constexpr int kXposeSlots64 = 64 + 8, kXposeSlots128 = 128 + 16;
-__device__ __forceinline__ int xpose_slot(int p) { return p + (p >> 3); }
-
 template <typename R>
-__device__ __forceinline__ void fft8_pass_a(Cplx (&v)[8], const R &rnd) {
+__device__ __forceinline__ void fft8_pass_a(Cplx (&v)[8], R &rnd) {
 #pragma unroll
   for (int s = 0; s < 3; s++) {
     const int d = 1 << s;
@@ -145,91 +158,94 @@ __device__ __forceinline__ void fft8_pass_a(Cplx (&v)[8], const R &rnd) {
 }
 
 // v[m] = position base + 8m + u; stage 3 + ls pairs m with m + 2^ls, twiddle index
-// (pos & (half - 1)) = 8 (m & (2^ls - 1)) + u with half = 8 * 2^ls
+// (pos & (half - 1)) = 8 (m & (2^ls - 1)) + u with half = 8 * 2^ls.  tw_u = table + u.
 template <typename R>
-__device__ __forceinline__ void fft8_pass_b(Cplx (&v)[8], int u, const double2 *__restrict__ tw, const R &rnd) {
+__device__ __forceinline__ void fft8_pass_b(Cplx (&v)[8], const double2 *__restrict__ tw_u, R &rnd) {
 #pragma unroll
   for (int ls = 0; ls < 3; ls++) {
     const int d = 1 << ls, half = 8 << ls;
 #pragma unroll
     for (int m = 0; m < 8; m++)
-      if (!(m & d)) butterfly(v[m], v[m + d], __ldg(&tw[half - 1 + 8 * (m & (d - 1)) + u]), rnd);
+      if (!(m & d)) butterfly(v[m], v[m + d], __ldg(tw_u + half - 1 + 8 * (m & (d - 1))), rnd);
   }
 }
 
-// v[k] = position 8 (4h + k) + u, v[4 + k] = that + 64: stage 6, twiddle index 8 (4h + k) + u
+// v[k] = position 8 (4h + k) + u, v[4 + k] = that + 64: stage 6, twiddle index 8 (4h + k) + u.
+// tw_uh = table + 32 h + u.
 template <typename R>
-__device__ __forceinline__ void fft8_pass_c(Cplx (&v)[8], int u, int h, const double2 *__restrict__ tw, const R &rnd) {
+__device__ __forceinline__ void fft8_pass_c(Cplx (&v)[8], const double2 *__restrict__ tw_uh, R &rnd) {
 #pragma unroll
-  for (int k = 0; k < 4; k++) butterfly(v[k], v[4 + k], __ldg(&tw[63 + 8 * (4 * h + k) + u]), rnd);
+  for (int k = 0; k < 4; k++) butterfly(v[k], v[4 + k], __ldg(tw_uh + 63 + 8 * k), rnd);
 }
 
-__device__ __forceinline__ void xpose_put(double2 *buf, int p, const Cplx &z) { buf[xpose_slot(p)] = make_double2(z.re, z.im); }
-__device__ __forceinline__ Cplx xpose_get(const double2 *buf, int p) {
-  const double2 t = buf[xpose_slot(p)];
-  Cplx z;
-  z.re = t.x;
-  z.im = t.y;
-  return z;
-}
-
-// Lane geometry of the three concurrent long-block transforms of one sound unit.
-struct LongLanes {
-  int band;      // 0 low, 1 mid, 2 high
-  int t;         // thread index inside the band's transform (0..7 or 0..15)
-  int nl;        // threads of the transform = FFT size / 8
-  int rev_t;     // bit reversal of t over log2(nl) bits
-  int u, b6;     // pass B: positions 64 b6 + 8m + u
-  __device__ __forceinline__ explicit LongLanes(int lane) {
-    band = lane < 8 ? 0 : (lane < 16 ? 1 : 2);
-    t = band == 2 ? lane - 16 : (lane & 7);
-    nl = band == 2 ? 16 : 8;
-    rev_t = band == 2 ? brev_bits(t, 4) : brev_bits(t, 3);
+template <int kRole>
+struct LongGeom {
+  static constexpr int kFft = kRole == 0 ? 64 : 128;    // complex FFT size
+  static constexpr int kN = 4 * kFft;                   // MDCT size (256 / 512)
+  static constexpr int kSize = kN / 2;                  // band samples per frame (128 / 256)
+  static constexpr int kLanes = kFft / 8;               // threads per transform
+  static constexpr int kPerWarp = 32 / kLanes;          // transforms per warp (4 / 2)
+  static constexpr int kSlots = kFft + kFft / 8;        // 16-byte slots of the transpose buffer
+  int x;       // transform index inside the warp
+  int t;       // thread index inside the transform
+  int rev_t;   // bit reversal of t
+  int u, b6;   // pass B: positions 64 b6 + 8m + u
+  __device__ __forceinline__ explicit LongGeom(int lane) {
+    x = lane / kLanes;
+    t = lane % kLanes;
+    rev_t = (int)(__brev((unsigned)t) >> (kRole == 0 ? 29 : 28));
     u = t & 7;
     b6 = t >> 3;
   }
-  // natural FFT-input index held at array position 8t + j (bit-reversed order, fft.js:21-32)
-  __device__ __forceinline__ int q_of(int j) const { return (int)(__brev((unsigned)j) >> 29) * nl + rev_t; }
+  // natural FFT-input index held at array position 8t + j (bit-reversed order, fft.js:21-32):
+  // q = brev3(j) * kLanes + rev_t
+  static __device__ __forceinline__ constexpr int q_step(int j) {
+    return (((j & 1) << 2) | (j & 2) | ((j >> 2) & 1)) * kLanes;
+  }
+  // natural-order output index of v[k] after fft_long_inthread, minus the per-lane part
+  // out_base() = u (role 0) or 32 b6 + u (role 1)
+  __device__ __forceinline__ int out_base() const { return kRole == 0 ? u : 32 * b6 + u; }
+  static __device__ __forceinline__ constexpr int out_step(int k) {
+    return kRole == 0 ? 8 * k : 8 * (k & 3) + 64 * (k >> 2);
+  }
 };
 
 // Runs passes A..C on v (pass-A layout on entry: v[j] = position 8t + j); on exit v[k] holds the
-// natural-order output whose index is out_index(k).  xbuf: this transform's transpose buffer.
-template <typename R>
-__device__ __forceinline__ void fft_long_inthread(Cplx (&v)[8], const LongLanes &G, double2 *xbuf,
-                                                  const double2 *__restrict__ tw, bool active, const R &rnd) {
+// natural-order output of index out_base() + out_step(k).  xbuf: this transform's transpose
+// buffer (LongGeom::kSlots double2).  Every lane runs every instruction.
+template <int kRole, typename R>
+__device__ __forceinline__ void fft_long_inthread(Cplx (&v)[8], const LongGeom<kRole> &G, double2 *xbuf,
+                                                  const double2 *__restrict__ tw, R &rnd) {
   fft8_pass_a(v, rnd);
   __syncwarp();
-  if (active) {
+  double2 *put_a = xbuf + 9 * G.t;  // slot(8t + j) = 9t + j
 #pragma unroll
-    for (int j = 0; j < 8; j++) xpose_put(xbuf, 8 * G.t + j, v[j]);
-  }
+  for (int j = 0; j < 8; j++) put_a[j] = make_double2(v[j].re, v[j].im);
   __syncwarp();
-  if (active) {
+  double2 *at_b = xbuf + 72 * G.b6 + G.u;  // slot(64 b6 + 8m + u) = 72 b6 + 9m + u
 #pragma unroll
-    for (int m = 0; m < 8; m++) v[m] = xpose_get(xbuf, 64 * G.b6 + 8 * m + G.u);
+  for (int m = 0; m < 8; m++) {
+    const double2 z = at_b[9 * m];
+    v[m].re = z.x;
+    v[m].im = z.y;
   }
-  fft8_pass_b(v, G.u, tw, rnd);
-  if (G.band == 2) {  // lanes 16-31: one more stage
-    __syncwarp(0xffff0000u);
-    if (active) {
+  fft8_pass_b(v, tw + G.u, rnd);
+  if (kRole == 1) {
+    __syncwarp();
 #pragma unroll
-      for (int m = 0; m < 8; m++) xpose_put(xbuf, 64 * G.b6 + 8 * m + G.u, v[m]);
-    }
-    __syncwarp(0xffff0000u);
-    if (active) {
+    for (int m = 0; m < 8; m++) at_b[9 * m] = make_double2(v[m].re, v[m].im);
+    __syncwarp();
+    const double2 *at_c = xbuf + 36 * G.b6 + G.u;  // slot(8 (4h + k) + u) = 36 h + 9k + u; +64 -> +72
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        v[k] = xpose_get(xbuf, 8 * (4 * G.b6 + k) + G.u);
-        v[4 + k] = xpose_get(xbuf, 64 + 8 * (4 * G.b6 + k) + G.u);
-      }
+    for (int k = 0; k < 4; k++) {
+      const double2 lo = at_c[9 * k], hi = at_c[9 * k + 72];
+      v[k].re = lo.x;
+      v[k].im = lo.y;
+      v[4 + k].re = hi.x;
+      v[4 + k].im = hi.y;
     }
-    fft8_pass_c(v, G.u, G.b6, tw, rnd);
+    fft8_pass_c(v, tw + 32 * G.b6 + G.u, rnd);
   }
-}
-// natural-order output index of v[k] after fft_long_inthread
-__device__ __forceinline__ int long_out_index(const LongLanes &G, int k) {
-  if (G.band == 2) return 8 * (4 * G.b6 + (k & 3)) + G.u + 64 * (k >> 2);
-  return 8 * k + G.u;
 }
 
 }  // namespace c1

@@ -55,7 +55,7 @@ struct DecodeLaunch {
   int n_out_frames;
   const DevTables *tables;
   // scratch, [n_streams][frames_total][...]
-  float *coefs_dbg;         // optional 512 per unit: dequantised coefficients (stage tap)
+  float *coefs;             // 512 per unit: dequantised coefficients
   uint8_t *modes;           // 4 per unit
   float *inv;               // 512 per unit: IMDCT output before overlap-add
   float *bands_dbg;         // optional 512 per unit: time-domain bands (stage tap)
@@ -69,7 +69,7 @@ struct DecodeLaunch {
 // Launch accounting and optional per-kernel CUDA-event timing (bench.py's roofline leg).
 enum KernelId {
   K_QMF_ANALYSIS = 0, K_BAND_MAGS, K_TRANSIENT_MODES, K_MDCT, K_ALLOC, K_QUANT_PACK,
-  K_UNPACK_IMDCT, K_BANDS_TIME, K_SYNTH, K_COUNT
+  K_UNPACK, K_IMDCT, K_BANDS_TIME, K_SYNTH, K_COUNT
 };
 const char *kernel_name(int id);
 
@@ -92,6 +92,7 @@ struct Prof {
 };
 
 size_t alloc_rec_bytes();
+int persistent_ctas(int per_sm);  // SM count of the current device x per_sm
 // QMF taps and FFT twiddles go to __constant__ memory of the current device (once per context).
 cudaError_t upload_encode_constants(const DevTables *host_tables);
 cudaError_t upload_decode_constants(const DevTables *host_tables);
