@@ -46,26 +46,35 @@ __device__ __forceinline__ void warp_fft(float *re, float *im, int n, const doub
 __device__ __forceinline__ int bitrev(int x, int log2n) { return (int)(__brev((unsigned)x) >> (32 - log2n)); }
 
 // ------------------------------------------------------------------------------------
-// K1: two-stage QMF analysis over a tile of frames, with halos recomputed per CTA.
+// K1: two-stage QMF analysis, streamed: a warp walks a run of consecutive frames of one row
+// and carries the filter state in shared memory, exactly as the reference carries its delay
+// lines from frame to frame (qmf.js:19-50, encoder.js:69-95).
 //   S1lo/S1hi[n] = f32(E +- O), E = sum_j x[2n+1-2j]*EVEN[j], O = sum_j x[2n-2j]*ODD[j]
 //   L/M[m]       = the same filter applied to S1lo;  H[n] = S1hi[n-39].
 // fma() is exact-product here (both factors are widened f32), so it equals mul-then-add.
 //
-// Layout: the input is widened to binary64 once and kept in shared memory as its two
-// polyphase sequences xo[k] = x[2k+1], xe[k] = x[2k].  Each thread produces 8 consecutive
-// outputs, so a 24-tap filter needs a window of 31 polyphase values for 192 DFMA.  Element
-// kk of a sequence lives at row kk&7, column kk>>3 (row stride == 2 mod 16 doubles): a warp's
-// window reads and the tile fill are both bank-conflict free.
+// A run that does not start at the row start is primed from the frame before it: the state
+// after a frame (46 PCM samples, 46 S1lo values, 39 S1hi values) is a function of the last
+// 174 samples of that frame alone.
+//
+// Layout: a signal is widened to binary64 once and kept as its two polyphase sequences
+// xo[k] = x[2k+1], xe[k] = x[2k], each with 24 entries of history in front.  Stage 1: a lane
+// produces 8 consecutive outputs, so a 24-tap filter needs a window of 31 values for 192 DFMA;
+// element e lives at row e&7, column e>>3 (row stride == 2 mod 16 doubles): the warp's window
+// reads and the frame fill are both bank-conflict free.  Stage 2: 4 consecutive outputs per
+// lane, window of 27, element e at row e&3, column e>>2.
 // ------------------------------------------------------------------------------------
-constexpr int kQmfTile = 4;                       // frames per CTA
-constexpr int kQmfS1Threads = 32 * kQmfTile + 6;  // stage-1 work items (8 outputs each)
-constexpr int kQmfThreads = 160;
-constexpr int kQmfStride1 = 146;                  // >= (8*kQmfS1Threads + 31)/8 + 1, == 2 mod 16
-constexpr int kQmfStride2 = 82;                   // >= (8*16*kQmfTile + 31)/8 + 1,   == 2 mod 16
-constexpr int kQmfFill = 2 * (8 * kQmfS1Threads + 32);
-static_assert((8 * kQmfS1Threads + 31) / 8 + 1 <= kQmfStride1 && kQmfStride1 % 16 == 2, "stride 1");
-static_assert((8 * 16 * kQmfTile + 31) / 8 + 1 <= kQmfStride2 && kQmfStride2 % 16 == 2, "stride 2");
-static_assert(kQmfS1Threads <= kQmfThreads, "stage 1 must fit the block");
+constexpr int kQaWarps = 8, kQaCtasPerSm = 2;
+constexpr int kQaRun = 32;        // frames per run
+constexpr int kQaStride1 = 50;    // >= (24 + 256) / 8, == 2 mod 16
+constexpr int kQaStride2 = 40;    // >= (24 + 128) / 4
+static_assert(kQaStride1 * 8 >= 280 && kQaStride1 % 16 == 2 && kQaStride2 * 4 >= 152, "ring strides");
+struct QaWarpSmem {
+  double x[2][8 * kQaStride1];   // odd, even polyphase of the PCM frame
+  double s[2][4 * kQaStride2];   // odd, even polyphase of S1lo
+  float hi[40 + 256];            // S1hi with 40 entries of history (39 used)
+};
+constexpr size_t kQaSmemBytes = sizeof(QaWarpSmem) * kQaWarps;
 
 __constant__ double c_qmf_even[24];
 __constant__ double c_qmf_odd[24];
@@ -77,103 +86,158 @@ cudaError_t upload_encode_constants(const DevTables *host_tables) {
   return e;
 }
 
-// acc[r] = sum_j w[8t + 24 + r - j] * taps[j], j ascending, for r = 0..7 (thread t)
-template <int kStride>
-__device__ __forceinline__ void fir8_analysis(const double *__restrict__ seq, int t, const double *taps,
-                                              double (&acc)[8]) {
+// acc[r] = sum_j seq[kR*t + 24 + r - j] * taps[j], j ascending, r = 0..kR-1: element kR*t + i
+// sits at row i & (kR-1), column t + i / kR of a kR-row ring
+template <int kR, int kStride>
+__device__ __forceinline__ void fir_analysis(const double *__restrict__ seq, int t, const double *taps,
+                                             double (&acc)[kR]) {
 #pragma unroll
-  for (int r = 0; r < 8; r++) acc[r] = 0.0;
+  for (int r = 0; r < kR; r++) acc[r] = 0.0;
 #pragma unroll
   for (int j = 0; j < 24; j++) {
     const double c = taps[j];
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-      const int i = r - j + 24;  // kk = 8t + i, i in 1..31
-      acc[r] = fma(seq[(i & 7) * kStride + t + (i >> 3)], c, acc[r]);
+    for (int r = 0; r < kR; r++) {
+      const int i = r - j + 24;
+      acc[r] = fma(seq[(i & (kR - 1)) * kStride + t + i / kR], c, acc[r]);
     }
   }
 }
 
-template <int kFmt>  // 0: f32 planar rows, 1: s16 interleaved
-__global__ void __launch_bounds__(kQmfThreads, 5)
-qmf_analysis_kernel(const void *__restrict__ pcm_v, size_t row_stride, int n_ch, long long valid_samples,
-                    int frames, float *__restrict__ bands) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *x1 = reinterpret_cast<double *>(smem_raw);  // [2][8*kQmfStride1]: odd, even polyphase of x
-  double *x2 = x1 + 2 * 8 * kQmfStride1;               // [2][8*kQmfStride2]: odd, even polyphase of S1lo
-  const int tid = threadIdx.x;
-  const int f0 = blockIdx.x * kQmfTile;
-  const int stream = blockIdx.y;
-  const int nb = 256 * f0 - 48;  // first stage-1 output of the tile
-  const int kb = nb - 24;        // polyphase index of kk == 0
-  // fill: kk in [0, 8*kQmfS1Threads + 32), both polyphases; all loads are issued before the
-  // first conversion so one round trip to memory covers the whole tile
-  {
-    constexpr int kPer = (kQmfFill + kQmfThreads - 1) / kQmfThreads;
-    float v[kPer];
+// PCM frame -> polyphase ring (elements 24..279).  Lane l owns samples 4l + 128k + c.
+template <int kFmt>
+__device__ __forceinline__ void qa_fill(QaWarpSmem &S, const void *__restrict__ pcm_v, size_t row_off, int n_ch,
+                                        int stream, long long first, long long valid_samples, bool vec_ok, int lane) {
+  float v[4][4];
 #pragma unroll
-    for (int it = 0; it < kPer; it++) {
-      const int idx = tid + it * kQmfThreads;
-      const long long g = 2ll * kb + idx;  // == 2*(kb + kk) + par
-      v[it] = 0.0f;
-      if (idx < kQmfFill && g >= 0 && g < valid_samples) {
-        if (kFmt == 0) {
-          v[it] = __ldg(static_cast<const float *>(pcm_v) + (size_t)stream * row_stride + (size_t)g);
-        } else {  // bin/cli.js:395  readInt16LE / 32768.0 -> Float32Array
-          const short sv = __ldg(static_cast<const short *>(pcm_v) + (size_t)g * n_ch + stream);
-          v[it] = (float)((double)sv / 32768.0);
+  for (int k = 0; k < 4; k++) {
+    const long long g = first + 4 * lane + 128 * k;
+    if (kFmt == 0) {
+      const float *src = static_cast<const float *>(pcm_v) + row_off + g;
+      if (vec_ok && g + 3 < valid_samples) {
+        const float4 q = __ldg(reinterpret_cast<const float4 *>(src));
+        v[k][0] = q.x; v[k][1] = q.y; v[k][2] = q.z; v[k][3] = q.w;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; c++) v[k][c] = g + c < valid_samples ? __ldg(src + c) : 0.0f;
+      }
+    } else {  // bin/cli.js:395  readInt16LE / 32768.0 -> Float32Array
+      const short *src = static_cast<const short *>(pcm_v);
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+        v[k][c] = g + c < valid_samples ? (float)((double)__ldg(src + (size_t)(g + c) * n_ch + stream) / 32768.0) : 0.0f;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int e = 24 + 2 * lane + 64 * k + (c >> 1);  // sample 4l + 128k + c: polyphase index (g >> 1) + 24
+      S.x[(c & 1) ? 0 : 1][(e & 7) * kQaStride1 + (e >> 3)] = (double)v[k][c];
+    }
+}
+
+// stage 1 of the frame in the ring: S1lo -> stage-2 ring (elements 24..151), S1hi -> hi ring (40..295)
+__device__ __forceinline__ void qa_stage1(QaWarpSmem &S, int lane) {
+  double e[8], o[8];
+  fir_analysis<8, kQaStride1>(S.x[0], lane, c_qmf_even, e);
+  fir_analysis<8, kQaStride1>(S.x[1], lane, c_qmf_odd, o);
+  float hi[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const float lo = (float)(e[r] + o[r]);
+    hi[r] = (float)(e[r] - o[r]);
+    // S1lo[8 lane + r] feeds stage 2: polyphase r & 1, element 24 + 4 lane + (r >> 1) = 4 (lane + 6) + (r >> 1)
+    S.s[(r & 1) ? 0 : 1][(r >> 1) * kQaStride2 + lane + 6] = (double)lo;
+  }
+  float4 *h4 = reinterpret_cast<float4 *>(S.hi + 40 + 8 * lane);
+  h4[0] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+  h4[1] = make_float4(hi[4], hi[5], hi[6], hi[7]);
+}
+
+// frame end: the last 24 polyphase entries / 40 S1hi values become the history of the next frame
+__device__ __forceinline__ void qa_shift(QaWarpSmem &S, int lane) {
+  double keep_x[2], keep_s[2];
+  float keep_h[2];
+  if (lane < 24) {
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      const int ex = 256 + lane, es = 128 + lane;
+      keep_x[p] = S.x[p][(ex & 7) * kQaStride1 + (ex >> 3)];
+      keep_s[p] = S.s[p][(es & 3) * kQaStride2 + (es >> 2)];
+    }
+  }
+  keep_h[0] = S.hi[256 + lane];
+  keep_h[1] = lane < 8 ? S.hi[288 + lane] : 0.0f;
+  __syncwarp();
+  if (lane < 24) {
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      S.x[p][(lane & 7) * kQaStride1 + (lane >> 3)] = keep_x[p];
+      S.s[p][(lane & 3) * kQaStride2 + (lane >> 2)] = keep_s[p];
+    }
+  }
+  S.hi[lane] = keep_h[0];
+  if (lane < 8) S.hi[32 + lane] = keep_h[1];
+}
+
+template <int kFmt>  // 0: f32 planar rows, 1: s16 interleaved
+__global__ void __launch_bounds__(kQaWarps * 32, kQaCtasPerSm)
+qmf_analysis_kernel(const void *__restrict__ pcm_v, size_t row_stride, int n_ch, long long valid_samples,
+                    int frames, int n_streams, float *__restrict__ bands) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  QaWarpSmem &S = reinterpret_cast<QaWarpSmem *>(smem_raw)[warp];
+  const int runs_per_row = (frames + kQaRun - 1) / kQaRun;
+  const int n_runs = runs_per_row * n_streams;
+  for (int run = blockIdx.x * kQaWarps + warp; run < n_runs; run += gridDim.x * kQaWarps) {
+    const int stream = run / runs_per_row;
+    const int f0 = (run - stream * runs_per_row) * kQaRun;
+    const int f1 = min(f0 + kQaRun, frames);
+    const size_t row_off = kFmt == 0 ? (size_t)stream * row_stride : 0;
+    const bool vec_ok = kFmt == 0 && ((reinterpret_cast<uintptr_t>(static_cast<const float *>(pcm_v) + row_off) & 15) == 0);
+    __syncwarp();
+    if (f0 == 0) {  // row start: silent history (new BufferPool, buffers.js:31-42)
+      if (lane < 24) {
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+          S.x[p][(lane & 7) * kQaStride1 + (lane >> 3)] = 0.0;
+          S.s[p][(lane & 3) * kQaStride2 + (lane >> 2)] = 0.0;
         }
       }
+      S.hi[lane] = 0.0f;
+      if (lane < 8) S.hi[32 + lane] = 0.0f;
+    } else {        // prime the state from the frame before the run (only its last 64 S1 outputs matter)
+      qa_fill<kFmt>(S, pcm_v, row_off, n_ch, stream, 512ll * (f0 - 1), valid_samples, vec_ok, lane);
+      __syncwarp();
+      qa_stage1(S, lane);
+      __syncwarp();
+      qa_shift(S, lane);
     }
-#pragma unroll
-    for (int it = 0; it < kPer; it++) {
-      const int idx = tid + it * kQmfThreads;
-      const int kk = idx >> 1, par = idx & 1;
-      if (idx < kQmfFill) x1[(par ? 0 : 8 * kQmfStride1) + (kk & 7) * kQmfStride1 + (kk >> 3)] = (double)v[it];
-    }
-  }
-  __syncthreads();
-  float *out = bands + ((size_t)stream * frames) * 512;
-  const int mb = 128 * f0;
-  if (tid < kQmfS1Threads) {
-    double e[8], o[8];
-    fir8_analysis<kQmfStride1>(x1, tid, c_qmf_even, e);
-    fir8_analysis<kQmfStride1>(x1 + 8 * kQmfStride1, tid, c_qmf_odd, o);
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      const int n = nb + 8 * tid + r;
-      const float lo = (float)(e[r] + o[r]);
-      const float hi = (float)(e[r] - o[r]);
-      // S1lo[n] feeds stage 2: polyphase (n & 1), index (n >> 1) - (mb - 24)
-      const int kk2 = (n >> 1) - (mb - 24);
-      x2[((n & 1) ? 0 : 8 * kQmfStride2) + (kk2 & 7) * kQmfStride2 + (kk2 >> 3)] = (double)lo;
-      const int nh = n + 39;  // delayed high band (encoder.js:84-90)
-      if (nh >= 256 * f0 && nh < 256 * (f0 + kQmfTile)) {
-        const int fr = nh >> 8;
-        if (fr < frames) out[(size_t)fr * 512 + 256 + (nh & 255)] = hi;
+    for (int f = f0; f < f1; f++) {
+      __syncwarp();
+      qa_fill<kFmt>(S, pcm_v, row_off, n_ch, stream, 512ll * f, valid_samples, vec_ok, lane);
+      __syncwarp();
+      qa_stage1(S, lane);
+      __syncwarp();
+      float *out = bands + ((size_t)stream * frames + f) * 512;
+      {  // stage 2: low / mid samples 4 lane .. 4 lane + 3
+        double e[4], o[4];
+        fir_analysis<4, kQaStride2>(S.s[0], lane, c_qmf_even, e);
+        fir_analysis<4, kQaStride2>(S.s[1], lane, c_qmf_odd, o);
+        reinterpret_cast<float4 *>(out)[lane] = make_float4((float)(e[0] + o[0]), (float)(e[1] + o[1]),
+                                                            (float)(e[2] + o[2]), (float)(e[3] + o[3]));
+        reinterpret_cast<float4 *>(out + 128)[lane] = make_float4((float)(e[0] - o[0]), (float)(e[1] - o[1]),
+                                                                  (float)(e[2] - o[2]), (float)(e[3] - o[3]));
       }
-    }
-  }
-  __syncthreads();
-  if (tid < 16 * kQmfTile) {
-    double e[8], o[8];
-    fir8_analysis<kQmfStride2>(x2, tid, c_qmf_even, e);
-    fir8_analysis<kQmfStride2>(x2 + 8 * kQmfStride2, tid, c_qmf_odd, o);
-    const int fr = f0 + (tid >> 4);
-    if (fr < frames) {
-      float lo[8], hi[8];
+      // high band delayed by 39 (encoder.js:84-90): H[n] = S1hi[n - 39] = ring[n + 1]
 #pragma unroll
-      for (int r = 0; r < 8; r++) { lo[r] = (float)(e[r] + o[r]); hi[r] = (float)(e[r] - o[r]); }
-      float4 *dl = reinterpret_cast<float4 *>(out + (size_t)fr * 512 + 8 * (tid & 15));
-      float4 *dm = reinterpret_cast<float4 *>(out + (size_t)fr * 512 + 128 + 8 * (tid & 15));
-      dl[0] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-      dl[1] = make_float4(lo[4], lo[5], lo[6], lo[7]);
-      dm[0] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-      dm[1] = make_float4(hi[4], hi[5], hi[6], hi[7]);
+      for (int r = 0; r < 8; r++) out[256 + lane + 32 * r] = S.hi[lane + 32 * r + 1];
+      __syncwarp();
+      qa_shift(S, lane);
     }
   }
 }
-constexpr size_t kQmfSmemBytes = (size_t)(2 * 8 * kQmfStride1 + 2 * 8 * kQmfStride2) * sizeof(double);
 
 // ------------------------------------------------------------------------------------
 // K2a: magnitude spectra for transient detection, one warp per sound unit.
@@ -1048,18 +1112,19 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
   const int n_su = L.n_streams * frames;
   if (n_su == 0) return cudaSuccess;
   {
-    dim3 grid((frames + kQmfTile - 1) / kQmfTile, L.n_streams);
-    cudaError_t e0 = cudaFuncSetAttribute(qmf_analysis_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQmfSmemBytes);
+    cudaError_t e0 = cudaFuncSetAttribute(qmf_analysis_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQaSmemBytes);
     if (e0 == cudaSuccess)
-      e0 = cudaFuncSetAttribute(qmf_analysis_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQmfSmemBytes);
+      e0 = cudaFuncSetAttribute(qmf_analysis_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQaSmemBytes);
     if (e0 != cudaSuccess) return e0;
+    const int n_runs = ((frames + kQaRun - 1) / kQaRun) * L.n_streams;
+    const int grid = std::min((n_runs + kQaWarps - 1) / kQaWarps, persistent_ctas(kQaCtasPerSm));
     prof->begin(K_QMF_ANALYSIS, st);
     if (L.pcm_fmt == 0)
-      qmf_analysis_kernel<0><<<grid, kQmfThreads, kQmfSmemBytes, st>>>(L.pcm, L.row_stride, L.n_ch_interleave,
-                                                                        L.valid_samples, frames, L.bands);
+      qmf_analysis_kernel<0><<<grid, kQaWarps * 32, kQaSmemBytes, st>>>(L.pcm, L.row_stride, L.n_ch_interleave,
+                                                                         L.valid_samples, frames, L.n_streams, L.bands);
     else
-      qmf_analysis_kernel<1><<<grid, kQmfThreads, kQmfSmemBytes, st>>>(L.pcm, L.row_stride, L.n_ch_interleave,
-                                                                        L.valid_samples, frames, L.bands);
+      qmf_analysis_kernel<1><<<grid, kQaWarps * 32, kQaSmemBytes, st>>>(L.pcm, L.row_stride, L.n_ch_interleave,
+                                                                         L.valid_samples, frames, L.n_streams, L.bands);
     prof->end(K_QMF_ANALYSIS, st);
   }
   if (!L.use_fixed) {
