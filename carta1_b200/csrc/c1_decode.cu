@@ -456,23 +456,32 @@ bands_time_kernel(const float *__restrict__ inv, const uint8_t *__restrict__ mod
 }
 
 // ------------------------------------------------------------------------------------
-// K7: overlap-add + QMF synthesis for a tile of frames of one row.
+// K7: overlap-add + two-stage QMF synthesis, streamed: a warp walks a run of consecutive frames
+// of one row and carries the decoder state (IMDCT tails, QMF delay lines) in shared memory, as
+// the reference carries it from frame to frame (decoder.js:360-388, qmf.js:60-105).
 //   S[m], D[m]   = f32(.5(L[m] +- M[m]))                              (qmf.js:77-83)
 //   out2[2i]     = f32(sum_j D[i-23+j] * ODD[j]),  out2[2i+1] = f32(sum_j S[i-23+j] * EVEN[j])
 //   S1[n], D1[n] = f32(.5(out2[n] +- H[n-39]))                        (decoder.js:362-367)
 //   pcm[2n]      = f32(sum_j D1[n-23+j] * ODD[j]), pcm[2n+1]  = f32(sum_j S1[n-23+j] * EVEN[j])
-// Negative indices are the zero-initialised delay lines.  As in K1 the sequences live in
-// shared memory as binary64, row kk&7 / column kk>>3, and every thread produces 8 outputs
-// of each polyphase from a 31-value register window.
+// A run that does not start at the row start is primed from the band record of the unit
+// before it: the state after a frame depends on that unit alone.
+// Rings: S/D with 24 entries of history, 4 rows (element e at row e&3, column e>>2; a lane
+// produces 4 consecutive i); S1/D1 with 24, 8 rows (8 consecutive n per lane); the delayed
+// high band with 40.
 // ------------------------------------------------------------------------------------
-constexpr int kSynTile = 4;
-constexpr int kSynThreads = 32 * kSynTile;
-constexpr int kSynS2Threads = 16 * kSynTile + 2;
-constexpr int kSynStrideA = 82;   // >= (8*kSynS2Threads + 31)/8 + 1, == 2 mod 16
-constexpr int kSynStrideB = 146;  // >= (8*32*kSynTile + 31)/8 + 1,   == 2 mod 16
-static_assert((8 * kSynS2Threads + 31) / 8 + 1 <= kSynStrideA && kSynStrideA % 16 == 2, "stride A");
-static_assert((8 * 32 * kSynTile + 31) / 8 + 1 <= kSynStrideB && kSynStrideB % 16 == 2, "stride B");
-constexpr int kSynHd = 256 * kSynTile + 24;
+constexpr int kSyWarps = 8, kSyCtasPerSm = 2;
+constexpr int kSyRun = 32;        // frames per run
+constexpr int kSyStrideA = 40;    // >= (24 + 128) / 4
+constexpr int kSyStrideB = 50;    // >= (24 + 256) / 8, == 2 mod 16
+static_assert(kSyStrideA * 4 >= 152 && kSyStrideB * 8 >= 280 && kSyStrideB % 16 == 2, "ring strides");
+struct SyWarpSmem {
+  double a[2][4 * kSyStrideA];   // D, S of stage 2
+  double b[2][8 * kSyStrideB];   // D1, S1 of stage 1
+  float hd[40 + 256];            // high band with 40 entries of history (39 used)
+  float td[512];                 // time-domain band frame: low 128 | mid 128 | high 256
+  float tail[48];                // tail16 of the previous unit's three band records
+};
+constexpr size_t kSySmemBytes = sizeof(SyWarpSmem) * kSyWarps;
 
 __constant__ double c_syn_even[24];
 __constant__ double c_syn_odd[24];
@@ -484,137 +493,198 @@ cudaError_t upload_decode_constants(const DevTables *host_tables) {
   return e;
 }
 
-// acc[r] = sum_j w[8t + 1 + r + j] * taps[j], j ascending, for r = 0..7 (thread t)
-template <int kStride>
-__device__ __forceinline__ void fir8_synthesis(const double *__restrict__ seq, int t, const double *taps,
-                                               double (&acc)[8]) {
+// acc[r] = sum_j seq[kR*t + 1 + r + j] * taps[j], j ascending, r = 0..kR-1: element kR*t + i
+// sits at row i & (kR-1), column t + i / kR of a kR-row ring
+template <int kR, int kStride>
+__device__ __forceinline__ void fir_synthesis(const double *__restrict__ seq, int t, const double *taps,
+                                              double (&acc)[kR]) {
 #pragma unroll
-  for (int r = 0; r < 8; r++) acc[r] = 0.0;
+  for (int r = 0; r < kR; r++) acc[r] = 0.0;
 #pragma unroll
   for (int j = 0; j < 24; j++) {
     const double c = taps[j];
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
+    for (int r = 0; r < kR; r++) {
       const int i = r + j + 1;
-      acc[r] = fma(seq[(i & 7) * kStride + t + (i >> 3)], c, acc[r]);
+      acc[r] = fma(seq[(i & (kR - 1)) * kStride + t + i / kR], c, acc[r]);
     }
   }
+}
+
+// Band record of one unit -> time-domain frame in S.td (first 32 samples of a band: overlap-add
+// with the previous unit's tail, mdct.js:230-245), merged low/mid -> S/D ring (elements 24..151),
+// high -> hd ring (40..295); the unit's tails replace the previous ones.
+__device__ __forceinline__ void sy_load_unit(SyWarpSmem &S, const float *__restrict__ rec, const double w1,
+                                             const double w2, int lane) {
+  const float4 *r4 = reinterpret_cast<const float4 *>(rec);
+  float4 x[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) x[k] = __ldg(r4 + lane + 32 * k);
+  // lane p finishes sample p of each band: i = p < 16 ? p : 31 - p, w1 = WIN[i], w2 = WIN[31 - i]
+  const int i = lane < 16 ? lane : 31 - lane;
+  float ola[3];
+#pragma unroll
+  for (int b = 0; b < 3; b++) {
+    const int off = b == 0 ? 0 : b == 1 ? 128 : 256;
+    const double pv = (double)S.tail[16 * b + i];
+    const double cv = (double)__ldg(rec + off + 15 - i);
+    ola[b] = lane < 16 ? (float)(pv * w2 - cv * w1) : (float)(pv * w1 + cv * w2);
+  }
+  __syncwarp();  // every lane has read the old tails
+#pragma unroll
+  for (int k = 0; k < 4; k++) reinterpret_cast<float4 *>(S.td)[lane + 32 * k] = x[k];
+  __syncwarp();
+#pragma unroll
+  for (int b = 0; b < 3; b++) {
+    const int off = b == 0 ? 0 : b == 1 ? 128 : 256;
+    if (lane >= 16) S.tail[16 * b + lane - 16] = S.td[off + lane];  // record[16..32) is tail16
+    S.td[off + lane] = ola[b];                                          // (read above before this write)
+  }
+  __syncwarp();
+  // merge low / mid (qmf.js:77-83): m = 4 lane + r -> element 24 + m = 4 (lane + 6) + r
+  {
+    const float4 l4 = reinterpret_cast<const float4 *>(S.td)[lane], m4 = reinterpret_cast<const float4 *>(S.td + 128)[lane];
+    const float l[4] = {l4.x, l4.y, l4.z, l4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const float sum = (float)(0.5 * ((double)l[r] + (double)m[r]));
+      const float dif = (float)(0.5 * ((double)l[r] - (double)m[r]));
+      S.a[0][r * kSyStrideA + lane + 6] = (double)dif;
+      S.a[1][r * kSyStrideA + lane + 6] = (double)sum;
+    }
+  }
+  // high band into its delay ring
+  {
+    const float4 h0 = reinterpret_cast<const float4 *>(S.td + 256)[2 * lane], h1 = reinterpret_cast<const float4 *>(S.td + 256)[2 * lane + 1];
+    float4 *d = reinterpret_cast<float4 *>(S.hd + 40 + 8 * lane);
+    d[0] = h0;
+    d[1] = h1;
+  }
+}
+
+// stage 2 + merge with the delayed high band -> D1/S1 ring (elements 24..279)
+__device__ __forceinline__ void sy_stage2(SyWarpSmem &S, int lane) {
+  double ev[4], od[4];
+  fir_synthesis<4, kSyStrideA>(S.a[0], lane, c_syn_odd, od);   // out2[2i],   i = 4 lane + r
+  fir_synthesis<4, kSyStrideA>(S.a[1], lane, c_syn_even, ev);  // out2[2i+1]
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+#pragma unroll
+    for (int par = 0; par < 2; par++) {
+      const int c = 2 * r + par;  // n = 8 lane + c
+      const float x = (float)(par ? ev[r] : od[r]);
+      const float h = S.hd[8 * lane + c + 1];  // H[n - 39]
+      const float s1 = (float)(0.5 * ((double)x + (double)h));
+      const float d1 = (float)(0.5 * ((double)x - (double)h));
+      // element 24 + n = 8 (lane + 3) + c
+      S.b[0][c * kSyStrideB + lane + 3] = (double)d1;
+      S.b[1][c * kSyStrideB + lane + 3] = (double)s1;
+    }
+  }
+}
+
+__device__ __forceinline__ void sy_shift(SyWarpSmem &S, int lane) {
+  double keep_a[2], keep_b[2];
+  if (lane < 24) {
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      const int ea = 128 + lane, eb = 256 + lane;
+      keep_a[p] = S.a[p][(ea & 3) * kSyStrideA + (ea >> 2)];
+      keep_b[p] = S.b[p][(eb & 7) * kSyStrideB + (eb >> 3)];
+    }
+  }
+  const float h0 = S.hd[256 + lane], h1 = lane < 8 ? S.hd[288 + lane] : 0.0f;
+  __syncwarp();
+  if (lane < 24) {
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      S.a[p][(lane & 3) * kSyStrideA + (lane >> 2)] = keep_a[p];
+      S.b[p][(lane & 7) * kSyStrideB + (lane >> 3)] = keep_b[p];
+    }
+  }
+  S.hd[lane] = h0;
+  if (lane < 8) S.hd[32 + lane] = h1;
 }
 
 template <int kFmt>  // 0: f32 planar rows, 1: s16 interleaved (processor.js:382-389)
-__global__ void __launch_bounds__(kSynThreads, 8)
-synth_kernel(const float *__restrict__ inv, const uint8_t *__restrict__ modes, int frames, int halo,
+__global__ void __launch_bounds__(kSyWarps * 32, kSyCtasPerSm)
+synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams,
              const DevTables *__restrict__ T, void *__restrict__ pcm_v, size_t row_stride, int n_ch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *sa = reinterpret_cast<double *>(smem_raw);  // [2][8*kSynStrideA]: D, S of stage 2
-  double *sb = sa + 2 * 8 * kSynStrideA;               // [2][8*kSynStrideB]: D1, S1 of stage 1
-  float *hd = reinterpret_cast<float *>(sb + 2 * 8 * kSynStrideB);  // delayed high band, n >= 256*f0 - 24
-  __shared__ double win[32];
-  const int tid = threadIdx.x;
-  const int f0 = blockIdx.x * kSynTile;
-  const int stream = blockIdx.y;
-  if (tid < 32) win[tid] = T->win[tid];
-  __syncthreads();
-  const float *inv_row = inv + (size_t)stream * frames * 512;
-  const int f_end = min(f0 + kSynTile, frames);
-
-  // merged low/mid pairs: kk -> m = 128*f0 - 40 + kk
-  const int m_lo = 128 * f0 - 40;
-  constexpr int kFillA = 8 * kSynS2Threads + 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  SyWarpSmem &S = reinterpret_cast<SyWarpSmem *>(smem_raw)[warp];
+  const int wi = lane < 16 ? lane : 31 - lane;
+  const double w1 = T->win[wi], w2 = T->win[31 - wi];
+  const int out_frames = frames - halo;
+  const int runs_per_row = (out_frames + kSyRun - 1) / kSyRun;
+  const int n_runs = runs_per_row * n_streams;
+  for (int run = blockIdx.x * kSyWarps + warp; run < n_runs; run += gridDim.x * kSyWarps) {
+    const int stream = run / runs_per_row;
+    const int f0 = halo + (run - stream * runs_per_row) * kSyRun;
+    const int f1 = min(f0 + kSyRun, frames);
+    const float *inv_row = inv + (size_t)stream * frames * 512;
+    __syncwarp();
+    // silent state (new BufferPool, buffers.js:31-35,67-72)
+    if (lane < 24) {
 #pragma unroll
-  for (int it = 0; it < (kFillA + kSynThreads - 1) / kSynThreads; it++) {
-    const int kk = tid + it * kSynThreads;
-    if (kk >= kFillA) break;
-    const int m = m_lo + kk;
-    float sum = 0.0f, dif = 0.0f;
-    if (m >= 0 && m < 128 * f_end) {
-      const int fr = m >> 7, p = m & 127;
-      const float *fl = inv_row + (size_t)fr * 512;
-      const float l = band_sample(fl, fr > 0 ? fl - 512 : nullptr, p, win);
-      const float h = band_sample(fl + 128, fr > 0 ? fl - 384 : nullptr, p, win);
-      sum = (float)(0.5 * ((double)l + (double)h));
-      dif = (float)(0.5 * ((double)l - (double)h));
-    }
-    const int at = (kk & 7) * kSynStrideA + (kk >> 3);
-    sa[at] = (double)dif;
-    sa[8 * kSynStrideA + at] = (double)sum;
-  }
-  // delayed high band: hd[q] = H[n - 39], n = 256*f0 - 24 + q
-#pragma unroll
-  for (int it = 0; it < (kSynHd + kSynThreads - 1) / kSynThreads; it++) {
-    const int q = tid + it * kSynThreads;
-    if (q >= kSynHd) break;
-    const int g = 256 * f0 - 24 + q - 39;
-    float h = 0.0f;
-    if (g >= 0 && g < 256 * f_end) {
-      const int fr = g >> 8, p = g & 255;
-      const float *fh = inv_row + (size_t)fr * 512 + 256;
-      h = band_sample(fh, fr > 0 ? fh - 512 : nullptr, p, win);
-    }
-    hd[q] = h;
-  }
-  __syncthreads();
-  // stage 2 (low + mid -> 256-rate signal) and the merge with the delayed high band
-  if (tid < kSynS2Threads) {
-    double ev[8], od[8];
-    fir8_synthesis<kSynStrideA>(sa, tid, c_syn_odd, od);                     // out2[2i]
-    fir8_synthesis<kSynStrideA>(sa + 8 * kSynStrideA, tid, c_syn_even, ev);  // out2[2i+1]
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-#pragma unroll
-      for (int par = 0; par < 2; par++) {
-        const int n = 2 * (128 * f0 - 16 + 8 * tid + r) + par;
-        const int kk1 = n - (256 * f0 - 24);
-        if (kk1 < 0) continue;
-        float s1 = 0.0f, d1 = 0.0f;
-        if (n >= 0 && n < 256 * f_end) {
-          const float x = (float)(par ? ev[r] : od[r]);
-          const float h = hd[kk1];
-          s1 = (float)(0.5 * ((double)x + (double)h));
-          d1 = (float)(0.5 * ((double)x - (double)h));
-        }
-        const int at = (kk1 & 7) * kSynStrideB + (kk1 >> 3);
-        sb[at] = (double)d1;
-        sb[8 * kSynStrideB + at] = (double)s1;
+      for (int p = 0; p < 2; p++) {
+        S.a[p][(lane & 3) * kSyStrideA + (lane >> 2)] = 0.0;
+        S.b[p][(lane & 7) * kSyStrideB + (lane >> 3)] = 0.0;
       }
     }
-  }
-  __syncthreads();
-  // stage 1 -> PCM: thread t covers samples [16t, 16t+16) of the tile
-  {
-    const int fr = f0 + (tid >> 5);
-    if (fr < frames && fr >= halo) {
-      double ev[8], od[8];
-      fir8_synthesis<kSynStrideB>(sb, tid, c_syn_odd, od);
-      fir8_synthesis<kSynStrideB>(sb + 8 * kSynStrideB, tid, c_syn_even, ev);
-      const size_t sample = (size_t)(fr - halo) * 512 + 16 * (tid & 31);
-      if (kFmt == 0) {
-        float *dstf = static_cast<float *>(pcm_v) + (size_t)stream * row_stride + sample;
-        if ((reinterpret_cast<uintptr_t>(dstf) & 15) == 0) {
-          float4 *dst = reinterpret_cast<float4 *>(dstf);
+    S.hd[lane] = 0.0f;
+    if (lane < 8) S.hd[32 + lane] = 0.0f;
+    S.tail[lane] = 0.0f;
+    if (lane < 16) S.tail[32 + lane] = 0.0f;
+    __syncwarp();
+    if (f0 > 0) {
+      // prime from unit f0 - 1: only samples >= 32 of its bands reach the state (they do not depend
+      // on the tails before it), so the zero state above is as good as the true one
+      sy_load_unit(S, inv_row + (size_t)(f0 - 1) * 512, w1, w2, lane);
+      __syncwarp();
+      sy_stage2(S, lane);
+      __syncwarp();
+      sy_shift(S, lane);
+    }
+    for (int f = f0; f < f1; f++) {
+      __syncwarp();
+      sy_load_unit(S, inv_row + (size_t)f * 512, w1, w2, lane);
+      __syncwarp();
+      sy_stage2(S, lane);
+      __syncwarp();
+      {  // stage 1 -> PCM: lane covers samples [16 lane, 16 lane + 16) of the frame
+        double ev[8], od[8];
+        fir_synthesis<8, kSyStrideB>(S.b[0], lane, c_syn_odd, od);
+        fir_synthesis<8, kSyStrideB>(S.b[1], lane, c_syn_even, ev);
+        const size_t sample = (size_t)(f - halo) * 512 + 16 * lane;
+        if (kFmt == 0) {
+          float *dstf = static_cast<float *>(pcm_v) + (size_t)stream * row_stride + sample;
+          if ((reinterpret_cast<uintptr_t>(dstf) & 15) == 0) {
+            float4 *dst = reinterpret_cast<float4 *>(dstf);
 #pragma unroll
-          for (int q = 0; q < 4; q++)
-            dst[q] = make_float4((float)od[2 * q], (float)ev[2 * q], (float)od[2 * q + 1], (float)ev[2 * q + 1]);
+            for (int q = 0; q < 4; q++)
+              dst[q] = make_float4((float)od[2 * q], (float)ev[2 * q], (float)od[2 * q + 1], (float)ev[2 * q + 1]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) { dstf[2 * q] = (float)od[q]; dstf[2 * q + 1] = (float)ev[q]; }
+          }
         } else {
+          short *dst = static_cast<short *>(pcm_v);
 #pragma unroll
-          for (int q = 0; q < 8; q++) { dstf[2 * q] = (float)od[q]; dstf[2 * q + 1] = (float)ev[q]; }
-        }
-      } else {
-        short *dst = static_cast<short *>(pcm_v);
-#pragma unroll
-        for (int r = 0; r < 16; r++) {
-          double d = (double)(float)((r & 1) ? ev[r >> 1] : od[r >> 1]);  // Math.max(-1, Math.min(1, x))
-          d = d > 1.0 ? 1.0 : d;
-          d = d < -1.0 ? -1.0 : d;
-          const double w = d < 0.0 ? d * 32768.0 : d * 32767.0;
-          dst[(sample + r) * n_ch + stream] = (short)(isnan(w) ? 0 : __double2int_rz(w));
+          for (int r = 0; r < 16; r++) {
+            double d = (double)(float)((r & 1) ? ev[r >> 1] : od[r >> 1]);  // Math.max(-1, Math.min(1, x))
+            d = d > 1.0 ? 1.0 : d;
+            d = d < -1.0 ? -1.0 : d;
+            const double w = d < 0.0 ? d * 32768.0 : d * 32767.0;
+            dst[(sample + r) * n_ch + stream] = (short)(isnan(w) ? 0 : __double2int_rz(w));
+          }
         }
       }
+      __syncwarp();
+      sy_shift(S, lane);
     }
   }
 }
-constexpr size_t kSynSmemBytes =
-    (size_t)(2 * 8 * kSynStrideA + 2 * 8 * kSynStrideB) * sizeof(double) + (size_t)kSynHd * sizeof(float);
 
 // ------------------------------------------------------------------------------------
 // Self-test of the two arithmetic shortcuts against the IEEE operations they replace:
@@ -691,19 +761,20 @@ cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, Prof *prof) {
     bands_time_kernel<<<n_units, 256, 0, st>>>(L.inv, L.modes, L.frames_total, n_units, L.tables, L.bands_dbg);
     prof->end(K_BANDS_TIME, st);
   }
-  if (L.pcm) {
-    dim3 grid((L.frames_total + kSynTile - 1) / kSynTile, L.n_streams);
-    cudaError_t e0 = cudaFuncSetAttribute(synth_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSynSmemBytes);
+  if (L.pcm && L.frames_total > L.halo_frames) {
+    cudaError_t e0 = cudaFuncSetAttribute(synth_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSySmemBytes);
     if (e0 == cudaSuccess)
-      e0 = cudaFuncSetAttribute(synth_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSynSmemBytes);
+      e0 = cudaFuncSetAttribute(synth_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSySmemBytes);
     if (e0 != cudaSuccess) return e0;
+    const int n_runs = ((L.frames_total - L.halo_frames + kSyRun - 1) / kSyRun) * L.n_streams;
+    const int grid = std::min((n_runs + kSyWarps - 1) / kSyWarps, persistent_ctas(kSyCtasPerSm));
     prof->begin(K_SYNTH, st);
     if (L.pcm_fmt == 0)
-      synth_kernel<0><<<grid, kSynThreads, kSynSmemBytes, st>>>(L.inv, L.modes, L.frames_total, L.halo_frames,
-                                                                 L.tables, L.pcm, L.row_stride, L.n_ch_interleave);
+      synth_kernel<0><<<grid, kSyWarps * 32, kSySmemBytes, st>>>(L.inv, L.frames_total, L.halo_frames, L.n_streams,
+                                                                  L.tables, L.pcm, L.row_stride, L.n_ch_interleave);
     else
-      synth_kernel<1><<<grid, kSynThreads, kSynSmemBytes, st>>>(L.inv, L.modes, L.frames_total, L.halo_frames,
-                                                                 L.tables, L.pcm, L.row_stride, L.n_ch_interleave);
+      synth_kernel<1><<<grid, kSyWarps * 32, kSySmemBytes, st>>>(L.inv, L.frames_total, L.halo_frames, L.n_streams,
+                                                                  L.tables, L.pcm, L.row_stride, L.n_ch_interleave);
     prof->end(K_SYNTH, st);
   }
   return cudaGetLastError();
