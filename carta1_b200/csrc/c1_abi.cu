@@ -212,7 +212,7 @@ struct carta1_ctx {
   bool params_valid = false;
   carta1_enc_opts params_opts;
   double params_bsf[64];
-  DevBuf bands, mags, modes, coefs, inv, scores, stage_pcm, stage_su, dbg, recs;
+  DevBuf bands, mags, modes, coefs, sfi, inv, scores, stage_pcm, stage_su, dbg, recs;
   size_t max_units_per_pass = 1u << 19;  // frames*channels per pass of the chunked host entry points
 };
 
@@ -278,6 +278,7 @@ int upload_params(carta1_ctx *ctx, const carta1_enc_opts *opts, DevEncParams *d_
 int ensure_encode_scratch(carta1_ctx *ctx, size_t units, bool auto_modes) {
   CU(ctx, ctx->bands.ensure(units * 512 * sizeof(float)));
   CU(ctx, ctx->coefs.ensure(units * 512 * sizeof(float)));
+  CU(ctx, ctx->sfi.ensure(units * 64));
   CU(ctx, ctx->modes.ensure(units * 4));
   if (auto_modes) CU(ctx, ctx->mags.ensure(units * 256 * sizeof(float)));
   return CARTA1_OK;
@@ -363,7 +364,7 @@ void carta1_ctx_destroy(carta1_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  ctx->bands.release(); ctx->mags.release(); ctx->modes.release(); ctx->coefs.release();
+  ctx->bands.release(); ctx->mags.release(); ctx->modes.release(); ctx->coefs.release(); ctx->sfi.release();
   ctx->inv.release(); ctx->scores.release(); ctx->stage_pcm.release(); ctx->stage_su.release();
   ctx->dbg.release(); ctx->recs.release();
   if (ctx->d_tables) cudaFree(ctx->d_tables);
@@ -445,6 +446,7 @@ static int encode_device_impl(carta1_ctx *ctx, const void *d_pcm, int pcm_fmt, s
   L.modes = dbg_modes ? dbg_modes : (uint8_t *)ctx->modes.p;
   L.coefs = dbg_coefs ? dbg_coefs : (float *)ctx->coefs.p;
   L.scores = nullptr;
+  L.sfi = (uint8_t *)ctx->sfi.p;
   L.alloc_recs = ctx->recs.p;
   L.su_out = d_su; L.su_frame_stride = su_frame_stride; L.su_stream_stride = su_stream_stride;
   CU(ctx, launch_encode(L, ctx->stream, &ctx->prof));

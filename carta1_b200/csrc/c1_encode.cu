@@ -590,14 +590,31 @@ __device__ __noinline__ void mdct_short_band(int band, const float *__restrict__
   __syncwarp();
 }
 
+// findScaleFactor (bitallocation.js:290-299) from the largest |coefficient| of a BFU.  The
+// log2 / ceil of the reference equals 3*(E+21) + #{thresholds of the binade below max}
+// (DevTables::sf_thr, exact: SURVEY.md section 0.3).  NaN never wins the max, as in the reference.
+__device__ __forceinline__ int scale_factor_index(float mx, const DevTables *__restrict__ T) {
+  int sfi = 0;
+  if (mx > 0.0f) {
+    const uint32_t bits = __float_as_uint(mx);
+    const int e3 = 3 * ((int)(bits >> 23) - 127 + 21);
+    if (e3 >= 63) sfi = 63;
+    else if (e3 >= 0) {
+      sfi = e3 + (mx > T->sf_thr[e3]) + (mx > T->sf_thr[e3 + 1]) + (mx > T->sf_thr[e3 + 2]);
+      if (sfi > 63) sfi = 63;
+    }
+  }
+  return sfi;
+}
+
 // One warp task: sound units su0 = 2 * pair and su0 + 1 (consecutive frames of a row, unless
 // the row ends in between).
 template <int kRole>
 __device__ __forceinline__ void mdct_warp_task(int pair, const float *__restrict__ bands,
                                                const uint8_t *__restrict__ modes, int frames, int n_su,
                                                const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
-                                               float *__restrict__ coefs, MdctWarpSmem &S, int lane, double w_fwd,
-                                               double w_rev) {
+                                               float *__restrict__ coefs, uint8_t *__restrict__ sfi_out,
+                                               MdctWarpSmem &S, int lane, double w_fwd, double w_rev) {
   using G = LongGeom<kRole>;
   constexpr int kSize = G::kSize, kBuf = kSize + 32, kPer = G::kPerWarp / 2;  // transforms per unit
   constexpr int kOff = kRole == 0 ? 0 : 256;                                // first band sample of the role
@@ -674,6 +691,26 @@ __device__ __forceinline__ void mdct_warp_task(int pair, const float *__restrict
                       arr, out + x * kSize, T, lane, w_fwd, w_rev);
     }
   }
+  // scale-factor index of every BFU of the role (groupIntoBFUs, quantization.js:106-149 +
+  // findScaleFactor): role 0 owns BFUs 0..35 of both units, role 1 BFUs 36..51
+  {
+    constexpr int kBfus = kRole == 0 ? 36 : 16, kFirst = kRole == 0 ? 0 : 36;
+    const FormatTables &F = T->fmt;
+    for (int item = lane; item < 2 * kBfus; item += 32) {
+      const int unit = item / kBfus, b = kFirst + item % kBfus;
+      if (unit == 1 && !have1) break;
+      const int x = kRole == 0 ? unit * 2 + (b >= 20) : unit;
+      const int start = (mode[x] == 0 ? F.start_long[b] : F.start_short[b]) - (kRole == 0 ? (b >= 20 ? 128 : 0) : 256);
+      const float *c = out + x * kSize + start;
+      const int sz = F.specs[b];
+      float mx = 0.0f;
+      for (int j = 0; j < sz; j++) {
+        const float a = fabsf(c[j]);
+        if (a > mx) mx = a;
+      }
+      sfi_out[(size_t)(su0 + unit) * 64 + b] = (uint8_t)scale_factor_index(mx, T);
+    }
+  }
   // 256 coefficients of the role per unit
   const float4 *src = reinterpret_cast<const float4 *>(out);
 #pragma unroll
@@ -690,7 +727,7 @@ template <int kRole>
 __global__ void __launch_bounds__(kMdctWarps * 32, kMdctCtasPerSm)
 mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, int frames, int n_su,
             const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
-            float *__restrict__ coefs) {
+            float *__restrict__ coefs, uint8_t *__restrict__ sfi_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   MdctWarpSmem &S = reinterpret_cast<MdctWarpSmem *>(smem_raw)[warp];
@@ -698,7 +735,7 @@ mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, 
   const int n_pairs = (n_su + 1) >> 1;
   // persistent warps: the grid is sized to the machine and every warp walks the unit pairs
   for (int pair = blockIdx.x * kMdctWarps + warp; pair < n_pairs; pair += gridDim.x * kMdctWarps)
-    mdct_warp_task<kRole>(pair, bands, modes, frames, n_su, T, P, coefs, S, lane, w_fwd, w_rev);
+    mdct_warp_task<kRole>(pair, bands, modes, frames, n_su, T, P, coefs, sfi_out, S, lane, w_fwd, w_rev);
 }
 
 // ------------------------------------------------------------------------------------
@@ -846,7 +883,7 @@ __device__ __forceinline__ double run_candidate(AlSmem &S, const DevEncParams *_
 }
 
 __global__ void __launch_bounds__(kAlThreads)
-alloc_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes, int frames, int halo,
+alloc_kernel(const uint8_t *__restrict__ sfi_all, const uint8_t *__restrict__ modes, int frames, int halo,
              int n_out_frames, int n_streams, const DevTables *__restrict__ T,
              const DevEncParams *__restrict__ P, AllocRec *__restrict__ recs, AllocCand *__restrict__ cands) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -874,33 +911,16 @@ alloc_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes,
   }
   __syncthreads();
 
-  // ---- phase A: scale-factor index per BFU (bitallocation.js:290-299).  The log2/ceil of
-  // the reference equals 3*(E+21) + #{thresholds of the binade below max} (DevTables::sf_thr).
-  for (int item = tid; item < kAlThreads * 52; item += kAlThreads) {
-    const int u = item / 52, b = item - u * 52;
+  // ---- phase A: the scale-factor indices the MDCT kernels left per unit (64-byte records)
+  for (int item = tid; item < kAlThreads * 13; item += kAlThreads) {
+    const int u = item / 13, w = item - u * 13;
     const long long unit = unit0 + u;
-    int sfi = 0;
+    uint32_t v = 0;
     if (unit < n_units) {
       const size_t su = (size_t)(unit / n_out_frames) * frames + halo + (size_t)(unit % n_out_frames);
-      const int sz = F.specs[b];
-      const int start = S.mode[u][band_of_bfu(b)] == 0 ? F.start_long[b] : F.start_short[b];
-      const float *src = coefs + su * 512 + start;
-      float mx = 0.0f;
-      for (int j = 0; j < sz; j++) {
-        const float a = fabsf(src[j]);
-        if (a > mx) mx = a;  // NaN never wins, as in the reference
-      }
-      if (mx > 0.0f) {
-        const uint32_t bits = __float_as_uint(mx);
-        const int e3 = 3 * ((int)(bits >> 23) - 127 + 21);
-        if (e3 >= 63) sfi = 63;
-        else if (e3 >= 0) {
-          sfi = e3 + (mx > T->sf_thr[e3]) + (mx > T->sf_thr[e3 + 1]) + (mx > T->sf_thr[e3 + 2]);
-          if (sfi > 63) sfi = 63;
-        }
-      }
+      v = __ldg(reinterpret_cast<const uint32_t *>(sfi_all + su * 64) + w);
     }
-    S.sfi[u][b] = (uint8_t)sfi;
+    reinterpret_cast<uint32_t *>(&S.sfi[u][0])[w] = v;
   }
   __syncthreads();
 
@@ -1144,8 +1164,8 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
     if (e1 != cudaSuccess) return e1;
     const int n_pairs = (n_su + 1) / 2;
     const int grid = std::min((n_pairs + kMdctWarps - 1) / kMdctWarps, persistent_ctas(kMdctCtasPerSm));
-    mdct_kernel<0><<<grid, kMdctWarps * 32, kMdctSmemBytes, st>>>(L.bands, L.modes, frames, n_su, L.tables, L.params, L.coefs);
-    mdct_kernel<1><<<grid, kMdctWarps * 32, kMdctSmemBytes, st>>>(L.bands, L.modes, frames, n_su, L.tables, L.params, L.coefs);
+    mdct_kernel<0><<<grid, kMdctWarps * 32, kMdctSmemBytes, st>>>(L.bands, L.modes, frames, n_su, L.tables, L.params, L.coefs, L.sfi);
+    mdct_kernel<1><<<grid, kMdctWarps * 32, kMdctSmemBytes, st>>>(L.bands, L.modes, frames, n_su, L.tables, L.params, L.coefs, L.sfi);
     prof->launches++;
   }
   prof->end(K_MDCT, st);
@@ -1158,7 +1178,7 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
     AllocCand *cands = reinterpret_cast<AllocCand *>(recs + n_units);
     prof->begin(K_ALLOC, st);
     alloc_kernel<<<(unsigned)((n_units + kAlThreads - 1) / kAlThreads), kAlThreads, sizeof(AlSmem), st>>>(
-        L.coefs, L.modes, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params, recs, cands);
+        L.sfi, L.modes, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params, recs, cands);
     prof->end(K_ALLOC, st);
     prof->begin(K_QUANT_PACK, st);
     quant_pack_kernel<<<(unsigned)((n_units + kQpWarps - 1) / kQpWarps), kQpWarps * 32, 0, st>>>(

@@ -33,6 +33,7 @@ struct EncodeLaunch {
   uint8_t *modes;           // 4 per unit   (auto modes only)
   double *scores;           // 3 per unit, optional
   float *coefs;             // 512 per unit
+  uint8_t *sfi;             // 64 per unit: scale-factor index per BFU (52 used)
   void *alloc_recs;         // alloc_rec_bytes() per emitted unit
   // output
   uint8_t *su_out;          // may be NULL (stage taps only)
