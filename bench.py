@@ -27,6 +27,11 @@ SR = 44100
 BYTES_PER_AUDIO_SEC_ENC = 2 * SR * 4 + 2 * (SR / 512) * 212      # 389,320.3
 BYTES_PER_AUDIO_SEC = 2 * BYTES_PER_AUDIO_SEC_ENC                # encode + decode
 BYTES_PER_SU = 2048 + 212
+# FP64 warp-instructions the numerical contract needs per sound unit and direction (counted in the
+# SASS of the kernels: QMF 576 DFMA + 24 DADD, transform ~650 incl. its binary32 roundings, quantise
+# or dequantise ~50).  An FP64 instruction holds a sub-partition's issue port for 2 clocks on B200
+# (profiles/r01_ubench2_butterfly_rounding.txt), so 2 * this is the floor in issue clocks per unit.
+FP64_WARP_INSTR_PER_SU = 1300
 METRIC = "encoded audio-sec/sec per B200 (stereo 44.1k) at 1/2/4/8 GPU; % of HBM roofline"
 UNIT = "audio-s/s"
 WORKLOAD = "cfg2: 1 h stereo 44.1 kHz synthetic PCM, encode+decode, fixedBlockModes [0,0,0]"
@@ -283,6 +288,9 @@ def run_ours(args, rank, local_rank, world):
         step_ms_prof = sum(v[0] for v in prof.values()) / max(args.steps, 1)
         achieved = BYTES_PER_SU * n_su / (dom_ms / 1000.0) / 1e9 if dom_ms > 0 else 0.0
         step_gbs = BYTES_PER_AUDIO_SEC * seconds / (ms_step / 1000.0) / 1e9
+        props = torch.cuda.get_device_properties(dev)
+        clk_mhz = sampler.max_mhz or 1965
+        fp64_floor_ms = 2 * n_su * 2.0 * FP64_WARP_INSTR_PER_SU / (props.multi_processor_count * 4 * clk_mhz * 1e6) * 1e3
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -300,6 +308,10 @@ def run_ours(args, rank, local_rank, world):
                 "step": {"achieved": step_gbs, "frac": step_gbs / peak,
                          "algorithmic_bytes_per_step": BYTES_PER_AUDIO_SEC * seconds},
                 "kernels_ms_per_step": {k: v[0] / max(args.steps, 1) for k, v in prof.items()},
+                # the bound that actually binds under the bit-exact FP64 contract
+                "fp64_issue": {"floor_ms_per_step": fp64_floor_ms, "frac": fp64_floor_ms / ms_step,
+                               "fp64_warp_instr_per_unit_per_direction": FP64_WARP_INSTR_PER_SU,
+                               "sms": props.multi_processor_count, "sm_mhz": clk_mhz},
             },
             "e2e": {"value": world * seconds / (ms_e2e / e2e_steps / 1000.0), "unit": UNIT,
                     "h2d_bytes_per_step": int(2 * n * 4 + n_su * 212), "d2h_bytes_per_step": int(n_su * 212 + 2 * frames * 512 * 4),
