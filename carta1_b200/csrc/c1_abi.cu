@@ -118,6 +118,11 @@ void build_dev_tables(const carta1_tables &t, DevTables *d) {
   for (int k = 0; k < 63; k++) d->sf_thr[k] = (float)ldexp((double)root[k % 3], k / 3 - 21 - 23);
   d->sf_thr[63] = INFINITY;
   d->log1p10 = fdlibm_log1p_10();
+  for (int wl = 1; wl < 16; wl++)
+    for (int i = 0; i < 64; i++) {
+      volatile double range = (double)((1 << wl) - 1);
+      d->norm[wl][i] = range / t.scale_factors[i];
+    }
   for (int b = 0; b < 52; b++) {
     d->fmt.specs[b] = (uint8_t)kSpecs[b];
     d->fmt.start_long[b] = (uint16_t)kStartLong[b];
@@ -125,6 +130,8 @@ void build_dev_tables(const carta1_tables &t, DevTables *d) {
     for (int j = 0; j < kSpecs[b]; j++) {
       d->fmt.bfu_of_long[kStartLong[b] + j] = (uint8_t)b;
       d->fmt.bfu_of_short[kStartShort[b] + j] = (uint8_t)b;
+      d->fmt.bj_long[kStartLong[b] + j] = (uint16_t)((b << 5) | j);
+      d->fmt.bj_short[kStartShort[b] + j] = (uint16_t)((b << 5) | j);
     }
     static const int kSizes[8] = {4, 6, 7, 8, 9, 10, 12, 20};
     for (int c = 0; c < 8; c++)

@@ -25,6 +25,8 @@ struct FormatTables {
   uint8_t bfu_of_long[512]; // inverse maps: coefficient position -> BFU index
   uint8_t bfu_of_short[512];
   uint8_t size_class[52];   // index of SPECS_PER_BFU[b] in {4,6,7,8,9,10,12,20}
+  uint16_t bj_long[512];    // coefficient position -> (BFU << 5) | index inside the BFU
+  uint16_t bj_short[512];
 };
 
 // libm-derived tables, uploaded once per context (global memory, read through L1).
@@ -40,6 +42,10 @@ struct DevTables {
   double2 fft_tw[255];
   float sf_thr[64];     // 63 thresholds of the exact findScaleFactor table (+1 pad)
   double log1p10;       // fdlibm log1p(10), the constant divisor of transient.js:211
+  // quantize()'s normFactor = quantRange / scaleFactor (quantization.js:43-45) for word-length
+  // index wl (bits = wl + 1, quantRange = 2^wl - 1) and scale-factor index: the IEEE division is
+  // done once on the host
+  double norm[16][64];
   FormatTables fmt;
 };
 

@@ -1006,7 +1006,10 @@ alloc_kernel(const uint8_t *__restrict__ sfi_all, const uint8_t *__restrict__ mo
 
 // ------------------------------------------------------------------------------------
 // K4b: quantise (quantization.js:34-56) and pack the 212-byte unit
-// (serialization.js:41-98, bitstream.js:15-39).  One warp per sound unit.
+// (serialization.js:41-98, bitstream.js:15-39).  One warp per sound unit, persistent.
+// Lane l owns coefficients l + 32k: all 16 are loaded before anything else happens; a
+// position table gives (BFU, index inside the BFU) in one load, a 16-byte record per BFU the
+// norm factor, bit offset, width and range in another.
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ void put_bits(uint32_t *words, int pos, uint32_t value, int bits) {
   const int w = pos >> 5, off = pos & 31;
@@ -1017,92 +1020,108 @@ __device__ __forceinline__ void put_bits(uint32_t *words, int pos, uint32_t valu
 }
 
 constexpr int kQpWarps = 8;
+struct QpBfu {          // per BFU of the unit being packed
+  double norm;          // quantRange / scaleFactor, 0 when the BFU carries no bits or sfi == 0
+  uint32_t base_bits;   // bit offset | width << 11 | quantRange << 16
+  uint32_t pad;
+};
+struct QpWarpSmem {
+  QpBfu bfu[52];
+  uint32_t words[56];
+};
 
 __global__ void __launch_bounds__(kQpWarps * 32)
 quant_pack_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes,
                   const AllocRec *__restrict__ recs, int frames, int halo, int n_out_frames, int n_streams,
                   const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
                   uint8_t *__restrict__ su_out, size_t su_frame_stride, size_t su_stream_stride) {
-  __shared__ uint32_t s_words[kQpWarps][56];
-  __shared__ double s_nf[kQpWarps][52];
-  __shared__ uint16_t s_base[kQpWarps][52];
-  __shared__ uint8_t s_bits[kQpWarps][52];
-  __shared__ uint8_t s_bfu_long[512], s_bfu_short[512];
-  __shared__ uint16_t s_start_long[52], s_start_short[52];
+  __shared__ __align__(16) QpWarpSmem s_warp[kQpWarps];
+  __shared__ uint16_t s_bj[2][512];  // long, short
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const FormatTables &F = T->fmt;
-  for (int i = tid; i < 512; i += kQpWarps * 32) { s_bfu_long[i] = F.bfu_of_long[i]; s_bfu_short[i] = F.bfu_of_short[i]; }
-  if (tid < 52) { s_start_long[tid] = F.start_long[tid]; s_start_short[tid] = F.start_short[tid]; }
+  for (int i = tid; i < 512; i += kQpWarps * 32) { s_bj[0][i] = F.bj_long[i]; s_bj[1][i] = F.bj_short[i]; }
   __syncthreads();
+  QpWarpSmem &S = s_warp[warp];
+  uint32_t *words = S.words;
+  const int sz0 = F.specs[lane], sz1 = lane < 20 ? F.specs[lane + 32] : 0;
   const long long n_units = (long long)n_streams * n_out_frames;
-  const long long unit = (long long)blockIdx.x * kQpWarps + warp;
-  if (unit >= n_units) return;
-  const int stream = (int)(unit / n_out_frames);
-  const int frame_out = (int)(unit % n_out_frames);
-  const size_t su = (size_t)stream * frames + halo + frame_out;
-  const AllocRec *r = recs + unit;
-  const int n = r->n_bfu;
-  uint32_t *words = s_words[warp];
-  for (int i = lane; i < 56; i += 32) words[i] = 0;
-  int m0, m1, m2, l0, l1, l2;
-  if (P->use_fixed) { m0 = P->fixed[0]; m1 = P->fixed[1]; m2 = P->fixed[2]; }
-  else { m0 = modes[su * 4]; m1 = modes[su * 4 + 1]; m2 = modes[su * 4 + 2]; }
-  l0 = m0 == 0; l1 = m1 == 0; l2 = m2 == 0;
-  // per-BFU bit widths, offsets (exclusive scan over bits*size) and 1/step factors
-  int run = 16 + 10 * n;
+  for (long long unit = (long long)blockIdx.x * kQpWarps + warp; unit < n_units; unit += (long long)gridDim.x * kQpWarps) {
+    const int stream = (int)(unit / n_out_frames);
+    const int frame_out = (int)(unit % n_out_frames);
+    const size_t su = (size_t)stream * frames + halo + frame_out;
+    const float *src = coefs + su * 512;
+    float c[16];
 #pragma unroll
-  for (int h = 0; h < 2; h++) {
-    const int b = lane + 32 * h;
-    int wl = 0, sfi = 0, sz = 0;
-    if (b < 52) { wl = r->wl[b]; sfi = r->sfi[b]; sz = F.specs[b]; }
-    const int bits = b < n ? wl_bits(wl) : 0;
-    int incl = bits * sz;
+    for (int k = 0; k < 16; k++) c[k] = __ldg(src + lane + 32 * k);
+    const AllocRec *r = recs + unit;
+    const int n = r->n_bfu;
+    int m0, m1, m2;
+    if (P->use_fixed) { m0 = P->fixed[0]; m1 = P->fixed[1]; m2 = P->fixed[2]; }
+    else { m0 = modes[su * 4]; m1 = modes[su * 4 + 1]; m2 = modes[su * 4 + 2]; }
+    __syncwarp();  // the previous unit's words have been stored
+    for (int i = lane; i < 56; i += 32) words[i] = 0;
+    __syncwarp();
+    // per-BFU records: widths, bit offsets (exclusive scan over bits * size), norm factors; the
+    // word-length and scale-factor fields of the unit
+    int run = 16 + 10 * n;
+    bool wrap = false;  // a BFU at the top scale factor: |coefficient| may exceed it, ToInt32 may wrap
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += t;
+    for (int h = 0; h < 2; h++) {
+      const int b = lane + 32 * h;
+      const int sz = h == 0 ? sz0 : sz1;
+      int wl = 0, sfi = 0;
+      if (b < 52) { wl = r->wl[b]; sfi = r->sfi[b]; }
+      const int bits = b < n ? wl_bits(wl) : 0;
+      int incl = bits * sz;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (b < 52) {
+        const int base = run + incl - bits * sz;
+        const bool coded = bits > 0 && sfi > 0;
+        S.bfu[b].norm = coded ? __ldg(&T->norm[wl][sfi]) : 0.0;
+        S.bfu[b].base_bits = (uint32_t)base | ((uint32_t)bits << 11) | ((uint32_t)((1 << wl) - 1) << 16);
+        wrap |= coded && sfi == 63;
+        if (b < n) {
+          put_bits(words, 16 + 4 * b, (uint32_t)wl, 4);
+          put_bits(words, 16 + 4 * n + 6 * b, (uint32_t)sfi, 6);
+        }
+      }
+      run += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (b < 52) {
-      s_base[warp][b] = (uint16_t)(run + incl - bits * sz);
-      s_bits[warp][b] = (uint8_t)bits;
-      s_nf[warp][b] = (bits > 0 && sfi > 0) ? (double)((1 << (bits - 1)) - 1) / T->sf[sfi] : 0.0;
-      if (b < n) {
-        put_bits(words, 16 + 4 * b, (uint32_t)wl, 4);
-        put_bits(words, 16 + 4 * n + 6 * b, (uint32_t)sfi, 6);
+    if (lane == 0) {
+      const int idx = n == 20 ? 0 : (n - 24) / 4;
+      const uint32_t header = (((uint32_t)(2 - m0) << 14) | ((uint32_t)(2 - m1) << 12) |
+                               ((uint32_t)(3 - m2) << 10) | ((uint32_t)idx << 5)) & 0xFFFFu;
+      atomicOr(&words[0], header << 16);
+    }
+    wrap = __any_sync(0xffffffffu, wrap);
+    __syncwarp();
+    const uint16_t *bj0 = s_bj[m0 != 0] + lane, *bj1 = s_bj[m1 != 0] + lane, *bj2 = s_bj[m2 != 0] + lane;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const uint32_t bj = (k < 4 ? bj0 : (k < 8 ? bj1 : bj2))[32 * k];
+      const QpBfu rec = S.bfu[bj >> 5];
+      const int bits = (rec.base_bits >> 11) & 31;
+      if (bits) {
+        const int range = (int)(rec.base_bits >> 16);
+        // x = c * normFactor; y = (x + (x >= 0 ? 0.5 : -0.5)) | 0; clamp to +-range.  norm == 0
+        // (sfi == 0) gives x = +-0 or NaN and y = 0, as the reference's early return does.
+        const double x = (double)c[k] * rec.norm;
+        const double xs = x + copysign(0.5, x);
+        int y = wrap ? js_to_int32(x + (x >= 0.0 ? 0.5 : -0.5)) : __double2int_rz(xs);
+        if (rec.norm == 0.0) y = 0;  // covers c == +-inf with norm == 0 (inf * 0 = NaN either way) and NaN signs
+        const int q = min(max(y, -range), range);
+        put_bits(words, (int)(rec.base_bits & 2047u) + (int)(bj & 31u) * bits, (uint32_t)q & ((1u << bits) - 1u), bits);
       }
     }
-    run += __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+    uint32_t *dst = reinterpret_cast<uint32_t *>(
+        su_out + ((size_t)frame_out * su_frame_stride + (size_t)stream * su_stream_stride) * kSuBytes);
+    for (int i = lane; i < kSuWords; i += 32) dst[i] = __byte_perm(words[i], 0, 0x0123);
   }
-  if (lane == 0) {
-    const int idx = n == 20 ? 0 : (n - 24) / 4;
-    const uint32_t header = (((uint32_t)(2 - m0) << 14) | ((uint32_t)(2 - m1) << 12) |
-                             ((uint32_t)(3 - m2) << 10) | ((uint32_t)idx << 5)) & 0xFFFFu;
-    atomicOr(&words[0], header << 16);
-  }
-  __syncwarp();
-  const float *src = coefs + su * 512;
-#pragma unroll 4
-  for (int k = 0; k < 16; k++) {
-    const int cidx = lane + 32 * k;
-    const int long_mode = k < 4 ? l0 : (k < 8 ? l1 : l2);
-    const int b = long_mode ? s_bfu_long[cidx] : s_bfu_short[cidx];
-    const int bits = s_bits[warp][b];
-    if (bits == 0) continue;
-    const double nf = s_nf[warp][b];
-    int q = 0;
-    if (nf != 0.0) {
-      const int range = (1 << (bits - 1)) - 1;
-      const double x = (double)src[cidx] * nf;
-      const int y = js_to_int32(x + (x >= 0.0 ? 0.5 : -0.5));
-      q = y > range ? range : (y < -range ? -range : y);
-    }
-    const int j = cidx - (long_mode ? s_start_long[b] : s_start_short[b]);
-    put_bits(words, s_base[warp][b] + j * bits, (uint32_t)q & ((1u << bits) - 1u), bits);
-  }
-  __syncwarp();
-  uint32_t *dst = reinterpret_cast<uint32_t *>(
-      su_out + ((size_t)frame_out * su_frame_stride + (size_t)stream * su_stream_stride) * kSuBytes);
-  for (int i = lane; i < kSuWords; i += 32) dst[i] = __byte_perm(words[i], 0, 0x0123);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1181,7 +1200,7 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
         L.sfi, L.modes, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params, recs, cands);
     prof->end(K_ALLOC, st);
     prof->begin(K_QUANT_PACK, st);
-    quant_pack_kernel<<<(unsigned)((n_units + kQpWarps - 1) / kQpWarps), kQpWarps * 32, 0, st>>>(
+    quant_pack_kernel<<<(unsigned)std::min<long long>((n_units + kQpWarps - 1) / kQpWarps, persistent_ctas(6)), kQpWarps * 32, 0, st>>>(
         L.coefs, L.modes, recs, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params,
         L.su_out, L.su_frame_stride, L.su_stream_stride);
     prof->end(K_QUANT_PACK, st);
