@@ -118,6 +118,10 @@ void build_dev_tables(const carta1_tables &t, DevTables *d) {
   for (int k = 0; k < 63; k++) d->sf_thr[k] = (float)ldexp((double)root[k % 3], k / 3 - 21 - 23);
   d->sf_thr[63] = INFINITY;
   d->log1p10 = fdlibm_log1p_10();
+  for (int wl = 1; wl < 16; wl++) {
+    volatile double range = (double)((1 << wl) - 1);
+    d->rcp_range[wl] = 1.0 / range;
+  }
   for (int wl = 1; wl < 16; wl++)
     for (int i = 0; i < 64; i++) {
       volatile double range = (double)((1 << wl) - 1);

@@ -46,6 +46,7 @@ struct DevTables {
   // index wl (bits = wl + 1, quantRange = 2^wl - 1) and scale-factor index: the IEEE division is
   // done once on the host
   double norm[16][64];
+  double rcp_range[16];  // 1 / (2^wl - 1): dequantize()'s division by quantRange via div_by_range
   FormatTables fmt;
 };
 

@@ -140,12 +140,16 @@ __device__ __noinline__ void imdct_band_exact(int band, bool is_long, const floa
 // K5: unpack + dequantise, one warp per sound unit -> 512 coefficients + block modes.
 // ------------------------------------------------------------------------------------
 constexpr int kUnpackWarps = 8;
+struct UpBfu {          // per BFU of the unit being unpacked
+  double sf;            // SCALE_FACTORS[sfi]; 0 when sfi == 0 (dequantize returns zeros)
+  double rcp;           // 1 / quantRange
+  double range;         // quantRange = 2^(bits-1) - 1
+  uint32_t base_bits;   // bit offset (malformed units: up to 16 + 520 + 16 * 512) | width << 16
+  uint32_t pad;
+};
 struct UnpackWarpSmem {
-  float row[512];
-  double rcp[52];
+  UpBfu bfu[52];
   uint32_t words[56];
-  uint16_t base[52];
-  uint8_t wl[52], sfi[52];
 };
 
 // modes[unit * 4 + 0..2]: 1 = short blocks; modes[unit * 4 + 3]: 1 = the unit's band record is
@@ -157,14 +161,18 @@ unpack_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_
               float *__restrict__ coefs, uint8_t *__restrict__ modes, float *__restrict__ inv,
               const float *__restrict__ prev_rec, ExpandedFrames xf) {
   __shared__ __align__(16) UnpackWarpSmem s_all[kUnpackWarps];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  UnpackWarpSmem &S = s_all[warp];
+  __shared__ uint16_t s_bj[2][512];  // long, short: position -> (BFU << 5) | index inside the BFU
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const FormatTables &F = T->fmt;
+  for (int i = tid; i < 512; i += kUnpackWarps * 32) { s_bj[0][i] = F.bj_long[i]; s_bj[1][i] = F.bj_short[i]; }
+  __syncthreads();
+  UnpackWarpSmem &S = s_all[warp];
+  uint32_t *words = S.words;
+  const int sz0 = F.specs[lane], sz1 = lane < 20 ? F.specs[lane + 32] : 0;
   const int su_skip = prev_rec ? 1 : 0;
-  float *row = S.row;
   for (int unit = blockIdx.x * kUnpackWarps + warp; unit < n_units; unit += gridDim.x * kUnpackWarps) {
-    __syncwarp();
     const int stream = unit / frames, frame = unit - stream * frames;
+    float *dst = coefs + (size_t)unit * 512;
     if (prev_rec && frame == 0) {
       const float4 *s4 = reinterpret_cast<const float4 *>(prev_rec + (size_t)stream * 512);
       float4 *dst4 = reinterpret_cast<float4 *>(inv + (size_t)unit * 512);
@@ -189,15 +197,17 @@ unpack_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_
           const double range = (double)((1 << (bits - 1)) - 1);
           val = (float)(((double)xf.q[xu * 512 + c] * T->sf[sfi]) / range);
         }
-        row[c] = val;
+        dst[c] = val;
       }
     } else if (lin >= n_su_valid) {  // dummy frame {nBfu: 0, blockModes: [0,0,0]} (processor.js:299-307)
       // all-zero coefficients: every IMDCT output is +0 or -0; the transform runs for the signs
-      for (int k = 0; k < 16; k++) row[lane + 32 * k] = 0.0f;
+      for (int k = 0; k < 16; k++) dst[lane + 32 * k] = 0.0f;
     } else {
-      uint32_t *words = S.words;
       const uint32_t *src = reinterpret_cast<const uint32_t *>(su + (size_t)lin * kSuBytes);
-      for (int i = lane; i < 56; i += 32) words[i] = i < kSuWords ? __byte_perm(__ldg(src + i), 0, 0x0123) : 0u;
+      const uint32_t w0 = __ldg(src + lane), w1 = lane < kSuWords - 32 ? __ldg(src + 32 + lane) : 0u;
+      __syncwarp();  // the previous unit's reads of S are done
+      words[lane] = __byte_perm(w0, 0, 0x0123);
+      if (lane < 24) words[32 + lane] = __byte_perm(w1, 0, 0x0123);
       __syncwarp();
       const uint32_t header = words[0] >> 16;  // serialization.js:118-126
       const int m0 = 2 - (int)((header >> 14) & 3), m1 = 2 - (int)((header >> 12) & 3),
@@ -214,7 +224,7 @@ unpack_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_
           sfi = (int)get_bits(words, 16 + 4 * n + 6 * b, 6);
         }
         const int bits = wl_bits(wl);
-        const int cost = b < n ? bits * (int)F.specs[b < 52 ? b : 0] : 0;
+        const int cost = bits * (h == 0 ? sz0 : sz1);
         int incl = cost;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -222,41 +232,44 @@ unpack_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_
           if (lane >= d) incl += t;
         }
         if (b < 52) {
-          S.wl[b] = (uint8_t)(b < n ? wl : 0);
-          S.sfi[b] = (uint8_t)sfi;
-          S.base[b] = (uint16_t)(run + incl - cost);
-          S.rcp[b] = bits > 0 ? 1.0 / (double)((1 << (bits - 1)) - 1) : 0.0;
+          UpBfu &r = S.bfu[b];
+          const int range = (1 << wl) - 1;  // 2^(bits-1) - 1
+          r.sf = sfi ? __ldg(&T->sf[sfi]) : 0.0;
+          r.rcp = __ldg(&T->rcp_range[wl]);
+          r.range = (double)range;
+          r.base_bits = (uint32_t)(run + incl - cost) | ((uint32_t)bits << 16);
         }
         run += __shfl_sync(0xffffffffu, incl, 31);
       }
       __syncwarp();
       short_mask = (m0 != 0) | ((m1 != 0) << 1) | ((m2 != 0) << 2);
-#pragma unroll 4
+      // `run` is the end of the coefficient bits: a unit that claims more than the 1696 it has
+      // (malformed input) needs unpackBits' behaviour at the end of the buffer (bitstream.js:55-68)
+      const bool overrun = run > kFrameBits;
+      const uint16_t *bj0 = s_bj[m0 != 0] + lane, *bj1 = s_bj[m1 != 0] + lane, *bj2 = s_bj[m2 != 0] + lane;
+#pragma unroll
       for (int k = 0; k < 16; k++) {  // serialization.js:153-166 + decoder.js:65-94
-        const int c = lane + 32 * k;
-        const int mode = k < 4 ? m0 : (k < 8 ? m1 : m2);
-        const int b = mode == 0 ? F.bfu_of_long[c] : F.bfu_of_short[c];
+        const uint32_t bj = (k < 4 ? bj0 : (k < 8 ? bj1 : bj2))[32 * k];
+        const UpBfu r = S.bfu[bj >> 5];
+        const int bits = (int)(r.base_bits >> 16);
         float val = 0.0f;
-        const int bits = wl_bits(S.wl[b]);  // 0 for b >= n
         if (bits > 0) {
-          const int j = c - (mode == 0 ? F.start_long[b] : F.start_short[b]);
-          const int v = (int)get_bits(words, (int)S.base[b] + j * bits, bits);
-          const int q = v >= (1 << (bits - 1)) ? v - (1 << bits) : v;  // bitstream.js:78-82
-          const int sfi = S.sfi[b];
-          if (sfi != 0) {
-            const double range = (double)((1 << (bits - 1)) - 1);
-            val = (float)div_by_range(int_to_double(q) * T->sf[sfi], range, S.rcp[b]);
+          const int pos = (int)(r.base_bits & 0xFFFFu) + (int)(bj & 31u) * bits;
+          int q;
+          if (!overrun) {
+            const int w = pos >> 5, off = pos & 31;
+            const uint32_t top = __funnelshift_l(words[w + 1], words[w], off);  // bits pos.. at the top
+            q = (int)top >> (32 - bits);  // sign-extending (bitstream.js:78-82)
+          } else {
+            const int v = (int)get_bits(words, pos, bits);
+            q = v >= (1 << (bits - 1)) ? v - (1 << bits) : v;
           }
+          if (r.sf != 0.0) val = (float)div_by_range(int_to_double(q) * r.sf, r.range, r.rcp);
         }
-        row[c] = val;
+        dst[lane + 32 * k] = val;
       }
     }
-    __syncwarp();
     if (lane < 4) modes[(size_t)unit * 4 + lane] = lane == 3 ? 0 : (uint8_t)((short_mask >> lane) & 1);
-    float4 *d = reinterpret_cast<float4 *>(coefs + (size_t)unit * 512);
-    const float4 *s4 = reinterpret_cast<const float4 *>(row);
-#pragma unroll
-    for (int k = 0; k < 4; k++) d[lane + 32 * k] = s4[lane + 32 * k];
   }
 }
 
