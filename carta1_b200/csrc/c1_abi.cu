@@ -223,8 +223,13 @@ struct carta1_ctx {
   bool params_valid = false;
   carta1_enc_opts params_opts;
   double params_bsf[64];
-  DevBuf bands, mags, modes, coefs, sfi, inv, scores, stage_pcm, stage_su, dbg, recs;
-  size_t max_units_per_pass = 1u << 19;  // frames*channels per pass of the chunked host entry points
+  DevBuf bands, mags, modes, coefs, sfi, inv, scores, dbg, recs;
+  // Host entry points: passes are double-buffered so that the H2D copy of pass i+1 and the D2H
+  // copy of pass i-1 run while pass i computes (three streams, events between them).
+  DevBuf stage_pcm[2], stage_su[2];
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  size_t max_units_per_pass = 1u << 16;  // frames*channels per pass of the chunked host entry points
 };
 
 struct carta1_encoder {
@@ -356,6 +361,13 @@ int carta1_ctx_create(int device, const carta1_tables *tables, carta1_ctx **out)
   DevTables *ht = new DevTables();
   build_dev_tables(ctx->tables, ht);
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+    e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming);
+  }
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_tables, sizeof(DevTables));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_params, sizeof(DevEncParams));
   if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tables, ht, sizeof(DevTables), cudaMemcpyHostToDevice);
@@ -376,8 +388,17 @@ void carta1_ctx_destroy(carta1_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->bands.release(); ctx->mags.release(); ctx->modes.release(); ctx->coefs.release(); ctx->sfi.release();
-  ctx->inv.release(); ctx->scores.release(); ctx->stage_pcm.release(); ctx->stage_su.release();
-  ctx->dbg.release(); ctx->recs.release();
+  if (ctx->h2d) cudaStreamSynchronize(ctx->h2d);
+  if (ctx->d2h) cudaStreamSynchronize(ctx->d2h);
+  ctx->inv.release(); ctx->scores.release(); ctx->dbg.release(); ctx->recs.release();
+  for (int i = 0; i < 2; i++) {
+    ctx->stage_pcm[i].release(); ctx->stage_su[i].release();
+    if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+    if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
+    if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+  }
+  if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
+  if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_params) cudaFree(ctx->d_params);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -428,7 +449,7 @@ size_t carta1_frame_count(size_t n_samples) { return (n_samples + 511) / 512; }
 
 int carta1_ctx_set_max_units_per_pass(carta1_ctx *ctx, size_t units) {
   if (!ctx) return CARTA1_ERR_ARG;
-  ctx->max_units_per_pass = units ? units : (size_t)1 << 19;
+  ctx->max_units_per_pass = units ? units : (size_t)1 << 16;
   return CARTA1_OK;
 }
 
@@ -547,36 +568,51 @@ static int encode_host_impl(carta1_ctx *ctx, const float *const *channels, const
   if (rc) return rc;
   const bool fixed = opts && opts->use_fixed_block_modes;
   const size_t chunk = std::max<size_t>(2, ctx->max_units_per_pass / (size_t)n_ch);
-  for (size_t a = 0; a < frames; a += chunk) {
+  // size every buffer for the largest pass up front: nothing may be reallocated while passes are in flight
+  const size_t max_span = (std::min(frames, chunk) + 2) * 512;
+  const size_t in_elem = channels ? sizeof(float) : sizeof(int16_t);
+  for (int sl = 0; sl < 2; sl++) {
+    CU(ctx, ctx->stage_pcm[sl].ensure((size_t)n_ch * max_span * in_elem));
+    CU(ctx, ctx->stage_su[sl].ensure(std::min(frames, chunk) * (size_t)n_ch * CARTA1_SU_BYTES));
+  }
+  rc = ensure_encode_scratch(ctx, (std::min(frames, chunk) + 2) * (size_t)n_ch, !fixed);
+  if (rc) return rc;
+  CU(ctx, ctx->recs.ensure(std::min(frames, chunk) * (size_t)n_ch * alloc_rec_bytes()));
+  size_t pass = 0;
+  for (size_t a = 0; a < frames; a += chunk, pass++) {
+    const int sl = (int)(pass & 1);
     const size_t b = std::min(frames, a + chunk);
     const size_t halo = a >= 2 ? 2 : 0;  // a is 0 or >= chunk
     const size_t first = a - halo;
     const size_t span = (b - first) * 512;                       // samples staged per row
     const size_t have = std::min(n_samples - first * 512, span); // samples that exist
-    const void *d_in;
-    size_t row_stride = span;
+    // H2D of this pass: its staging slot was last read by the compute of pass - 2
+    if (pass >= 2) CU(ctx, cudaStreamWaitEvent(ctx->h2d, ctx->ev_comp[sl], 0));
     if (channels) {
-      CU(ctx, ctx->stage_pcm.ensure((size_t)n_ch * span * sizeof(float)));
       for (int c = 0; c < n_ch; c++)
-        CU(ctx, cudaMemcpyAsync((float *)ctx->stage_pcm.p + (size_t)c * span, channels[c] + first * 512,
-                                have * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-      d_in = ctx->stage_pcm.p;
+        CU(ctx, cudaMemcpyAsync((float *)ctx->stage_pcm[sl].p + (size_t)c * span, channels[c] + first * 512,
+                                have * sizeof(float), cudaMemcpyHostToDevice, ctx->h2d));
     } else {
-      CU(ctx, ctx->stage_pcm.ensure((size_t)n_ch * span * sizeof(int16_t)));
-      CU(ctx, cudaMemcpyAsync(ctx->stage_pcm.p, interleaved + first * 512 * (size_t)n_ch,
-                              have * (size_t)n_ch * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
-      d_in = ctx->stage_pcm.p;
+      CU(ctx, cudaMemcpyAsync(ctx->stage_pcm[sl].p, interleaved + first * 512 * (size_t)n_ch,
+                              have * (size_t)n_ch * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->h2d));
     }
+    CU(ctx, cudaEventRecord(ctx->ev_in[sl], ctx->h2d));
+    // compute: needs the input, and its output slot drained by the D2H of pass - 2
+    CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[sl], 0));
+    if (pass >= 2) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[sl], 0));
     const size_t out_units = (b - a) * (size_t)n_ch;
-    CU(ctx, ctx->stage_su.ensure(out_units * CARTA1_SU_BYTES));
-    rc = encode_device_impl(ctx, d_in, channels ? 0 : 1, row_stride, n_ch, n_ch, have, halo, b - a,
-                            ctx->d_params, fixed, (uint8_t *)ctx->stage_su.p, (size_t)n_ch, 1, nullptr,
+    rc = encode_device_impl(ctx, ctx->stage_pcm[sl].p, channels ? 0 : 1, span, n_ch, n_ch, have, halo, b - a,
+                            ctx->d_params, fixed, (uint8_t *)ctx->stage_su[sl].p, (size_t)n_ch, 1, nullptr,
                             nullptr, nullptr, nullptr);
     if (rc) return rc;
-    CU(ctx, cudaMemcpyAsync(su_out + a * (size_t)n_ch * CARTA1_SU_BYTES, ctx->stage_su.p,
-                            out_units * CARTA1_SU_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev_comp[sl], ctx->stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->d2h, ctx->ev_comp[sl], 0));
+    CU(ctx, cudaMemcpyAsync(su_out + a * (size_t)n_ch * CARTA1_SU_BYTES, ctx->stage_su[sl].p,
+                            out_units * CARTA1_SU_BYTES, cudaMemcpyDeviceToHost, ctx->d2h));
+    CU(ctx, cudaEventRecord(ctx->ev_out[sl], ctx->d2h));
   }
+  CU(ctx, cudaStreamSynchronize(ctx->d2h));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
   return CARTA1_OK;
 }
 
@@ -605,35 +641,46 @@ static int decode_host_impl(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int
   if (frames == 0) return CARTA1_OK;
   CU(ctx, cudaSetDevice(ctx->device));
   const size_t chunk = std::max<size_t>(2, ctx->max_units_per_pass / (size_t)n_ch);
-  for (size_t a = 0; a < frames; a += chunk) {
+  const size_t max_frames = std::min(frames, chunk);
+  const size_t out_elem = channels_out ? sizeof(float) : sizeof(int16_t);
+  for (int sl = 0; sl < 2; sl++) {
+    CU(ctx, ctx->stage_su[sl].ensure((max_frames + 1) * (size_t)n_ch * CARTA1_SU_BYTES));
+    CU(ctx, ctx->stage_pcm[sl].ensure((size_t)n_ch * max_frames * 512 * out_elem));
+  }
+  int rc = ensure_decode_scratch(ctx, (max_frames + 1) * (size_t)n_ch);
+  if (rc) return rc;
+  size_t pass = 0;
+  for (size_t a = 0; a < frames; a += chunk, pass++) {
+    const int sl = (int)(pass & 1);
     const size_t b = std::min(frames, a + chunk);
     const size_t halo = a >= 1 ? 1 : 0;
     const size_t first = a - halo;
     const size_t want_units = (b - first) * (size_t)n_ch;
     const size_t have_units = std::min(n_su - first * (size_t)n_ch, want_units);
-    CU(ctx, ctx->stage_su.ensure(want_units * CARTA1_SU_BYTES));
-    CU(ctx, cudaMemcpyAsync(ctx->stage_su.p, su + first * (size_t)n_ch * CARTA1_SU_BYTES,
-                            have_units * CARTA1_SU_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    if (pass >= 2) CU(ctx, cudaStreamWaitEvent(ctx->h2d, ctx->ev_comp[sl], 0));
+    CU(ctx, cudaMemcpyAsync(ctx->stage_su[sl].p, su + first * (size_t)n_ch * CARTA1_SU_BYTES,
+                            have_units * CARTA1_SU_BYTES, cudaMemcpyHostToDevice, ctx->h2d));
+    CU(ctx, cudaEventRecord(ctx->ev_in[sl], ctx->h2d));
+    CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[sl], 0));
+    if (pass >= 2) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[sl], 0));
     const size_t span = (b - a) * 512;
-    int rc;
+    rc = decode_device_impl(ctx, (const uint8_t *)ctx->stage_su[sl].p, (size_t)n_ch, 1, have_units, n_ch, halo,
+                            b - a, ctx->stage_pcm[sl].p, channels_out ? 0 : 1, span, n_ch, nullptr, nullptr);
+    if (rc) return rc;
+    CU(ctx, cudaEventRecord(ctx->ev_comp[sl], ctx->stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->d2h, ctx->ev_comp[sl], 0));
     if (channels_out) {
-      CU(ctx, ctx->stage_pcm.ensure((size_t)n_ch * span * sizeof(float)));
-      rc = decode_device_impl(ctx, (const uint8_t *)ctx->stage_su.p, (size_t)n_ch, 1, have_units, n_ch, halo,
-                              b - a, ctx->stage_pcm.p, 0, span, n_ch, nullptr, nullptr);
-      if (rc) return rc;
       for (int c = 0; c < n_ch; c++)
-        CU(ctx, cudaMemcpyAsync(channels_out[c] + a * 512, (float *)ctx->stage_pcm.p + (size_t)c * span,
-                                span * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(channels_out[c] + a * 512, (float *)ctx->stage_pcm[sl].p + (size_t)c * span,
+                                span * sizeof(float), cudaMemcpyDeviceToHost, ctx->d2h));
     } else {
-      CU(ctx, ctx->stage_pcm.ensure((size_t)n_ch * span * sizeof(int16_t)));
-      rc = decode_device_impl(ctx, (const uint8_t *)ctx->stage_su.p, (size_t)n_ch, 1, have_units, n_ch, halo,
-                              b - a, ctx->stage_pcm.p, 1, span, n_ch, nullptr, nullptr);
-      if (rc) return rc;
-      CU(ctx, cudaMemcpyAsync(interleaved_out + a * 512 * (size_t)n_ch, ctx->stage_pcm.p,
-                              (size_t)n_ch * span * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(ctx, cudaMemcpyAsync(interleaved_out + a * 512 * (size_t)n_ch, ctx->stage_pcm[sl].p,
+                              (size_t)n_ch * span * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->d2h));
     }
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev_out[sl], ctx->d2h));
   }
+  CU(ctx, cudaStreamSynchronize(ctx->d2h));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
   return CARTA1_OK;
 }
 

@@ -82,7 +82,8 @@ int carta1_device_count(void);
 size_t carta1_frame_count(size_t n_samples); /* frameBufferToFrames, processor.js:246-279 */
 /* The host entry points below stage at most `units` sound units (frames x channels) per pass
  * through device memory, re-reading a 2-frame PCM halo (decode: 1 unit) at every pass boundary
- * (SURVEY.md Appendix B).  0 restores the default of 2^19.  Results never depend on it. */
+ * (SURVEY.md Appendix B); passes are double-buffered (copies overlap compute).  0 restores
+ * the default of 2^16.  Results never depend on it. */
 int carta1_ctx_set_max_units_per_pass(carta1_ctx *ctx, size_t units);
 
 /* channels[c] points to n_samples f32 samples (planar; caller zero-pads the shorter stereo
