@@ -202,7 +202,7 @@ def run_ours(args, rank, local_rank, world):
     n_su = frames * 2
     d_su = torch.zeros(n_su * 212, dtype=torch.uint8, device=dev)
     d_out = torch.zeros((2, frames * 512), dtype=torch.float32, device=dev)
-    opts = carta1_b200.make_enc_opts(fixed_block_modes=[0, 0, 0])
+    opts = carta1_b200.make_enc_opts(fixed_block_modes=None if args.auto_modes else [0, 0, 0])
     torch.cuda.synchronize()
 
     def encode():
@@ -329,7 +329,7 @@ def run_ours(args, rank, local_rank, world):
             sample_s = min(seconds, float(args.cpu_sample_seconds))
             ns = int(sample_s * SR) // 512 * 512
             chans = [np.ascontiguousarray(pcm_h[c, :ns].numpy()) for c in range(2)]
-            oopts = O.make_options(fixed_modes=[0, 0, 0])
+            oopts = O.make_options(fixed_modes=None if args.auto_modes else [0, 0, 0])
             su_ref, pcm_ref, te, td = cpu_pass(O, chans, oopts, threads)
             k = su_ref.shape[0]
             # frame f depends on samples <= 512 f + 511 only, so the prefix must agree exactly
@@ -357,6 +357,8 @@ def main():
     ap.add_argument("--seconds", type=float, default=3600.0, help="audio seconds per GPU (default: the 1 h of cfg2)")
     ap.add_argument("--cpu-sample-seconds", type=float, default=600.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--auto-modes", action="store_true",
+                    help="development aid: transient-driven block modes instead of the headline fixed [0,0,0] (not a bench line)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

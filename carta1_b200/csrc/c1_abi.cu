@@ -223,7 +223,7 @@ struct carta1_ctx {
   bool params_valid = false;
   carta1_enc_opts params_opts;
   double params_bsf[64];
-  DevBuf bands, mags, modes, coefs, sfi, inv, scores, dbg, recs;
+  DevBuf bands, mags, feats, modes, coefs, sfi, inv, scores, dbg, recs;
   // Host entry points: passes are double-buffered so that the H2D copy of pass i+1 and the D2H
   // copy of pass i-1 run while pass i computes (three streams, events between them).
   DevBuf stage_pcm[2], stage_su[2];
@@ -297,6 +297,7 @@ int ensure_encode_scratch(carta1_ctx *ctx, size_t units, bool auto_modes) {
   CU(ctx, ctx->sfi.ensure(units * 64));
   CU(ctx, ctx->modes.ensure(units * 4));
   if (auto_modes) CU(ctx, ctx->mags.ensure(units * 256 * sizeof(float)));
+  if (auto_modes) CU(ctx, ctx->feats.ensure(units * 9 * sizeof(double)));
   return CARTA1_OK;
 }
 int ensure_decode_scratch(carta1_ctx *ctx, size_t units) {
@@ -387,7 +388,7 @@ void carta1_ctx_destroy(carta1_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  ctx->bands.release(); ctx->mags.release(); ctx->modes.release(); ctx->coefs.release(); ctx->sfi.release();
+  ctx->bands.release(); ctx->mags.release(); ctx->feats.release(); ctx->modes.release(); ctx->coefs.release(); ctx->sfi.release();
   if (ctx->h2d) cudaStreamSynchronize(ctx->h2d);
   if (ctx->d2h) cudaStreamSynchronize(ctx->d2h);
   ctx->inv.release(); ctx->scores.release(); ctx->dbg.release(); ctx->recs.release();
@@ -478,6 +479,7 @@ static int encode_device_impl(carta1_ctx *ctx, const void *d_pcm, int pcm_fmt, s
   L.modes = dbg_modes ? dbg_modes : (uint8_t *)ctx->modes.p;
   L.coefs = dbg_coefs ? dbg_coefs : (float *)ctx->coefs.p;
   L.scores = nullptr;
+  L.feats = ctx->feats.p;
   L.sfi = (uint8_t *)ctx->sfi.p;
   L.alloc_recs = ctx->recs.p;
   L.su_out = d_su; L.su_frame_stride = su_frame_stride; L.su_stream_stride = su_stream_stride;

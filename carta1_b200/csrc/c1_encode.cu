@@ -240,38 +240,225 @@ qmf_analysis_kernel(const void *__restrict__ pcm_v, size_t row_stride, int n_ch,
 }
 
 // ------------------------------------------------------------------------------------
-// K2a: magnitude spectra for transient detection, one warp per sound unit.
+// K2a: magnitude spectra and spectrum features for transient detection, one warp per sound
+// unit (transient.js:17-35,116-189).  performFFT runs the complex FFT on the real band: 128
+// points for low and mid (16 lanes each, concurrently), 256 for high (32 lanes), in the
+// in-thread formulation of c1_fft.cuh.  Exact shortcuts that only use what the reference
+// arithmetic itself produces:
+//   - the imaginary parts start as +0, so the stage-0 butterflies and the k = 0 butterflies of
+//     stage 1 (twiddle (1, 0)) are real: t = (b.re * 1 - (+0) * 0, b.re * 0 + (+0) * 1) = (b.re, +0);
+//   - only bins below N/2 are read (transient.js:29), i.e. the "even" outputs of the last stage.
+// The per-band sums of spectrum_features run serially in index order as the reference's loops
+// do, one lane per accumulator; the logarithms they add are computed by all lanes first.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-band_mags_kernel(const float *__restrict__ bands, int n_su, const DevTables *__restrict__ T,
-                 float *__restrict__ mags) {
-  __shared__ float s_re[4][256], s_im[4][256];
+template <typename R>
+__device__ __forceinline__ void butterfly_real(Cplx &a, Cplx &b, R &rnd) {  // im(a) = im(b) = +0, twiddle (1, 0)
+  const double er = a.re, tr = b.re;
+  a.re = rnd.r0(er + tr);
+  b.re = rnd.r2(er - tr);
+}
+template <typename R>
+__device__ __forceinline__ void butterfly_even_only(Cplx &a, const Cplx &b, const double2 w, R &rnd) {
+  const double tr = b.re * w.x - b.im * w.y;
+  const double ti = b.re * w.y + b.im * w.x;
+  a.re = rnd.r0(a.re + tr);
+  a.im = rnd.r1(a.im + ti);
+}
+
+// stages 0..2 on positions 8t + j of a real signal
+template <typename R>
+__device__ __forceinline__ void fft8_pass_a_real(Cplx (&v)[8], R &rnd) {
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) butterfly_real(v[j], v[j + 1], rnd);  // stage 0
+  butterfly_real(v[0], v[2], rnd);                                    // stage 1, k = 0
+  butterfly_real(v[4], v[6], rnd);
+  butterfly(v[1], v[3], c_fft_tw[2], rnd);                            // stage 1, k = 1
+  butterfly(v[5], v[7], c_fft_tw[2], rnd);
+#pragma unroll
+  for (int j = 0; j < 4; j++) butterfly(v[j], v[j + 4], c_fft_tw[3 + j], rnd);  // stage 2
+}
+
+constexpr int kTsWarps = 8, kTsCtasPerSm = 3;
+struct TsWarpSmem {
+  double2 xbuf[256 + 32];  // transpose buffer (slot p + p/8)
+  double logm[256];        // log(magnitude) where magnitude > 1e-10
+  float mag[256];          // low 64 | mid 64 | high 128
+};
+constexpr size_t kTsSmemBytes = sizeof(TsWarpSmem) * kTsWarps;
+
+// one band's FFT on kLanes = N/8 lanes of the warp; bins [0, N/2) -> mag[]
+template <int kLog2N, typename R>
+__device__ __forceinline__ void transient_fft(const float *__restrict__ x, double2 *xbuf, float *mag, int t,
+                                              const double2 *__restrict__ tw, R &rnd) {
+  constexpr int kN = 1 << kLog2N, kLanes = kN / 8;
+  const int rev_t = (int)(__brev((unsigned)t) >> (32 - (kLog2N - 3)));
+  const int u = t & 7, b = t >> 3;
+  Cplx v[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {  // position 8t + j holds x[brev(8t + j)] = x[brev3(j) * kLanes + rev_t]
+    v[j].re = (double)__ldg(x + ((((j & 1) << 2) | (j & 2) | ((j >> 2) & 1)) * kLanes) + rev_t);
+    v[j].im = 0.0;
+  }
+  fft8_pass_a_real(v, rnd);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; j++) xbuf[9 * t + j] = make_double2(v[j].re, v[j].im);
+  __syncwarp();
+  double2 *at_b = xbuf + 72 * b + u;  // positions 64 b + 8m + u
+#pragma unroll
+  for (int m = 0; m < 8; m++) {
+    const double2 z = at_b[9 * m];
+    v[m].re = z.x;
+    v[m].im = z.y;
+  }
+  fft8_pass_b(v, tw + u, rnd);
+  __syncwarp();
+#pragma unroll
+  for (int m = 0; m < 8; m++) at_b[9 * m] = make_double2(v[m].re, v[m].im);
+  __syncwarp();
+  if (kLog2N == 7) {
+    // stage 6: thread (u, h = b) pairs positions 8 (4h + k) + u and + 64; only the former is a bin < 64
+    const double2 *at_c = xbuf + 36 * b + u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const double2 lo = at_c[9 * k], hi = at_c[9 * k + 72];
+      Cplx a, o;
+      a.re = lo.x; a.im = lo.y; o.re = hi.x; o.im = hi.y;
+      butterfly_even_only(a, o, __ldg(tw + 63 + 32 * b + 8 * k + u), rnd);
+      mag[32 * b + 8 * k + u] = (float)sqrt(a.re * a.re + a.im * a.im);  // transient.js:31
+    }
+  } else {
+    // stages 6, 7: thread (u, h = b in 0..3) owns p0 = 8 (2h + e) + u, e = 0..1, and p0 + 64 c, c = 0..3
+    const double2 *at_c = xbuf + 18 * b + u;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      Cplx c0, c1, c2, c3;
+      { const double2 z = at_c[9 * e]; c0.re = z.x; c0.im = z.y; }
+      { const double2 z = at_c[9 * e + 72]; c1.re = z.x; c1.im = z.y; }
+      { const double2 z = at_c[9 * e + 144]; c2.re = z.x; c2.im = z.y; }
+      { const double2 z = at_c[9 * e + 216]; c3.re = z.x; c3.im = z.y; }
+      const int k6 = 16 * b + 8 * e + u;  // p & 63
+      const double2 w6 = __ldg(tw + 63 + k6);
+      butterfly(c0, c1, w6, rnd);  // stage 6: (p0, p0 + 64), (p0 + 128, p0 + 192)
+      butterfly(c2, c3, w6, rnd);
+      butterfly_even_only(c0, c2, __ldg(tw + 127 + k6), rnd);       // stage 7: (p0, p0 + 128)
+      butterfly_even_only(c1, c3, __ldg(tw + 127 + 64 + k6), rnd);  //          (p0 + 64, p0 + 192)
+      mag[k6] = (float)sqrt(c0.re * c0.re + c0.im * c0.im);
+      mag[64 + k6] = (float)sqrt(c1.re * c1.re + c1.im * c1.im);
+    }
+  }
+}
+
+template <typename R>
+__device__ __forceinline__ void transient_ffts(const float *__restrict__ band, TsWarpSmem &S, int lane,
+                                               const DevTables *__restrict__ T) {
+  R rnd;
+  // low and mid: 16 lanes each, their transposes in separate halves of the buffer
+  transient_fft<7>(band + 128 * (lane >> 4), S.xbuf + 144 * (lane >> 4), S.mag + 64 * (lane >> 4), lane & 15, T->fft_tw, rnd);
+  __syncwarp();
+  transient_fft<8>(band + 256, S.xbuf, S.mag + 128, lane, T->fft_tw, rnd);
+}
+__device__ __noinline__ void transient_ffts_exact(const float *__restrict__ band, TsWarpSmem &S, int lane,
+                                                  const DevTables *__restrict__ T) {
+  transient_ffts<ExactRound>(band, S, lane, T);
+}
+
+struct SpectrumFeatures {  // transient.js:116-189 of one band's magnitude spectrum
+  double flatness, hf_ratio, energy;
+};
+
+__global__ void __launch_bounds__(kTsWarps * 32, kTsCtasPerSm)
+transient_spectrum_kernel(const float *__restrict__ bands, int n_su, const DevTables *__restrict__ T,
+                          float *__restrict__ mags, SpectrumFeatures *__restrict__ feats) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int su = blockIdx.x * 4 + warp;
-  if (su >= n_su) return;
-  float *re = s_re[warp], *im = s_im[warp];
-  for (int band = 0; band < 3; band++) {
-    const int n = band == 2 ? 256 : 128;
-    const int lg = band == 2 ? 8 : 7;
-    const float *src = bands + (size_t)su * 512 + (band == 0 ? 0 : band == 1 ? 128 : 256);
-    for (int i = lane; i < n; i += 32) {
-      re[bitrev(i, lg)] = src[i];
-      im[i] = 0.0f;
+  TsWarpSmem &S = reinterpret_cast<TsWarpSmem *>(smem_raw)[warp];
+  for (int su = blockIdx.x * kTsWarps + warp; su < n_su; su += gridDim.x * kTsWarps) {
+    const float *band = bands + (size_t)su * 512;
+    unsigned big = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float4 q = __ldg(reinterpret_cast<const float4 *>(band) + lane + 32 * k);
+      big = max(big, max(max(__float_as_uint(q.x) & 0x7FFFFFFFu, __float_as_uint(q.y) & 0x7FFFFFFFu),
+                         max(__float_as_uint(q.z) & 0x7FFFFFFFu, __float_as_uint(q.w) & 0x7FFFFFFFu)));
     }
     __syncwarp();
-    warp_fft(re, im, n, T->fft_tw, lane);
-    float *dst = mags + (size_t)su * 256 + (band == 0 ? 0 : band == 1 ? 64 : 128);
-    for (int i = lane; i < (n >> 1); i += 32) {
-      const double r = re[i], m = im[i];
-      dst[i] = (float)sqrt(r * r + m * m);  // transient.js:31
+    if (__reduce_max_sync(0xffffffffu, big) < 0x71800000u) transient_ffts<FastRound>(band, S, lane, T);
+    else transient_ffts_exact(band, S, lane, T);
+    __syncwarp();
+    // magnitudes out; per-bin terms of the sums (logarithm, magnitude, square) and the mask of
+    // bins above EPS, computed by all lanes (bin lane + 32k); the term arrays reuse the transpose buffer
+    const double EPS = 1e-10;
+    double *t_mag = reinterpret_cast<double *>(S.xbuf), *t_sq = t_mag + 256;
+    unsigned ok_mask[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int i = lane + 32 * k;
+      const float m = S.mag[i];
+      mags[(size_t)su * 256 + i] = m;
+      const double v = (double)m, md = fabs(v);
+      const bool ok = md > EPS;
+      S.logm[i] = ok ? fd::log(md) : 0.0;
+      t_mag[i] = md;
+      t_sq[i] = v * v;
+      ok_mask[k] = __ballot_sync(0xffffffffu, ok);
+    }
+    __syncwarp();
+    // serial sums in index order, one lane per (band, accumulator): 0 sum_log (+ valid count),
+    // 1 sum_lin, 2 lo then hi, 3 energy.  Every lane runs the same loop over its own term array;
+    // accumulators 0 and 1 skip the bins at or below EPS (transient.js:126-131), 2 and 3 take all.
+    const int band_i = lane >> 2, acc = lane & 3;
+    double r0 = 0.0, r1 = 0.0;
+    int valid = 0;
+    {
+      const int bi = band_i < 3 ? band_i : 0;
+      const int n = bi == 2 ? 128 : 64, off = bi == 0 ? 0 : bi == 1 ? 64 : 128, mid = n >> 1;
+      const double *term = (acc == 0 ? S.logm : acc == 1 ? t_mag : t_sq) + off;
+      const unsigned all = acc < 2 ? 0u : 0xffffffffu;
+      // masks of this band's bins: words off/32 ..
+      const unsigned k0 = bi == 0 ? ok_mask[0] : (bi == 1 ? ok_mask[2] : ok_mask[4]);
+      const unsigned k1 = bi == 0 ? ok_mask[1] : (bi == 1 ? ok_mask[3] : ok_mask[5]);
+      const unsigned k2 = bi == 2 ? ok_mask[6] : 0u, k3 = bi == 2 ? ok_mask[7] : 0u;
+      const unsigned w0 = k0 | all, w1 = k1 | all, w2 = k2 | all, w3 = k3 | all;
+      valid = __popc(k0) + __popc(k1) + __popc(k2) + __popc(k3);
+      for (int i = 0; i < mid; i++) {
+        const unsigned w = (i < 32 ? w0 : w1) >> (i & 31);
+        if (w & 1u) r0 += term[i];
+      }
+      double rr = acc == 2 ? 0.0 : r0;
+      for (int i = mid; i < n; i++) {
+        const unsigned w = (i < 32 ? w0 : (i < 64 ? w1 : (i < 96 ? w2 : w3))) >> (i & 31);
+        if (w & 1u) rr += term[i];
+      }
+      if (acc == 2) r1 = rr; else r0 = rr;
+    }
+    // gather the four lanes of a band on its first lane
+    const int base = lane & ~3;
+    const double sum_log = __shfl_sync(0xffffffffu, r0, base), sum_lin = __shfl_sync(0xffffffffu, r0, base + 1);
+    const double lo = __shfl_sync(0xffffffffu, r0, base + 2), hi = __shfl_sync(0xffffffffu, r1, base + 2);
+    const double energy = __shfl_sync(0xffffffffu, r0, base + 3);
+    const int nvalid = __shfl_sync(0xffffffffu, valid, base);
+    if (band_i < 3 && acc == 0) {
+      SpectrumFeatures f;
+      if (nvalid == 0) {
+        f.flatness = 0.0;
+      } else {
+        const double geo = fd::exp(sum_log / nvalid);
+        const double arith = sum_lin / nvalid;
+        f.flatness = arith > EPS ? geo / arith : 0.0;
+      }
+      const double total = lo + hi;
+      f.hf_ratio = total > 0.0 ? hi / total : 0.0;
+      f.energy = energy;
+      feats[(size_t)su * 3 + band_i] = f;
     }
     __syncwarp();
   }
 }
 
 // ------------------------------------------------------------------------------------
-// K2b: transient score (transient.js:63-226), one thread per (sound unit, band).  All sums
-// run serially in index order, as the reference's loops do.
+// K2b: transient score (transient.js:44-112,197-226), one thread per (sound unit, band): the
+// spectral-flux sum (serial, index order) and the four-feature score.
 // ------------------------------------------------------------------------------------
 __device__ double js_max(double a, double b) {
   if (isnan(a) || isnan(b)) return nan("");
@@ -284,70 +471,9 @@ __device__ double js_min(double a, double b) {
   return a < b ? a : b;
 }
 
-struct SpectrumFeatures {
-  double flatness, hf_ratio, energy;
-};
-
-__device__ SpectrumFeatures spectrum_features(const float *__restrict__ x, int n) {
-  SpectrumFeatures f;
-  const double EPS = 1e-10;
-  double sum_log = 0.0, sum_lin = 0.0, lo = 0.0, hi = 0.0, energy = 0.0;
-  int valid = 0;
-  const int mid = n >> 1;
-  for (int i = 0; i < n; i++) {
-    const double v = x ? (double)x[i] : 0.0;
-    const double m = fabs(v);
-    if (m > EPS) {
-      sum_log += fd::log(m);
-      sum_lin += m;
-      valid++;
-    }
-    const double sq = v * v;
-    if (i < mid) lo += sq; else hi += sq;
-    energy += sq;
-  }
-  if (valid == 0) {
-    f.flatness = 0.0;
-  } else {
-    const double geo = fd::exp(sum_log / valid);
-    const double arith = sum_lin / valid;
-    f.flatness = arith > EPS ? geo / arith : 0.0;
-  }
-  const double total = lo + hi;
-  f.hf_ratio = total > 0.0 ? hi / total : 0.0;
-  f.energy = energy;
-  return f;
-}
-
-__device__ double transient_score(const float *__restrict__ cur, const float *__restrict__ prev, int n,
-                                  double log1p10) {
-  double flux = 0.0, cur_energy = 0.0;
-  for (int i = 0; i < n; i++) {  // transient.js:92-112
-    const double c = fabs((double)cur[i]);
-    const double p = prev ? fabs((double)prev[i]) : 0.0;
-    const double d = c - p;
-    if (d > 0.0) flux += d;
-    cur_energy += c * c;
-  }
-  double norm = sqrt(cur_energy);
-  if (norm == 0.0 || isnan(norm)) norm = 1e-6;
-  const double spectral_flux = flux / norm;
-  const SpectrumFeatures fc = spectrum_features(cur, n);
-  const SpectrumFeatures fp = spectrum_features(prev, n);
-  const double flat_change = fabs(fc.flatness - fp.flatness);
-  const double hf_change = fabs(fc.hf_ratio - fp.hf_ratio);
-  const double ce = js_max(fc.energy, 1e-10), pe = js_max(fp.energy, 1e-10);  // :182-183
-  const double db = 10.0 * fd::log10(ce / pe);
-  const double e_change = js_max(0.0, db);
-  const double flat_c = sqrt(flat_change);
-  const double hf_c = fd::log1p(hf_change * 10.0) / log1p10;
-  const double e_c = js_min(e_change / 30.0, 1.0);
-  return (spectral_flux + flat_c + hf_c + e_c) / 4.0;
-}
-
 __global__ void __launch_bounds__(128)
-transient_modes_kernel(const float *__restrict__ mags, int frames, int n_su,
-                       const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
+transient_modes_kernel(const float *__restrict__ mags, const SpectrumFeatures *__restrict__ feats, int frames,
+                       int n_su, const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
                        uint8_t *__restrict__ modes, double *__restrict__ scores) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int su = idx / 3, band = idx - su * 3;
@@ -357,7 +483,30 @@ transient_modes_kernel(const float *__restrict__ mags, int frames, int n_su,
   const int off = band == 0 ? 0 : band == 1 ? 64 : 128;
   const float *cur = mags + (size_t)su * 256 + off;
   const float *prev = frame > 0 ? cur - 256 : nullptr;  // frame 0: all-zero previous spectrum
-  const double score = transient_score(cur, prev, n, T->log1p10);
+  double flux = 0.0;
+  for (int i = 0; i < n; i++) {  // transient.js:92-112
+    const double c = fabs((double)cur[i]);
+    const double p = prev ? fabs((double)prev[i]) : 0.0;
+    const double d = c - p;
+    if (d > 0.0) flux += d;
+  }
+  const SpectrumFeatures fc = feats[(size_t)su * 3 + band];
+  SpectrumFeatures fp;  // features of the all-zero spectrum: no valid bin, no energy
+  fp.flatness = 0.0; fp.hf_ratio = 0.0; fp.energy = 0.0;
+  if (prev) fp = feats[(size_t)(su - 1) * 3 + band];
+  // the flux loop's own energy sum adds the same squares in the same order as the features' one
+  double norm = sqrt(fc.energy);
+  if (norm == 0.0 || isnan(norm)) norm = 1e-6;
+  const double spectral_flux = flux / norm;
+  const double flat_change = fabs(fc.flatness - fp.flatness);
+  const double hf_change = fabs(fc.hf_ratio - fp.hf_ratio);
+  const double ce = js_max(fc.energy, 1e-10), pe = js_max(fp.energy, 1e-10);  // :182-183
+  const double db = 10.0 * fd::log10(ce / pe);
+  const double e_change = js_max(0.0, db);
+  const double flat_c = sqrt(flat_change);
+  const double hf_c = fd::log1p(hf_change * 10.0) / T->log1p10;
+  const double e_c = js_min(e_change / 30.0, 1.0);
+  const double score = (spectral_flux + flat_c + hf_c + e_c) / 4.0;
   // every band compares against transientThresholdLow (encoder.js:137-141); mode = t*max(b+1,2)
   const int transient = score > P->threshold;
   modes[(size_t)su * 4 + band] = (uint8_t)(transient ? (band == 2 ? 3 : 2) : 0);
@@ -1167,12 +1316,15 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
     prof->end(K_QMF_ANALYSIS, st);
   }
   if (!L.use_fixed) {
+    cudaError_t e2 = cudaFuncSetAttribute(transient_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTsSmemBytes);
+    if (e2 != cudaSuccess) return e2;
     prof->begin(K_BAND_MAGS, st);
-    band_mags_kernel<<<(n_su + 3) / 4, 128, 0, st>>>(L.bands, n_su, L.tables, L.mags);
+    transient_spectrum_kernel<<<std::min((n_su + kTsWarps - 1) / kTsWarps, persistent_ctas(kTsCtasPerSm)), kTsWarps * 32, kTsSmemBytes, st>>>(
+        L.bands, n_su, L.tables, L.mags, static_cast<SpectrumFeatures *>(L.feats));
     prof->end(K_BAND_MAGS, st);
     prof->begin(K_TRANSIENT_MODES, st);
-    transient_modes_kernel<<<(n_su * 3 + 127) / 128, 128, 0, st>>>(L.mags, frames, n_su, L.tables, L.params,
-                                                                  L.modes, L.scores);
+    transient_modes_kernel<<<(n_su * 3 + 127) / 128, 128, 0, st>>>(L.mags, static_cast<const SpectrumFeatures *>(L.feats),
+                                                                  frames, n_su, L.tables, L.params, L.modes, L.scores);
     prof->end(K_TRANSIENT_MODES, st);
   }
   prof->begin(K_MDCT, st);

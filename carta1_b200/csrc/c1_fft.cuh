@@ -30,9 +30,9 @@ namespace c1 {
 // conversions", which is the cost this avoids.
 struct FastRound {
   // Carriers for C: 64-bit registers whose low word stays zero for the whole kernel; a rounding
-  // only rewrites the high word (no per-rounding move to zero a fresh low word).  Four of them so
-  // that the four roundings of a butterfly do not serialise on one register.
-  double cz0 = 0.0, cz1 = 0.0, cz2 = 0.0, cz3 = 0.0;
+  // only rewrites the high word (no per-rounding move to zero a fresh low word).  Two of them so
+  // that the roundings of a butterfly do not serialise on one register.
+  double cz0 = 0.0, cz2 = 0.0;
   int clamp;  // exponent field of 2^(-126 + 29), kept in a register so add + max fuse (VIADDMNMX)
   __device__ __forceinline__ FastRound() { asm("mov.u32 %0, 0x39E00000;" : "=r"(clamp)); }
   __device__ __forceinline__ double round_with(double v, double &cz) const {
@@ -43,9 +43,13 @@ struct FastRound {
     return copysign(r, v);
   }
   __device__ __forceinline__ double r0(double v) { return round_with(v, cz0); }
-  __device__ __forceinline__ double r1(double v) { return round_with(v, cz1); }
+  // Two roundings in four go through the conversion pipe instead (cvt.rn.f32.f64 + cvt.f64.f32 is
+  // the rounding by definition): two issue slots instead of eight issue clocks each, and the XU
+  // pipe (one conversion per 8 clocks per sub-partition) has room for half of the roundings --
+  // measured: 0 of 4 -> 1.67 ms, 1 -> 1.61, 2 -> 1.57, 3 -> 1.59 (MDCT kernels, 1 h stereo).
+  __device__ __forceinline__ double r1(double v) { return (double)(float)v; }
   __device__ __forceinline__ double r2(double v) { return round_with(v, cz2); }
-  __device__ __forceinline__ double r3(double v) { return round_with(v, cz3); }
+  __device__ __forceinline__ double r3(double v) { return (double)(float)v; }
 };
 struct ExactRound {
   __device__ __forceinline__ double operator()(double v) const { return (double)(float)v; }

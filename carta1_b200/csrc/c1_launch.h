@@ -30,6 +30,7 @@ struct EncodeLaunch {
   // scratch, [n_streams][frames_total][...]
   float *bands;             // 512 per unit
   float *mags;              // 256 per unit (auto modes only)
+  void *feats;              // 3 x {flatness, hf ratio, energy} doubles per unit (auto modes only)
   uint8_t *modes;           // 4 per unit   (auto modes only)
   double *scores;           // 3 per unit, optional
   float *coefs;             // 512 per unit
