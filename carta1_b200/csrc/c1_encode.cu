@@ -901,8 +901,9 @@ mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, 
 // total, candidate n can neither win nor tie and is not run.  On broadband material fewer
 // than 1 % of the smaller candidates survive; on silence all do (and cost nothing).
 //
-// One CTA = 128 threads = 128 sound units.  Pass 1: thread u runs the 52-BFU candidate of
-// unit u.  Survivors of all units are compacted into a CTA-wide list and run 128 at a time.
+// One warp = 32 sound units, one per lane; warps are independent and persistent.  Pass 1: lane u
+// runs the 52-BFU candidate of unit u.  Survivors of the warp's units are compacted into a list
+// and run 32 at a time.
 //
 // Heap entries are one 32-bit word: key[24:10] | wl[9:6] | bfu[5:0].  `key` is an
 // order-isomorphic 15-bit image of the reference's f32 priority (DevEncParams::key0/key1):
@@ -910,7 +911,7 @@ mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, 
 // wl >= 1 the priority halves exactly with every step, i.e. key -= 128.  Heaps are stored
 // node-major / thread-minor, so a warp's 32 lanes always hit 32 distinct banks.
 // ------------------------------------------------------------------------------------
-constexpr int kAlThreads = 128;
+constexpr int kAlWarps = 4;
 
 struct AllocRec {  // per sound unit, global scratch between K4a and K4b
   uint8_t n_bfu, pad[3];
@@ -927,15 +928,16 @@ struct AllocCand {  // per sound unit: results of surviving smaller candidates
 };
 static_assert(sizeof(AllocCand) == 424, "AllocCand layout");
 
+struct AlWarpSmem {  // one warp = 32 sound units, one per lane
+  uint32_t heap[53][32];
+  uint8_t wl[52][32];
+  uint8_t sfi[32][52];
+  uint16_t list[32 * 7];
+};
 struct AlSmem {
-  uint32_t heap[53][kAlThreads];
-  uint8_t wl[52][kAlThreads];
-  uint8_t sfi[kAlThreads][52];
-  uint16_t list[kAlThreads * 7];
+  AlWarpSmem w[kAlWarps];
   uint16_t key0[64], key1[64];
-  uint8_t mode[kAlThreads][4];
   uint8_t specs[52];
-  int n_list;
 };
 
 // Shared-memory byte addresses (32-bit) keep the sift loop free of 64-bit pointer math.
@@ -947,7 +949,7 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-constexpr uint32_t kNode = kAlThreads * 4;  // byte stride between heap nodes
+constexpr uint32_t kNode = 32 * 4;  // byte stride between heap nodes
 
 // bitallocation.js:314-341.  `hole` is the address of the node being filled, `end` the
 // address of node `size`, `h0` the address of node 0; v is the entry being placed.
@@ -969,20 +971,22 @@ __device__ __forceinline__ void heap_sift(uint32_t h0, uint32_t hole, uint32_t e
 }
 
 // Greedy spend for one candidate (bitallocation.js:203-281) followed by its total
-// distortion (:157-190).  col = this thread's column in the heap / wl arrays.
-__device__ __forceinline__ double run_candidate(AlSmem &S, const DevEncParams *__restrict__ P,
+// distortion (:157-190).  col = this lane's column in the heap / wl arrays.
+__device__ __forceinline__ double run_candidate(AlWarpSmem &S, const AlSmem &C, const DevEncParams *__restrict__ P,
                                                 const FormatTables &F, const uint8_t *sfi_row, int cand,
                                                 int col) {
   const uint32_t h0 = (uint32_t)__cvta_generic_to_shared(&S.heap[0][col]);
   uint8_t *W = &S.wl[0][col];
   int remaining = kFrameBits - 40 - 10 * cand;  // bitallocation.js:97-100
   int count = 0;
+  int min_sz = 32;  // smallest BFU in the heap: nothing can be bought for less
   for (int b = 0; b < cand; b++) {  // bitallocation.js:216-232
-    W[b * kAlThreads] = 0;
+    W[b * 32] = 0;
     const uint32_t sfi = sfi_row[b];
     if (sfi) {
-      sts32(h0 + count * kNode, ((uint32_t)S.key0[sfi] << 10) | (uint32_t)b);
+      sts32(h0 + count * kNode, ((uint32_t)C.key0[sfi] << 10) | (uint32_t)b);
       count++;
+      min_sz = min(min_sz, (int)C.specs[b]);
     }
   }
   sts32(h0 + count * kNode, 0);
@@ -990,19 +994,22 @@ __device__ __forceinline__ double run_candidate(AlSmem &S, const DevEncParams *_
     uint32_t end = h0 + count * kNode;
     for (int i = (count >> 1) - 1; i >= 0; i--) heap_sift(h0, h0 + i * kNode, end, lds32(h0 + i * kNode));
     uint32_t e = lds32(h0);
-    while (remaining > 0) {  // bitallocation.js:244-278 (size > 0 is the loop's other exit)
+    // bitallocation.js:244-278 (size > 0 is the loop's other exit).  Once fewer bits remain than
+    // the smallest BFU costs, every further iteration of the reference's loop is a pop that
+    // changes nothing: stop there.
+    while (remaining >= min_sz) {
       const int b = e & 63;
       const int wl = (e >> 6) & 15;
-      const int cost = (int)S.specs[b] << (wl == 0);
+      const int cost = (int)C.specs[b] << (wl == 0);
       bool pop = cost > remaining;
       if (!pop) {
         remaining -= cost;
-        if (wl == 0) e = ((uint32_t)S.key1[sfi_row[b]] << 10) | (1u << 6) | (uint32_t)b;
+        if (wl == 0) e = ((uint32_t)C.key1[sfi_row[b]] << 10) | (1u << 6) | (uint32_t)b;
         else e += 64u - (128u << 10);  // wl + 1, priority halves exactly
         pop = wl == 14;                // reached MAX_WORD_LENGTH_INDEX
       }
       if (pop) {
-        W[b * kAlThreads] = (uint8_t)((e >> 6) & 15);
+        W[b * 32] = (uint8_t)((e >> 6) & 15);
         end -= kNode;
         if (end == h0) break;
         e = lds32(end);
@@ -1013,143 +1020,133 @@ __device__ __forceinline__ double run_candidate(AlSmem &S, const DevEncParams *_
     }
     for (uint32_t a = h0; a < end; a += kNode) {  // entries still in the heap keep their wl
       const uint32_t x = lds32(a);
-      W[(x & 63) * kAlThreads] = (uint8_t)((x >> 6) & 15);
+      W[(x & 63) * 32] = (uint8_t)((x >> 6) & 15);
     }
   }
   double total = 0.0;
   for (int i = 0; i < 52; i++) {
     const int sfi = sfi_row[i];
     if (sfi == 0) continue;  // the reference adds +0.0 or skips
-    const int bits = i < cand ? wl_bits(W[i * kAlThreads]) : 0;
+    const int bits = i < cand ? wl_bits(W[i * 32]) : 0;
     if (bits == 0) {
       total += (double)P->zero_bit[sfi * 8 + F.size_class[i]];
     } else {
       const double inv = __hiloint2double((1023 - bits) << 20, 0);
-      total += P->bsf[sfi] * inv * (double)S.specs[i];
+      total += P->bsf[sfi] * inv * (double)C.specs[i];
     }
   }
   return total;
 }
 
-__global__ void __launch_bounds__(kAlThreads)
-alloc_kernel(const uint8_t *__restrict__ sfi_all, const uint8_t *__restrict__ modes, int frames, int halo,
-             int n_out_frames, int n_streams, const DevTables *__restrict__ T,
-             const DevEncParams *__restrict__ P, AllocRec *__restrict__ recs, AllocCand *__restrict__ cands) {
+// Warps are independent (no CTA barrier after the tables are staged) and persistent: a warp
+// walks groups of 32 consecutive output units, one unit per lane.
+__global__ void __launch_bounds__(kAlWarps * 32)
+alloc_kernel(const uint8_t *__restrict__ sfi_all, int frames, int halo, int n_out_frames, int n_streams,
+             const DevTables *__restrict__ T, const DevEncParams *__restrict__ P, AllocRec *__restrict__ recs,
+             AllocCand *__restrict__ cands) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  AlSmem &S = *reinterpret_cast<AlSmem *>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31;
+  AlSmem &C = *reinterpret_cast<AlSmem *>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  AlWarpSmem &S = C.w[warp];
   const long long n_units = (long long)n_streams * n_out_frames;
-  const long long unit0 = (long long)blockIdx.x * kAlThreads;
   const FormatTables &F = T->fmt;
-
-  if (tid < 64) { S.key0[tid] = P->key0[tid]; S.key1[tid] = P->key1[tid]; }
-  if (tid < 52) S.specs[tid] = F.specs[tid];
-  if (tid == 0) S.n_list = 0;
-  {
-    const long long unit = unit0 + tid;
-    uint8_t m0 = 0, m1 = 0, m2 = 0;
-    if (unit < n_units) {
-      if (P->use_fixed) {
-        m0 = P->fixed[0] != 0; m1 = P->fixed[1] != 0; m2 = P->fixed[2] != 0;
-      } else {
+  if (tid < 64) { C.key0[tid] = P->key0[tid]; C.key1[tid] = P->key1[tid]; }
+  if (tid < 52) C.specs[tid] = F.specs[tid];
+  __syncthreads();
+  const long long n_groups = (n_units + 31) / 32;
+  for (long long group = (long long)blockIdx.x * kAlWarps + warp; group < n_groups; group += (long long)gridDim.x * kAlWarps) {
+    const long long unit0 = group * 32;
+    __syncwarp();
+    // ---- phase A: the scale-factor indices the MDCT kernels left per unit (64-byte records)
+    for (int item = lane; item < 32 * 13; item += 32) {
+      const int u = item / 13, w = item - u * 13;
+      const long long unit = unit0 + u;
+      uint32_t v = 0;
+      if (unit < n_units) {
         const size_t su = (size_t)(unit / n_out_frames) * frames + halo + (size_t)(unit % n_out_frames);
-        m0 = modes[su * 4]; m1 = modes[su * 4 + 1]; m2 = modes[su * 4 + 2];
+        v = __ldg(reinterpret_cast<const uint32_t *>(sfi_all + su * 64) + w);
+      }
+      reinterpret_cast<uint32_t *>(&S.sfi[u][0])[w] = v;
+    }
+    __syncwarp();
+    // ---- pass 1: the 52-BFU candidate of the lane's unit; its result is the provisional record
+    const bool live = unit0 + lane < n_units;
+    double total52 = 0.0;
+    uint32_t survive = 0;
+    if (live) {
+      total52 = run_candidate(S, C, P, F, S.sfi[lane], 52, lane);
+      AllocRec *r = recs + (unit0 + lane);
+      r->n_bfu = 52;
+      for (int b = 0; b < 52; b++) { r->wl[b] = S.wl[b][lane]; r->sfi[b] = S.sfi[lane][b]; }
+      // Candidate pruning (exact): candidate n leaves BFUs >= n uncoded, which alone costs
+      // tail(n) = sum_{i>=n} zeroBit[i]; if that, deflated by the worst-case rounding of the
+      // reference's own 52-term summation (1 - 2^-40), already exceeds the 52-BFU total, the
+      // candidate can neither win nor tie and is not run.
+      double tail = 0.0;
+      int c = 6;
+      for (int i = 51; i >= 20; i--) {
+        const int sfi = S.sfi[lane][i];
+        if (sfi) tail += (double)P->zero_bit[sfi * 8 + F.size_class[i]];
+        const int bound = c == 0 ? 20 : 24 + 4 * c;  // BFU_AMOUNTS[c]
+        if (i == bound) {
+          if (!(tail * (1.0 - 9.094947017729282e-13) > total52)) survive |= 1u << c;
+          c--;
+        }
       }
     }
-    S.mode[tid][0] = m0; S.mode[tid][1] = m1; S.mode[tid][2] = m2;
-  }
-  __syncthreads();
-
-  // ---- phase A: the scale-factor indices the MDCT kernels left per unit (64-byte records)
-  for (int item = tid; item < kAlThreads * 13; item += kAlThreads) {
-    const int u = item / 13, w = item - u * 13;
-    const long long unit = unit0 + u;
-    uint32_t v = 0;
-    if (unit < n_units) {
-      const size_t su = (size_t)(unit / n_out_frames) * frames + halo + (size_t)(unit % n_out_frames);
-      v = __ldg(reinterpret_cast<const uint32_t *>(sfi_all + su * 64) + w);
-    }
-    reinterpret_cast<uint32_t *>(&S.sfi[u][0])[w] = v;
-  }
-  __syncthreads();
-
-  // ---- pass 1: the 52-BFU candidate of unit `tid`; its result is the provisional record
-  const bool live = unit0 + tid < n_units;
-  double total52 = 0.0;
-  uint32_t survive = 0;
-  if (live) {
-    total52 = run_candidate(S, P, F, S.sfi[tid], 52, tid);
-    AllocRec *r = recs + (unit0 + tid);
-    r->n_bfu = 52;
-    for (int b = 0; b < 52; b++) { r->wl[b] = S.wl[b][tid]; r->sfi[b] = S.sfi[tid][b]; }
-    // tails of the smaller candidates, from the top BFU down
-    double tail = 0.0;
-    int c = 6;
-    for (int i = 51; i >= 20; i--) {
-      const int sfi = S.sfi[tid][i];
-      if (sfi) tail += (double)P->zero_bit[sfi * 8 + F.size_class[i]];
-      const int bound = c == 0 ? 20 : 24 + 4 * c;  // BFU_AMOUNTS[c]
-      if (i == bound) {
-        // 1 - 2^-40 covers the rounding of the reference's own 52-term summation
-        if (!(tail * (1.0 - 9.094947017729282e-13) > total52)) survive |= 1u << c;
-        c--;
-      }
-    }
-  }
-  // ---- compact the surviving (unit, candidate) pairs of the CTA
-  {
-    const int n = __popc(survive);
-    int incl = n;
+    // ---- compact the surviving (unit, candidate) pairs of the warp and run them 32 at a time
+    const int n_mine = __popc(survive);
+    int incl = n_mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += t;
     }
-    int base = 0;
-    if (lane == 31 && incl) base = atomicAdd(&S.n_list, incl);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    int at = base + incl - n;
-    for (uint32_t m = survive; m; m &= m - 1) S.list[at++] = (uint16_t)((tid << 3) | (__ffs(m) - 1));
-  }
-  __syncthreads();
-  const int n_list = S.n_list;
-  for (int base = 0; base < n_list; base += kAlThreads) {  // uniform trip count
-    const int k = base + tid;
-    if (k < n_list) {
-      const int u = S.list[k] >> 3, c = S.list[k] & 7;
-      const int cand = c == 0 ? 20 : 24 + 4 * c;
-      const double total = run_candidate(S, P, F, S.sfi[u], cand, tid);
-      AllocCand *ac = cands + (unit0 + u);
-      ac->total[c] = total;
-      for (int b = 0; b < cand; b++) ac->wl[c][b] = S.wl[b][tid];
+    const int n_list = __shfl_sync(0xffffffffu, incl, 31);
+    {
+      int at = incl - n_mine;
+      for (uint32_t m = survive; m; m &= m - 1) S.list[at++] = (uint16_t)((lane << 3) | (__ffs(m) - 1));
     }
-    __syncthreads();  // also orders the global writes before the selection below
-  }
-  __threadfence_block();
-  // ---- first strict minimum over ascending candidates (bitallocation.js:91-130)
-  if (live && survive) {
-    const AllocCand *ac = cands + (unit0 + tid);
-    double min_total = __longlong_as_double(0x7ff0000000000000ll);
-    int best = -1;
-    for (int c = 0; c < 7; c++) {
-      if (!(survive >> c & 1)) continue;
-      const double t = ac->total[c];
-      if (t < min_total) { min_total = t; best = c; }
+    __syncwarp();
+    for (int base = 0; base < n_list; base += 32) {  // uniform trip count
+      const int k = base + lane;
+      if (k < n_list) {
+        const int u = S.list[k] >> 3, c = S.list[k] & 7;
+        const int cand = c == 0 ? 20 : 24 + 4 * c;
+        const double total = run_candidate(S, C, P, F, S.sfi[u], cand, lane);
+        AllocCand *ac = cands + (unit0 + u);
+        ac->total[c] = total;
+        for (int b = 0; b < cand; b++) ac->wl[c][b] = S.wl[b][lane];
+      }
+      __syncwarp();
     }
-    if (total52 < min_total) best = 7;
-    AllocRec *r = recs + (unit0 + tid);
-    if (best < 0) {  // bitallocation.js:132-139
+    __threadfence_block();
+    __syncwarp();
+    // ---- first strict minimum over ascending candidates (bitallocation.js:91-130)
+    if (live && survive) {
+      const AllocCand *ac = cands + (unit0 + lane);
+      double min_total = __longlong_as_double(0x7ff0000000000000ll);
+      int best = -1;
+      for (int c = 0; c < 7; c++) {
+        if (!(survive >> c & 1)) continue;
+        const double t = ac->total[c];
+        if (t < min_total) { min_total = t; best = c; }
+      }
+      if (total52 < min_total) best = 7;
+      AllocRec *r = recs + (unit0 + lane);
+      if (best < 0) {  // bitallocation.js:132-139
+        r->n_bfu = 20;
+        for (int b = 0; b < 52; b++) { r->wl[b] = 0; r->sfi[b] = 0; }
+      } else if (best < 7) {
+        const int cand = best == 0 ? 20 : 24 + 4 * best;
+        r->n_bfu = (uint8_t)cand;
+        for (int b = 0; b < 52; b++) r->wl[b] = b < cand ? ac->wl[best][b] : 0;
+      }
+    } else if (live && !(total52 < __longlong_as_double(0x7ff0000000000000ll))) {
+      AllocRec *r = recs + (unit0 + lane);  // no finite candidate at all: the reference's fallback
       r->n_bfu = 20;
       for (int b = 0; b < 52; b++) { r->wl[b] = 0; r->sfi[b] = 0; }
-    } else if (best < 7) {
-      const int cand = best == 0 ? 20 : 24 + 4 * best;
-      r->n_bfu = (uint8_t)cand;
-      for (int b = 0; b < 52; b++) r->wl[b] = b < cand ? ac->wl[best][b] : 0;
     }
-  } else if (live && !(total52 < __longlong_as_double(0x7ff0000000000000ll))) {
-    AllocRec *r = recs + (unit0 + tid);  // no finite candidate at all: the reference's fallback
-    r->n_bfu = 20;
-    for (int b = 0; b < 52; b++) { r->wl[b] = 0; r->sfi[b] = 0; }
   }
 }
 
@@ -1347,9 +1344,10 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
     if (e != cudaSuccess) return e;
     AllocRec *recs = static_cast<AllocRec *>(L.alloc_recs);
     AllocCand *cands = reinterpret_cast<AllocCand *>(recs + n_units);
+    const long long n_groups = (n_units + 31) / 32;
     prof->begin(K_ALLOC, st);
-    alloc_kernel<<<(unsigned)((n_units + kAlThreads - 1) / kAlThreads), kAlThreads, sizeof(AlSmem), st>>>(
-        L.sfi, L.modes, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params, recs, cands);
+    alloc_kernel<<<(unsigned)std::min<long long>((n_groups + kAlWarps - 1) / kAlWarps, persistent_ctas(5)), kAlWarps * 32, sizeof(AlSmem), st>>>(
+        L.sfi, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params, recs, cands);
     prof->end(K_ALLOC, st);
     prof->begin(K_QUANT_PACK, st);
     quant_pack_kernel<<<(unsigned)std::min<long long>((n_units + kQpWarps - 1) / kQpWarps, persistent_ctas(6)), kQpWarps * 32, 0, st>>>(
