@@ -316,12 +316,15 @@ class StreamEncoder:
         ctx._check(ctx.L.carta1_enc_create(ctx.h, C.byref(opts) if opts is not None else None, n_streams, C.byref(h)))
         self.h = h
 
-    def frames(self, pcm: np.ndarray) -> np.ndarray:
+    def frames(self, pcm: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """pcm [n_streams][n_frames][512] -> sound units [n_streams][n_frames][212] (into `out` if given,
+        e.g. a pinned buffer)."""
         pcm = np.ascontiguousarray(pcm, np.float32).reshape(self.n_streams, -1, FRAME)
         nf = pcm.shape[1]
-        su = np.zeros((self.n_streams, nf, SU_BYTES), np.uint8)
+        su = np.empty((self.n_streams, nf, SU_BYTES), np.uint8) if out is None else out
+        assert su.dtype == np.uint8 and su.size == self.n_streams * nf * SU_BYTES and su.flags.c_contiguous
         self.ctx._check(self.ctx.L.carta1_enc_frames(self.h, _ptr(pcm), nf, _ptr(su)))
-        return su
+        return su.reshape(self.n_streams, nf, SU_BYTES)
 
     def reset(self):
         self.ctx._check(self.ctx.L.carta1_enc_reset(self.h))
@@ -347,12 +350,14 @@ class StreamDecoder:
         ctx._check(ctx.L.carta1_dec_create(ctx.h, n_streams, C.byref(h)))
         self.h = h
 
-    def frames(self, su: np.ndarray) -> np.ndarray:
+    def frames(self, su: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """sound units [n_streams][n_frames][212] -> pcm [n_streams][n_frames][512] (into `out` if given)."""
         su = np.ascontiguousarray(su, np.uint8).reshape(self.n_streams, -1, SU_BYTES)
         nf = su.shape[1]
-        pcm = np.zeros((self.n_streams, nf, FRAME), np.float32)
+        pcm = np.empty((self.n_streams, nf, FRAME), np.float32) if out is None else out
+        assert pcm.dtype == np.float32 and pcm.size == self.n_streams * nf * FRAME and pcm.flags.c_contiguous
         self.ctx._check(self.ctx.L.carta1_dec_frames(self.h, _ptr(su), nf, _ptr(pcm)))
-        return pcm
+        return pcm.reshape(self.n_streams, nf, FRAME)
 
     def frames_expanded(self, q: np.ndarray, sfi: np.ndarray, bits: np.ndarray, modes: np.ndarray) -> np.ndarray:
         """Frame objects in position-expanded form (carta1_dec_frames_expanded)."""
