@@ -290,14 +290,13 @@ unpack_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_
 // ------------------------------------------------------------------------------------
 template <int kRole, typename R>
 __device__ __forceinline__ void imdct_long_task(unsigned long_mask, float *rows, double2 *xbuf_all,
-                                                const DevTables *__restrict__ T, int lane) {
+                                                const double *tab, const double2 *tw, int lane) {
   using G = LongGeom<kRole>;
   constexpr int kSize = G::kSize;
   R rnd;
   const G g(lane);
   float *xb = rows + g.x * kSize;
   const bool rev = kRole == 1 || (g.x & 1);  // utils.js:42-48: un-reverse mid / high spectra
-  const double *tab = kRole == 0 ? T->mdct_inv256 : T->mdct_inv512;
   const float *pa = xb + 2 * g.rev_t, *pb = xb + (kSize - 1) - 2 * g.rev_t;
   const double *ptab = tab + 2 * g.rev_t;
   Cplx v[8];
@@ -307,11 +306,11 @@ __device__ __forceinline__ void imdct_long_task(unsigned long_mask, float *rows,
     const float fa = pa[i0], fb = pb[-i0];  // x[2q], x[size - 1 - 2q]
     const double r = -(double)(rev ? fb : fa);
     const double m = -(double)(rev ? fa : fb);
-    const double2 cs = __ldg(reinterpret_cast<const double2 *>(ptab + i0));
+    const double2 cs = *reinterpret_cast<const double2 *>(ptab + i0);
     v[j].re = rnd.r0(m * cs.y + r * cs.x);
     v[j].im = rnd.r1(m * cs.x - r * cs.y);
   }
-  fft_long_inthread<kRole>(v, g, xbuf_all + g.x * G::kSlots, T->fft_tw, rnd);
+  fft_long_inthread<kRole>(v, g, xbuf_all + g.x * G::kSlots, tw, rnd);
   if ((long_mask >> g.x) & 1) {
     // mdct.js:177-208 restricted to output[n/4 .. 3n/4): FFT output i gives y[2i] and y[size-1-2i].
     // Record position of y[q]: q + 16, except q < 16 -> q (head) and q >= size - 16 -> q - size + 32
@@ -324,7 +323,7 @@ __device__ __forceinline__ void imdct_long_task(unsigned long_mask, float *rows,
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int st = G::out_step(k);
-      const double2 cs = __ldg(pt + st);
+      const double2 cs = pt[st];
       const float y1 = (float)(v[k].re * cs.x + v[k].im * cs.y);  // y[size - 1 - 2i]
       const float y0 = (float)(v[k].re * cs.y - v[k].im * cs.x);  // y[2i]
       int d0 = 2 * st, d1 = -2 * st;
@@ -338,8 +337,8 @@ __device__ __forceinline__ void imdct_long_task(unsigned long_mask, float *rows,
 
 template <int kRole>
 __device__ __noinline__ void imdct_long_task_exact(unsigned long_mask, float *rows, double2 *xbuf_all,
-                                                   const DevTables *__restrict__ T, int lane) {
-  imdct_long_task<kRole, ExactRound>(long_mask, rows, xbuf_all, T, lane);
+                                                   const double *tab, const double2 *tw, int lane) {
+  imdct_long_task<kRole, ExactRound>(long_mask, rows, xbuf_all, tab, tw, lane);
 }
 
 // Short blocks of one band (rare: out of line): transform in place, then assemble the record
@@ -372,7 +371,11 @@ struct ImdctWarpSmem {
   float rows[512];                         // role 0: 4 x 128, role 1: 2 x 256
 };
 static_assert(4 * LongGeom<0>::kSlots == 2 * LongGeom<1>::kSlots, "xbuf");
-constexpr size_t kImdctSmemBytes = sizeof(ImdctWarpSmem) * kImdctWarps;
+struct ImdctTables {  // staged once per CTA: pre/post table (N/2 doubles), FFT twiddles of stages 3..
+  double tab[256];
+  double2 tw[128];
+};
+constexpr size_t kImdctSmemBytes = sizeof(ImdctWarpSmem) * kImdctWarps + sizeof(ImdctTables);
 
 // One kernel per role (see mdct_kernel): the hot loop stays inside the instruction cache.
 template <int kRole>
@@ -385,6 +388,13 @@ imdct_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes,
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   ImdctWarpSmem &S = reinterpret_cast<ImdctWarpSmem *>(smem_raw)[warp];
+  ImdctTables &ST = *reinterpret_cast<ImdctTables *>(smem_raw + sizeof(ImdctWarpSmem) * kImdctWarps);
+  {
+    const double *tab = kRole == 0 ? T->mdct_inv256 : T->mdct_inv512;
+    for (int i = threadIdx.x; i < G::kN / 2; i += blockDim.x) ST.tab[i] = tab[i];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) ST.tw[i] = T->fft_tw[i];
+  }
+  __syncthreads();
   const int n_pairs = (n_units + 1) >> 1;
   for (int pair = blockIdx.x * kImdctWarps + warp; pair < n_pairs; pair += gridDim.x * kImdctWarps) {
     __syncwarp();
@@ -420,8 +430,8 @@ imdct_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes,
     // 0x71800000 is 2^100 as binary32: below it FastRound is exact for every transform value
     const bool fast = __reduce_max_sync(0xffffffffu, big) < 0x71800000u;
     if (long_mask) {
-      if (fast) imdct_long_task<kRole, FastRound>(long_mask, S.rows, S.xbuf, T, lane);
-      else imdct_long_task_exact<kRole>(long_mask, S.rows, S.xbuf, T, lane);
+      if (fast) imdct_long_task<kRole, FastRound>(long_mask, S.rows, S.xbuf, ST.tab, ST.tw, lane);
+      else imdct_long_task_exact<kRole>(long_mask, S.rows, S.xbuf, ST.tab, ST.tw, lane);
       __syncwarp();
     }
     if (short_mask) {

@@ -645,7 +645,7 @@ __device__ __forceinline__ Cplx mdct_pre_long(const double *pr, const double *pm
   } else {
     m = m + 0.0;
   }
-  const double2 cs = __ldg(reinterpret_cast<const double2 *>(ptab + i0));
+  const double2 cs = *reinterpret_cast<const double2 *>(ptab + i0);
   Cplx z;
   z.re = rnd.r0(r * cs.x + m * cs.y);
   z.im = rnd.r1(m * cs.x - r * cs.y);
@@ -668,19 +668,18 @@ __device__ __forceinline__ void mdct_pre_all(Cplx (&v)[8], const double *pr, con
 // kPerWarp x kSize coefficients.  Transforms whose bit in long_mask is clear (short mode) run the
 // same instructions on whatever their buffer holds and do not store.
 template <int kRole, typename R>
-__device__ __forceinline__ void mdct_long_task(unsigned long_mask, double *arr, float *out,
-                                               const DevTables *__restrict__ T, int lane) {
+__device__ __forceinline__ void mdct_long_task(unsigned long_mask, double *arr, float *out, const double *tab,
+                                               const double2 *tw, int lane) {
   using G = LongGeom<kRole>;
   constexpr int kWs = kRole == 0 ? 48 : 112;  // constants.js:115-119
   constexpr int kN = G::kN, kBuf = G::kSize + 32;
   R rnd;
   const G g(lane);
   double *a = arr + g.x * kBuf;
-  const double *tab = kRole == 0 ? T->mdct_fwd256 : T->mdct_fwd512;
   Cplx v[8];
   mdct_pre_all<kRole, 0>(v, a + (3 * kN / 4 - 1 - kWs) - 2 * g.rev_t, a + (kN / 4 - kWs) + 2 * g.rev_t,
                          tab + 2 * g.rev_t, g.t, rnd);
-  fft_long_inthread<kRole>(v, g, reinterpret_cast<double2 *>(a), T->fft_tw, rnd);
+  fft_long_inthread<kRole>(v, g, reinterpret_cast<double2 *>(a), tw, rnd);
   if ((long_mask >> g.x) & 1) {
     // mdct.js:111-119; spectrum reversed for the mid and high bands (utils.js:42-48)
     const bool reverse = kRole == 1 || (g.x & 1);
@@ -692,7 +691,7 @@ __device__ __forceinline__ void mdct_long_task(unsigned long_mask, double *arr, 
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int st = G::out_step(k);
-      const double2 cs = __ldg(pt + st);
+      const double2 cs = pt[st];
       const float c0 = (float)(-v[k].re * cs.x - v[k].im * cs.y);
       const float c1 = (float)(-v[k].re * cs.y + v[k].im * cs.x);
       if (reverse) { o0[-2 * st] = c0; o1[2 * st] = c1; }
@@ -703,9 +702,9 @@ __device__ __forceinline__ void mdct_long_task(unsigned long_mask, double *arr, 
 static_assert(LongGeom<0>::kSlots * 2 <= 160 && LongGeom<1>::kSlots * 2 <= 288, "transpose buffers alias the input buffers");
 
 template <int kRole>
-__device__ __noinline__ void mdct_long_task_exact(unsigned long_mask, double *arr, float *out,
-                                                  const DevTables *__restrict__ T, int lane) {
-  mdct_long_task<kRole, ExactRound>(long_mask, arr, out, T, lane);
+__device__ __noinline__ void mdct_long_task_exact(unsigned long_mask, double *arr, float *out, const double *tab,
+                                                  const double2 *tw, int lane) {
+  mdct_long_task<kRole, ExactRound>(long_mask, arr, out, tab, tw, lane);
 }
 
 constexpr int kMdctWarps = 8, kMdctCtasPerSm = 3;
@@ -715,7 +714,13 @@ struct MdctWarpSmem {
   double arr[640];  // role 0: 4 x 160, role 1: 2 x 288; short blocks: up to 512
   float out[512];   // role 0: 4 x 128, role 1: 2 x 256 (also absorbs the overshoot past arr)
 };
-constexpr size_t kMdctSmemBytes = sizeof(MdctWarpSmem) * kMdctWarps;
+// twiddle tables of the role, staged once per CTA: pre/post table (N/2 doubles) and the FFT
+// recurrence twiddles of stages 3.. (indices below 128)
+struct MdctTables {
+  double tab[256];
+  double2 tw[128];
+};
+constexpr size_t kMdctSmemBytes = sizeof(MdctWarpSmem) * kMdctWarps + sizeof(MdctTables);
 
 // Short blocks of one band (encoder.js:279-304): block b transforms
 // [WIN * previous block (32) | block * reversed WIN (32)].  c: the band's samples of this frame
@@ -763,7 +768,8 @@ __device__ __forceinline__ void mdct_warp_task(int pair, const float *__restrict
                                                const uint8_t *__restrict__ modes, int frames, int n_su,
                                                const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
                                                float *__restrict__ coefs, uint8_t *__restrict__ sfi_out,
-                                               MdctWarpSmem &S, int lane, double w_fwd, double w_rev) {
+                                               MdctWarpSmem &S, const double *s_tab, const double2 *s_tw, int lane,
+                                               double w_fwd, double w_rev) {
   using G = LongGeom<kRole>;
   constexpr int kSize = G::kSize, kBuf = kSize + 32, kPer = G::kPerWarp / 2;  // transforms per unit
   constexpr int kOff = kRole == 0 ? 0 : 256;                                // first band sample of the role
@@ -827,8 +833,8 @@ __device__ __forceinline__ void mdct_warp_task(int pair, const float *__restrict
   // threshold, the one case FastRound cannot round
   const bool fast = __reduce_max_sync(0xffffffffu, big) < 0x71800000u;
   if (long_mask) {
-    if (fast) mdct_long_task<kRole, FastRound>(long_mask, arr, out, T, lane);
-    else mdct_long_task_exact<kRole>(long_mask, arr, out, T, lane);
+    if (fast) mdct_long_task<kRole, FastRound>(long_mask, arr, out, s_tab, s_tw, lane);
+    else mdct_long_task_exact<kRole>(long_mask, arr, out, s_tab, s_tw, lane);
     __syncwarp();
   }
   // ---- short blocks, one band at a time (rare: out of line)
@@ -880,11 +886,18 @@ mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   MdctWarpSmem &S = reinterpret_cast<MdctWarpSmem *>(smem_raw)[warp];
+  MdctTables &ST = *reinterpret_cast<MdctTables *>(smem_raw + sizeof(MdctWarpSmem) * kMdctWarps);
+  {
+    const double *tab = kRole == 0 ? T->mdct_fwd256 : T->mdct_fwd512;
+    for (int i = threadIdx.x; i < LongGeom<kRole>::kN / 2; i += blockDim.x) ST.tab[i] = tab[i];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) ST.tw[i] = T->fft_tw[i];
+  }
+  __syncthreads();
   const double w_fwd = T->win[lane], w_rev = T->win[31 - lane];  // WINDOW_SHORT[i], [31 - i]
   const int n_pairs = (n_su + 1) >> 1;
   // persistent warps: the grid is sized to the machine and every warp walks the unit pairs
   for (int pair = blockIdx.x * kMdctWarps + warp; pair < n_pairs; pair += gridDim.x * kMdctWarps)
-    mdct_warp_task<kRole>(pair, bands, modes, frames, n_su, T, P, coefs, sfi_out, S, lane, w_fwd, w_rev);
+    mdct_warp_task<kRole>(pair, bands, modes, frames, n_su, T, P, coefs, sfi_out, S, ST.tab, ST.tw, lane, w_fwd, w_rev);
 }
 
 // ------------------------------------------------------------------------------------

@@ -170,7 +170,7 @@ __device__ __forceinline__ void fft8_pass_b(Cplx (&v)[8], const double2 *__restr
     const int d = 1 << ls, half = 8 << ls;
 #pragma unroll
     for (int m = 0; m < 8; m++)
-      if (!(m & d)) butterfly(v[m], v[m + d], __ldg(tw_u + half - 1 + 8 * (m & (d - 1))), rnd);
+      if (!(m & d)) butterfly(v[m], v[m + d], tw_u[half - 1 + 8 * (m & (d - 1))], rnd);
   }
 }
 
@@ -179,7 +179,7 @@ __device__ __forceinline__ void fft8_pass_b(Cplx (&v)[8], const double2 *__restr
 template <typename R>
 __device__ __forceinline__ void fft8_pass_c(Cplx (&v)[8], const double2 *__restrict__ tw_uh, R &rnd) {
 #pragma unroll
-  for (int k = 0; k < 4; k++) butterfly(v[k], v[4 + k], __ldg(tw_uh + 63 + 8 * k), rnd);
+  for (int k = 0; k < 4; k++) butterfly(v[k], v[4 + k], tw_uh[63 + 8 * k], rnd);
 }
 
 template <int kRole>
