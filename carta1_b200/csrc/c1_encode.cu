@@ -1170,12 +1170,18 @@ alloc_kernel(const uint8_t *__restrict__ sfi_all, int frames, int halo, int n_ou
 // position table gives (BFU, index inside the BFU) in one load, a 16-byte record per BFU the
 // norm factor, bit offset, width and range in another.
 // ------------------------------------------------------------------------------------
+// OR the low `bits` bits of value into the big-endian bit image at bit position pos (MSB first,
+// bitstream.js:15-39).  The code is aligned to the top of a word, split at the word boundary with
+// two funnel shifts and merged with predicated shared-memory reductions (no branches).
+__device__ __forceinline__ void red_or_shared(uint32_t addr, uint32_t v) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.or.b32 [%0], %1;\n\t}" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void put_bits(uint32_t *words, int pos, uint32_t value, int bits) {
-  const int w = pos >> 5, off = pos & 31;
-  const unsigned long long v = (unsigned long long)value << (64 - off - bits);
-  const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
-  if (hi) atomicOr(&words[w], hi);
-  if (lo) atomicOr(&words[w + 1], lo);
+  const uint32_t t = value << (32 - bits);  // also drops the sign-extension bits of a negative code
+  const int off = pos & 31;
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(words) + ((pos >> 5) << 2);
+  red_or_shared(addr, t >> off);
+  red_or_shared(addr + 4, __funnelshift_r(0u, t, off));  // off == 0: nothing spills over
 }
 
 constexpr int kQpWarps = 8;
@@ -1273,7 +1279,7 @@ quant_pack_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ m
         int y = wrap ? js_to_int32(x + (x >= 0.0 ? 0.5 : -0.5)) : __double2int_rz(xs);
         if (rec.norm == 0.0) y = 0;  // covers c == +-inf with norm == 0 (inf * 0 = NaN either way) and NaN signs
         const int q = min(max(y, -range), range);
-        put_bits(words, (int)(rec.base_bits & 2047u) + (int)(bj & 31u) * bits, (uint32_t)q & ((1u << bits) - 1u), bits);
+        put_bits(words, (int)(rec.base_bits & 2047u) + (int)(bj & 31u) * bits, (uint32_t)q, bits);
       }
     }
     __syncwarp();
