@@ -193,6 +193,47 @@ bool build_enc_params(const carta1_tables &t, const carta1_enc_opts &o, DevEncPa
   return true;
 }
 
+constexpr int kSlots = 4;       // PCM staging slots of the pipelined host entry points
+constexpr int kUnitSlots = 32;  // sound-unit input slots of the decoder (a tenth of the PCM bytes): deep enough that
+                                // the uploads of a whole hour are queued before anything else competes for the copy engine
+
+// Development aid (CARTA1_TRACE_PASSES=1): device timestamps of every pass's H2D, compute and D2H
+// phases, printed to stderr when the call returns.
+struct PassTrace {
+  bool on = false;
+  cudaEvent_t t0 = nullptr;
+  std::vector<cudaEvent_t> ev;  // 6 per pass: h2d begin/end, compute begin/end, d2h begin/end
+  const char *what = "";
+  void start(const char *w, cudaStream_t st) {
+    const char *v = getenv("CARTA1_TRACE_PASSES");
+    on = v && *v && *v != '0';
+    what = w;
+    if (!on) return;
+    cudaEventCreate(&t0);
+    cudaEventRecord(t0, st);
+  }
+  void mark(cudaStream_t st) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+  }
+  void report() {
+    if (!on) return;
+    for (size_t i = 0; i + 5 < ev.size(); i += 6) {
+      float t[6];
+      for (int k = 0; k < 6; k++) cudaEventElapsedTime(&t[k], t0, ev[i + k]);
+      fprintf(stderr, "[carta1 %s] pass %2zu  h2d %7.2f-%7.2f  compute %7.2f-%7.2f  d2h %7.2f-%7.2f ms\n", what, i / 6,
+              t[0], t[1], t[2], t[3], t[4], t[5]);
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    cudaEventDestroy(t0);
+    ev.clear();
+    on = false;
+  }
+};
+
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
@@ -224,11 +265,13 @@ struct carta1_ctx {
   carta1_enc_opts params_opts;
   double params_bsf[64];
   DevBuf bands, mags, feats, modes, coefs, sfi, inv, scores, dbg, recs;
-  // Host entry points: passes are double-buffered so that the H2D copy of pass i+1 and the D2H
+  // Host entry points: passes rotate through kSlots staging slots so that the H2D copy of pass i+1 and the D2H
   // copy of pass i-1 run while pass i computes (three streams, events between them).
-  DevBuf stage_pcm[2], stage_su[2];
+  DevBuf stage_pcm[kSlots], stage_su[kUnitSlots];
   cudaStream_t h2d = nullptr, d2h = nullptr;
-  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  cudaStream_t small = nullptr;  // highest priority: the sound-unit side of a host call (see small_copy)
+  cudaEvent_t ev_in[kSlots] = {}, ev_comp[kSlots] = {}, ev_out[kSlots] = {};
+  cudaEvent_t ev_uin[kUnitSlots] = {}, ev_ucomp[kUnitSlots] = {};
   size_t max_units_per_pass = 1u << 16;  // frames*channels per pass of the chunked host entry points
 };
 
@@ -364,10 +407,19 @@ int carta1_ctx_create(int device, const carta1_tables *tables, carta1_ctx **out)
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking);
-  for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+  if (e == cudaSuccess) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    e = cudaStreamCreateWithPriority(&ctx->small, cudaStreamNonBlocking, hi);
+  }
+  for (int i = 0; i < kSlots && e == cudaSuccess; i++) {
     e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming);
+  }
+  for (int i = 0; i < kUnitSlots && e == cudaSuccess; i++) {
+    e = cudaEventCreateWithFlags(&ctx->ev_uin[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_ucomp[i], cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_tables, sizeof(DevTables));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_params, sizeof(DevEncParams));
@@ -391,15 +443,22 @@ void carta1_ctx_destroy(carta1_ctx *ctx) {
   ctx->bands.release(); ctx->mags.release(); ctx->feats.release(); ctx->modes.release(); ctx->coefs.release(); ctx->sfi.release();
   if (ctx->h2d) cudaStreamSynchronize(ctx->h2d);
   if (ctx->d2h) cudaStreamSynchronize(ctx->d2h);
+  if (ctx->small) cudaStreamSynchronize(ctx->small);
   ctx->inv.release(); ctx->scores.release(); ctx->dbg.release(); ctx->recs.release();
-  for (int i = 0; i < 2; i++) {
-    ctx->stage_pcm[i].release(); ctx->stage_su[i].release();
+  for (int i = 0; i < kUnitSlots; i++) {
+    ctx->stage_su[i].release();
+    if (ctx->ev_uin[i]) cudaEventDestroy(ctx->ev_uin[i]);
+    if (ctx->ev_ucomp[i]) cudaEventDestroy(ctx->ev_ucomp[i]);
+  }
+  for (int i = 0; i < kSlots; i++) {
+    ctx->stage_pcm[i].release();
     if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
     if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
     if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
   }
   if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
   if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
+  if (ctx->small) cudaStreamDestroy(ctx->small);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_params) cudaFree(ctx->d_params);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -548,6 +607,59 @@ int carta1_decode_device(carta1_ctx *ctx, const uint8_t *d_su, size_t su_frame_s
 }
 
 // ------------------------------------------------------------------ whole buffers (host)
+// The sound-unit side of a host call is a tenth of the PCM side and travels in the opposite
+// direction.  When an encode and a decode call are in flight together (two contexts), a copy-engine
+// D2H of the units queues behind the other call's whole backlog of PCM D2H copies (measured with
+// CARTA1_TRACE_PASSES, tools/e2e_probe.py: every encode D2H waited ~17 ms), so the encoder's
+// pipeline drains.  The encoder therefore writes its units with a copy *kernel* straight into the
+// caller's buffer when that buffer is pinned (mapped into the device address space by UVA); posted
+// PCIe writes from the SMs are not held up by the copy engines.  The reverse does not hold: SM
+// *reads* of pinned memory starve behind a copy engine's H2D stream (measured: 24 ms for 14 MB),
+// so the decoder's unit upload stays on a copy engine, on a highest-priority stream.  Pageable
+// buffers always take cudaMemcpyAsync.
+__global__ void __launch_bounds__(256) small_copy_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16,
+                                                         uint8_t *__restrict__ dst_tail, const uint8_t *__restrict__ src_tail, int n_tail) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
+  if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+
+// Device-visible alias of a pinned host pointer, or nullptr.
+static void *mapped_alias(const void *host) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+  return a.devicePointer;
+}
+
+// Development switch CARTA1_SMALL_COPY: 0 copy engines on the h2d/d2h streams, 1 copy engines on the
+// priority stream, 2 copy kernel in both directions, 3 (default) copy kernel for writes to the host only.
+static int small_copy_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char *v = getenv("CARTA1_SMALL_COPY");
+    mode = v && *v ? atoi(v) : 3;
+  }
+  return mode;
+}
+
+// Copies `bytes` between the caller's unit buffer and a staging slot on stream st.
+static cudaError_t small_copy(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, void *dst_alias,
+                              const void *src_alias, cudaStream_t st, Prof *prof) {
+  const bool to_host = kind == cudaMemcpyDeviceToHost;
+  void *d = to_host ? dst_alias : dst;
+  const void *s = to_host ? src : src_alias;
+  const int mode = small_copy_mode();
+  if (mode < 2 || (mode == 3 && !to_host) || !d || !s || (((uintptr_t)d | (uintptr_t)s) & 15))
+    return cudaMemcpyAsync(dst, src, bytes, kind, st);
+  const size_t n16 = bytes / 16;
+  const int grid = (int)std::min<size_t>(296, (n16 + 255) / 256 + 1);
+  small_copy_kernel<<<grid, 256, 0, st>>>((uint4 *)d, (const uint4 *)s, n16, (uint8_t *)d + n16 * 16,
+                                          (const uint8_t *)s + n16 * 16, (int)(bytes - n16 * 16));
+  prof->launches++;
+  return cudaGetLastError();
+}
+
 static int encode_host_impl(carta1_ctx *ctx, const float *const *channels, const int16_t *interleaved,
                             int n_ch, size_t n_samples, const carta1_enc_opts *opts, uint8_t *su_out,
                             size_t su_capacity_bytes, size_t *n_su_out) {
@@ -573,7 +685,7 @@ static int encode_host_impl(carta1_ctx *ctx, const float *const *channels, const
   // size every buffer for the largest pass up front: nothing may be reallocated while passes are in flight
   const size_t max_span = (std::min(frames, chunk) + 2) * 512;
   const size_t in_elem = channels ? sizeof(float) : sizeof(int16_t);
-  for (int sl = 0; sl < 2; sl++) {
+  for (int sl = 0; sl < kSlots; sl++) {
     CU(ctx, ctx->stage_pcm[sl].ensure((size_t)n_ch * max_span * in_elem));
     CU(ctx, ctx->stage_su[sl].ensure(std::min(frames, chunk) * (size_t)n_ch * CARTA1_SU_BYTES));
   }
@@ -581,15 +693,20 @@ static int encode_host_impl(carta1_ctx *ctx, const float *const *channels, const
   if (rc) return rc;
   CU(ctx, ctx->recs.ensure(std::min(frames, chunk) * (size_t)n_ch * alloc_rec_bytes()));
   size_t pass = 0;
+  uint8_t *su_alias = (uint8_t *)mapped_alias(su_out);
+  cudaStream_t s_out = small_copy_mode() == 0 ? ctx->d2h : ctx->small;
+  PassTrace tr;
+  tr.start("encode", ctx->h2d);
   for (size_t a = 0; a < frames; a += chunk, pass++) {
-    const int sl = (int)(pass & 1);
+    const int sl = (int)(pass % kSlots);
     const size_t b = std::min(frames, a + chunk);
     const size_t halo = a >= 2 ? 2 : 0;  // a is 0 or >= chunk
     const size_t first = a - halo;
     const size_t span = (b - first) * 512;                       // samples staged per row
     const size_t have = std::min(n_samples - first * 512, span); // samples that exist
     // H2D of this pass: its staging slot was last read by the compute of pass - 2
-    if (pass >= 2) CU(ctx, cudaStreamWaitEvent(ctx->h2d, ctx->ev_comp[sl], 0));
+    if (pass >= (size_t)kSlots) CU(ctx, cudaStreamWaitEvent(ctx->h2d, ctx->ev_comp[sl], 0));
+    tr.mark(ctx->h2d);
     if (channels) {
       for (int c = 0; c < n_ch; c++)
         CU(ctx, cudaMemcpyAsync((float *)ctx->stage_pcm[sl].p + (size_t)c * span, channels[c] + first * 512,
@@ -599,22 +716,29 @@ static int encode_host_impl(carta1_ctx *ctx, const float *const *channels, const
                               have * (size_t)n_ch * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->h2d));
     }
     CU(ctx, cudaEventRecord(ctx->ev_in[sl], ctx->h2d));
-    // compute: needs the input, and its output slot drained by the D2H of pass - 2
+    tr.mark(ctx->h2d);
+    // compute: needs the input, and its output slot drained by the D2H of pass - kSlots
     CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[sl], 0));
-    if (pass >= 2) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[sl], 0));
+    if (pass >= (size_t)kSlots) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[sl], 0));
+    tr.mark(ctx->stream);
     const size_t out_units = (b - a) * (size_t)n_ch;
     rc = encode_device_impl(ctx, ctx->stage_pcm[sl].p, channels ? 0 : 1, span, n_ch, n_ch, have, halo, b - a,
                             ctx->d_params, fixed, (uint8_t *)ctx->stage_su[sl].p, (size_t)n_ch, 1, nullptr,
                             nullptr, nullptr, nullptr);
     if (rc) return rc;
     CU(ctx, cudaEventRecord(ctx->ev_comp[sl], ctx->stream));
-    CU(ctx, cudaStreamWaitEvent(ctx->d2h, ctx->ev_comp[sl], 0));
-    CU(ctx, cudaMemcpyAsync(su_out + a * (size_t)n_ch * CARTA1_SU_BYTES, ctx->stage_su[sl].p,
-                            out_units * CARTA1_SU_BYTES, cudaMemcpyDeviceToHost, ctx->d2h));
-    CU(ctx, cudaEventRecord(ctx->ev_out[sl], ctx->d2h));
+    tr.mark(ctx->stream);
+    CU(ctx, cudaStreamWaitEvent(s_out, ctx->ev_comp[sl], 0));
+    tr.mark(s_out);
+    const size_t off = a * (size_t)n_ch * CARTA1_SU_BYTES;
+    CU(ctx, small_copy(su_out + off, ctx->stage_su[sl].p, out_units * CARTA1_SU_BYTES, cudaMemcpyDeviceToHost,
+                       su_alias ? su_alias + off : nullptr, nullptr, s_out, &ctx->prof));
+    CU(ctx, cudaEventRecord(ctx->ev_out[sl], s_out));
+    tr.mark(s_out);
   }
-  CU(ctx, cudaStreamSynchronize(ctx->d2h));
+  CU(ctx, cudaStreamSynchronize(s_out));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
+  tr.report();
   return CARTA1_OK;
 }
 
@@ -645,32 +769,43 @@ static int decode_host_impl(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int
   const size_t chunk = std::max<size_t>(2, ctx->max_units_per_pass / (size_t)n_ch);
   const size_t max_frames = std::min(frames, chunk);
   const size_t out_elem = channels_out ? sizeof(float) : sizeof(int16_t);
-  for (int sl = 0; sl < 2; sl++) {
-    CU(ctx, ctx->stage_su[sl].ensure((max_frames + 1) * (size_t)n_ch * CARTA1_SU_BYTES));
-    CU(ctx, ctx->stage_pcm[sl].ensure((size_t)n_ch * max_frames * 512 * out_elem));
-  }
+  const size_t n_passes = (frames + chunk - 1) / chunk;
+  for (int sl = 0; sl < kSlots; sl++) CU(ctx, ctx->stage_pcm[sl].ensure((size_t)n_ch * max_frames * 512 * out_elem));
+  for (size_t us = 0; us < std::min<size_t>(n_passes, kUnitSlots); us++)
+    CU(ctx, ctx->stage_su[us].ensure((max_frames + 1) * (size_t)n_ch * CARTA1_SU_BYTES));
   int rc = ensure_decode_scratch(ctx, (max_frames + 1) * (size_t)n_ch);
   if (rc) return rc;
   size_t pass = 0;
+  const uint8_t *su_alias = (const uint8_t *)mapped_alias(su);
+  cudaStream_t s_in = small_copy_mode() == 0 ? ctx->h2d : ctx->small;
+  PassTrace tr;
+  tr.start("decode", s_in);
   for (size_t a = 0; a < frames; a += chunk, pass++) {
-    const int sl = (int)(pass & 1);
+    const int sl = (int)(pass % kSlots), us = (int)(pass % kUnitSlots);
     const size_t b = std::min(frames, a + chunk);
     const size_t halo = a >= 1 ? 1 : 0;
     const size_t first = a - halo;
     const size_t want_units = (b - first) * (size_t)n_ch;
     const size_t have_units = std::min(n_su - first * (size_t)n_ch, want_units);
-    if (pass >= 2) CU(ctx, cudaStreamWaitEvent(ctx->h2d, ctx->ev_comp[sl], 0));
-    CU(ctx, cudaMemcpyAsync(ctx->stage_su[sl].p, su + first * (size_t)n_ch * CARTA1_SU_BYTES,
-                            have_units * CARTA1_SU_BYTES, cudaMemcpyHostToDevice, ctx->h2d));
-    CU(ctx, cudaEventRecord(ctx->ev_in[sl], ctx->h2d));
-    CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[sl], 0));
-    if (pass >= 2) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[sl], 0));
+    if (pass >= (size_t)kUnitSlots) CU(ctx, cudaStreamWaitEvent(s_in, ctx->ev_ucomp[us], 0));
+    tr.mark(s_in);
+    const size_t off = first * (size_t)n_ch * CARTA1_SU_BYTES;
+    CU(ctx, small_copy(ctx->stage_su[us].p, su + off, have_units * CARTA1_SU_BYTES, cudaMemcpyHostToDevice, nullptr,
+                       su_alias ? su_alias + off : nullptr, s_in, &ctx->prof));
+    CU(ctx, cudaEventRecord(ctx->ev_uin[us], s_in));
+    tr.mark(s_in);
+    CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_uin[us], 0));
+    if (pass >= (size_t)kSlots) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[sl], 0));
+    tr.mark(ctx->stream);
     const size_t span = (b - a) * 512;
-    rc = decode_device_impl(ctx, (const uint8_t *)ctx->stage_su[sl].p, (size_t)n_ch, 1, have_units, n_ch, halo,
+    rc = decode_device_impl(ctx, (const uint8_t *)ctx->stage_su[us].p, (size_t)n_ch, 1, have_units, n_ch, halo,
                             b - a, ctx->stage_pcm[sl].p, channels_out ? 0 : 1, span, n_ch, nullptr, nullptr);
     if (rc) return rc;
     CU(ctx, cudaEventRecord(ctx->ev_comp[sl], ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev_ucomp[us], ctx->stream));
+    tr.mark(ctx->stream);
     CU(ctx, cudaStreamWaitEvent(ctx->d2h, ctx->ev_comp[sl], 0));
+    tr.mark(ctx->d2h);
     if (channels_out) {
       for (int c = 0; c < n_ch; c++)
         CU(ctx, cudaMemcpyAsync(channels_out[c] + a * 512, (float *)ctx->stage_pcm[sl].p + (size_t)c * span,
@@ -680,9 +815,11 @@ static int decode_host_impl(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int
                               (size_t)n_ch * span * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->d2h));
     }
     CU(ctx, cudaEventRecord(ctx->ev_out[sl], ctx->d2h));
+    tr.mark(ctx->d2h);
   }
   CU(ctx, cudaStreamSynchronize(ctx->d2h));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
+  tr.report();
   return CARTA1_OK;
 }
 
