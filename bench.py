@@ -47,6 +47,23 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel, n_su):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r*_dram_traffic_*.json),
+    scaled by sound units when this run's workload differs from the captured one; None if absent."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_dram_traffic_*.json")))
+    if not files:
+        return None, None
+    try:
+        doc = json.load(open(files[-1]))
+        k = doc["kernels"][kernel]
+        total = (k["dram_bytes_read"] + k["dram_bytes_write"]) * (n_su / float(doc["sound_units"]))
+        return int(total), os.path.relpath(files[-1], ROOT)
+    except Exception:
+        return None, None
+
+
 # --------------------------------------------------------------------------------------
 # clocks sampler (NVML)
 # --------------------------------------------------------------------------------------
@@ -332,6 +349,7 @@ def run_ours(args, rank, local_rank, world):
         step_ms_prof = sum(v[0] for v in prof.values()) / max(args.steps, 1)
         achieved = BYTES_PER_SU * n_su / (dom_ms / 1000.0) / 1e9 if dom_ms > 0 else 0.0
         step_gbs = BYTES_PER_AUDIO_SEC * seconds / (ms_step / 1000.0) / 1e9
+        traffic, traffic_src = ncu_traffic(dom[0], n_su)
         props = torch.cuda.get_device_properties(dev)
         clk_mhz = sampler.max_mhz or 1965
         fp64_floor_ms = 2 * n_su * 2.0 * FP64_WARP_INSTR_PER_SU / (props.multi_processor_count * 4 * clk_mhz * 1e6) * 1e3
@@ -346,7 +364,7 @@ def run_ours(args, rank, local_rank, world):
             "decode_only": {"value": world * seconds / (ms_dec / args.steps / 1000.0), "unit": UNIT},
             "roofline": {
                 "bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel_ms": dom_ms, "kernel_share_of_step": (dom_ms * dom[1][1] / max(args.steps, 1)) / step_ms_prof if step_ms_prof else None,
                 "algorithmic_bytes_per_launch": BYTES_PER_SU * n_su,
                 "step": {"achieved": step_gbs, "frac": step_gbs / peak,
