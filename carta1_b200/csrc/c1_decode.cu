@@ -493,7 +493,6 @@ bands_time_kernel(const float *__restrict__ inv, const uint8_t *__restrict__ mod
 // high band with 40.
 // ------------------------------------------------------------------------------------
 constexpr int kSyWarps = 8, kSyCtasPerSm = 2;
-constexpr int kSyRun = 32;        // frames per run
 constexpr int kSyStrideA = 40;    // >= (24 + 128) / 4
 constexpr int kSyStrideB = 50;    // >= (24 + 256) / 8, == 2 mod 16
 static_assert(kSyStrideA * 4 >= 152 && kSyStrideB * 8 >= 280 && kSyStrideB % 16 == 2, "ring strides");
@@ -631,7 +630,7 @@ __device__ __forceinline__ void sy_shift(SyWarpSmem &S, int lane) {
 
 template <int kFmt>  // 0: f32 planar rows, 1: s16 interleaved (processor.js:382-389)
 __global__ void __launch_bounds__(kSyWarps * 32, kSyCtasPerSm)
-synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams,
+synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams, int run_len,
              const DevTables *__restrict__ T, void *__restrict__ pcm_v, size_t row_stride, int n_ch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -639,12 +638,12 @@ synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams,
   const int wi = lane < 16 ? lane : 31 - lane;
   const double w1 = T->win[wi], w2 = T->win[31 - wi];
   const int out_frames = frames - halo;
-  const int runs_per_row = (out_frames + kSyRun - 1) / kSyRun;
+  const int runs_per_row = (out_frames + run_len - 1) / run_len;
   const int n_runs = runs_per_row * n_streams;
   for (int run = blockIdx.x * kSyWarps + warp; run < n_runs; run += gridDim.x * kSyWarps) {
     const int stream = run / runs_per_row;
-    const int f0 = halo + (run - stream * runs_per_row) * kSyRun;
-    const int f1 = min(f0 + kSyRun, frames);
+    const int f0 = halo + (run - stream * runs_per_row) * run_len;
+    const int f1 = min(f0 + run_len, frames);
     const float *inv_row = inv + (size_t)stream * frames * 512;
     __syncwarp();
     // silent state (new BufferPool, buffers.js:31-35,67-72)
@@ -789,14 +788,15 @@ cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, Prof *prof) {
     if (e0 == cudaSuccess)
       e0 = cudaFuncSetAttribute(synth_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSySmemBytes);
     if (e0 != cudaSuccess) return e0;
-    const int n_runs = ((L.frames_total - L.halo_frames + kSyRun - 1) / kSyRun) * L.n_streams;
+    const int run_len = pick_run_len(L.frames_total - L.halo_frames, L.n_streams, persistent_ctas(kSyCtasPerSm) * kSyWarps);
+    const int n_runs = ((L.frames_total - L.halo_frames + run_len - 1) / run_len) * L.n_streams;
     const int grid = std::min((n_runs + kSyWarps - 1) / kSyWarps, persistent_ctas(kSyCtasPerSm));
     prof->begin(K_SYNTH, st);
     if (L.pcm_fmt == 0)
-      synth_kernel<0><<<grid, kSyWarps * 32, kSySmemBytes, st>>>(L.inv, L.frames_total, L.halo_frames, L.n_streams,
+      synth_kernel<0><<<grid, kSyWarps * 32, kSySmemBytes, st>>>(L.inv, L.frames_total, L.halo_frames, L.n_streams, run_len,
                                                                   L.tables, L.pcm, L.row_stride, L.n_ch_interleave);
     else
-      synth_kernel<1><<<grid, kSyWarps * 32, kSySmemBytes, st>>>(L.inv, L.frames_total, L.halo_frames, L.n_streams,
+      synth_kernel<1><<<grid, kSyWarps * 32, kSySmemBytes, st>>>(L.inv, L.frames_total, L.halo_frames, L.n_streams, run_len,
                                                                   L.tables, L.pcm, L.row_stride, L.n_ch_interleave);
     prof->end(K_SYNTH, st);
   }

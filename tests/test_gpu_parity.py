@@ -217,6 +217,88 @@ def test_chunked_host_path(ctx, oracle, units):
         ctx.set_max_units_per_pass(0)
 
 
+@pytest.mark.parametrize("units", [4, 6, 64, 250])
+def test_pinned_host_buffers(ctx, oracle, units):
+    """Pinned caller buffers: the encoder writes its units with a copy kernel straight into the mapped
+    host buffer (c1_abi.cu small_copy); pass sizes that give 16-byte aligned and unaligned unit
+    offsets, more passes than PCM slots (4) and than unit slots (32)."""
+    import torch
+
+    chans = S.cfg3_transients(1.7, seed=91, n_ch=2)
+    n = len(chans[0])
+    want = oracle.encode_pcm(chans, threads=8, chunk_frames=32)
+    ref = oracle.decode_su(want, 2, threads=8, chunk_frames=32)
+    n_su = want.shape[0]
+    pcm_h = torch.empty((2, n), dtype=torch.float32).pin_memory()
+    for c in range(2):
+        pcm_h[c].copy_(torch.from_numpy(chans[c]))
+    su_h = torch.full((n_su * 212 + 64,), 0xEE, dtype=torch.uint8).pin_memory()
+    out_h = torch.empty((2, (n_su // 2) * 512), dtype=torch.float32).pin_memory()
+    ctx.set_max_units_per_pass(units)
+    try:
+        for shift in (0, 4):  # a unit buffer that is only 4-byte aligned takes the cudaMemcpyAsync path
+            su_np = su_h.numpy()[shift:shift + n_su * 212]
+            got = ctx.encode_pcm_into([pcm_h[0].numpy(), pcm_h[1].numpy()], su_np, None)
+            assert got == n_su
+            assert np.array_equal(su_np.reshape(-1, 212), want), (units, shift)
+            assert np.all(su_h.numpy()[shift + n_su * 212:] == 0xEE)
+            out_h.zero_()
+            ctx.decode_su_into(su_np, n_su, 2, [out_h[0].numpy(), out_h[1].numpy()])
+            for c in range(2):
+                assert np.array_equal(bits(out_h[c].numpy()), bits(ref[c])), (units, shift, c)
+    finally:
+        ctx.set_max_units_per_pass(0)
+
+
+def test_encode_and_decode_calls_in_flight_together(oracle):
+    """Two contexts, two host threads: carta1_encode_pcm and carta1_decode_su overlap (the e2e leg of
+    bench.py); results equal the one-after-the-other results."""
+    import threading
+
+    import torch
+
+    import carta1_b200
+
+    chans = S.cfg2_stereo(20.0, seed=5)
+    n = len(chans[0])
+    want = oracle.encode_pcm(chans, threads=8, chunk_frames=64)
+    ref = oracle.decode_su(want, 2, threads=8, chunk_frames=64)
+    n_su = want.shape[0]
+    pcm_h = torch.empty((2, n), dtype=torch.float32).pin_memory()
+    for c in range(2):
+        pcm_h[c].copy_(torch.from_numpy(chans[c]))
+    su_a = torch.zeros(n_su * 212, dtype=torch.uint8).pin_memory()
+    su_b = torch.from_numpy(want.reshape(-1).copy()).pin_memory()
+    out_h = torch.zeros((2, (n_su // 2) * 512), dtype=torch.float32).pin_memory()
+    c1, c2 = carta1_b200.Context(0), carta1_b200.Context(0)
+    try:
+        for c in (c1, c2):
+            c.set_max_units_per_pass(128)
+        opts = carta1_b200.make_enc_opts()
+        for _ in range(3):
+            su_a.zero_()
+            out_h.zero_()
+            errs = []
+
+            def dec():
+                try:
+                    c2.decode_su_into(su_b.numpy(), n_su, 2, [out_h[0].numpy(), out_h[1].numpy()])
+                except Exception as ex:
+                    errs.append(ex)
+
+            th = threading.Thread(target=dec)
+            th.start()
+            got = c1.encode_pcm_into([pcm_h[0].numpy(), pcm_h[1].numpy()], su_a.numpy(), opts)
+            th.join()
+            assert not errs and got == n_su
+            assert np.array_equal(su_a.numpy().reshape(-1, 212), want)
+            for c in range(2):
+                assert np.array_equal(bits(out_h[c].numpy()), bits(ref[c]))
+    finally:
+        c1.close()
+        c2.close()
+
+
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_sharded_device_path(ctx, oracle, world):
     """Config 5's shape at test size: (stream, frame-range) shards with halos through the
