@@ -73,7 +73,9 @@ struct QaWarpSmem {
   double x[2][8 * kQaStride1];   // odd, even polyphase of the PCM frame
   double s[2][4 * kQaStride2];   // odd, even polyphase of S1lo
   float hi[40 + 256];            // S1hi with 40 entries of history (39 used)
+  float raw[512];                // the next PCM frame, in flight (cp.async) while this one is filtered
 };
+static_assert(sizeof(QaWarpSmem) % 16 == 0 && (sizeof(double) * (2 * 8 * kQaStride1 + 2 * 4 * kQaStride2) + 4 * 296) % 16 == 0, "raw is 16-byte aligned");
 constexpr size_t kQaSmemBytes = sizeof(QaWarpSmem) * kQaWarps;
 
 __constant__ double c_qmf_even[24];
@@ -104,28 +106,57 @@ __device__ __forceinline__ void fir_analysis(const double *__restrict__ seq, int
   }
 }
 
-// PCM frame -> polyphase ring (elements 24..279).  Lane l owns samples 4l + 128k + c.
-template <int kFmt>
-__device__ __forceinline__ void qa_fill(QaWarpSmem &S, const void *__restrict__ pcm_v, size_t row_off, int n_ch,
-                                        int stream, long long first, long long valid_samples, bool vec_ok, int lane) {
-  float v[4][4];
+// 16-byte asynchronous copy global -> shared; bytes beyond src_bytes are zero-filled.
+__device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gsrc, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// f32 planar, 16-byte aligned rows: the frame starting at sample `first` is fetched into the warp's raw
+// staging buffer while the previous frame is being filtered.  Lane l copies, and later reads, bytes
+// [16 l + 512 k, +16) only, so no warp barrier is needed around the staging buffer.
+__device__ __forceinline__ void qa_prefetch(QaWarpSmem &S, const float *__restrict__ row, long long first,
+                                            long long valid_samples, int lane) {
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const long long g = first + 4 * lane + 128 * k;
-    if (kFmt == 0) {
-      const float *src = static_cast<const float *>(pcm_v) + row_off + g;
-      if (vec_ok && g + 3 < valid_samples) {
-        const float4 q = __ldg(reinterpret_cast<const float4 *>(src));
-        v[k][0] = q.x; v[k][1] = q.y; v[k][2] = q.z; v[k][3] = q.w;
-      } else {
+    const long long left = valid_samples - g;  // samples that exist from g on
+    const int bytes = left >= 4 ? 16 : (left > 0 ? (int)left * 4 : 0);
+    cp_async16_zfill(S.raw + 4 * lane + 128 * k, row + (bytes ? g : 0), bytes);
+  }
+}
+
+// PCM frame -> polyphase ring (elements 24..279).  Lane l owns samples 4l + 128k + c.
+template <int kFmt>
+__device__ __forceinline__ void qa_fill(QaWarpSmem &S, const void *__restrict__ pcm_v, size_t row_off, int n_ch,
+                                        int stream, long long first, long long valid_samples, bool vec_ok, int lane,
+                                        long long next_first) {
+  float v[4][4];
+  if (kFmt == 0 && vec_ok) {
+    cp_async_commit_wait_all();
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float4 q = *reinterpret_cast<const float4 *>(S.raw + 4 * lane + 128 * k);
+      v[k][0] = q.x; v[k][1] = q.y; v[k][2] = q.z; v[k][3] = q.w;
+    }
+    if (next_first >= 0) qa_prefetch(S, static_cast<const float *>(pcm_v) + row_off, next_first, valid_samples, lane);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const long long g = first + 4 * lane + 128 * k;
+      if (kFmt == 0) {
+        const float *src = static_cast<const float *>(pcm_v) + row_off + g;
 #pragma unroll
         for (int c = 0; c < 4; c++) v[k][c] = g + c < valid_samples ? __ldg(src + c) : 0.0f;
-      }
-    } else {  // bin/cli.js:395  readInt16LE / 32768.0 -> Float32Array
-      const short *src = static_cast<const short *>(pcm_v);
+      } else {  // bin/cli.js:395  readInt16LE / 32768.0 -> Float32Array
+        const short *src = static_cast<const short *>(pcm_v);
 #pragma unroll
-      for (int c = 0; c < 4; c++)
-        v[k][c] = g + c < valid_samples ? (float)((double)__ldg(src + (size_t)(g + c) * n_ch + stream) / 32768.0) : 0.0f;
+        for (int c = 0; c < 4; c++)
+          v[k][c] = g + c < valid_samples ? (float)((double)__ldg(src + (size_t)(g + c) * n_ch + stream) / 32768.0) : 0.0f;
+      }
     }
   }
 #pragma unroll
@@ -197,6 +228,9 @@ qmf_analysis_kernel(const void *__restrict__ pcm_v, size_t row_stride, int n_ch,
     const size_t row_off = kFmt == 0 ? (size_t)stream * row_stride : 0;
     const bool vec_ok = kFmt == 0 && ((reinterpret_cast<uintptr_t>(static_cast<const float *>(pcm_v) + row_off) & 15) == 0);
     __syncwarp();
+    const bool async_ok = kFmt == 0 && vec_ok;
+    if (async_ok)
+      qa_prefetch(S, static_cast<const float *>(pcm_v) + row_off, 512ll * (f0 > 0 ? f0 - 1 : f0), valid_samples, lane);
     if (f0 == 0) {  // row start: silent history (new BufferPool, buffers.js:31-42)
       if (lane < 24) {
 #pragma unroll
@@ -208,7 +242,7 @@ qmf_analysis_kernel(const void *__restrict__ pcm_v, size_t row_stride, int n_ch,
       S.hi[lane] = 0.0f;
       if (lane < 8) S.hi[32 + lane] = 0.0f;
     } else {        // prime the state from the frame before the run (only its last 64 S1 outputs matter)
-      qa_fill<kFmt>(S, pcm_v, row_off, n_ch, stream, 512ll * (f0 - 1), valid_samples, vec_ok, lane);
+      qa_fill<kFmt>(S, pcm_v, row_off, n_ch, stream, 512ll * (f0 - 1), valid_samples, vec_ok, lane, 512ll * f0);
       __syncwarp();
       qa_stage1(S, lane);
       __syncwarp();
@@ -216,7 +250,8 @@ qmf_analysis_kernel(const void *__restrict__ pcm_v, size_t row_stride, int n_ch,
     }
     for (int f = f0; f < f1; f++) {
       __syncwarp();
-      qa_fill<kFmt>(S, pcm_v, row_off, n_ch, stream, 512ll * f, valid_samples, vec_ok, lane);
+      qa_fill<kFmt>(S, pcm_v, row_off, n_ch, stream, 512ll * f, valid_samples, vec_ok, lane,
+                    f + 1 < f1 ? 512ll * (f + 1) : -1);
       __syncwarp();
       qa_stage1(S, lane);
       __syncwarp();
