@@ -155,7 +155,7 @@ struct UnpackWarpSmem {
 // modes[unit * 4 + 0..2]: 1 = short blocks; modes[unit * 4 + 3]: 1 = the unit's band record is
 // already in place (stateful handles: frame 0 of every row is the record kept from the
 // previous call), the IMDCT kernels skip it.
-__global__ void __launch_bounds__(kUnpackWarps * 32)
+__global__ void __launch_bounds__(kUnpackWarps * 32, 6)
 unpack_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_stream_stride,
               long long n_su_valid, int frames, int n_units, const DevTables *__restrict__ T,
               float *__restrict__ coefs, uint8_t *__restrict__ modes, float *__restrict__ inv,
@@ -761,7 +761,8 @@ cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, Prof *prof) {
   const int n_units = L.n_streams * L.frames_total;
   if (n_units == 0) return cudaSuccess;
   prof->begin(K_UNPACK, st);
-  unpack_kernel<<<std::min((n_units + kUnpackWarps - 1) / kUnpackWarps, persistent_ctas(6)), kUnpackWarps * 32, 0, st>>>(
+  unpack_kernel<<<std::min((n_units + kUnpackWarps - 1) / kUnpackWarps, resident_ctas((const void *)unpack_kernel, kUnpackWarps * 32, 0)),
+                  kUnpackWarps * 32, 0, st>>>(
       L.su, L.su_frame_stride, L.su_stream_stride, L.n_su_valid, L.frames_total, n_units, L.tables, L.coefs,
       L.modes, L.inv, L.prev_rec, ExpandedFrames{L.x_q, L.x_sfi, L.x_bits, L.x_modes});
   prof->end(K_UNPACK, st);

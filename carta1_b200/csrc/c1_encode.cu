@@ -1352,6 +1352,26 @@ int pick_run_len(int frames, int n_streams, int warps) {
   return best;
 }
 
+// CTAs of a persistent kernel: as many as are resident at once (a larger grid would run a second,
+// partly empty wave; the kernels stride over their work lists).  Cached per kernel.
+int resident_ctas(const void *kernel, int threads, size_t dyn_smem) {
+  struct Entry { const void *k; int dev; int ctas; };
+  static Entry cache[32];
+  static int n_cache = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (int i = 0; i < n_cache; i++)
+    if (cache[i].k == kernel && cache[i].dev == dev) return cache[i].ctas;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess || per_sm <= 0) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  const int ctas = persistent_ctas(per_sm);
+  if (n_cache < 32) cache[n_cache++] = {kernel, dev, ctas};
+  return ctas;
+}
+
 // CTAs of a persistent kernel: every SM filled to `per_sm` resident CTAs.
 int persistent_ctas(int per_sm) {
   static int sms = 0;
@@ -1418,11 +1438,15 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
     AllocCand *cands = reinterpret_cast<AllocCand *>(recs + n_units);
     const long long n_groups = (n_units + 31) / 32;
     prof->begin(K_ALLOC, st);
-    alloc_kernel<<<(unsigned)std::min<long long>((n_groups + kAlWarps - 1) / kAlWarps, persistent_ctas(5)), kAlWarps * 32, sizeof(AlSmem), st>>>(
+    alloc_kernel<<<(unsigned)std::min<long long>((n_groups + kAlWarps - 1) / kAlWarps,
+                                                 resident_ctas((const void *)alloc_kernel, kAlWarps * 32, sizeof(AlSmem))),
+                   kAlWarps * 32, sizeof(AlSmem), st>>>(
         L.sfi, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params, recs, cands);
     prof->end(K_ALLOC, st);
     prof->begin(K_QUANT_PACK, st);
-    quant_pack_kernel<<<(unsigned)std::min<long long>((n_units + kQpWarps - 1) / kQpWarps, persistent_ctas(6)), kQpWarps * 32, 0, st>>>(
+    quant_pack_kernel<<<(unsigned)std::min<long long>((n_units + kQpWarps - 1) / kQpWarps,
+                                                      resident_ctas((const void *)quant_pack_kernel, kQpWarps * 32, 0)),
+                        kQpWarps * 32, 0, st>>>(
         L.coefs, L.modes, recs, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params,
         L.su_out, L.su_frame_stride, L.su_stream_stride);
     prof->end(K_QUANT_PACK, st);

@@ -95,7 +95,8 @@ struct Prof {
 
 size_t alloc_rec_bytes();
 int pick_run_len(int frames, int n_streams, int warps);  // frames per run of the streaming QMF kernels
-int persistent_ctas(int per_sm);  // SM count of the current device x per_sm
+int persistent_ctas(int per_sm);
+int resident_ctas(const void *kernel, int threads, size_t dyn_smem);  // SM count x CTAs of `kernel` resident per SM  // SM count of the current device x per_sm
 // QMF taps and FFT twiddles go to __constant__ memory of the current device (once per context).
 cudaError_t upload_encode_constants(const DevTables *host_tables);
 cudaError_t upload_decode_constants(const DevTables *host_tables);
