@@ -327,14 +327,43 @@ def run_ours(args, rank, local_rank, world):
     ms_e2e = wall_ms(e2e_duplex_step, e2e_steps)
     barrier()
     duplex_equal = bool(np.array_equal(su_np, su2_np))
+    # WAV-shaped I/O: int16 interleaved PCM in and out, as the reference CLI reads and writes it
+    # (bin/cli.js:394-404, processor.js:382-389); the conversions run inside the QMF kernels, so the PCM side of
+    # the link carries half the bytes.  Same two calls in flight together.
+    wav_h = torch.empty(n * 2, dtype=torch.int16).pin_memory()
+    wav_h.copy_((pcm.t().contiguous().clamp(-1.0, 1.0) * 32767.0).to(torch.int16).reshape(-1))
+    wav_out_h = torch.empty(frames * 512 * 2, dtype=torch.int16).pin_memory()
+    wav_np, wav_out_np = wav_h.numpy(), wav_out_h.numpy()
+    su3_h = torch.empty(n_su * 212, dtype=torch.uint8).pin_memory()
+    su3_np = su3_h.numpy()
+
+    def e2e_s16_step():
+        def dec():
+            try:
+                ctx2.decode_su_s16_into(su2_np, n_su, 2, wav_out_np)
+            except Exception as ex:
+                errs.append(ex)
+
+        th = threading.Thread(target=dec)
+        th.start()
+        got = ctx.encode_pcm_s16_into(wav_np, 2, su3_np, opts)
+        th.join()
+        if errs:
+            raise errs[0]
+        assert got == n_su
+
+    e2e_s16_step()
+    barrier()
+    ms_e2e_s16 = wall_ms(e2e_s16_step, e2e_steps)
+    barrier()
     ctx2.close()
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
     if dist is not None:
-        t = torch.tensor([ms, ms_enc, ms_dec, ms_e2e, ms_e2e_seq], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, ms_enc, ms_dec, ms_e2e, ms_e2e_seq, ms_e2e_s16], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_enc, ms_dec, ms_e2e, ms_e2e_seq = t.tolist()
+        ms, ms_enc, ms_dec, ms_e2e, ms_e2e_seq, ms_e2e_s16 = t.tolist()
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt.item())
@@ -382,6 +411,9 @@ def run_ours(args, rank, local_rank, world):
                            "each), pinned host buffers, H2D and D2H inside; host wall clock, max over ranks",
                     "sequential": {"value": world * seconds / (ms_e2e_seq / e2e_steps / 1000.0), "unit": UNIT,
                                    "api": "carta1_encode_pcm then carta1_decode_su on one context"},
+                    "wav_int16": {"value": world * seconds / (ms_e2e_s16 / e2e_steps / 1000.0), "unit": UNIT,
+                                  "h2d_bytes_per_step": int(2 * n * 2 + n_su * 212), "d2h_bytes_per_step": int(n_su * 212 + 2 * frames * 512 * 2),
+                                  "api": "carta1_encode_pcm_s16 || carta1_decode_su_s16 (WAV-shaped int16 PCM in and out)"},
                     "units_identical_across_steps": duplex_equal},
             "gpu_launches": launches,
             "clocks": sampler.summary(t_start, t_end),

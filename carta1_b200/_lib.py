@@ -278,6 +278,16 @@ class Context:
         ptrs = (C.POINTER(C.c_float) * len(outs))(*[c.ctypes.data_as(C.POINTER(C.c_float)) for c in outs])
         self._check(self.L.carta1_decode_su(self.h, _ptr(su), n_su, n_ch, ptrs))
 
+    def encode_pcm_s16_into(self, interleaved: np.ndarray, n_ch: int, su_out: np.ndarray, opts: EncOpts | None = None) -> int:
+        n = interleaved.size // n_ch
+        n_su = C.c_size_t()
+        self._check(self.L.carta1_encode_pcm_s16(self.h, _ptr(interleaved), n_ch, n, C.byref(opts) if opts is not None else None,
+                                                 _ptr(su_out), su_out.nbytes, C.byref(n_su)))
+        return n_su.value
+
+    def decode_su_s16_into(self, su: np.ndarray, n_su: int, n_ch: int, out: np.ndarray) -> None:
+        self._check(self.L.carta1_decode_su_s16(self.h, _ptr(su), n_su, n_ch, _ptr(out)))
+
     def selftest(self) -> int:
         bad = C.c_uint64()
         self._check(self.L.carta1_debug_selftest(self.h, C.byref(bad)))
