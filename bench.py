@@ -357,13 +357,30 @@ def run_ours(args, rank, local_rank, world):
     ms_e2e_s16 = wall_ms(e2e_s16_step, e2e_steps)
     barrier()
     ctx2.close()
+    # pageable caller arrays (what a host runtime that cannot pin its typed arrays passes): staged through the
+    # context's pinned bounce slots by parallel memcpy; one call after the other
+    chans_pg = [np.array(c) for c in chans_np]
+    outs_pg = [np.empty_like(o) for o in outs_np]
+    su_pg = np.empty_like(su_np)
+
+    def e2e_pageable_step():
+        got = ctx.encode_pcm_into(chans_pg, su_pg, opts)
+        assert got == n_su
+        ctx.decode_su_into(su_pg, n_su, 2, outs_pg)
+
+    e2e_pageable_step()
+    barrier()
+    ms_e2e_pg = wall_ms(e2e_pageable_step, e2e_steps)
+    barrier()
+    pageable_equal = bool(np.array_equal(su_pg, su_np)) and all(np.array_equal(a.view(np.uint32), b.view(np.uint32))
+                                                                 for a, b in zip(outs_pg, outs_np))
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
     if dist is not None:
-        t = torch.tensor([ms, ms_enc, ms_dec, ms_e2e, ms_e2e_seq, ms_e2e_s16], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, ms_enc, ms_dec, ms_e2e, ms_e2e_seq, ms_e2e_s16, ms_e2e_pg], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_enc, ms_dec, ms_e2e, ms_e2e_seq, ms_e2e_s16 = t.tolist()
+        ms, ms_enc, ms_dec, ms_e2e, ms_e2e_seq, ms_e2e_s16, ms_e2e_pg = t.tolist()
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt.item())
@@ -414,6 +431,9 @@ def run_ours(args, rank, local_rank, world):
                     "wav_int16": {"value": world * seconds / (ms_e2e_s16 / e2e_steps / 1000.0), "unit": UNIT,
                                   "h2d_bytes_per_step": int(2 * n * 2 + n_su * 212), "d2h_bytes_per_step": int(n_su * 212 + 2 * frames * 512 * 2),
                                   "api": "carta1_encode_pcm_s16 || carta1_decode_su_s16 (WAV-shaped int16 PCM in and out)"},
+                    "pageable": {"value": world * seconds / (ms_e2e_pg / e2e_steps / 1000.0), "unit": UNIT,
+                                 "api": "carta1_encode_pcm then carta1_decode_su with pageable (unpinned) caller arrays",
+                                 "identical_to_pinned_run": pageable_equal},
                     "units_identical_across_steps": duplex_equal},
             "gpu_launches": launches,
             "clocks": sampler.summary(t_start, t_end),

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/carta1_b200.h"
@@ -193,6 +194,11 @@ bool build_enc_params(const carta1_tables &t, const carta1_enc_opts &o, DevEncPa
   return true;
 }
 
+// Pageable transfers below this go straight to cudaMemcpyAsync (CARTA1_BOUNCE_MIN_BYTES overrides it: tests).
+size_t bounce_min_bytes() {
+  const char *v = getenv("CARTA1_BOUNCE_MIN_BYTES");
+  return v && *v ? (size_t)strtoull(v, nullptr, 10) : (size_t)8 << 20;
+}
 constexpr int kSlots = 4;       // PCM staging slots of the pipelined host entry points
 constexpr int kUnitSlots = 32;  // sound-unit input slots of the decoder (a tenth of the PCM bytes): deep enough that
                                 // the uploads of a whole hour are queued before anything else competes for the copy engine
@@ -250,6 +256,38 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// Pinned host memory owned by the context: bounce buffers for callers whose arrays are pageable.
+struct HostBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + (bytes >> 3) + 256;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// memcpy split over a few host threads (one thread moves ~10 GB/s; the PCIe link takes 55).
+void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)std::min<size_t>(std::max(1u, std::min(8u, hw / 2)), bytes >> 21);  // >= 2 MiB per thread
+  if (nt <= 1) { memcpy(dst, src, bytes); return; }
+  const size_t piece = ((bytes / (size_t)nt) + 4095) & ~(size_t)4095;
+  std::vector<std::thread> th;
+  for (int i = 1; i < nt; i++) {
+    const size_t a = std::min(bytes, piece * (size_t)i), b = std::min(bytes, a + piece);
+    if (b > a) th.emplace_back([=] { memcpy((char *)dst + a, (const char *)src + a, b - a); });
+  }
+  memcpy(dst, src, std::min(bytes, piece));
+  for (auto &t : th) t.join();
+}
+
 }  // namespace
 
 struct carta1_ctx {
@@ -272,6 +310,9 @@ struct carta1_ctx {
   cudaStream_t small = nullptr;  // highest priority: the sound-unit side of a host call (see small_copy)
   cudaEvent_t ev_in[kSlots] = {}, ev_comp[kSlots] = {}, ev_out[kSlots] = {};
   cudaEvent_t ev_uin[kUnitSlots] = {}, ev_ucomp[kUnitSlots] = {};
+  // pageable caller buffers are staged through these (filled / drained by parallel_memcpy, one pass behind)
+  HostBuf bounce_pcm[kSlots], bounce_su[kSlots];
+  cudaEvent_t ev_bin[kSlots] = {};  // the H2D that read bounce slot i has finished
   size_t max_units_per_pass = 1u << 16;  // frames*channels per pass of the chunked host entry points
 };
 
@@ -417,6 +458,7 @@ int carta1_ctx_create(int device, const carta1_tables *tables, carta1_ctx **out)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming);
   }
+  for (int i = 0; i < kSlots && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_bin[i], cudaEventDisableTiming);
   for (int i = 0; i < kUnitSlots && e == cudaSuccess; i++) {
     e = cudaEventCreateWithFlags(&ctx->ev_uin[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_ucomp[i], cudaEventDisableTiming);
@@ -451,6 +493,8 @@ void carta1_ctx_destroy(carta1_ctx *ctx) {
     if (ctx->ev_ucomp[i]) cudaEventDestroy(ctx->ev_ucomp[i]);
   }
   for (int i = 0; i < kSlots; i++) {
+    ctx->bounce_pcm[i].release(); ctx->bounce_su[i].release();
+    if (ctx->ev_bin[i]) cudaEventDestroy(ctx->ev_bin[i]);
     ctx->stage_pcm[i].release();
     if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
     if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
@@ -695,6 +739,31 @@ static int encode_host_impl(carta1_ctx *ctx, const float *const *channels, const
   size_t pass = 0;
   uint8_t *su_alias = (uint8_t *)mapped_alias(su_out);
   cudaStream_t s_out = small_copy_mode() == 0 ? ctx->d2h : ctx->small;
+  // Pageable caller arrays (anything a host runtime did not pin): cudaMemcpyAsync would stage them through
+  // the driver on one thread and block this one (measured 125 ms instead of 24 for the 1 h stereo encode),
+  // so they go through the context's pinned bounce slots, filled by parallel_memcpy while earlier passes run.
+  const size_t kBounceMinBytes = bounce_min_bytes();
+  const size_t pcm_bytes = n_samples * (size_t)n_ch * in_elem;
+  bool bounce_in = pcm_bytes >= kBounceMinBytes;
+  if (bounce_in) {
+    bool pinned = true;
+    if (channels) { for (int c = 0; c < n_ch; c++) pinned = pinned && mapped_alias(channels[c]); }
+    else pinned = mapped_alias(interleaved) != nullptr;
+    bounce_in = !pinned;
+  }
+  const bool bounce_out = !su_alias && n_su * CARTA1_SU_BYTES >= kBounceMinBytes / 8;
+  for (int sl = 0; sl < kSlots; sl++) {
+    if (bounce_in) CU(ctx, ctx->bounce_pcm[sl].ensure((size_t)n_ch * max_span * in_elem));
+    if (bounce_out) CU(ctx, ctx->bounce_su[sl].ensure(std::min(frames, chunk) * (size_t)n_ch * CARTA1_SU_BYTES));
+  }
+  struct Pending { bool on = false; int sl = 0; size_t off = 0, bytes = 0; } pend;  // unit bounce slot to drain
+  auto drain = [&]() -> cudaError_t {
+    if (!pend.on) return cudaSuccess;
+    cudaError_t e = cudaEventSynchronize(ctx->ev_out[pend.sl]);
+    if (e == cudaSuccess) parallel_memcpy(su_out + pend.off, ctx->bounce_su[pend.sl].p, pend.bytes);
+    pend.on = false;
+    return e;
+  };
   PassTrace tr;
   tr.start("encode", ctx->h2d);
   for (size_t a = 0; a < frames; a += chunk, pass++) {
@@ -704,18 +773,37 @@ static int encode_host_impl(carta1_ctx *ctx, const float *const *channels, const
     const size_t first = a - halo;
     const size_t span = (b - first) * 512;                       // samples staged per row
     const size_t have = std::min(n_samples - first * 512, span); // samples that exist
-    // H2D of this pass: its staging slot was last read by the compute of pass - 2
+    const void *src_rows[2] = {nullptr, nullptr};                // what the H2D copies read
+    if (bounce_in) {
+      if (pass >= (size_t)kSlots) CU(ctx, cudaEventSynchronize(ctx->ev_bin[sl]));  // the H2D of pass - kSlots has read the slot
+      char *bb = (char *)ctx->bounce_pcm[sl].p;
+      if (channels) {
+        for (int c = 0; c < n_ch; c++) {
+          parallel_memcpy(bb + (size_t)c * span * sizeof(float), channels[c] + first * 512, have * sizeof(float));
+          src_rows[c] = bb + (size_t)c * span * sizeof(float);
+        }
+      } else {
+        parallel_memcpy(bb, interleaved + first * 512 * (size_t)n_ch, have * (size_t)n_ch * sizeof(int16_t));
+        src_rows[0] = bb;
+      }
+    } else if (channels) {
+      for (int c = 0; c < n_ch; c++) src_rows[c] = channels[c] + first * 512;
+    } else {
+      src_rows[0] = interleaved + first * 512 * (size_t)n_ch;
+    }
+    // H2D of this pass: its device slot was last read by the compute of pass - kSlots
     if (pass >= (size_t)kSlots) CU(ctx, cudaStreamWaitEvent(ctx->h2d, ctx->ev_comp[sl], 0));
     tr.mark(ctx->h2d);
     if (channels) {
       for (int c = 0; c < n_ch; c++)
-        CU(ctx, cudaMemcpyAsync((float *)ctx->stage_pcm[sl].p + (size_t)c * span, channels[c] + first * 512,
-                                have * sizeof(float), cudaMemcpyHostToDevice, ctx->h2d));
+        CU(ctx, cudaMemcpyAsync((float *)ctx->stage_pcm[sl].p + (size_t)c * span, src_rows[c], have * sizeof(float),
+                                cudaMemcpyHostToDevice, ctx->h2d));
     } else {
-      CU(ctx, cudaMemcpyAsync(ctx->stage_pcm[sl].p, interleaved + first * 512 * (size_t)n_ch,
-                              have * (size_t)n_ch * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->h2d));
+      CU(ctx, cudaMemcpyAsync(ctx->stage_pcm[sl].p, src_rows[0], have * (size_t)n_ch * sizeof(int16_t),
+                              cudaMemcpyHostToDevice, ctx->h2d));
     }
     CU(ctx, cudaEventRecord(ctx->ev_in[sl], ctx->h2d));
+    if (bounce_in) CU(ctx, cudaEventRecord(ctx->ev_bin[sl], ctx->h2d));
     tr.mark(ctx->h2d);
     // compute: needs the input, and its output slot drained by the D2H of pass - kSlots
     CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[sl], 0));
@@ -731,11 +819,22 @@ static int encode_host_impl(carta1_ctx *ctx, const float *const *channels, const
     CU(ctx, cudaStreamWaitEvent(s_out, ctx->ev_comp[sl], 0));
     tr.mark(s_out);
     const size_t off = a * (size_t)n_ch * CARTA1_SU_BYTES;
-    CU(ctx, small_copy(su_out + off, ctx->stage_su[sl].p, out_units * CARTA1_SU_BYTES, cudaMemcpyDeviceToHost,
-                       su_alias ? su_alias + off : nullptr, nullptr, s_out, &ctx->prof));
+    if (bounce_out) {
+      uint8_t *bs = (uint8_t *)ctx->bounce_su[sl].p;  // drained (pass - 1 at the latest) before it is reused
+      CU(ctx, small_copy(bs, ctx->stage_su[sl].p, out_units * CARTA1_SU_BYTES, cudaMemcpyDeviceToHost,
+                         (uint8_t *)mapped_alias(bs), nullptr, s_out, &ctx->prof));
+    } else {
+      CU(ctx, small_copy(su_out + off, ctx->stage_su[sl].p, out_units * CARTA1_SU_BYTES, cudaMemcpyDeviceToHost,
+                         su_alias ? su_alias + off : nullptr, nullptr, s_out, &ctx->prof));
+    }
     CU(ctx, cudaEventRecord(ctx->ev_out[sl], s_out));
     tr.mark(s_out);
+    if (bounce_out) {
+      CU(ctx, drain());  // the previous pass, while this one runs
+      pend.on = true; pend.sl = sl; pend.off = off; pend.bytes = out_units * CARTA1_SU_BYTES;
+    }
   }
+  CU(ctx, drain());
   CU(ctx, cudaStreamSynchronize(s_out));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   tr.report();
@@ -778,6 +877,37 @@ static int decode_host_impl(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int
   size_t pass = 0;
   const uint8_t *su_alias = (const uint8_t *)mapped_alias(su);
   cudaStream_t s_in = small_copy_mode() == 0 ? ctx->h2d : ctx->small;
+  // pageable caller arrays go through the pinned bounce slots (see encode_host_impl)
+  const size_t kBounceMinBytes = bounce_min_bytes();
+  const bool bounce_in = !su_alias && n_su * CARTA1_SU_BYTES >= kBounceMinBytes / 8;
+  const size_t pcm_bytes = frames * 512 * (size_t)n_ch * out_elem;
+  bool bounce_out = pcm_bytes >= kBounceMinBytes;
+  if (bounce_out) {
+    bool pinned = true;
+    if (channels_out) { for (int c = 0; c < n_ch; c++) pinned = pinned && channels_out[c] && mapped_alias(channels_out[c]); }
+    else pinned = mapped_alias(interleaved_out) != nullptr;
+    bounce_out = !pinned;
+  }
+  for (int sl = 0; sl < kSlots; sl++) {
+    if (bounce_in) CU(ctx, ctx->bounce_su[sl].ensure((max_frames + 1) * (size_t)n_ch * CARTA1_SU_BYTES));
+    if (bounce_out) CU(ctx, ctx->bounce_pcm[sl].ensure((size_t)n_ch * max_frames * 512 * out_elem));
+  }
+  struct Pending { bool on = false; int sl = 0; size_t a = 0, span = 0; } pend;  // PCM bounce slot to drain
+  auto drain = [&]() -> cudaError_t {
+    if (!pend.on) return cudaSuccess;
+    cudaError_t e = cudaEventSynchronize(ctx->ev_out[pend.sl]);
+    if (e == cudaSuccess) {
+      const char *bb = (const char *)ctx->bounce_pcm[pend.sl].p;
+      if (channels_out) {
+        for (int c = 0; c < n_ch; c++)
+          parallel_memcpy(channels_out[c] + pend.a * 512, bb + (size_t)c * pend.span * sizeof(float), pend.span * sizeof(float));
+      } else {
+        parallel_memcpy(interleaved_out + pend.a * 512 * (size_t)n_ch, bb, (size_t)n_ch * pend.span * sizeof(int16_t));
+      }
+    }
+    pend.on = false;
+    return e;
+  };
   PassTrace tr;
   tr.start("decode", s_in);
   for (size_t a = 0; a < frames; a += chunk, pass++) {
@@ -787,12 +917,20 @@ static int decode_host_impl(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int
     const size_t first = a - halo;
     const size_t want_units = (b - first) * (size_t)n_ch;
     const size_t have_units = std::min(n_su - first * (size_t)n_ch, want_units);
+    const size_t off = first * (size_t)n_ch * CARTA1_SU_BYTES;
+    const uint8_t *src = su + off, *src_alias = su_alias ? su_alias + off : nullptr;
+    if (bounce_in) {
+      if (pass >= (size_t)kSlots) CU(ctx, cudaEventSynchronize(ctx->ev_bin[sl]));
+      parallel_memcpy(ctx->bounce_su[sl].p, su + off, have_units * CARTA1_SU_BYTES);
+      src = (const uint8_t *)ctx->bounce_su[sl].p;
+      src_alias = (const uint8_t *)mapped_alias(src);
+    }
     if (pass >= (size_t)kUnitSlots) CU(ctx, cudaStreamWaitEvent(s_in, ctx->ev_ucomp[us], 0));
     tr.mark(s_in);
-    const size_t off = first * (size_t)n_ch * CARTA1_SU_BYTES;
-    CU(ctx, small_copy(ctx->stage_su[us].p, su + off, have_units * CARTA1_SU_BYTES, cudaMemcpyHostToDevice, nullptr,
-                       su_alias ? su_alias + off : nullptr, s_in, &ctx->prof));
+    CU(ctx, small_copy(ctx->stage_su[us].p, src, have_units * CARTA1_SU_BYTES, cudaMemcpyHostToDevice, nullptr, src_alias,
+                       s_in, &ctx->prof));
     CU(ctx, cudaEventRecord(ctx->ev_uin[us], s_in));
+    if (bounce_in) CU(ctx, cudaEventRecord(ctx->ev_bin[sl], s_in));
     tr.mark(s_in);
     CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_uin[us], 0));
     if (pass >= (size_t)kSlots) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[sl], 0));
@@ -806,7 +944,10 @@ static int decode_host_impl(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int
     tr.mark(ctx->stream);
     CU(ctx, cudaStreamWaitEvent(ctx->d2h, ctx->ev_comp[sl], 0));
     tr.mark(ctx->d2h);
-    if (channels_out) {
+    if (bounce_out) {  // the slot was drained at pass - 3 at the latest
+      CU(ctx, cudaMemcpyAsync(ctx->bounce_pcm[sl].p, ctx->stage_pcm[sl].p, (size_t)n_ch * span * out_elem,
+                              cudaMemcpyDeviceToHost, ctx->d2h));
+    } else if (channels_out) {
       for (int c = 0; c < n_ch; c++)
         CU(ctx, cudaMemcpyAsync(channels_out[c] + a * 512, (float *)ctx->stage_pcm[sl].p + (size_t)c * span,
                                 span * sizeof(float), cudaMemcpyDeviceToHost, ctx->d2h));
@@ -816,7 +957,12 @@ static int decode_host_impl(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int
     }
     CU(ctx, cudaEventRecord(ctx->ev_out[sl], ctx->d2h));
     tr.mark(ctx->d2h);
+    if (bounce_out) {
+      CU(ctx, drain());  // the previous pass, while this one runs
+      pend.on = true; pend.sl = sl; pend.a = a; pend.span = span;
+    }
   }
+  CU(ctx, drain());
   CU(ctx, cudaStreamSynchronize(ctx->d2h));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   tr.report();

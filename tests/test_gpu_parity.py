@@ -250,6 +250,34 @@ def test_pinned_host_buffers(ctx, oracle, units):
         ctx.set_max_units_per_pass(0)
 
 
+@pytest.mark.parametrize("units", [6, 64, 4096])
+def test_pageable_buffers_take_the_bounce_path(ctx, oracle, units, monkeypatch):
+    """Pageable caller arrays are staged through the context's pinned bounce slots (parallel memcpy, one pass
+    behind); CARTA1_BOUNCE_MIN_BYTES=0 forces that path at test size.  f32 and int16 PCM, both directions."""
+    monkeypatch.setenv("CARTA1_BOUNCE_MIN_BYTES", "0")
+    chans = S.cfg3_transients(2.3, seed=17, n_ch=2)
+    want = oracle.encode_pcm(chans, threads=8, chunk_frames=32)
+    ref = oracle.decode_su(want, 2, threads=8, chunk_frames=32)
+    ctx.set_max_units_per_pass(units)
+    try:
+        su = ctx.encode_pcm(chans)
+        assert np.array_equal(su, want)
+        pcm = ctx.decode_su(su, 2)
+        for x, y in zip(pcm, ref):
+            assert np.array_equal(bits(x), bits(y))
+        s16 = ctx.decode_su_s16(su, 2).reshape(-1, 2)
+        for c in range(2):
+            assert np.array_equal(s16[:, c], oracle.pcm_to_int16(ref[c]))
+        x16 = np.stack([oracle.pcm_to_int16(c) for c in chans], axis=1)
+        back = [oracle.int16_to_pcm(x16[:, c].copy()) for c in range(2)]
+        assert np.array_equal(ctx.encode_pcm_s16(x16, 2), oracle.encode_pcm(back, threads=8, chunk_frames=32))
+        mono = ctx.encode_pcm([chans[0][:70001]])
+        assert np.array_equal(mono, oracle.encode_pcm([chans[0][:70001]]))
+        assert np.array_equal(bits(ctx.decode_su(mono, 1)[0]), bits(oracle.decode_su(mono, 1)[0]))
+    finally:
+        ctx.set_max_units_per_pass(0)
+
+
 def test_encode_and_decode_calls_in_flight_together(oracle):
     """Two contexts, two host threads: carta1_encode_pcm and carta1_decode_su overlap (the e2e leg of
     bench.py); results equal the one-after-the-other results."""

@@ -67,3 +67,30 @@ if trace:
     print("-- encode alone", file=sys.stderr); enc()
     print("-- decode alone", file=sys.stderr); dec()
     print("-- duplex", file=sys.stderr); duplex()
+
+# pageable caller buffers (what a host that cannot pin its arrays passes): cudaMemcpyAsync stages through the driver
+chans_p = [np.array(c) for c in chans]
+outs_p = [np.empty_like(o) for o in outs]
+su_p = np.empty_like(su)
+
+
+def enc_p():
+    c1.encode_pcm_into(chans_p, su_p, opts)
+
+
+def dec_p():
+    c2.decode_su_into(su_p, n_su, 2, outs_p)
+
+
+tep, tdp = wall(enc_p), wall(dec_p)
+print("pageable buffers: encode %.2f ms  decode %.2f ms  sum %.2f ms (%.0f audio-s/s)" % (
+    tep, tdp, tep + tdp, seconds / (tep + tdp) * 1e3), flush=True)
+t0 = time.perf_counter()
+for a in chans_p + outs_p + [su_p]:
+    torch.cuda.cudart().cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+t1 = time.perf_counter()
+tep, tdp = wall(enc_p), wall(dec_p)
+print("after cudaHostRegister (%.1f ms for %.2f GB): encode %.2f ms  decode %.2f ms" % (
+    (t1 - t0) * 1e3, sum(a.nbytes for a in chans_p + outs_p + [su_p]) / 1e9, tep, tdp), flush=True)
+for a in chans_p + outs_p + [su_p]:
+    torch.cuda.cudart().cudaHostUnregister(a.ctypes.data)
