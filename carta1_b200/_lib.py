@@ -58,7 +58,7 @@ EXPORTED_SYMBOLS = [
     "carta1_ctx_launch_count", "carta1_debug_encode_stages", "carta1_debug_decode_stages",
     "carta1_aea_write_header", "carta1_aea_parse_header", "carta1_kernel_count", "carta1_kernel_name",
     "carta1_ctx_profile", "carta1_ctx_profile_read", "carta1_debug_selftest",
-    "carta1_ctx_set_max_units_per_pass",
+    "carta1_ctx_set_max_units_per_pass", "carta1_host_alloc", "carta1_host_free",
 ]
 
 _lib = None
@@ -118,6 +118,9 @@ def load():
     L.carta1_ctx_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
     L.carta1_debug_selftest.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.carta1_ctx_set_max_units_per_pass.argtypes = [vp, sz]
+    L.carta1_host_alloc.argtypes = [sz, C.POINTER(vp)]
+    L.carta1_host_free.argtypes = [vp]
+    L.carta1_host_free.restype = None
     L.carta1_debug_encode_stages.argtypes = [vp, vp, sz, C.POINTER(EncOpts), vp, vp, vp, vp, vp]
     L.carta1_debug_decode_stages.argtypes = [vp, vp, sz, vp, vp, vp]
     L.carta1_aea_write_header.argtypes = [C.c_char_p, C.c_uint32, C.c_int, vp]
@@ -394,6 +397,24 @@ class StreamDecoder:
             self.close()
         except Exception:
             pass
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """A numpy array on page-locked host memory (carta1_host_alloc): the device reads and writes it in place.
+    The memory is released when the array (and every view of it) is garbage-collected."""
+    L = load()
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+    p = C.c_void_p()
+    rc = L.carta1_host_alloc(n * dt.itemsize, C.byref(p))
+    if rc != 0:
+        raise Carta1Error("carta1_host_alloc failed: " + L.carta1_last_error(None).decode())
+    buf = (C.c_char * max(n * dt.itemsize, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+    import weakref
+
+    weakref.finalize(buf, L.carta1_host_free, p.value)
+    return arr
 
 
 def aea_write_header(title: str, su_count: int, n_ch: int) -> np.ndarray:

@@ -551,6 +551,15 @@ int carta1_ctx_profile_read(carta1_ctx *ctx, double *ms_out, uint64_t *count_out
 }
 size_t carta1_frame_count(size_t n_samples) { return (n_samples + 511) / 512; }
 
+int carta1_host_alloc(size_t bytes, void **out) {
+  if (!out) return CARTA1_ERR_ARG;
+  *out = nullptr;
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaHostAlloc");
+  return CARTA1_OK;
+}
+void carta1_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 int carta1_ctx_set_max_units_per_pass(carta1_ctx *ctx, size_t units) {
   if (!ctx) return CARTA1_ERR_ARG;
   ctx->max_units_per_pass = units ? units : (size_t)1 << 16;

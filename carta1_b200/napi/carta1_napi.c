@@ -280,9 +280,11 @@ typedef struct {
   /* decode */
   const uint8_t *su;
   size_t n_su;
-  /* results (malloc'd by the worker, copied into JS memory on completion) */
+  /* results: typed arrays created on the main thread before the work is queued; the library writes into
+   * them (pageable memory: staged through the context's pinned bounce slots), so completion copies nothing */
+  napi_ref out_ref[2];
   uint8_t *su_out;
-  size_t n_su_out;
+  size_t su_cap, n_su_out;
   float *pcm_out[2];
   size_t frames;
   int rc;
@@ -292,16 +294,8 @@ typedef struct {
 static void job_execute(napi_env env, void *data) {
   job *j = (job *)data;
   (void)env;
-  if (j->encode) {
-    const size_t cap = carta1_frame_count(j->n_samples) * (size_t)j->n_ch * CARTA1_SU_BYTES;
-    j->su_out = (uint8_t *)malloc(cap ? cap : 1);
-    j->rc = carta1_encode_pcm(j->ctx, j->chan, j->n_ch, j->n_samples, &j->opts, j->su_out, cap, &j->n_su_out);
-  } else {
-    int c;
-    j->frames = (j->n_su + (size_t)j->n_ch - 1) / (size_t)j->n_ch;
-    for (c = 0; c < j->n_ch; c++) j->pcm_out[c] = (float *)malloc((j->frames ? j->frames : 1) * 512 * sizeof(float));
-    j->rc = carta1_decode_su(j->ctx, j->su, j->n_su, j->n_ch, j->pcm_out);
-  }
+  if (j->encode) j->rc = carta1_encode_pcm(j->ctx, j->chan, j->n_ch, j->n_samples, &j->opts, j->su_out, j->su_cap, &j->n_su_out);
+  else j->rc = carta1_decode_su(j->ctx, j->su, j->n_su, j->n_ch, j->pcm_out);
   if (j->rc) { strncpy(j->err, carta1_last_error(j->ctx), sizeof j->err - 1); j->err[sizeof j->err - 1] = 0; }
 }
 
@@ -310,14 +304,12 @@ static void job_complete(napi_env env, napi_status status, void *data) {
   napi_value result = NULL, msg, err;
   int i;
   if (status == napi_ok && j->rc == 0) {
-    void *dst;
     if (j->encode) {
-      result = new_typed(env, napi_uint8_array, j->n_su_out * CARTA1_SU_BYTES, 1, &dst);
-      if (result) memcpy(dst, j->su_out, j->n_su_out * CARTA1_SU_BYTES);
+      if (napi_get_reference_value(env, j->out_ref[0], &result) != napi_ok) result = NULL;
     } else if (napi_create_array_with_length(env, (size_t)j->n_ch, &result) == napi_ok) {
       for (i = 0; i < j->n_ch; i++) {
-        napi_value ch = new_typed(env, napi_float32_array, j->frames * 512, 4, &dst);
-        if (ch) { memcpy(dst, j->pcm_out[i], j->frames * 512 * sizeof(float)); napi_set_element(env, result, (uint32_t)i, ch); }
+        napi_value ch;
+        if (napi_get_reference_value(env, j->out_ref[i], &ch) == napi_ok) napi_set_element(env, result, (uint32_t)i, ch);
       }
     }
   }
@@ -330,8 +322,8 @@ static void job_complete(napi_env env, napi_status status, void *data) {
     napi_reject_deferred(env, j->deferred, err);
   }
   for (i = 0; i < j->n_keep; i++) napi_delete_reference(env, j->keep[i]);
+  for (i = 0; i < 2; i++) if (j->out_ref[i]) napi_delete_reference(env, j->out_ref[i]);
   napi_delete_async_work(env, j->work);
-  free(j->su_out); free(j->pcm_out[0]); free(j->pcm_out[1]);
   free(j);
 }
 
@@ -375,6 +367,14 @@ static napi_value EncodePcm(napi_env env, napi_callback_info info) {
     napi_create_reference(env, e, 1, &j->keep[j->n_keep++]);
   }
   if (argc < 3 || !read_opts(env, argv[2], &j->opts, j->bsf)) carta1_default_enc_opts(&j->opts);
+  {
+    napi_value out;
+    void *dst;
+    j->su_cap = carta1_frame_count(j->n_samples) * (size_t)n_ch * CARTA1_SU_BYTES;
+    out = new_typed(env, napi_uint8_array, j->su_cap, 1, &dst);
+    if (!out || napi_create_reference(env, out, 1, &j->out_ref[0]) != napi_ok) { free(j); return NULL; }
+    j->su_out = (uint8_t *)dst;
+  }
   return queue_job(env, j, "carta1_b200.encodePcm");
 }
 
@@ -396,6 +396,16 @@ static napi_value DecodeSu(napi_env env, napi_callback_info info) {
   j = (job *)calloc(1, sizeof *j);
   j->ctx = (carta1_ctx *)hc->ptr; j->n_ch = n_ch; j->su = (const uint8_t *)data; j->n_su = len / CARTA1_SU_BYTES;
   napi_create_reference(env, argv[1], 1, &j->keep[j->n_keep++]);
+  j->frames = (j->n_su + (size_t)n_ch - 1) / (size_t)n_ch;
+  {
+    int c;
+    for (c = 0; c < n_ch; c++) {
+      void *dst;
+      napi_value out = new_typed(env, napi_float32_array, j->frames * 512, 4, &dst);
+      if (!out || napi_create_reference(env, out, 1, &j->out_ref[c]) != napi_ok) { free(j); return NULL; }
+      j->pcm_out[c] = (float *)dst;
+    }
+  }
   return queue_job(env, j, "carta1_b200.decodeSu");
 }
 

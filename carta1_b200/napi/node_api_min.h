@@ -80,6 +80,8 @@ napi_status napi_is_typedarray(napi_env, napi_value, bool *result);
 napi_status napi_get_typedarray_info(napi_env, napi_value typedarray, napi_typedarray_type *type, size_t *length,
                                      void **data, napi_value *arraybuffer, size_t *byte_offset);
 napi_status napi_create_arraybuffer(napi_env, size_t byte_length, void **data, napi_value *result);
+napi_status napi_create_external_arraybuffer(napi_env, void *external_data, size_t byte_length, napi_finalize finalize_cb,
+                                             void *finalize_hint, napi_value *result);
 napi_status napi_create_typedarray(napi_env, napi_typedarray_type type, size_t length, napi_value arraybuffer,
                                    size_t byte_offset, napi_value *result);
 napi_status napi_create_external(napi_env, void *data, napi_finalize finalize_cb, void *finalize_hint, napi_value *result);
@@ -89,6 +91,7 @@ napi_status napi_throw_type_error(napi_env, const char *code, const char *msg);
 napi_status napi_create_error(napi_env, napi_value code, napi_value msg, napi_value *result);
 napi_status napi_create_type_error(napi_env, napi_value code, napi_value msg, napi_value *result);
 napi_status napi_create_reference(napi_env, napi_value value, uint32_t initial_refcount, napi_ref *result);
+napi_status napi_get_reference_value(napi_env, napi_ref ref, napi_value *result);
 napi_status napi_delete_reference(napi_env, napi_ref ref);
 napi_status napi_create_promise(napi_env, napi_deferred *deferred, napi_value *promise);
 napi_status napi_resolve_deferred(napi_env, napi_deferred deferred, napi_value resolution);

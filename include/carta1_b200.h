@@ -82,9 +82,20 @@ int carta1_device_count(void);
 size_t carta1_frame_count(size_t n_samples); /* frameBufferToFrames, processor.js:246-279 */
 /* The host entry points below stage at most `units` sound units (frames x channels) per pass
  * through device memory, re-reading a 2-frame PCM halo (decode: 1 unit) at every pass boundary
- * (SURVEY.md Appendix B); passes are double-buffered (copies overlap compute).  0 restores
- * the default of 2^16.  Results never depend on it. */
+ * (SURVEY.md Appendix B); passes rotate through four staging slots (copies overlap compute).
+ * 0 restores the default of 2^16.  Results never depend on it. */
 int carta1_ctx_set_max_units_per_pass(carta1_ctx *ctx, size_t units);
+
+/* Caller buffers may be pinned or pageable.  Pinned buffers (carta1_host_alloc, cudaHostAlloc,
+ * cudaHostRegister) are read and written in place by the copy engines and kernels: 1 h of stereo
+ * PCM encodes in 24 ms.  Pageable buffers of 8 MiB and more are staged through pinned bounce slots
+ * owned by the context, filled and drained by a multi-threaded memcpy one pass behind: 44 ms.  An
+ * encode call and a decode call on two contexts (two host threads) overlap on the PCIe link.
+ * carta1_host_alloc returns page-locked host memory for a host runtime to build its typed arrays
+ * on (Node: napi_create_external_arraybuffer); it has no counterpart in the reference, whose
+ * Float32Array / Uint8Array results are plain allocations (processor.js:641-654). */
+int carta1_host_alloc(size_t bytes, void **out);
+void carta1_host_free(void *p);
 
 /* channels[c] points to n_samples f32 samples (planar; caller zero-pads the shorter stereo
  * channel as frameBufferToFrames does).  Writes frame_count*n_ch sound units interleaved
