@@ -1086,6 +1086,109 @@ __device__ __forceinline__ double run_candidate(AlWarpSmem &S, const AlSmem &C, 
   return total;
 }
 
+// One group of 32 consecutive output units, one unit per lane (the body of K4a).
+__device__ __forceinline__ void alloc_group(AlWarpSmem &S, const AlSmem &C, const uint8_t *__restrict__ sfi_all, int frames,
+                                            int halo, int n_out_frames, long long n_units, const FormatTables &F,
+                                            const DevEncParams *__restrict__ P, AllocRec *recs, AllocCand *cands,
+                                            long long unit0, int lane) {
+  __syncwarp();
+  // ---- phase A: the scale-factor indices the MDCT kernels left per unit (64-byte records)
+  for (int item = lane; item < 32 * 13; item += 32) {
+    const int u = item / 13, w = item - u * 13;
+    const long long unit = unit0 + u;
+    uint32_t v = 0;
+    if (unit < n_units) {
+      const size_t su = (size_t)(unit / n_out_frames) * frames + halo + (size_t)(unit % n_out_frames);
+      v = __ldg(reinterpret_cast<const uint32_t *>(sfi_all + su * 64) + w);
+    }
+    reinterpret_cast<uint32_t *>(&S.sfi[u][0])[w] = v;
+  }
+  __syncwarp();
+  // ---- pass 1: the 52-BFU candidate of the lane's unit; its result is the provisional record
+  const bool live = unit0 + lane < n_units;
+  double total52 = 0.0;
+  uint32_t survive = 0;
+  if (live) {
+    total52 = run_candidate(S, C, P, F, S.sfi[lane], 52, lane);
+    AllocRec *r = recs + (unit0 + lane);
+    r->n_bfu = 52;
+    for (int b = 0; b < 52; b++) { r->wl[b] = S.wl[b][lane]; r->sfi[b] = S.sfi[lane][b]; }
+    // Candidate pruning (exact): candidate n leaves BFUs >= n uncoded, which alone costs
+    // tail(n) = sum_{i>=n} zeroBit[i]; if that, deflated by the worst-case rounding of the
+    // reference's own 52-term summation (1 - 2^-40), already exceeds the 52-BFU total, the
+    // candidate can neither win nor tie and is not run.
+    double tail = 0.0;
+    int c = 6;
+    for (int i = 51; i >= 20; i--) {
+      const int sfi = S.sfi[lane][i];
+      if (sfi) tail += (double)P->zero_bit[sfi * 8 + F.size_class[i]];
+      const int bound = c == 0 ? 20 : 24 + 4 * c;  // BFU_AMOUNTS[c]
+      if (i == bound) {
+        if (!(tail * (1.0 - 9.094947017729282e-13) > total52)) survive |= 1u << c;
+        c--;
+      }
+    }
+  }
+  // ---- compact the surviving (unit, candidate) pairs of the warp and run them 32 at a time
+  const int n_mine = __popc(survive);
+  int incl = n_mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  const int n_list = __shfl_sync(0xffffffffu, incl, 31);
+  {
+    int at = incl - n_mine;
+    for (uint32_t m = survive; m; m &= m - 1) S.list[at++] = (uint16_t)((lane << 3) | (__ffs(m) - 1));
+  }
+  __syncwarp();
+  for (int base = 0; base < n_list; base += 32) {  // uniform trip count
+    const int k = base + lane;
+    if (k < n_list) {
+      const int u = S.list[k] >> 3, c = S.list[k] & 7;
+      const int cand = c == 0 ? 20 : 24 + 4 * c;
+      const double total = run_candidate(S, C, P, F, S.sfi[u], cand, lane);
+      AllocCand *ac = cands + (unit0 + u);
+      ac->total[c] = total;
+      for (int b = 0; b < cand; b++) ac->wl[c][b] = S.wl[b][lane];
+    }
+    __syncwarp();
+  }
+  __threadfence_block();
+  __syncwarp();
+  // ---- first strict minimum over ascending candidates (bitallocation.js:91-130)
+  if (live && survive) {
+    const AllocCand *ac = cands + (unit0 + lane);
+    double min_total = __longlong_as_double(0x7ff0000000000000ll);
+    int best = -1;
+    for (int c = 0; c < 7; c++) {
+      if (!(survive >> c & 1)) continue;
+      const double t = ac->total[c];
+      if (t < min_total) { min_total = t; best = c; }
+    }
+    if (total52 < min_total) best = 7;
+    AllocRec *r = recs + (unit0 + lane);
+    if (best < 0) {  // bitallocation.js:132-139
+      r->n_bfu = 20;
+      for (int b = 0; b < 52; b++) { r->wl[b] = 0; r->sfi[b] = 0; }
+    } else if (best < 7) {
+      const int cand = best == 0 ? 20 : 24 + 4 * best;
+      r->n_bfu = (uint8_t)cand;
+      for (int b = 0; b < 52; b++) r->wl[b] = b < cand ? ac->wl[best][b] : 0;
+    }
+  } else if (live && !(total52 < __longlong_as_double(0x7ff0000000000000ll))) {
+    AllocRec *r = recs + (unit0 + lane);  // no finite candidate at all: the reference's fallback
+    r->n_bfu = 20;
+    for (int b = 0; b < 52; b++) { r->wl[b] = 0; r->sfi[b] = 0; }
+  }
+}
+
+__device__ __forceinline__ void alloc_stage_tables(AlSmem &C, const DevEncParams *__restrict__ P, const FormatTables &F, int tid) {
+  if (tid < 64) { C.key0[tid] = P->key0[tid]; C.key1[tid] = P->key1[tid]; }
+  if (tid < 52) C.specs[tid] = F.specs[tid];
+}
+
 // Warps are independent (no CTA barrier after the tables are staged) and persistent: a warp
 // walks groups of 32 consecutive output units, one unit per lane.
 __global__ void __launch_bounds__(kAlWarps * 32)
@@ -1095,107 +1198,12 @@ alloc_kernel(const uint8_t *__restrict__ sfi_all, int frames, int halo, int n_ou
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AlSmem &C = *reinterpret_cast<AlSmem *>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  AlWarpSmem &S = C.w[warp];
   const long long n_units = (long long)n_streams * n_out_frames;
-  const FormatTables &F = T->fmt;
-  if (tid < 64) { C.key0[tid] = P->key0[tid]; C.key1[tid] = P->key1[tid]; }
-  if (tid < 52) C.specs[tid] = F.specs[tid];
+  alloc_stage_tables(C, P, T->fmt, tid);
   __syncthreads();
   const long long n_groups = (n_units + 31) / 32;
-  for (long long group = (long long)blockIdx.x * kAlWarps + warp; group < n_groups; group += (long long)gridDim.x * kAlWarps) {
-    const long long unit0 = group * 32;
-    __syncwarp();
-    // ---- phase A: the scale-factor indices the MDCT kernels left per unit (64-byte records)
-    for (int item = lane; item < 32 * 13; item += 32) {
-      const int u = item / 13, w = item - u * 13;
-      const long long unit = unit0 + u;
-      uint32_t v = 0;
-      if (unit < n_units) {
-        const size_t su = (size_t)(unit / n_out_frames) * frames + halo + (size_t)(unit % n_out_frames);
-        v = __ldg(reinterpret_cast<const uint32_t *>(sfi_all + su * 64) + w);
-      }
-      reinterpret_cast<uint32_t *>(&S.sfi[u][0])[w] = v;
-    }
-    __syncwarp();
-    // ---- pass 1: the 52-BFU candidate of the lane's unit; its result is the provisional record
-    const bool live = unit0 + lane < n_units;
-    double total52 = 0.0;
-    uint32_t survive = 0;
-    if (live) {
-      total52 = run_candidate(S, C, P, F, S.sfi[lane], 52, lane);
-      AllocRec *r = recs + (unit0 + lane);
-      r->n_bfu = 52;
-      for (int b = 0; b < 52; b++) { r->wl[b] = S.wl[b][lane]; r->sfi[b] = S.sfi[lane][b]; }
-      // Candidate pruning (exact): candidate n leaves BFUs >= n uncoded, which alone costs
-      // tail(n) = sum_{i>=n} zeroBit[i]; if that, deflated by the worst-case rounding of the
-      // reference's own 52-term summation (1 - 2^-40), already exceeds the 52-BFU total, the
-      // candidate can neither win nor tie and is not run.
-      double tail = 0.0;
-      int c = 6;
-      for (int i = 51; i >= 20; i--) {
-        const int sfi = S.sfi[lane][i];
-        if (sfi) tail += (double)P->zero_bit[sfi * 8 + F.size_class[i]];
-        const int bound = c == 0 ? 20 : 24 + 4 * c;  // BFU_AMOUNTS[c]
-        if (i == bound) {
-          if (!(tail * (1.0 - 9.094947017729282e-13) > total52)) survive |= 1u << c;
-          c--;
-        }
-      }
-    }
-    // ---- compact the surviving (unit, candidate) pairs of the warp and run them 32 at a time
-    const int n_mine = __popc(survive);
-    int incl = n_mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += t;
-    }
-    const int n_list = __shfl_sync(0xffffffffu, incl, 31);
-    {
-      int at = incl - n_mine;
-      for (uint32_t m = survive; m; m &= m - 1) S.list[at++] = (uint16_t)((lane << 3) | (__ffs(m) - 1));
-    }
-    __syncwarp();
-    for (int base = 0; base < n_list; base += 32) {  // uniform trip count
-      const int k = base + lane;
-      if (k < n_list) {
-        const int u = S.list[k] >> 3, c = S.list[k] & 7;
-        const int cand = c == 0 ? 20 : 24 + 4 * c;
-        const double total = run_candidate(S, C, P, F, S.sfi[u], cand, lane);
-        AllocCand *ac = cands + (unit0 + u);
-        ac->total[c] = total;
-        for (int b = 0; b < cand; b++) ac->wl[c][b] = S.wl[b][lane];
-      }
-      __syncwarp();
-    }
-    __threadfence_block();
-    __syncwarp();
-    // ---- first strict minimum over ascending candidates (bitallocation.js:91-130)
-    if (live && survive) {
-      const AllocCand *ac = cands + (unit0 + lane);
-      double min_total = __longlong_as_double(0x7ff0000000000000ll);
-      int best = -1;
-      for (int c = 0; c < 7; c++) {
-        if (!(survive >> c & 1)) continue;
-        const double t = ac->total[c];
-        if (t < min_total) { min_total = t; best = c; }
-      }
-      if (total52 < min_total) best = 7;
-      AllocRec *r = recs + (unit0 + lane);
-      if (best < 0) {  // bitallocation.js:132-139
-        r->n_bfu = 20;
-        for (int b = 0; b < 52; b++) { r->wl[b] = 0; r->sfi[b] = 0; }
-      } else if (best < 7) {
-        const int cand = best == 0 ? 20 : 24 + 4 * best;
-        r->n_bfu = (uint8_t)cand;
-        for (int b = 0; b < 52; b++) r->wl[b] = b < cand ? ac->wl[best][b] : 0;
-      }
-    } else if (live && !(total52 < __longlong_as_double(0x7ff0000000000000ll))) {
-      AllocRec *r = recs + (unit0 + lane);  // no finite candidate at all: the reference's fallback
-      r->n_bfu = 20;
-      for (int b = 0; b < 52; b++) { r->wl[b] = 0; r->sfi[b] = 0; }
-    }
-  }
+  for (long long group = (long long)blockIdx.x * kAlWarps + warp; group < n_groups; group += (long long)gridDim.x * kAlWarps)
+    alloc_group(C.w[warp], C, sfi_all, frames, halo, n_out_frames, n_units, T->fmt, P, recs, cands, group * 32, lane);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1230,6 +1238,91 @@ struct QpWarpSmem {
   uint32_t words[56];
 };
 
+// One sound unit by one warp (the body of K4b).
+__device__ __forceinline__ void qp_unit(QpWarpSmem &S, const uint16_t (*s_bj)[512], int sz0, int sz1,
+                                        const float *__restrict__ coefs, const uint8_t *__restrict__ modes,
+                                        const AllocRec *recs, int frames, int halo, int n_out_frames,
+                                        const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
+                                        uint8_t *__restrict__ su_out, size_t su_frame_stride, size_t su_stream_stride,
+                                        long long unit, int lane) {
+  uint32_t *words = S.words;
+  const int stream = (int)(unit / n_out_frames);
+  const int frame_out = (int)(unit % n_out_frames);
+  const size_t su = (size_t)stream * frames + halo + frame_out;
+  const float *src = coefs + su * 512;
+  float c[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) c[k] = __ldg(src + lane + 32 * k);
+  const AllocRec *r = recs + unit;
+  const int n = r->n_bfu;
+  int m0, m1, m2;
+  if (P->use_fixed) { m0 = P->fixed[0]; m1 = P->fixed[1]; m2 = P->fixed[2]; }
+  else { m0 = modes[su * 4]; m1 = modes[su * 4 + 1]; m2 = modes[su * 4 + 2]; }
+  __syncwarp();  // the previous unit's words have been stored
+  for (int i = lane; i < 56; i += 32) words[i] = 0;
+  __syncwarp();
+  // per-BFU records: widths, bit offsets (exclusive scan over bits * size), norm factors; the
+  // word-length and scale-factor fields of the unit
+  int run = 16 + 10 * n;
+  bool wrap = false;  // a BFU at the top scale factor: |coefficient| may exceed it, ToInt32 may wrap
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int b = lane + 32 * h;
+    const int sz = h == 0 ? sz0 : sz1;
+    int wl = 0, sfi = 0;
+    if (b < 52) { wl = r->wl[b]; sfi = r->sfi[b]; }
+    const int bits = b < n ? wl_bits(wl) : 0;
+    int incl = bits * sz;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (b < 52) {
+      const int base = run + incl - bits * sz;
+      const bool coded = bits > 0 && sfi > 0;
+      S.bfu[b].norm = coded ? __ldg(&T->norm[wl][sfi]) : 0.0;
+      S.bfu[b].base_bits = (uint32_t)base | ((uint32_t)bits << 11) | ((uint32_t)((1 << wl) - 1) << 16);
+      wrap |= coded && sfi == 63;
+      if (b < n) {
+        put_bits(words, 16 + 4 * b, (uint32_t)wl, 4);
+        put_bits(words, 16 + 4 * n + 6 * b, (uint32_t)sfi, 6);
+      }
+    }
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) {
+    const int idx = n == 20 ? 0 : (n - 24) / 4;
+    const uint32_t header = (((uint32_t)(2 - m0) << 14) | ((uint32_t)(2 - m1) << 12) |
+                             ((uint32_t)(3 - m2) << 10) | ((uint32_t)idx << 5)) & 0xFFFFu;
+    atomicOr(&words[0], header << 16);
+  }
+  wrap = __any_sync(0xffffffffu, wrap);
+  __syncwarp();
+  const uint16_t *bj0 = s_bj[m0 != 0] + lane, *bj1 = s_bj[m1 != 0] + lane, *bj2 = s_bj[m2 != 0] + lane;
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const uint32_t bj = (k < 4 ? bj0 : (k < 8 ? bj1 : bj2))[32 * k];
+    const QpBfu rec = S.bfu[bj >> 5];
+    const int bits = (rec.base_bits >> 11) & 31;
+    if (bits) {
+      const int range = (int)(rec.base_bits >> 16);
+      // x = c * normFactor; y = (x + (x >= 0 ? 0.5 : -0.5)) | 0; clamp to +-range.  norm == 0
+      // (sfi == 0) gives x = +-0 or NaN and y = 0, as the reference's early return does.
+      const double x = (double)c[k] * rec.norm;
+      const double xs = x + copysign(0.5, x);
+      int y = wrap ? js_to_int32(x + (x >= 0.0 ? 0.5 : -0.5)) : __double2int_rz(xs);
+      if (rec.norm == 0.0) y = 0;  // covers c == +-inf with norm == 0 (inf * 0 = NaN either way) and NaN signs
+      const int q = min(max(y, -range), range);
+      put_bits(words, (int)(rec.base_bits & 2047u) + (int)(bj & 31u) * bits, (uint32_t)q, bits);
+    }
+  }
+  __syncwarp();
+  uint32_t *dst = reinterpret_cast<uint32_t *>(
+      su_out + ((size_t)frame_out * su_frame_stride + (size_t)stream * su_stream_stride) * kSuBytes);
+  for (int i = lane; i < kSuWords; i += 32) dst[i] = __byte_perm(words[i], 0, 0x0123);
+}
+
 __global__ void __launch_bounds__(kQpWarps * 32)
 quant_pack_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes,
                   const AllocRec *__restrict__ recs, int frames, int halo, int n_out_frames, int n_streams,
@@ -1241,87 +1334,11 @@ quant_pack_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ m
   const FormatTables &F = T->fmt;
   for (int i = tid; i < 512; i += kQpWarps * 32) { s_bj[0][i] = F.bj_long[i]; s_bj[1][i] = F.bj_short[i]; }
   __syncthreads();
-  QpWarpSmem &S = s_warp[warp];
-  uint32_t *words = S.words;
   const int sz0 = F.specs[lane], sz1 = lane < 20 ? F.specs[lane + 32] : 0;
   const long long n_units = (long long)n_streams * n_out_frames;
-  for (long long unit = (long long)blockIdx.x * kQpWarps + warp; unit < n_units; unit += (long long)gridDim.x * kQpWarps) {
-    const int stream = (int)(unit / n_out_frames);
-    const int frame_out = (int)(unit % n_out_frames);
-    const size_t su = (size_t)stream * frames + halo + frame_out;
-    const float *src = coefs + su * 512;
-    float c[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) c[k] = __ldg(src + lane + 32 * k);
-    const AllocRec *r = recs + unit;
-    const int n = r->n_bfu;
-    int m0, m1, m2;
-    if (P->use_fixed) { m0 = P->fixed[0]; m1 = P->fixed[1]; m2 = P->fixed[2]; }
-    else { m0 = modes[su * 4]; m1 = modes[su * 4 + 1]; m2 = modes[su * 4 + 2]; }
-    __syncwarp();  // the previous unit's words have been stored
-    for (int i = lane; i < 56; i += 32) words[i] = 0;
-    __syncwarp();
-    // per-BFU records: widths, bit offsets (exclusive scan over bits * size), norm factors; the
-    // word-length and scale-factor fields of the unit
-    int run = 16 + 10 * n;
-    bool wrap = false;  // a BFU at the top scale factor: |coefficient| may exceed it, ToInt32 may wrap
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int b = lane + 32 * h;
-      const int sz = h == 0 ? sz0 : sz1;
-      int wl = 0, sfi = 0;
-      if (b < 52) { wl = r->wl[b]; sfi = r->sfi[b]; }
-      const int bits = b < n ? wl_bits(wl) : 0;
-      int incl = bits * sz;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-      }
-      if (b < 52) {
-        const int base = run + incl - bits * sz;
-        const bool coded = bits > 0 && sfi > 0;
-        S.bfu[b].norm = coded ? __ldg(&T->norm[wl][sfi]) : 0.0;
-        S.bfu[b].base_bits = (uint32_t)base | ((uint32_t)bits << 11) | ((uint32_t)((1 << wl) - 1) << 16);
-        wrap |= coded && sfi == 63;
-        if (b < n) {
-          put_bits(words, 16 + 4 * b, (uint32_t)wl, 4);
-          put_bits(words, 16 + 4 * n + 6 * b, (uint32_t)sfi, 6);
-        }
-      }
-      run += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane == 0) {
-      const int idx = n == 20 ? 0 : (n - 24) / 4;
-      const uint32_t header = (((uint32_t)(2 - m0) << 14) | ((uint32_t)(2 - m1) << 12) |
-                               ((uint32_t)(3 - m2) << 10) | ((uint32_t)idx << 5)) & 0xFFFFu;
-      atomicOr(&words[0], header << 16);
-    }
-    wrap = __any_sync(0xffffffffu, wrap);
-    __syncwarp();
-    const uint16_t *bj0 = s_bj[m0 != 0] + lane, *bj1 = s_bj[m1 != 0] + lane, *bj2 = s_bj[m2 != 0] + lane;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-      const uint32_t bj = (k < 4 ? bj0 : (k < 8 ? bj1 : bj2))[32 * k];
-      const QpBfu rec = S.bfu[bj >> 5];
-      const int bits = (rec.base_bits >> 11) & 31;
-      if (bits) {
-        const int range = (int)(rec.base_bits >> 16);
-        // x = c * normFactor; y = (x + (x >= 0 ? 0.5 : -0.5)) | 0; clamp to +-range.  norm == 0
-        // (sfi == 0) gives x = +-0 or NaN and y = 0, as the reference's early return does.
-        const double x = (double)c[k] * rec.norm;
-        const double xs = x + copysign(0.5, x);
-        int y = wrap ? js_to_int32(x + (x >= 0.0 ? 0.5 : -0.5)) : __double2int_rz(xs);
-        if (rec.norm == 0.0) y = 0;  // covers c == +-inf with norm == 0 (inf * 0 = NaN either way) and NaN signs
-        const int q = min(max(y, -range), range);
-        put_bits(words, (int)(rec.base_bits & 2047u) + (int)(bj & 31u) * bits, (uint32_t)q, bits);
-      }
-    }
-    __syncwarp();
-    uint32_t *dst = reinterpret_cast<uint32_t *>(
-        su_out + ((size_t)frame_out * su_frame_stride + (size_t)stream * su_stream_stride) * kSuBytes);
-    for (int i = lane; i < kSuWords; i += 32) dst[i] = __byte_perm(words[i], 0, 0x0123);
-  }
+  for (long long unit = (long long)blockIdx.x * kQpWarps + warp; unit < n_units; unit += (long long)gridDim.x * kQpWarps)
+    qp_unit(s_warp[warp], s_bj, sz0, sz1, coefs, modes, recs, frames, halo, n_out_frames, T, P, su_out, su_frame_stride,
+            su_stream_stride, unit, lane);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1431,25 +1448,26 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
   prof->end(K_MDCT, st);
   const long long n_units = (long long)L.n_streams * L.n_out_frames;
   if (n_units > 0 && L.su_out) {
-    cudaError_t e = cudaFuncSetAttribute(alloc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(AlSmem));
-    if (e != cudaSuccess) return e;
     AllocRec *recs = static_cast<AllocRec *>(L.alloc_recs);
     AllocCand *cands = reinterpret_cast<AllocCand *>(recs + n_units);
     const long long n_groups = (n_units + 31) / 32;
-    prof->begin(K_ALLOC, st);
-    alloc_kernel<<<(unsigned)std::min<long long>((n_groups + kAlWarps - 1) / kAlWarps,
-                                                 resident_ctas((const void *)alloc_kernel, kAlWarps * 32, sizeof(AlSmem))),
-                   kAlWarps * 32, sizeof(AlSmem), st>>>(
-        L.sfi, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params, recs, cands);
-    prof->end(K_ALLOC, st);
-    prof->begin(K_QUANT_PACK, st);
-    quant_pack_kernel<<<(unsigned)std::min<long long>((n_units + kQpWarps - 1) / kQpWarps,
-                                                      resident_ctas((const void *)quant_pack_kernel, kQpWarps * 32, 0)),
-                        kQpWarps * 32, 0, st>>>(
-        L.coefs, L.modes, recs, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params,
-        L.su_out, L.su_frame_stride, L.su_stream_stride);
-    prof->end(K_QUANT_PACK, st);
+    {
+      cudaError_t e = cudaFuncSetAttribute(alloc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AlSmem));
+      if (e != cudaSuccess) return e;
+      prof->begin(K_ALLOC, st);
+      alloc_kernel<<<(unsigned)std::min<long long>((n_groups + kAlWarps - 1) / kAlWarps,
+                                                   resident_ctas((const void *)alloc_kernel, kAlWarps * 32, sizeof(AlSmem))),
+                     kAlWarps * 32, sizeof(AlSmem), st>>>(
+          L.sfi, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params, recs, cands);
+      prof->end(K_ALLOC, st);
+      prof->begin(K_QUANT_PACK, st);
+      quant_pack_kernel<<<(unsigned)std::min<long long>((n_units + kQpWarps - 1) / kQpWarps,
+                                                        resident_ctas((const void *)quant_pack_kernel, kQpWarps * 32, 0)),
+                          kQpWarps * 32, 0, st>>>(
+          L.coefs, L.modes, recs, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params,
+          L.su_out, L.su_frame_stride, L.su_stream_stride);
+      prof->end(K_QUANT_PACK, st);
+    }
   }
   return cudaGetLastError();
 }

@@ -38,6 +38,13 @@ def main():
         audio = calls * N_STREAMS * nf * 512 / 44100.0
         print("frames/call %3d: encode %9.0f audio-s/s (%.2f ms/call)   decode %9.0f audio-s/s (%.2f ms/call)" % (
             nf, audio / (t1 - t0), 1e3 * (t1 - t0) / calls, audio / (t2 - t1), 1e3 * (t2 - t1) / calls))
+        ctx.profile(True)
+        for _ in range(20):
+            su = enc.frames(pcm, su_buf)
+            dec.frames(su, out_buf)
+        prof = ctx.profile_read()
+        ctx.profile(False)
+        print("      kernel ms per call: " + "  ".join("%s %.3f" % (k, v[0] / 20) for k, v in prof.items()))
         enc.close()
         dec.close()
     ctx.close()
