@@ -544,23 +544,24 @@ __device__ __forceinline__ void sy_load_unit(SyWarpSmem &S, const float *__restr
   for (int k = 0; k < 4; k++) x[k] = __ldg(r4 + lane + 32 * k);
   // lane p finishes sample p of each band: i = p < 16 ? p : 31 - p, w1 = WIN[i], w2 = WIN[31 - i]
   const int i = lane < 16 ? lane : 31 - lane;
-  float ola[3];
+#pragma unroll
+  for (int k = 0; k < 4; k++) reinterpret_cast<float4 *>(S.td)[lane + 32 * k] = x[k];
+  __syncwarp();
+  float ola[3], tl[3];
 #pragma unroll
   for (int b = 0; b < 3; b++) {
     const int off = b == 0 ? 0 : b == 1 ? 128 : 256;
     const double pv = (double)S.tail[16 * b + i];
-    const double cv = (double)__ldg(rec + off + 15 - i);
+    const double cv = (double)S.td[off + 15 - i];
     ola[b] = lane < 16 ? (float)(pv * w2 - cv * w1) : (float)(pv * w1 + cv * w2);
+    tl[b] = S.td[off + lane];  // record[16..32) is tail16 (lanes >= 16)
   }
-  __syncwarp();  // every lane has read the old tails
-#pragma unroll
-  for (int k = 0; k < 4; k++) reinterpret_cast<float4 *>(S.td)[lane + 32 * k] = x[k];
-  __syncwarp();
+  __syncwarp();  // every lane has read the old tails and the head of the record
 #pragma unroll
   for (int b = 0; b < 3; b++) {
     const int off = b == 0 ? 0 : b == 1 ? 128 : 256;
-    if (lane >= 16) S.tail[16 * b + lane - 16] = S.td[off + lane];  // record[16..32) is tail16
-    S.td[off + lane] = ola[b];                                          // (read above before this write)
+    if (lane >= 16) S.tail[16 * b + lane - 16] = tl[b];
+    S.td[off + lane] = ola[b];
   }
   __syncwarp();
   // merge low / mid (qmf.js:77-83): m = 4 lane + r -> element 24 + m = 4 (lane + 6) + r
@@ -589,13 +590,17 @@ __device__ __forceinline__ void sy_stage2(SyWarpSmem &S, int lane) {
   double ev[4], od[4];
   fir_synthesis<4, kSyStrideA>(S.a[0], lane, c_syn_odd, od);   // out2[2i],   i = 4 lane + r
   fir_synthesis<4, kSyStrideA>(S.a[1], lane, c_syn_even, ev);  // out2[2i+1]
+  // H[n - 39] = hd[8 lane + c + 1], c = 0..7: three aligned 16-byte reads instead of eight 8-way conflicting ones
+  const float4 ha = reinterpret_cast<const float4 *>(S.hd)[2 * lane], hb = reinterpret_cast<const float4 *>(S.hd)[2 * lane + 1],
+               hc = reinterpret_cast<const float4 *>(S.hd)[2 * lane + 2];
+  const float hv[8] = {ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w, hc.x};
 #pragma unroll
   for (int r = 0; r < 4; r++) {
 #pragma unroll
     for (int par = 0; par < 2; par++) {
       const int c = 2 * r + par;  // n = 8 lane + c
       const float x = (float)(par ? ev[r] : od[r]);
-      const float h = S.hd[8 * lane + c + 1];  // H[n - 39]
+      const float h = hv[c];
       const float s1 = (float)(0.5 * ((double)x + (double)h));
       const float d1 = (float)(0.5 * ((double)x - (double)h));
       // element 24 + n = 8 (lane + 3) + c
