@@ -506,46 +506,77 @@ __device__ double js_min(double a, double b) {
   return a < b ? a : b;
 }
 
-__global__ void __launch_bounds__(128)
+// A warp takes 8 consecutive sound units: their magnitude rows (and the row before the first) are
+// loaded coalesced into shared memory, then lane l < 24 runs unit l / 3, band l % 3.  Row stride
+// 273 floats and 8 floats of padding in front of each band keep the 24 lanes' serial walks on 24
+// different banks.
+constexpr int kTmWarps = 4, kTmUnits = 8, kTmRow = 273;
+__device__ __forceinline__ int tm_off(int band) { return band == 0 ? 0 : band == 1 ? 64 + 8 : 128 + 16; }
+
+__global__ void __launch_bounds__(kTmWarps * 32)
 transient_modes_kernel(const float *__restrict__ mags, const SpectrumFeatures *__restrict__ feats, int frames,
                        int n_su, const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
                        uint8_t *__restrict__ modes, double *__restrict__ scores) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int su = idx / 3, band = idx - su * 3;
-  if (su >= n_su) return;
-  const int frame = su % frames;
-  const int n = band == 2 ? 128 : 64;
-  const int off = band == 0 ? 0 : band == 1 ? 64 : 128;
-  const float *cur = mags + (size_t)su * 256 + off;
-  const float *prev = frame > 0 ? cur - 256 : nullptr;  // frame 0: all-zero previous spectrum
-  double flux = 0.0;
-  for (int i = 0; i < n; i++) {  // transient.js:92-112
-    const double c = fabs((double)cur[i]);
-    const double p = prev ? fabs((double)prev[i]) : 0.0;
-    const double d = c - p;
-    if (d > 0.0) flux += d;
+  __shared__ float s_rows[kTmWarps][(kTmUnits + 1) * kTmRow];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *rows = s_rows[warp];
+  const int n_groups = (n_su + kTmUnits - 1) / kTmUnits;
+  for (int group = blockIdx.x * kTmWarps + warp; group < n_groups; group += gridDim.x * kTmWarps) {
+    const int su0 = group * kTmUnits;
+    __syncwarp();
+    // rows[r] = magnitudes of unit su0 - 1 + r, r = 0..8 (64 float4 per row: lane covers two of them)
+    for (int r = 0; r <= kTmUnits; r++) {
+      const int su = su0 - 1 + r;
+      if (su < 0 || su >= n_su) continue;
+      const float4 *src = reinterpret_cast<const float4 *>(mags + (size_t)su * 256);
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const int q = lane + 32 * k;  // float4 index: bins 4q .. 4q + 3
+        const float4 v = __ldg(src + q);
+        const int band = q < 16 ? 0 : q < 32 ? 1 : 2;
+        float *dst = rows + r * kTmRow + 4 * q + 8 * band;
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+      }
+    }
+    __syncwarp();
+    const int u = lane / 3, band = lane - 3 * u;
+    const int su = su0 + u;
+    if (lane < 3 * kTmUnits && su < n_su) {
+      const int frame = su % frames;
+      const int n = band == 2 ? 128 : 64;
+      const float *cur = rows + (u + 1) * kTmRow + tm_off(band);
+      const float *prev = cur - kTmRow;
+      const bool has_prev = frame > 0;  // frame 0: all-zero previous spectrum
+      double flux = 0.0;
+      for (int i = 0; i < n; i++) {  // transient.js:92-112
+        const double c = fabs((double)cur[i]);
+        const double p = has_prev ? fabs((double)prev[i]) : 0.0;
+        const double d = c - p;
+        if (d > 0.0) flux += d;
+      }
+      const SpectrumFeatures fc = feats[(size_t)su * 3 + band];
+      SpectrumFeatures fp;  // features of the all-zero spectrum: no valid bin, no energy
+      fp.flatness = 0.0; fp.hf_ratio = 0.0; fp.energy = 0.0;
+      if (has_prev) fp = feats[(size_t)(su - 1) * 3 + band];
+      // the flux loop's own energy sum adds the same squares in the same order as the features' one
+      double norm = sqrt(fc.energy);
+      if (norm == 0.0 || isnan(norm)) norm = 1e-6;
+      const double spectral_flux = flux / norm;
+      const double flat_change = fabs(fc.flatness - fp.flatness);
+      const double hf_change = fabs(fc.hf_ratio - fp.hf_ratio);
+      const double ce = js_max(fc.energy, 1e-10), pe = js_max(fp.energy, 1e-10);  // :182-183
+      const double db = 10.0 * fd::log10(ce / pe);
+      const double e_change = js_max(0.0, db);
+      const double flat_c = sqrt(flat_change);
+      const double hf_c = fd::log1p(hf_change * 10.0) / T->log1p10;
+      const double e_c = js_min(e_change / 30.0, 1.0);
+      const double score = (spectral_flux + flat_c + hf_c + e_c) / 4.0;
+      // every band compares against transientThresholdLow (encoder.js:137-141); mode = t*max(b+1,2)
+      const int transient = score > P->threshold;
+      modes[(size_t)su * 4 + band] = (uint8_t)(transient ? (band == 2 ? 3 : 2) : 0);
+      if (scores) scores[(size_t)su * 3 + band] = score;
+    }
   }
-  const SpectrumFeatures fc = feats[(size_t)su * 3 + band];
-  SpectrumFeatures fp;  // features of the all-zero spectrum: no valid bin, no energy
-  fp.flatness = 0.0; fp.hf_ratio = 0.0; fp.energy = 0.0;
-  if (prev) fp = feats[(size_t)(su - 1) * 3 + band];
-  // the flux loop's own energy sum adds the same squares in the same order as the features' one
-  double norm = sqrt(fc.energy);
-  if (norm == 0.0 || isnan(norm)) norm = 1e-6;
-  const double spectral_flux = flux / norm;
-  const double flat_change = fabs(fc.flatness - fp.flatness);
-  const double hf_change = fabs(fc.hf_ratio - fp.hf_ratio);
-  const double ce = js_max(fc.energy, 1e-10), pe = js_max(fp.energy, 1e-10);  // :182-183
-  const double db = 10.0 * fd::log10(ce / pe);
-  const double e_change = js_max(0.0, db);
-  const double flat_c = sqrt(flat_change);
-  const double hf_c = fd::log1p(hf_change * 10.0) / T->log1p10;
-  const double e_c = js_min(e_change / 30.0, 1.0);
-  const double score = (spectral_flux + flat_c + hf_c + e_c) / 4.0;
-  // every band compares against transientThresholdLow (encoder.js:137-141); mode = t*max(b+1,2)
-  const int transient = score > P->threshold;
-  modes[(size_t)su * 4 + band] = (uint8_t)(transient ? (band == 2 ? 3 : 2) : 0);
-  if (scores) scores[(size_t)su * 3 + band] = score;
 }
 
 // ------------------------------------------------------------------------------------
@@ -1429,7 +1460,10 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
         L.bands, n_su, L.tables, L.mags, static_cast<SpectrumFeatures *>(L.feats));
     prof->end(K_BAND_MAGS, st);
     prof->begin(K_TRANSIENT_MODES, st);
-    transient_modes_kernel<<<(n_su * 3 + 127) / 128, 128, 0, st>>>(L.mags, static_cast<const SpectrumFeatures *>(L.feats),
+    const int n_tm_groups = (n_su + kTmUnits - 1) / kTmUnits;
+    transient_modes_kernel<<<std::min((n_tm_groups + kTmWarps - 1) / kTmWarps,
+                                      resident_ctas((const void *)transient_modes_kernel, kTmWarps * 32, 0)),
+                             kTmWarps * 32, 0, st>>>(L.mags, static_cast<const SpectrumFeatures *>(L.feats),
                                                                   frames, n_su, L.tables, L.params, L.modes, L.scores);
     prof->end(K_TRANSIENT_MODES, st);
   }
