@@ -421,8 +421,11 @@ transient_spectrum_kernel(const float *__restrict__ bands, int n_su, const DevTa
     if (__reduce_max_sync(0xffffffffu, big) < 0x71800000u) transient_ffts<FastRound>(band, S, lane, T);
     else transient_ffts_exact(band, S, lane, T);
     __syncwarp();
-    // magnitudes out; per-bin terms of the sums (logarithm, magnitude, square) and the mask of
-    // bins above EPS, computed by all lanes (bin lane + 32k); the term arrays reuse the transpose buffer
+    // magnitudes out; per-bin terms of the sums (logarithm, magnitude, square), computed by all lanes
+    // (bin lane + 32k); the term arrays reuse the transpose buffer.  The reference skips the bins at
+    // or below EPS in the first two sums (transient.js:126-131); here those bins contribute +0.0,
+    // which leaves a sum that started at +0.0 bit-identical (such a sum is never -0.0: an exact
+    // cancellation rounds to +0.0 and fdlibm's log(1) is +0.0), so the serial loops need no masks.
     const double EPS = 1e-10;
     double *t_mag = reinterpret_cast<double *>(S.xbuf), *t_sq = t_mag + 256;
     unsigned ok_mask[8];
@@ -434,14 +437,13 @@ transient_spectrum_kernel(const float *__restrict__ bands, int n_su, const DevTa
       const double v = (double)m, md = fabs(v);
       const bool ok = md > EPS;
       S.logm[i] = ok ? fd::log(md) : 0.0;
-      t_mag[i] = md;
+      t_mag[i] = ok ? md : 0.0;
       t_sq[i] = v * v;
       ok_mask[k] = __ballot_sync(0xffffffffu, ok);
     }
     __syncwarp();
     // serial sums in index order, one lane per (band, accumulator): 0 sum_log (+ valid count),
-    // 1 sum_lin, 2 lo then hi, 3 energy.  Every lane runs the same loop over its own term array;
-    // accumulators 0 and 1 skip the bins at or below EPS (transient.js:126-131), 2 and 3 take all.
+    // 1 sum_lin, 2 lo then hi, 3 energy.  Every lane runs the same loop over its own term array.
     const int band_i = lane >> 2, acc = lane & 3;
     double r0 = 0.0, r1 = 0.0;
     int valid = 0;
@@ -449,22 +451,15 @@ transient_spectrum_kernel(const float *__restrict__ bands, int n_su, const DevTa
       const int bi = band_i < 3 ? band_i : 0;
       const int n = bi == 2 ? 128 : 64, off = bi == 0 ? 0 : bi == 1 ? 64 : 128, mid = n >> 1;
       const double *term = (acc == 0 ? S.logm : acc == 1 ? t_mag : t_sq) + off;
-      const unsigned all = acc < 2 ? 0u : 0xffffffffu;
-      // masks of this band's bins: words off/32 ..
       const unsigned k0 = bi == 0 ? ok_mask[0] : (bi == 1 ? ok_mask[2] : ok_mask[4]);
       const unsigned k1 = bi == 0 ? ok_mask[1] : (bi == 1 ? ok_mask[3] : ok_mask[5]);
       const unsigned k2 = bi == 2 ? ok_mask[6] : 0u, k3 = bi == 2 ? ok_mask[7] : 0u;
-      const unsigned w0 = k0 | all, w1 = k1 | all, w2 = k2 | all, w3 = k3 | all;
       valid = __popc(k0) + __popc(k1) + __popc(k2) + __popc(k3);
-      for (int i = 0; i < mid; i++) {
-        const unsigned w = (i < 32 ? w0 : w1) >> (i & 31);
-        if (w & 1u) r0 += term[i];
-      }
+#pragma unroll 8
+      for (int i = 0; i < mid; i++) r0 += term[i];
       double rr = acc == 2 ? 0.0 : r0;
-      for (int i = mid; i < n; i++) {
-        const unsigned w = (i < 32 ? w0 : (i < 64 ? w1 : (i < 96 ? w2 : w3))) >> (i & 31);
-        if (w & 1u) rr += term[i];
-      }
+#pragma unroll 8
+      for (int i = mid; i < n; i++) rr += term[i];
       if (acc == 2) r1 = rr; else r0 = rr;
     }
     // gather the four lanes of a band on its first lane

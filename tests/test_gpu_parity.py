@@ -49,6 +49,10 @@ def mono_signals():
         "loud": (4.0 * rng.standard_normal(512 * 5)).astype(np.float32),
         "sparse": np.where(rng.uniform(size=512 * 6) > 0.97, rng.standard_normal(512 * 6), 0).astype(np.float32),
         "ragged": (0.3 * rng.standard_normal(512 * 3 + 77)).astype(np.float32),
+        # spectra that straddle the 1e-10 bin threshold of the transient detector (transient.js:126-131):
+        # some bins are skipped by the flatness sums, others are not, frame by frame
+        "threshold": (np.repeat(10.0 ** rng.uniform(-12.5, -9.5, 8), 512) * rng.standard_normal(512 * 8)).astype(np.float32),
+        "denormal": (1e-39 * rng.standard_normal(512 * 4)).astype(np.float32),
     }
     return sigs
 
