@@ -1116,10 +1116,10 @@ __device__ __forceinline__ double run_candidate(AlWarpSmem &S, const AlSmem &C, 
 __device__ __forceinline__ void alloc_group(AlWarpSmem &S, const AlSmem &C, const uint8_t *__restrict__ sfi_all, int frames,
                                             int halo, int n_out_frames, long long n_units, const FormatTables &F,
                                             const DevEncParams *__restrict__ P, AllocRec *recs, AllocCand *cands,
-                                            long long unit0, int lane) {
+                                            long long unit0, int group_lanes, int lane) {
   __syncwarp();
   // ---- phase A: the scale-factor indices the MDCT kernels left per unit (64-byte records)
-  for (int item = lane; item < 32 * 13; item += 32) {
+  for (int item = lane; item < group_lanes * 13; item += 32) {
     const int u = item / 13, w = item - u * 13;
     const long long unit = unit0 + u;
     uint32_t v = 0;
@@ -1131,7 +1131,7 @@ __device__ __forceinline__ void alloc_group(AlWarpSmem &S, const AlSmem &C, cons
   }
   __syncwarp();
   // ---- pass 1: the 52-BFU candidate of the lane's unit; its result is the provisional record
-  const bool live = unit0 + lane < n_units;
+  const bool live = lane < group_lanes && unit0 + lane < n_units;
   double total52 = 0.0;
   uint32_t survive = 0;
   if (live) {
@@ -1219,17 +1219,18 @@ __device__ __forceinline__ void alloc_stage_tables(AlSmem &C, const DevEncParams
 // walks groups of 32 consecutive output units, one unit per lane.
 __global__ void __launch_bounds__(kAlWarps * 32)
 alloc_kernel(const uint8_t *__restrict__ sfi_all, int frames, int halo, int n_out_frames, int n_streams,
-             const DevTables *__restrict__ T, const DevEncParams *__restrict__ P, AllocRec *__restrict__ recs,
-             AllocCand *__restrict__ cands) {
+             int group_lanes, const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
+             AllocRec *__restrict__ recs, AllocCand *__restrict__ cands) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AlSmem &C = *reinterpret_cast<AlSmem *>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long n_units = (long long)n_streams * n_out_frames;
   alloc_stage_tables(C, P, T->fmt, tid);
   __syncthreads();
-  const long long n_groups = (n_units + 31) / 32;
+  const long long n_groups = (n_units + group_lanes - 1) / group_lanes;
   for (long long group = (long long)blockIdx.x * kAlWarps + warp; group < n_groups; group += (long long)gridDim.x * kAlWarps)
-    alloc_group(C.w[warp], C, sfi_all, frames, halo, n_out_frames, n_units, T->fmt, P, recs, cands, group * 32, lane);
+    alloc_group(C.w[warp], C, sfi_all, frames, halo, n_out_frames, n_units, T->fmt, P, recs, cands, group * group_lanes,
+                group_lanes, lane);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1479,15 +1480,19 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
   if (n_units > 0 && L.su_out) {
     AllocRec *recs = static_cast<AllocRec *>(L.alloc_recs);
     AllocCand *cands = reinterpret_cast<AllocCand *>(recs + n_units);
-    const long long n_groups = (n_units + 31) / 32;
     {
       cudaError_t e = cudaFuncSetAttribute(alloc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AlSmem));
       if (e != cudaSuccess) return e;
+      // A lane walks its unit's heap serially and the lanes of a warp diverge, so a warp takes as long as
+      // its units together need; small batches therefore use fewer lanes per warp, as few as still leave
+      // no more groups than warps are resident (cfg1's 1,724 units: one lane each instead of 54 full warps).
+      const int ctas = resident_ctas((const void *)alloc_kernel, kAlWarps * 32, sizeof(AlSmem));
+      int group_lanes = 1;
+      while (group_lanes < 32 && (n_units + group_lanes - 1) / group_lanes > (long long)ctas * kAlWarps) group_lanes *= 2;
+      const long long n_groups = (n_units + group_lanes - 1) / group_lanes;
       prof->begin(K_ALLOC, st);
-      alloc_kernel<<<(unsigned)std::min<long long>((n_groups + kAlWarps - 1) / kAlWarps,
-                                                   resident_ctas((const void *)alloc_kernel, kAlWarps * 32, sizeof(AlSmem))),
-                     kAlWarps * 32, sizeof(AlSmem), st>>>(
-          L.sfi, frames, L.halo_frames, L.n_out_frames, L.n_streams, L.tables, L.params, recs, cands);
+      alloc_kernel<<<(unsigned)std::min<long long>((n_groups + kAlWarps - 1) / kAlWarps, ctas), kAlWarps * 32, sizeof(AlSmem), st>>>(
+          L.sfi, frames, L.halo_frames, L.n_out_frames, L.n_streams, group_lanes, L.tables, L.params, recs, cands);
       prof->end(K_ALLOC, st);
       prof->begin(K_QUANT_PACK, st);
       quant_pack_kernel<<<(unsigned)std::min<long long>((n_units + kQpWarps - 1) / kQpWarps,
