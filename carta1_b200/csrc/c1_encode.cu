@@ -979,7 +979,7 @@ mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, 
 // runs the 52-BFU candidate of unit u.  Survivors of the warp's units are compacted into a list
 // and run 32 at a time.
 //
-// Heap entries are one 32-bit word: key[24:10] | wl[9:6] | bfu[5:0].  `key` is an
+// Heap entries are one 32-bit word: key[29:15] | size[14:10] | wl[9:6] | bfu[5:0].  `key` is an
 // order-isomorphic 15-bit image of the reference's f32 priority (DevEncParams::key0/key1):
 // f32 exponent (8 bits) over the rank of the f32 mantissa among the 126 possible ones.  For
 // wl >= 1 the priority halves exactly with every step, i.e. key -= 128.  Heaps are stored
@@ -1025,23 +1025,58 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
 }
 constexpr uint32_t kNode = 32 * 4;  // byte stride between heap nodes
 
+constexpr uint32_t kLow = 0x7FFFu;  // everything below the key: size[14:10] | wl[9:6] | bfu[5:0]
+constexpr int kKeyShift = 15;
+
 // bitallocation.js:314-341.  `hole` is the address of the node being filled, `end` the
 // address of node `size`, `h0` the address of node 0; v is the entry being placed.
 __device__ __forceinline__ void heap_sift(uint32_t h0, uint32_t hole, uint32_t end, uint32_t v) {
-  const uint32_t vm = v | 0x3FFu;
+  const uint32_t vm = v | kLow;
   for (;;) {
     const uint32_t l = 2u * hole - h0 + kNode;  // node 2i+1
     if (l >= end) break;
     const uint32_t cl = lds32(l);
     const uint32_t cr = lds32(l + kNode);  // node `size` is kept zero
     const bool pl = cl > vm;
-    const uint32_t m = pl ? (cl | 0x3FFu) : vm;
+    const uint32_t m = pl ? (cl | kLow) : vm;
     const bool pr = cr > m;
     if (!(pl || pr)) break;
     sts32(hole, pr ? cr : cl);
     hole = pr ? l + kNode : l;
   }
   sts32(hole, v);
+}
+
+// The same from the root, for the greedy loop, where this walk is the critical path of every step:
+// the four grandchildren are fetched while the two children are compared (a level costs the
+// compare-select chain instead of a shared-memory round trip on top of it), and the entry that ends
+// up at the root is returned instead of being read back.  Nodes past `end` are not heap entries
+// (stale), so addresses are clamped to node `end`, which is kept zero.
+__device__ __forceinline__ uint32_t heap_sift_root(uint32_t h0, uint32_t end, uint32_t v) {
+  const uint32_t vm = v | kLow;
+  uint32_t hole = h0, l = h0 + kNode, root = v;
+  if (l < end) {
+    uint32_t cl = lds32(l), cr = lds32(l + kNode);
+    for (;;) {
+      const uint32_t ll = 2u * l - h0 + kNode;  // children of l: ll, ll + 1; of l + 1: ll + 2, ll + 3 (in nodes)
+      const uint32_t g0 = lds32(min(ll, end)), g1 = lds32(min(ll + kNode, end));
+      const uint32_t g2 = lds32(min(ll + 2 * kNode, end)), g3 = lds32(min(ll + 3 * kNode, end));
+      const bool pl = cl > vm;
+      const uint32_t m = pl ? (cl | kLow) : vm;
+      const bool pr = cr > m;
+      if (!(pl || pr)) break;
+      const uint32_t up = pr ? cr : cl;
+      sts32(hole, up);
+      if (hole == h0) root = up;
+      hole = pr ? l + kNode : l;
+      l = pr ? ll + 2 * kNode : ll;
+      if (l >= end) break;
+      cl = pr ? g2 : g0;
+      cr = pr ? g3 : g1;
+    }
+  }
+  sts32(hole, v);
+  return root;
 }
 
 // Greedy spend for one candidate (bitallocation.js:203-281) followed by its total
@@ -1058,9 +1093,10 @@ __device__ __forceinline__ double run_candidate(AlWarpSmem &S, const AlSmem &C, 
     W[b * 32] = 0;
     const uint32_t sfi = sfi_row[b];
     if (sfi) {
-      sts32(h0 + count * kNode, ((uint32_t)C.key0[sfi] << 10) | (uint32_t)b);
+      const uint32_t sz = C.specs[b];
+      sts32(h0 + count * kNode, ((uint32_t)C.key0[sfi] << kKeyShift) | (sz << 10) | (uint32_t)b);
       count++;
-      min_sz = min(min_sz, (int)C.specs[b]);
+      min_sz = min(min_sz, (int)sz);
     }
   }
   sts32(h0 + count * kNode, 0);
@@ -1074,12 +1110,12 @@ __device__ __forceinline__ double run_candidate(AlWarpSmem &S, const AlSmem &C, 
     while (remaining >= min_sz) {
       const int b = e & 63;
       const int wl = (e >> 6) & 15;
-      const int cost = (int)C.specs[b] << (wl == 0);
+      const int cost = (int)((e >> 10) & 31u) << (wl == 0);
       bool pop = cost > remaining;
       if (!pop) {
         remaining -= cost;
-        if (wl == 0) e = ((uint32_t)C.key1[sfi_row[b]] << 10) | (1u << 6) | (uint32_t)b;
-        else e += 64u - (128u << 10);  // wl + 1, priority halves exactly
+        if (wl == 0) e = ((uint32_t)C.key1[sfi_row[b]] << kKeyShift) | (e & (31u << 10)) | (1u << 6) | (uint32_t)b;
+        else e += 64u - (128u << kKeyShift);  // wl + 1, priority halves exactly
         pop = wl == 14;                // reached MAX_WORD_LENGTH_INDEX
       }
       if (pop) {
@@ -1089,8 +1125,7 @@ __device__ __forceinline__ double run_candidate(AlWarpSmem &S, const AlSmem &C, 
         e = lds32(end);
         sts32(end, 0);
       }
-      heap_sift(h0, h0, end, e);
-      e = lds32(h0);
+      e = heap_sift_root(h0, end, e);
     }
     for (uint32_t a = h0; a < end; a += kNode) {  // entries still in the heap keep their wl
       const uint32_t x = lds32(a);
