@@ -993,7 +993,7 @@ struct AllocRec {  // per sound unit, global scratch between K4a and K4b
   uint8_t sfi[52];
   uint8_t pad2[4];
 };
-static_assert(sizeof(AllocRec) == 112, "AllocRec layout");
+static_assert(sizeof(AllocRec) == 112 && offsetof(AllocRec, wl) == 4 && offsetof(AllocRec, sfi) == 56, "AllocRec layout");
 
 struct AllocCand {  // per sound unit: results of surviving smaller candidates
   double total[7];
@@ -1006,12 +1006,14 @@ struct AlWarpSmem {  // one warp = 32 sound units, one per lane
   uint32_t heap[53][32];
   uint8_t wl[52][32];
   uint8_t sfi[32][52];
-  uint16_t list[32 * 7];
+  uint8_t list[32 * 7];  // surviving (lane << 3 | candidate) pairs
 };
 struct AlSmem {
   AlWarpSmem w[kAlWarps];
+  double bsf[64];          // DevEncParams::bsf
+  float zero_bit[64 * 8];  // DevEncParams::zero_bit
   uint16_t key0[64], key1[64];
-  uint8_t specs[52];
+  uint8_t specs[52], size_class[52];
 };
 
 // Shared-memory byte addresses (32-bit) keep the sift loop free of 64-bit pointer math.
@@ -1132,17 +1134,18 @@ __device__ __forceinline__ double run_candidate(AlWarpSmem &S, const AlSmem &C, 
       W[(x & 63) * 32] = (uint8_t)((x >> 6) & 15);
     }
   }
+  // bitallocation.js:157-190.  A BFU with scale-factor index 0 adds +0.0 or is skipped by the reference;
+  // `total` starts at +0.0 and only ever grows, so adding +0.0 is the same: the loop is branch-free and
+  // only the additions are serial.
   double total = 0.0;
+#pragma unroll 4
   for (int i = 0; i < 52; i++) {
     const int sfi = sfi_row[i];
-    if (sfi == 0) continue;  // the reference adds +0.0 or skips
     const int bits = i < cand ? wl_bits(W[i * 32]) : 0;
-    if (bits == 0) {
-      total += (double)P->zero_bit[sfi * 8 + F.size_class[i]];
-    } else {
-      const double inv = __hiloint2double((1023 - bits) << 20, 0);
-      total += P->bsf[sfi] * inv * (double)C.specs[i];
-    }
+    const double zb = (double)C.zero_bit[sfi * 8 + C.size_class[i]];
+    const double inv = __hiloint2double((1023 - bits) << 20, 0);
+    const double coded = C.bsf[sfi] * inv * (double)C.specs[i];
+    total += sfi == 0 ? 0.0 : (bits == 0 ? zb : coded);
   }
   return total;
 }
@@ -1172,22 +1175,31 @@ __device__ __forceinline__ void alloc_group(AlWarpSmem &S, const AlSmem &C, cons
   if (live) {
     total52 = run_candidate(S, C, P, F, S.sfi[lane], 52, lane);
     AllocRec *r = recs + (unit0 + lane);
-    r->n_bfu = 52;
-    for (int b = 0; b < 52; b++) { r->wl[b] = S.wl[b][lane]; r->sfi[b] = S.sfi[lane][b]; }
+    {  // the record, four BFUs per 32-bit store: n_bfu | wl[52] | sfi[52]
+      uint32_t *rw = reinterpret_cast<uint32_t *>(r);
+      rw[0] = 52u;
+      const uint32_t *srow = reinterpret_cast<const uint32_t *>(&S.sfi[lane][0]);
+#pragma unroll
+      for (int q = 0; q < 13; q++) {
+        rw[1 + q] = (uint32_t)S.wl[4 * q][lane] | ((uint32_t)S.wl[4 * q + 1][lane] << 8) |
+                    ((uint32_t)S.wl[4 * q + 2][lane] << 16) | ((uint32_t)S.wl[4 * q + 3][lane] << 24);
+        rw[14 + q] = srow[q];
+      }
+    }
     // Candidate pruning (exact): candidate n leaves BFUs >= n uncoded, which alone costs
     // tail(n) = sum_{i>=n} zeroBit[i]; if that, deflated by the worst-case rounding of the
     // reference's own 52-term summation (1 - 2^-40), already exceeds the 52-BFU total, the
-    // candidate can neither win nor tie and is not run.
+    // candidate can neither win nor tie and is not run.  (zeroBit is +0.0 where the index is 0.)
     double tail = 0.0;
-    int c = 6;
-    for (int i = 51; i >= 20; i--) {
-      const int sfi = S.sfi[lane][i];
-      if (sfi) tail += (double)P->zero_bit[sfi * 8 + F.size_class[i]];
+#pragma unroll
+    for (int c = 6; c >= 0; c--) {
       const int bound = c == 0 ? 20 : 24 + 4 * c;  // BFU_AMOUNTS[c]
-      if (i == bound) {
-        if (!(tail * (1.0 - 9.094947017729282e-13) > total52)) survive |= 1u << c;
-        c--;
+      const int upper = c == 6 ? 52 : 28 + 4 * c;  // BFU_AMOUNTS[c + 1]
+      for (int i = upper - 1; i >= bound; i--) {
+        const int sfi = S.sfi[lane][i];
+        tail += sfi ? (double)C.zero_bit[sfi * 8 + C.size_class[i]] : 0.0;
       }
+      if (!(tail * (1.0 - 9.094947017729282e-13) > total52)) survive |= 1u << c;
     }
   }
   // ---- compact the surviving (unit, candidate) pairs of the warp and run them 32 at a time
@@ -1201,7 +1213,7 @@ __device__ __forceinline__ void alloc_group(AlWarpSmem &S, const AlSmem &C, cons
   const int n_list = __shfl_sync(0xffffffffu, incl, 31);
   {
     int at = incl - n_mine;
-    for (uint32_t m = survive; m; m &= m - 1) S.list[at++] = (uint16_t)((lane << 3) | (__ffs(m) - 1));
+    for (uint32_t m = survive; m; m &= m - 1) S.list[at++] = (uint8_t)((lane << 3) | (__ffs(m) - 1));
   }
   __syncwarp();
   for (int base = 0; base < n_list; base += 32) {  // uniform trip count
@@ -1246,8 +1258,9 @@ __device__ __forceinline__ void alloc_group(AlWarpSmem &S, const AlSmem &C, cons
 }
 
 __device__ __forceinline__ void alloc_stage_tables(AlSmem &C, const DevEncParams *__restrict__ P, const FormatTables &F, int tid) {
-  if (tid < 64) { C.key0[tid] = P->key0[tid]; C.key1[tid] = P->key1[tid]; }
-  if (tid < 52) C.specs[tid] = F.specs[tid];
+  if (tid < 64) { C.key0[tid] = P->key0[tid]; C.key1[tid] = P->key1[tid]; C.bsf[tid] = P->bsf[tid]; }
+  if (tid < 52) { C.specs[tid] = F.specs[tid]; C.size_class[tid] = F.size_class[tid]; }
+  for (int i = tid; i < 64 * 8; i += kAlWarps * 32) C.zero_bit[i] = P->zero_bit[i];
 }
 
 // Warps are independent (no CTA barrier after the tables are staged) and persistent: a warp
