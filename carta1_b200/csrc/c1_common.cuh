@@ -77,4 +77,10 @@ __device__ __forceinline__ int band_of_bfu(int b) { return b < 20 ? 0 : (b < 36 
 __device__ __forceinline__ int band_of_coef(int c) { return c < 128 ? 0 : (c < 256 ? 1 : 2); }
 __device__ __forceinline__ int wl_bits(int wl) { return wl == 0 ? 0 : wl + 1; }  // WORD_LENGTH_BITS
 
+
+// Hint: bring the 128-byte line holding p into L2 (no register, no shared memory).  The persistent
+// warps issue it for the inputs of their NEXT work item while they work on the current one, so that
+// item's first loads pay an L2 hit instead of a DRAM round trip.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 }  // namespace c1

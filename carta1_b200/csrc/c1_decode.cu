@@ -398,6 +398,11 @@ imdct_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes,
   const int n_pairs = (n_units + 1) >> 1;
   for (int pair = blockIdx.x * kImdctWarps + warp; pair < n_pairs; pair += gridDim.x * kImdctWarps) {
     __syncwarp();
+    {  // the next pair's 2 x 1 KB of coefficients (this role's half of each unit): 16 lines, one per lane
+      const int next = pair + gridDim.x * kImdctWarps;
+      const int un = 2 * next + (lane >> 3);
+      if (lane < 16 && un < n_units) prefetch_l2(coefs + (size_t)un * 512 + kOff + 32 * (lane & 7));
+    }
     const int u0 = 2 * pair;
     bool live[2];
     unsigned long_mask = 0, short_mask = 0;

@@ -957,8 +957,14 @@ mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, 
   const double w_fwd = T->win[lane], w_rev = T->win[31 - lane];  // WINDOW_SHORT[i], [31 - i]
   const int n_pairs = (n_su + 1) >> 1;
   // persistent warps: the grid is sized to the machine and every warp walks the unit pairs
-  for (int pair = blockIdx.x * kMdctWarps + warp; pair < n_pairs; pair += gridDim.x * kMdctWarps)
+  for (int pair = blockIdx.x * kMdctWarps + warp; pair < n_pairs; pair += gridDim.x * kMdctWarps) {
+    {  // the next pair's 2 x 1 KB of band samples (this role's half of each unit): 16 lines, one per lane
+      const int next = pair + gridDim.x * kMdctWarps;
+      const int su = 2 * next + (lane >> 3);
+      if (lane < 16 && su < n_su) prefetch_l2(bands + (size_t)su * 512 + (kRole == 0 ? 0 : 256) + 32 * (lane & 7));
+    }
     mdct_warp_task<kRole>(pair, bands, modes, frames, n_su, T, P, coefs, sfi_out, S, ST.tab, ST.tw, lane, w_fwd, w_rev);
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -1411,9 +1417,10 @@ quant_pack_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ m
   __syncthreads();
   const int sz0 = F.specs[lane], sz1 = lane < 20 ? F.specs[lane + 32] : 0;
   const long long n_units = (long long)n_streams * n_out_frames;
-  for (long long unit = (long long)blockIdx.x * kQpWarps + warp; unit < n_units; unit += (long long)gridDim.x * kQpWarps)
+  for (long long unit = (long long)blockIdx.x * kQpWarps + warp; unit < n_units; unit += (long long)gridDim.x * kQpWarps) {
     qp_unit(s_warp[warp], s_bj, sz0, sz1, coefs, modes, recs, frames, halo, n_out_frames, T, P, su_out, su_frame_stride,
             su_stream_stride, unit, lane);
+  }
 }
 
 // ------------------------------------------------------------------------------------
