@@ -1168,7 +1168,9 @@ __device__ __forceinline__ void alloc_group(AlWarpSmem &S, const AlSmem &C, cons
     const long long unit = unit0 + u;
     uint32_t v = 0;
     if (unit < n_units) {
-      const size_t su = (size_t)(unit / n_out_frames) * frames + halo + (size_t)(unit % n_out_frames);
+      // (unit counts stay far below 2^32: a unit owns 2 KB of coefficients; 32-bit division is a tenth of the 64-bit one)
+      const unsigned st = (unsigned)unit / (unsigned)n_out_frames, fo = (unsigned)unit - st * (unsigned)n_out_frames;
+      const size_t su = (size_t)st * frames + halo + fo;
       v = __ldg(reinterpret_cast<const uint32_t *>(sfi_all + su * 64) + w);
     }
     reinterpret_cast<uint32_t *>(&S.sfi[u][0])[w] = v;
@@ -1327,8 +1329,8 @@ __device__ __forceinline__ void qp_unit(QpWarpSmem &S, const uint16_t (*s_bj)[51
                                         uint8_t *__restrict__ su_out, size_t su_frame_stride, size_t su_stream_stride,
                                         long long unit, int lane) {
   uint32_t *words = S.words;
-  const int stream = (int)(unit / n_out_frames);
-  const int frame_out = (int)(unit % n_out_frames);
+  const int stream = (int)((unsigned)unit / (unsigned)n_out_frames);  // unit counts stay far below 2^32
+  const int frame_out = (int)((unsigned)unit - (unsigned)stream * (unsigned)n_out_frames);
   const size_t su = (size_t)stream * frames + halo + frame_out;
   const float *src = coefs + su * 512;
   float c[16];
