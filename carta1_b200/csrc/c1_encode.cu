@@ -919,11 +919,12 @@ __device__ __forceinline__ void mdct_warp_task(int pair, const float *__restrict
       const int start = (mode[x] == 0 ? F.start_long[b] : F.start_short[b]) - (kRole == 0 ? (b >= 20 ? 128 : 0) : 256);
       const float *c = out + x * kSize + start;
       const int sz = F.specs[b];
+      // max |c| (NaN never wins, as with the reference's `if (a > max)`): one FMNMX per coefficient
+      constexpr int kMaxSz = kRole == 0 ? 10 : 20;
       float mx = 0.0f;
-      for (int j = 0; j < sz; j++) {
-        const float a = fabsf(c[j]);
-        if (a > mx) mx = a;
-      }
+#pragma unroll
+      for (int j = 0; j < kMaxSz; j++)
+        if (j < sz) mx = fmaxf(mx, fabsf(c[j]));
       sfi_out[(size_t)(su0 + unit) * 64 + b] = (uint8_t)scale_factor_index(mx, T);
     }
   }
