@@ -677,6 +677,28 @@ __global__ void __launch_bounds__(256) small_copy_kernel(uint4 *__restrict__ dst
   if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
 }
 
+// Strided row copy on the device (float4 granules): dst[r][0..width) = src[r][0..width).  The stateful handles
+// move one short row per stream and call; a copy-engine 2D copy pays per row, this is one small launch.
+__global__ void __launch_bounds__(256) copy_rows_kernel(float4 *__restrict__ dst, size_t dst_pitch4, const float4 *__restrict__ src,
+                                                        size_t src_pitch4, int width4, size_t n_rows) {
+  const size_t total = n_rows * (size_t)width4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / (size_t)width4;
+    const int c = (int)(i - r * (size_t)width4);
+    dst[r * dst_pitch4 + c] = src[r * src_pitch4 + c];
+  }
+}
+// widths and pitches in floats, all multiples of 4, both pointers 16-byte aligned
+static cudaError_t copy_rows(float *dst, size_t dst_pitch, const float *src, size_t src_pitch, int width, size_t n_rows,
+                             cudaStream_t st, Prof *prof) {
+  if (!n_rows) return cudaSuccess;
+  const size_t total4 = n_rows * (size_t)(width / 4);
+  const int grid = (int)std::min<size_t>(1184, (total4 + 255) / 256);
+  copy_rows_kernel<<<grid, 256, 0, st>>>((float4 *)dst, dst_pitch / 4, (const float4 *)src, src_pitch / 4, width / 4, n_rows);
+  prof->launches++;
+  return cudaGetLastError();
+}
+
 // Device-visible alias of a pinned host pointer, or nullptr.
 static void *mapped_alias(const void *host) {
   cudaPointerAttributes a;
@@ -1042,16 +1064,14 @@ int carta1_enc_frames(carta1_encoder *e, const float *pcm, int n_frames, uint8_t
   CU(ctx, e->work.ensure(ns * row * sizeof(float)));
   CU(ctx, e->su.ensure(ns * (size_t)n_frames * CARTA1_SU_BYTES));
   float *w = (float *)e->work.p;
-  CU(ctx, cudaMemcpy2DAsync(w, row * sizeof(float), e->d_hist, 1024 * sizeof(float), 1024 * sizeof(float), ns,
-                            cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(ctx, copy_rows(w, row, e->d_hist, 1024, 1024, ns, ctx->stream, &ctx->prof));
   CU(ctx, cudaMemcpy2DAsync(w + 1024, row * sizeof(float), pcm, (size_t)n_frames * 512 * sizeof(float),
                             (size_t)n_frames * 512 * sizeof(float), ns, cudaMemcpyHostToDevice, ctx->stream));
   int rc = encode_device_impl(ctx, w, 0, row, 1, e->n_streams, row, 2, (size_t)n_frames, e->d_params,
                               e->opts.use_fixed_block_modes != 0, (uint8_t *)e->su.p, 1, (size_t)n_frames,
                               nullptr, nullptr, nullptr, nullptr);
   if (rc) return rc;
-  CU(ctx, cudaMemcpy2DAsync(e->d_hist, 1024 * sizeof(float), w + (size_t)n_frames * 512, row * sizeof(float),
-                            1024 * sizeof(float), ns, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(ctx, copy_rows(e->d_hist, 1024, w + (size_t)n_frames * 512, row, 1024, ns, ctx->stream, &ctx->prof));
   CU(ctx, cudaMemcpyAsync(su_out, e->su.p, ns * (size_t)n_frames * CARTA1_SU_BYTES, cudaMemcpyDeviceToHost,
                           ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1122,9 +1142,7 @@ static int dec_frames_impl(carta1_decoder *d, const uint8_t *su, const int32_t *
   int rc = decode_device_impl(ctx, d_su, 1, nf, ns * nf, d->n_streams, halo, nf, d->pcm.p, 0, nf * 512, 1,
                               nullptr, nullptr, halo ? d->d_rec : nullptr, dq, dsfi, dbits, dmodes);
   if (rc) return rc;
-  CU(ctx, cudaMemcpy2DAsync(d->d_rec, 512 * sizeof(float), (const float *)ctx->inv.p + (fr - 1) * 512,
-                            fr * 512 * sizeof(float), 512 * sizeof(float), ns, cudaMemcpyDeviceToDevice,
-                            ctx->stream));
+  CU(ctx, copy_rows(d->d_rec, 512, (const float *)ctx->inv.p + (fr - 1) * 512, fr * 512, 512, ns, ctx->stream, &ctx->prof));
   CU(ctx, cudaMemcpyAsync(pcm_out, d->pcm.p, ns * nf * 512 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   d->has_prev = true;
