@@ -384,46 +384,63 @@ __device__ __forceinline__ void transient_fft(const float *__restrict__ x, doubl
   }
 }
 
-template <typename R>
-__device__ __forceinline__ void transient_ffts(const float *__restrict__ band, TsWarpSmem &S, int lane,
-                                               const DevTables *__restrict__ T) {
+// Warps are specialised by role, each role its own kernel (as in K3: the unrolled transforms of both
+// sizes in one kernel overflow the instruction cache, `no_instruction` stalls 0.65 per issue): role 0
+// takes the low and mid bands of two sound units (four FFT128, two at a time on 16 lanes each), role 1
+// their high bands (two FFT256).  S.mag holds [unit 0: 128 magnitudes | unit 1: 128 magnitudes].
+template <int kRole, typename R>
+__device__ __forceinline__ void transient_ffts(const float *__restrict__ bands, int su0, bool have1, TsWarpSmem &S,
+                                               int lane, const DevTables *__restrict__ T) {
   R rnd;
-  // low and mid: 16 lanes each, their transposes in separate halves of the buffer
-  transient_fft<7>(band + 128 * (lane >> 4), S.xbuf + 144 * (lane >> 4), S.mag + 64 * (lane >> 4), lane & 15, T->fft_tw, rnd);
-  __syncwarp();
-  transient_fft<8>(band + 256, S.xbuf, S.mag + 128, lane, T->fft_tw, rnd);
+#pragma unroll
+  for (int u = 0; u < 2; u++) {
+    if (u == 1 && !have1) break;
+    const float *band = bands + (size_t)(su0 + u) * 512;
+    if (kRole == 0)
+      transient_fft<7>(band + 128 * (lane >> 4), S.xbuf + 144 * (lane >> 4), S.mag + 128 * u + 64 * (lane >> 4), lane & 15,
+                       T->fft_tw, rnd);
+    else
+      transient_fft<8>(band + 256, S.xbuf, S.mag + 128 * u, lane, T->fft_tw, rnd);
+    __syncwarp();
+  }
 }
-__device__ __noinline__ void transient_ffts_exact(const float *__restrict__ band, TsWarpSmem &S, int lane,
-                                                  const DevTables *__restrict__ T) {
-  transient_ffts<ExactRound>(band, S, lane, T);
+template <int kRole>
+__device__ __noinline__ void transient_ffts_exact(const float *__restrict__ bands, int su0, bool have1, TsWarpSmem &S,
+                                                  int lane, const DevTables *__restrict__ T) {
+  transient_ffts<kRole, ExactRound>(bands, su0, have1, S, lane, T);
 }
 
 struct SpectrumFeatures {  // transient.js:116-189 of one band's magnitude spectrum
   double flatness, hf_ratio, energy;
 };
 
+template <int kRole>
 __global__ void __launch_bounds__(kTsWarps * 32, kTsCtasPerSm)
 transient_spectrum_kernel(const float *__restrict__ bands, int n_su, const DevTables *__restrict__ T,
                           float *__restrict__ mags, SpectrumFeatures *__restrict__ feats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   TsWarpSmem &S = reinterpret_cast<TsWarpSmem *>(smem_raw)[warp];
-  for (int su = blockIdx.x * kTsWarps + warp; su < n_su; su += gridDim.x * kTsWarps) {
-    const float *band = bands + (size_t)su * 512;
+  constexpr int kOff = kRole == 0 ? 0 : 256;  // first band sample / 2x first magnitude of the role
+  const int n_pairs = (n_su + 1) >> 1;
+  for (int pair = blockIdx.x * kTsWarps + warp; pair < n_pairs; pair += gridDim.x * kTsWarps) {
+    const int su0 = 2 * pair;
+    const bool have1 = su0 + 1 < n_su;
     unsigned big = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const float4 q = __ldg(reinterpret_cast<const float4 *>(band) + lane + 32 * k);
+    for (int k = 0; k < 4; k++) {  // the role's 256 samples of each unit: 2 float4 per lane and unit
+      if (k >= 2 && !have1) break;
+      const float4 q = __ldg(reinterpret_cast<const float4 *>(bands + (size_t)(su0 + (k >> 1)) * 512 + kOff) + lane + 32 * (k & 1));
       big = max(big, max(max(__float_as_uint(q.x) & 0x7FFFFFFFu, __float_as_uint(q.y) & 0x7FFFFFFFu),
                          max(__float_as_uint(q.z) & 0x7FFFFFFFu, __float_as_uint(q.w) & 0x7FFFFFFFu)));
     }
     __syncwarp();
-    if (__reduce_max_sync(0xffffffffu, big) < 0x71800000u) transient_ffts<FastRound>(band, S, lane, T);
-    else transient_ffts_exact(band, S, lane, T);
+    if (__reduce_max_sync(0xffffffffu, big) < 0x71800000u) transient_ffts<kRole, FastRound>(bands, su0, have1, S, lane, T);
+    else transient_ffts_exact<kRole>(bands, su0, have1, S, lane, T);
     __syncwarp();
     // magnitudes out; per-bin terms of the sums (logarithm, magnitude, square), computed by all lanes
-    // (bin lane + 32k); the term arrays reuse the transpose buffer.  The reference skips the bins at
-    // or below EPS in the first two sums (transient.js:126-131); here those bins contribute +0.0,
+    // (entry lane + 32k of S.mag); the term arrays reuse the transpose buffer.  The reference skips the
+    // bins at or below EPS in the first two sums (transient.js:126-131); here those bins contribute +0.0,
     // which leaves a sum that started at +0.0 bit-identical (such a sum is never -0.0: an exact
     // cancellation rounds to +0.0 and fdlibm's log(1) is +0.0), so the serial loops need no masks.
     const double EPS = 1e-10;
@@ -432,8 +449,9 @@ transient_spectrum_kernel(const float *__restrict__ bands, int n_su, const DevTa
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int i = lane + 32 * k;
-      const float m = S.mag[i];
-      mags[(size_t)su * 256 + i] = m;
+      const int u = i >> 7;
+      const float m = (u == 0 || have1) ? S.mag[i] : 0.0f;
+      if (u == 0 || have1) mags[(size_t)(su0 + u) * 256 + (kOff >> 1) + (i & 127)] = m;
       const double v = (double)m, md = fabs(v);
       const bool ok = md > EPS;
       S.logm[i] = ok ? fd::log(md) : 0.0;
@@ -442,33 +460,32 @@ transient_spectrum_kernel(const float *__restrict__ bands, int n_su, const DevTa
       ok_mask[k] = __ballot_sync(0xffffffffu, ok);
     }
     __syncwarp();
-    // serial sums in index order, one lane per (band, accumulator): 0 sum_log (+ valid count),
+    // serial sums in index order, one lane per (unit, band, accumulator): 0 sum_log (+ valid count),
     // 1 sum_lin, 2 lo then hi, 3 energy.  Every lane runs the same loop over its own term array.
-    const int band_i = lane >> 2, acc = lane & 3;
+    constexpr int kN = kRole == 0 ? 64 : 128, kGroups = 256 / kN, kMid = kN / 2;
+    const int g = (lane >> 2) < kGroups ? (lane >> 2) : 0, acc = lane & 3;
     double r0 = 0.0, r1 = 0.0;
     int valid = 0;
     {
-      const int bi = band_i < 3 ? band_i : 0;
-      const int n = bi == 2 ? 128 : 64, off = bi == 0 ? 0 : bi == 1 ? 64 : 128, mid = n >> 1;
-      const double *term = (acc == 0 ? S.logm : acc == 1 ? t_mag : t_sq) + off;
-      const unsigned k0 = bi == 0 ? ok_mask[0] : (bi == 1 ? ok_mask[2] : ok_mask[4]);
-      const unsigned k1 = bi == 0 ? ok_mask[1] : (bi == 1 ? ok_mask[3] : ok_mask[5]);
-      const unsigned k2 = bi == 2 ? ok_mask[6] : 0u, k3 = bi == 2 ? ok_mask[7] : 0u;
-      valid = __popc(k0) + __popc(k1) + __popc(k2) + __popc(k3);
+      const double *term = (acc == 0 ? S.logm : acc == 1 ? t_mag : t_sq) + kN * g;
+#pragma unroll
+      for (int w = 0; w < 8; w++)
+        if (w / (kN / 32) == g) valid += __popc(ok_mask[w]);
 #pragma unroll 8
-      for (int i = 0; i < mid; i++) r0 += term[i];
+      for (int i = 0; i < kMid; i++) r0 += term[i];
       double rr = acc == 2 ? 0.0 : r0;
 #pragma unroll 8
-      for (int i = mid; i < n; i++) rr += term[i];
+      for (int i = kMid; i < kN; i++) rr += term[i];
       if (acc == 2) r1 = rr; else r0 = rr;
     }
-    // gather the four lanes of a band on its first lane
+    // gather the four lanes of a group on its first lane
     const int base = lane & ~3;
     const double sum_log = __shfl_sync(0xffffffffu, r0, base), sum_lin = __shfl_sync(0xffffffffu, r0, base + 1);
     const double lo = __shfl_sync(0xffffffffu, r0, base + 2), hi = __shfl_sync(0xffffffffu, r1, base + 2);
     const double energy = __shfl_sync(0xffffffffu, r0, base + 3);
     const int nvalid = __shfl_sync(0xffffffffu, valid, base);
-    if (band_i < 3 && acc == 0) {
+    const int unit = kRole == 0 ? g >> 1 : g, band_i = kRole == 0 ? g & 1 : 2;
+    if ((lane >> 2) < kGroups && acc == 0 && (unit == 0 || have1)) {
       SpectrumFeatures f;
       if (nvalid == 0) {
         f.flatness = 0.0;
@@ -480,7 +497,7 @@ transient_spectrum_kernel(const float *__restrict__ bands, int n_su, const DevTa
       const double total = lo + hi;
       f.hf_ratio = total > 0.0 ? hi / total : 0.0;
       f.energy = energy;
-      feats[(size_t)su * 3 + band_i] = f;
+      feats[(size_t)(su0 + unit) * 3 + band_i] = f;
     }
     __syncwarp();
   }
@@ -1507,11 +1524,20 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
     prof->end(K_QMF_ANALYSIS, st);
   }
   if (!L.use_fixed) {
-    cudaError_t e2 = cudaFuncSetAttribute(transient_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTsSmemBytes);
+    cudaError_t e2 = cudaFuncSetAttribute(transient_spectrum_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTsSmemBytes);
+    if (e2 == cudaSuccess)
+      e2 = cudaFuncSetAttribute(transient_spectrum_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTsSmemBytes);
     if (e2 != cudaSuccess) return e2;
     prof->begin(K_BAND_MAGS, st);
-    transient_spectrum_kernel<<<std::min((n_su + kTsWarps - 1) / kTsWarps, persistent_ctas(kTsCtasPerSm)), kTsWarps * 32, kTsSmemBytes, st>>>(
-        L.bands, n_su, L.tables, L.mags, static_cast<SpectrumFeatures *>(L.feats));
+    {
+      const int n_ts_pairs = (n_su + 1) / 2;
+      const int grid = std::min((n_ts_pairs + kTsWarps - 1) / kTsWarps, persistent_ctas(kTsCtasPerSm));
+      transient_spectrum_kernel<0><<<grid, kTsWarps * 32, kTsSmemBytes, st>>>(L.bands, n_su, L.tables, L.mags,
+                                                                              static_cast<SpectrumFeatures *>(L.feats));
+      transient_spectrum_kernel<1><<<grid, kTsWarps * 32, kTsSmemBytes, st>>>(L.bands, n_su, L.tables, L.mags,
+                                                                              static_cast<SpectrumFeatures *>(L.feats));
+      prof->launches++;
+    }
     prof->end(K_BAND_MAGS, st);
     prof->begin(K_TRANSIENT_MODES, st);
     const int n_tm_groups = (n_su + kTmUnits - 1) / kTmUnits;
