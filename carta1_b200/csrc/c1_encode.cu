@@ -392,7 +392,7 @@ template <int kRole, typename R>
 __device__ __forceinline__ void transient_ffts(const float *__restrict__ bands, int su0, bool have1, TsWarpSmem &S,
                                                int lane, const DevTables *__restrict__ T) {
   R rnd;
-#pragma unroll
+#pragma unroll 1  // one copy of the unrolled transform: the kernel has to stay inside the instruction cache
   for (int u = 0; u < 2; u++) {
     if (u == 1 && !have1) break;
     const float *band = bands + (size_t)(su0 + u) * 512;
@@ -445,8 +445,10 @@ transient_spectrum_kernel(const float *__restrict__ bands, int n_su, const DevTa
     // cancellation rounds to +0.0 and fdlibm's log(1) is +0.0), so the serial loops need no masks.
     const double EPS = 1e-10;
     double *t_mag = reinterpret_cast<double *>(S.xbuf), *t_sq = t_mag + 256;
-    unsigned ok_mask[8];
-#pragma unroll
+    constexpr int kN = kRole == 0 ? 64 : 128, kGroups = 256 / kN, kMid = kN / 2;
+    const int g = (lane >> 2) < kGroups ? (lane >> 2) : 0, acc = lane & 3;
+    int valid = 0;  // bins above EPS in this lane's group (entries kN g .. kN g + kN - 1)
+#pragma unroll 2  // (fd::log is inlined: eight copies would be a sixth of the kernel)
     for (int k = 0; k < 8; k++) {
       const int i = lane + 32 * k;
       const int u = i >> 7;
@@ -457,20 +459,15 @@ transient_spectrum_kernel(const float *__restrict__ bands, int n_su, const DevTa
       S.logm[i] = ok ? fd::log(md) : 0.0;
       t_mag[i] = ok ? md : 0.0;
       t_sq[i] = v * v;
-      ok_mask[k] = __ballot_sync(0xffffffffu, ok);
+      const unsigned okm = __ballot_sync(0xffffffffu, ok);
+      if (k / (kN / 32) == g) valid += __popc(okm);
     }
     __syncwarp();
     // serial sums in index order, one lane per (unit, band, accumulator): 0 sum_log (+ valid count),
     // 1 sum_lin, 2 lo then hi, 3 energy.  Every lane runs the same loop over its own term array.
-    constexpr int kN = kRole == 0 ? 64 : 128, kGroups = 256 / kN, kMid = kN / 2;
-    const int g = (lane >> 2) < kGroups ? (lane >> 2) : 0, acc = lane & 3;
     double r0 = 0.0, r1 = 0.0;
-    int valid = 0;
     {
       const double *term = (acc == 0 ? S.logm : acc == 1 ? t_mag : t_sq) + kN * g;
-#pragma unroll
-      for (int w = 0; w < 8; w++)
-        if (w / (kN / 32) == g) valid += __popc(ok_mask[w]);
 #pragma unroll 8
       for (int i = 0; i < kMid; i++) r0 += term[i];
       double rr = acc == 2 ? 0.0 : r0;
