@@ -316,7 +316,7 @@ __device__ __forceinline__ void fft8_pass_a_real(Cplx (&v)[8], R &rnd) {
 constexpr int kTsWarps = 8, kTsCtasPerSm = 3;
 struct TsWarpSmem {
   double2 xbuf[256 + 32];  // transpose buffer (slot p + p/8)
-  double logm[256];        // log(magnitude) where magnitude > 1e-10
+  double logm[256 + 12];   // log(magnitude) where magnitude > 1e-10 (term arrays are skewed, see ts_skew)
   float mag[256];          // low 64 | mid 64 | high 128
 };
 constexpr size_t kTsSmemBytes = sizeof(TsWarpSmem) * kTsWarps;
@@ -444,7 +444,10 @@ transient_spectrum_kernel(const float *__restrict__ bands, int n_su, const DevTa
     // which leaves a sum that started at +0.0 bit-identical (such a sum is never -0.0: an exact
     // cancellation rounds to +0.0 and fdlibm's log(1) is +0.0), so the serial loops need no masks.
     const double EPS = 1e-10;
-    double *t_mag = reinterpret_cast<double *>(S.xbuf), *t_sq = t_mag + 256;
+    // Term array a (0 log, 1 magnitude, 2 square) of group g is shifted by 3 g + a doubles, so that the lanes
+    // of the serial loops (one per group and accumulator, all at the same i) read 12 different bank pairs;
+    // unshifted, the three arrays and the groups all start on bank 0.
+    double *t_mag = reinterpret_cast<double *>(S.xbuf), *t_sq = t_mag + 272;
     constexpr int kN = kRole == 0 ? 64 : 128, kGroups = 256 / kN, kMid = kN / 2;
     const int g = (lane >> 2) < kGroups ? (lane >> 2) : 0, acc = lane & 3;
     int valid = 0;  // bins above EPS in this lane's group (entries kN g .. kN g + kN - 1)
@@ -456,9 +459,10 @@ transient_spectrum_kernel(const float *__restrict__ bands, int n_su, const DevTa
       if (u == 0 || have1) mags[(size_t)(su0 + u) * 256 + (kOff >> 1) + (i & 127)] = m;
       const double v = (double)m, md = fabs(v);
       const bool ok = md > EPS;
-      S.logm[i] = ok ? fd::log(md) : 0.0;
-      t_mag[i] = ok ? md : 0.0;
-      t_sq[i] = v * v;
+      const int sk = i + 3 * (i / kN);
+      S.logm[sk] = ok ? fd::log(md) : 0.0;
+      t_mag[sk + 1] = ok ? md : 0.0;
+      t_sq[sk + 2] = v * v;
       const unsigned okm = __ballot_sync(0xffffffffu, ok);
       if (k / (kN / 32) == g) valid += __popc(okm);
     }
@@ -467,7 +471,7 @@ transient_spectrum_kernel(const float *__restrict__ bands, int n_su, const DevTa
     // 1 sum_lin, 2 lo then hi, 3 energy.  Every lane runs the same loop over its own term array.
     double r0 = 0.0, r1 = 0.0;
     {
-      const double *term = (acc == 0 ? S.logm : acc == 1 ? t_mag : t_sq) + kN * g;
+      const double *term = (acc == 0 ? S.logm : acc == 1 ? t_mag + 1 : t_sq + 2) + (kN + 3) * g;
 #pragma unroll 8
       for (int i = 0; i < kMid; i++) r0 += term[i];
       double rr = acc == 2 ? 0.0 : r0;
