@@ -477,7 +477,7 @@ def main():
     ap.add_argument("--cpu-sample-seconds", type=float, default=600.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--units-per-pass", type=int, default=0,
-                    help="development aid: sound units per double-buffered pass of the host entry points (default: the library's)")
+                    help="development aid: sound units per pipelined pass of the host entry points (default: the library's)")
     ap.add_argument("--auto-modes", action="store_true",
                     help="development aid: transient-driven block modes instead of the headline fixed [0,0,0] (not a bench line)")
     args = ap.parse_args()

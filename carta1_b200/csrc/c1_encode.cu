@@ -1384,7 +1384,9 @@ __device__ __forceinline__ void qp_unit(QpWarpSmem &S, const uint16_t (*s_bj)[51
       const int base = run + incl - bits * sz;
       const bool coded = bits > 0 && sfi > 0;
       S.bfu[b].norm = coded ? __ldg(&T->norm[wl][sfi]) : 0.0;
-      S.bfu[b].base_bits = (uint32_t)base | ((uint32_t)bits << 11) | ((uint32_t)((1 << wl) - 1) << 16);
+      // a BFU that carries bits but has scale-factor index 0 quantises to zeros (quantization.js:37-40):
+      // nothing to merge into the image, so its width field is 0 and the coefficient loop skips it
+      S.bfu[b].base_bits = (uint32_t)base | ((uint32_t)(coded ? bits : 0) << 11) | ((uint32_t)((1 << wl) - 1) << 16);
       wrap |= coded && sfi == 63;
       if (b < n) {
         put_bits(words, 16 + 4 * b, (uint32_t)wl, 4);
@@ -1409,12 +1411,10 @@ __device__ __forceinline__ void qp_unit(QpWarpSmem &S, const uint16_t (*s_bj)[51
     const int bits = (rec.base_bits >> 11) & 31;
     if (bits) {
       const int range = (int)(rec.base_bits >> 16);
-      // x = c * normFactor; y = (x + (x >= 0 ? 0.5 : -0.5)) | 0; clamp to +-range.  norm == 0
-      // (sfi == 0) gives x = +-0 or NaN and y = 0, as the reference's early return does.
+      // x = c * normFactor; y = (x + (x >= 0 ? 0.5 : -0.5)) | 0; clamp to +-range (norm > 0: uncoded BFUs were skipped)
       const double x = (double)c[k] * rec.norm;
       const double xs = x + copysign(0.5, x);
       int y = wrap ? js_to_int32(x + (x >= 0.0 ? 0.5 : -0.5)) : __double2int_rz(xs);
-      if (rec.norm == 0.0) y = 0;  // covers c == +-inf with norm == 0 (inf * 0 = NaN either way) and NaN signs
       const int q = min(max(y, -range), range);
       put_bits(words, (int)(rec.base_bits & 2047u) + (int)(bj & 31u) * bits, (uint32_t)q, bits);
     }
