@@ -1340,6 +1340,33 @@ struct QpWarpSmem {
   uint32_t words[56];
 };
 
+// The 16 coefficients of a lane (coefficient lane + 32 k): quantise (quantization.js:34-56) and merge the
+// codes into the unit's bit image.  kWrap: some BFU sits at the top scale factor, |coefficient| may exceed
+// it and the reference's `| 0` (ToInt32) may wrap: that variant follows ToInt32 literally.
+template <bool kWrap>
+__device__ __forceinline__ void qp_coefs(QpWarpSmem &S, const float (&c)[16], const uint16_t *bj0, const uint16_t *bj1,
+                                         const uint16_t *bj2) {
+  uint32_t *words = S.words;
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const uint32_t bj = (k < 4 ? bj0 : (k < 8 ? bj1 : bj2))[32 * k];
+    const QpBfu rec = S.bfu[bj >> 5];
+    const int bits = (rec.base_bits >> 11) & 31;
+    if (bits) {
+      const int range = (int)(rec.base_bits >> 16);
+      // x = c * normFactor; y = (x + (x >= 0 ? 0.5 : -0.5)) | 0; clamp to +-range (norm > 0: uncoded BFUs were skipped)
+      const double x = (double)c[k] * rec.norm;
+      const int y = kWrap ? js_to_int32(x + (x >= 0.0 ? 0.5 : -0.5)) : __double2int_rz(x + copysign(0.5, x));
+      const int q = min(max(y, -range), range);
+      put_bits(words, (int)(rec.base_bits & 2047u) + (int)(bj & 31u) * bits, (uint32_t)q, bits);
+    }
+  }
+}
+__device__ __noinline__ void qp_coefs_wrap(QpWarpSmem &S, const float (&c)[16], const uint16_t *bj0, const uint16_t *bj1,
+                                           const uint16_t *bj2) {
+  qp_coefs<true>(S, c, bj0, bj1, bj2);
+}
+
 // One sound unit by one warp (the body of K4b).
 __device__ __forceinline__ void qp_unit(QpWarpSmem &S, const uint16_t (*s_bj)[512], int sz0, int sz1,
                                         const float *__restrict__ coefs, const uint8_t *__restrict__ modes,
@@ -1404,21 +1431,8 @@ __device__ __forceinline__ void qp_unit(QpWarpSmem &S, const uint16_t (*s_bj)[51
   wrap = __any_sync(0xffffffffu, wrap);
   __syncwarp();
   const uint16_t *bj0 = s_bj[m0 != 0] + lane, *bj1 = s_bj[m1 != 0] + lane, *bj2 = s_bj[m2 != 0] + lane;
-#pragma unroll
-  for (int k = 0; k < 16; k++) {
-    const uint32_t bj = (k < 4 ? bj0 : (k < 8 ? bj1 : bj2))[32 * k];
-    const QpBfu rec = S.bfu[bj >> 5];
-    const int bits = (rec.base_bits >> 11) & 31;
-    if (bits) {
-      const int range = (int)(rec.base_bits >> 16);
-      // x = c * normFactor; y = (x + (x >= 0 ? 0.5 : -0.5)) | 0; clamp to +-range (norm > 0: uncoded BFUs were skipped)
-      const double x = (double)c[k] * rec.norm;
-      const double xs = x + copysign(0.5, x);
-      int y = wrap ? js_to_int32(x + (x >= 0.0 ? 0.5 : -0.5)) : __double2int_rz(xs);
-      const int q = min(max(y, -range), range);
-      put_bits(words, (int)(rec.base_bits & 2047u) + (int)(bj & 31u) * bits, (uint32_t)q, bits);
-    }
-  }
+  if (wrap) qp_coefs_wrap(S, c, bj0, bj1, bj2);  // rare (a BFU at the top scale factor), out of line
+  else qp_coefs<false>(S, c, bj0, bj1, bj2);
   __syncwarp();
   uint32_t *dst = reinterpret_cast<uint32_t *>(
       su_out + ((size_t)frame_out * su_frame_stride + (size_t)stream * su_stream_stride) * kSuBytes);
