@@ -122,6 +122,15 @@ void build_dev_tables(const carta1_tables &t, DevTables *d) {
   for (int wl = 1; wl < 16; wl++) {
     volatile double range = (double)((1 << wl) - 1);
     d->rcp_range[wl] = 1.0 / range;
+    if (wl >= 1 && wl <= kDeqMaxWl) {
+      const int bits = wl + 1;
+      for (int sfi = 0; sfi < 64; sfi++)
+        for (int code = 0; code < (1 << bits); code++) {
+          const int q = code >= (1 << (bits - 1)) ? code - (1 << bits) : code;  // bitstream.js:78-82
+          const volatile double prod = (double)q * t.scale_factors[sfi];      // quantization.js:75: two roundings
+          d->deq_tab[deq_off(wl) + (sfi << bits) + code] = sfi ? (float)(prod / range) : 0.0f;
+        }
+    }
   }
   for (int wl = 1; wl < 16; wl++)
     for (int i = 0; i < 64; i++) {

@@ -47,8 +47,17 @@ struct DevTables {
   // done once on the host
   double norm[16][64];
   double rcp_range[16];  // 1 / (2^wl - 1): dequantize()'s division by quantRange via div_by_range
+  // dequantize() itself for the short word lengths (wl 1..6, i.e. 2..7 bits): deq_tab[deq_off(wl) +
+  // (sfi << bits) + code] = f32((q * SF[sfi]) / (2^wl - 1)), code = q as a `bits`-bit two's-complement
+  // field, every one of the 2^bits patterns (quantization.js:65-78; the row of sfi == 0 is +0).  The
+  // IEEE multiplication and division are done on the host, once per context.
+  float deq_tab[64 * 252];
   FormatTables fmt;
 };
+
+// first entry of word-length index wl (1..6) in DevTables::deq_tab: 64 * (4 + 8 + ... + 2^wl)
+__host__ __device__ inline int deq_off(int wl) { return 64 * ((4 << (wl - 1)) - 4); }
+constexpr int kDeqMaxWl = 6;
 
 // Per-encoder parameters (EncoderOptions + tables derived from allocationBias).
 struct DevEncParams {

@@ -145,7 +145,7 @@ struct UpBfu {          // per BFU of the unit being unpacked
   double rcp;           // 1 / quantRange
   double range;         // quantRange = 2^(bits-1) - 1
   uint32_t base_bits;   // bit offset (malformed units: up to 16 + 520 + 16 * 512) | width << 16
-  uint32_t pad;
+  int32_t tab;          // first entry of (wl, sfi) in DevTables::deq_tab, or -1 (width above 7 bits)
 };
 struct UnpackWarpSmem {
   UpBfu bfu[52];
@@ -238,6 +238,7 @@ unpack_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_
           r.rcp = __ldg(&T->rcp_range[wl]);
           r.range = (double)range;
           r.base_bits = (uint32_t)(run + incl - cost) | ((uint32_t)bits << 16);
+          r.tab = wl >= 1 && wl <= kDeqMaxWl ? deq_off(wl) + (sfi << bits) : -1;
         }
         run += __shfl_sync(0xffffffffu, incl, 31);
       }
@@ -255,16 +256,23 @@ unpack_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_
         float val = 0.0f;
         if (bits > 0) {
           const int pos = (int)(r.base_bits & 0xFFFFu) + (int)(bj & 31u) * bits;
-          int q;
-          if (!overrun) {
+          if (!overrun && r.tab >= 0) {
+            // short codes (2..7 bits): f32((q * SF) / R) was tabulated on the host for every bit pattern
             const int w = pos >> 5, off = pos & 31;
             const uint32_t top = __funnelshift_l(words[w + 1], words[w], off);  // bits pos.. at the top
-            q = (int)top >> (32 - bits);  // sign-extending (bitstream.js:78-82)
+            val = __ldg(&T->deq_tab[r.tab + (int)(top >> (32 - bits))]);
           } else {
-            const int v = (int)get_bits(words, pos, bits);
-            q = v >= (1 << (bits - 1)) ? v - (1 << bits) : v;
+            int q;
+            if (!overrun) {
+              const int w = pos >> 5, off = pos & 31;
+              const uint32_t top = __funnelshift_l(words[w + 1], words[w], off);
+              q = (int)top >> (32 - bits);  // sign-extending (bitstream.js:78-82)
+            } else {
+              const int v = (int)get_bits(words, pos, bits);
+              q = v >= (1 << (bits - 1)) ? v - (1 << bits) : v;
+            }
+            if (r.sf != 0.0) val = (float)div_by_range(int_to_double(q) * r.sf, r.range, r.rcp);
           }
-          if (r.sf != 0.0) val = (float)div_by_range(int_to_double(q) * r.sf, r.range, r.rcp);
         }
         dst[lane + 32 * k] = val;
       }
@@ -740,6 +748,17 @@ __global__ void selftest_kernel(const DevTables *__restrict__ T, unsigned long l
       const double want = ((double)q * T->sf[sfi]) / range;
       const double got = div_by_range(x, range, rcp);
       if (__double_as_longlong(want) != __double_as_longlong(got)) local++;
+    }
+  }
+  // (a') the host-built dequantisation table against the device's own IEEE division, every entry
+  for (int wl = 1; wl <= kDeqMaxWl; wl++) {
+    const int bits = wl + 1;
+    const double range = (double)((1 << wl) - 1);
+    for (long long k = tid; k < (64ll << bits); k += stride) {
+      const int sfi = (int)(k >> bits), code = (int)(k & ((1 << bits) - 1));
+      const int q = code >= (1 << (bits - 1)) ? code - (1 << bits) : code;
+      const float want = sfi ? (float)(((double)q * T->sf[sfi]) / range) : 0.0f;
+      if (__float_as_uint(want) != __float_as_uint(T->deq_tab[deq_off(wl) + (sfi << bits) + code])) local++;
     }
   }
   // (b) rounding: f32 patterns stepped through all exponents, offsets of k/8 f32-ulp
