@@ -474,7 +474,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seconds", type=float, default=3600.0, help="audio seconds per GPU (default: the 1 h of cfg2)")
-    ap.add_argument("--cpu-sample-seconds", type=float, default=600.0)
+    ap.add_argument("--cpu-sample-seconds", type=float, default=3600.0,
+                    help="audio seconds of the workload the CPU baseline encodes and decodes (default: the whole hour, ~4 s on 16 threads; it doubles as the bit-exactness check of the GPU output)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--units-per-pass", type=int, default=0,
                     help="development aid: sound units per pipelined pass of the host entry points (default: the library's)")
