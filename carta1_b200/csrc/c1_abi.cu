@@ -249,11 +249,15 @@ struct PassTrace {
   }
 };
 
+// Bumped whenever a device buffer moves: captured launch sequences (GraphCache) hold raw pointers.
+static unsigned long long g_alloc_generation = 0;
+
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    g_alloc_generation++;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -297,6 +301,33 @@ void parallel_memcpy(void *dst, const void *src, size_t bytes) {
   for (auto &t : th) t.join();
 }
 
+// The stateful handles are called with a few frames at a time: eight to eleven small kernels whose launch
+// gaps are most of the call (131 us for one frame).  The kernel sequence of a call shape (frames per call) is
+// captured into a CUDA graph the second time the shape is seen and replayed afterwards; the host<->device
+// copies of the caller's buffers stay outside it.  A moved scratch buffer (g_alloc_generation) or a profiling
+// session invalidates / bypasses the graph.  Any failure while capturing disables graphs for the handle.
+struct GraphCache {
+  int shape = -1;            // frames per call (decoder: with a previous unit) the graph was captured for
+  int seen = 0;              // consecutive calls with this shape
+  unsigned long long generation = 0;
+  cudaGraphExec_t exec = nullptr;
+  unsigned long long kernels = 0;  // launches one replay stands for
+  bool disabled = false;
+  void drop() {
+    if (exec) cudaGraphExecDestroy(exec);
+    exec = nullptr;
+  }
+  // 0: run eagerly, 1: replay, 2: capture this call
+  int plan(int new_shape, bool profiling) {
+    if (disabled || profiling || getenv("CARTA1_NO_GRAPHS")) return 0;
+    if (new_shape != shape) { drop(); shape = new_shape; seen = 0; }
+    seen++;
+    if (exec && generation == g_alloc_generation) return 1;
+    drop();
+    return seen >= 2 ? 2 : 0;
+  }
+};
+
 }  // namespace
 
 struct carta1_ctx {
@@ -333,6 +364,7 @@ struct carta1_encoder {
   DevEncParams *d_params = nullptr;
   float *d_hist = nullptr;  // [n_streams][1024]: the last two frames of PCM per stream
   DevBuf work, su;
+  GraphCache graph;
 };
 
 struct carta1_decoder {
@@ -341,6 +373,7 @@ struct carta1_decoder {
   bool has_prev = false;
   float *d_rec = nullptr;  // [n_streams][512]: band record (IMDCT output) of the previous unit
   DevBuf work, pcm;
+  GraphCache graph;
 };
 
 namespace {
@@ -401,6 +434,39 @@ int ensure_decode_scratch(carta1_ctx *ctx, size_t units) {
 }
 
 }  // namespace
+
+// Runs `body` (kernel launches on ctx->stream only, returning a CARTA1 code) as planned by the cache.
+template <typename Body>
+static int run_graphed(carta1_ctx *ctx, GraphCache &g, int shape, Body body) {
+  const int plan = g.plan(shape, ctx->prof.on);
+  if (plan == 1) {
+    CU(ctx, cudaGraphLaunch(g.exec, ctx->stream));
+    ctx->prof.launches += g.kernels;
+    return CARTA1_OK;
+  }
+  if (plan == 2) {
+    const unsigned long long before = ctx->prof.launches;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      const int rc = body();
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ee = cudaStreamEndCapture(ctx->stream, &graph);
+      cudaGraphExec_t exec = nullptr;
+      if (rc == CARTA1_OK && ee == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        cudaGraphDestroy(graph);
+        g.exec = exec;
+        g.generation = g_alloc_generation;
+        g.kernels = ctx->prof.launches - before;
+        CU(ctx, cudaGraphLaunch(g.exec, ctx->stream));
+        return CARTA1_OK;
+      }
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      ctx->prof.launches = before;
+    }
+    g.disabled = true;  // nothing ran while capturing: fall through to the eager path
+  }
+  return body();
+}
 
 extern "C" {
 
@@ -1048,6 +1114,7 @@ void carta1_enc_destroy(carta1_encoder *e) {
   if (e->d_params) cudaFree(e->d_params);
   if (e->d_hist) cudaFree(e->d_hist);
   e->work.release(); e->su.release();
+  e->graph.drop();
   delete e;
 }
 
@@ -1073,14 +1140,18 @@ int carta1_enc_frames(carta1_encoder *e, const float *pcm, int n_frames, uint8_t
   CU(ctx, e->work.ensure(ns * row * sizeof(float)));
   CU(ctx, e->su.ensure(ns * (size_t)n_frames * CARTA1_SU_BYTES));
   float *w = (float *)e->work.p;
-  CU(ctx, copy_rows(w, row, e->d_hist, 1024, 1024, ns, ctx->stream, &ctx->prof));
   CU(ctx, cudaMemcpy2DAsync(w + 1024, row * sizeof(float), pcm, (size_t)n_frames * 512 * sizeof(float),
                             (size_t)n_frames * 512 * sizeof(float), ns, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = encode_device_impl(ctx, w, 0, row, 1, e->n_streams, row, 2, (size_t)n_frames, e->d_params,
-                              e->opts.use_fixed_block_modes != 0, (uint8_t *)e->su.p, 1, (size_t)n_frames,
-                              nullptr, nullptr, nullptr, nullptr);
+  int rc = run_graphed(ctx, e->graph, n_frames, [&]() -> int {
+    CU(ctx, copy_rows(w, row, e->d_hist, 1024, 1024, ns, ctx->stream, &ctx->prof));
+    const int r = encode_device_impl(ctx, w, 0, row, 1, e->n_streams, row, 2, (size_t)n_frames, e->d_params,
+                                     e->opts.use_fixed_block_modes != 0, (uint8_t *)e->su.p, 1, (size_t)n_frames,
+                                     nullptr, nullptr, nullptr, nullptr);
+    if (r) return r;
+    CU(ctx, copy_rows(e->d_hist, 1024, w + (size_t)n_frames * 512, row, 1024, ns, ctx->stream, &ctx->prof));
+    return CARTA1_OK;
+  });
   if (rc) return rc;
-  CU(ctx, copy_rows(e->d_hist, 1024, w + (size_t)n_frames * 512, row, 1024, ns, ctx->stream, &ctx->prof));
   CU(ctx, cudaMemcpyAsync(su_out, e->su.p, ns * (size_t)n_frames * CARTA1_SU_BYTES, cudaMemcpyDeviceToHost,
                           ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1106,6 +1177,7 @@ void carta1_dec_destroy(carta1_decoder *d) {
   cudaStreamSynchronize(d->ctx->stream);
   if (d->d_rec) cudaFree(d->d_rec);
   d->work.release(); d->pcm.release();
+  d->graph.drop();
   delete d;
 }
 
@@ -1148,10 +1220,16 @@ static int dec_frames_impl(carta1_decoder *d, const uint8_t *su, const int32_t *
     CU(ctx, cudaStreamSynchronize(ctx->stream));  // m lives on this stack frame
     dq = (const int32_t *)w; dsfi = w + n * 2048; dbits = w + n * 2560; dmodes = w + n * 3072;
   }
-  int rc = decode_device_impl(ctx, d_su, 1, nf, ns * nf, d->n_streams, halo, nf, d->pcm.p, 0, nf * 512, 1,
-                              nullptr, nullptr, halo ? d->d_rec : nullptr, dq, dsfi, dbits, dmodes);
+  auto body = [&]() -> int {
+    const int r = decode_device_impl(ctx, d_su, 1, nf, ns * nf, d->n_streams, halo, nf, d->pcm.p, 0, nf * 512, 1,
+                                     nullptr, nullptr, halo ? d->d_rec : nullptr, dq, dsfi, dbits, dmodes);
+    if (r) return r;
+    CU(ctx, copy_rows(d->d_rec, 512, (const float *)ctx->inv.p + (fr - 1) * 512, fr * 512, 512, ns, ctx->stream, &ctx->prof));
+    return CARTA1_OK;
+  };
+  // sound units with a previous unit in the handle: the steady state of a stream, worth a graph
+  const int rc = su && halo ? run_graphed(ctx, d->graph, n_frames, body) : body();
   if (rc) return rc;
-  CU(ctx, copy_rows(d->d_rec, 512, (const float *)ctx->inv.p + (fr - 1) * 512, fr * 512, 512, ns, ctx->stream, &ctx->prof));
   CU(ctx, cudaMemcpyAsync(pcm_out, d->pcm.p, ns * nf * 512 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   d->has_prev = true;

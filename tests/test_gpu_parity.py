@@ -197,6 +197,45 @@ def test_stateful_streams_match_whole_buffer(ctx, oracle):
         dec.close()
 
 
+def test_stateful_graph_replay_survives_reallocation_and_profiling(oracle):
+    """Same-shaped calls replay a captured CUDA graph (c1_abi.cu GraphCache).  The graph holds raw scratch
+    pointers: a larger call on another handle of the same context moves the scratch (new allocation
+    generation), a profiling session bypasses graphs; the stream must come out the same through all of it."""
+    import carta1_b200
+
+    c = carta1_b200.Context(0)  # a fresh context: its scratch starts small
+    try:
+        x = S.cfg4_mono_streams(3, 0.5, seed=77)
+        nf = x.shape[1] // 512
+        x = x[:, :nf * 512]
+        want = np.stack([oracle.encode_pcm([x[s]]) for s in range(3)])
+        enc, dec = carta1_b200.StreamEncoder(c, None, 3), carta1_b200.StreamDecoder(c, 3)
+        big = S.cfg4_mono_streams(40, 0.2, seed=5)
+        big = big[:, :(big.shape[1] // 512) * 512]
+        outs, pcms = [], []
+        for f in range(nf):
+            if f == 6:    # grows the context's scratch: the captured graphs must be dropped
+                e2 = carta1_b200.StreamEncoder(c, None, 40)
+                d2 = carta1_b200.StreamDecoder(c, 40)
+                d2.frames(e2.frames(big))
+                e2.close(); d2.close()
+            if f == 12:
+                c.profile(True)
+            if f == 15:
+                c.profile_read(); c.profile(False)
+            su = enc.frames(x[:, 512 * f:512 * (f + 1)])
+            outs.append(su)
+            pcms.append(dec.frames(su))
+        got = np.concatenate(outs, axis=1)
+        assert np.array_equal(got, want)
+        pcm = np.concatenate(pcms, axis=1).reshape(3, -1)
+        for s in range(3):
+            assert np.array_equal(bits(pcm[s]), bits(oracle.decode_su(want[s], 1)[0]))
+        enc.close(); dec.close()
+    finally:
+        c.close()
+
+
 @pytest.mark.parametrize("units", [4, 14, 250])
 def test_chunked_host_path(ctx, oracle, units):
     """More frames than one pass holds: the halo logic of the chunked entry points
