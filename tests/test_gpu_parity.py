@@ -92,6 +92,22 @@ def test_encode_stages_match_oracle(ctx, oracle, kw):
         assert np.array_equal(got["su"], want["su"]), (name, "sound units")
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(fixed_modes=[0, 0, 0]), dict(fixed_modes=[2, 2, 3]), dict(bias=2.5)],
+                         ids=["auto", "long", "short", "bias"])
+def test_non_finite_input(ctx, oracle, kw):
+    """+-Infinity, NaN and near-overflow PCM: the reference has no input validation, so whatever its arithmetic
+    does with them is the contract (ExactRound path of the transforms, NaN-aware max / min, ToInt32)."""
+    rng = np.random.default_rng(3)
+    for inject in ((np.inf,), (-np.inf,), (np.nan,), (3e38, -3e38), (np.inf, np.nan, -3e38, 3e38, -np.inf)):
+        pcm = (0.3 * rng.standard_normal(512 * 8)).astype(np.float32)
+        for i, v in enumerate(inject):
+            pcm[700 + 611 * i] = v
+        o_opt, g_opt = both_opts(oracle, kw)
+        want = oracle.encode_pcm([pcm], o_opt)
+        assert np.array_equal(ctx.encode_pcm([pcm], g_opt), want), inject
+        assert np.array_equal(bits(ctx.decode_su(want, 1)[0]), bits(oracle.decode_su(want, 1)[0])), inject
+
+
 def test_decode_stages_match_oracle(ctx, oracle):
     for name, pcm in mono_signals().items():
         su = oracle.encode_pcm([pcm])

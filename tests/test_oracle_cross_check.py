@@ -8,8 +8,21 @@ import signals as S
 from oracle import oracle_np as N
 
 
+# float32 stores of values beyond the binary32 range round to infinity, as a Float32Array store does
+pytestmark = pytest.mark.filterwarnings("ignore:overflow encountered in cast:RuntimeWarning",
+                                        "ignore:invalid value encountered:RuntimeWarning")
+
+
 def bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _non_finite(rng):
+    """+-Infinity, NaN and near-overflow samples: where JavaScript number semantics (Math.max / Math.min with
+    NaN, `| 0` of non-finite values, NaN never winning a `>`) are easiest to get wrong in a restatement."""
+    x = (0.3 * rng.standard_normal(512 * 8)).astype(np.float32)
+    x[700], x[1500], x[2600], x[2601], x[3300] = np.inf, np.nan, -3e38, 3e38, -np.inf
+    return x
 
 
 def cases():
@@ -25,6 +38,7 @@ def cases():
         "step": np.concatenate([np.zeros(700, np.float32), 0.8 * np.ones(1348, np.float32)]),
         "ragged_tone": (0.6 * np.sin(2 * np.pi * 3000 * t[:512 * 3 + 77])).astype(np.float32),
         "silence_then_burst": np.concatenate([np.zeros(1024, np.float32), rng.standard_normal(1024).astype(np.float32)]),
+        "non_finite": _non_finite(rng),
     }
 
 
@@ -35,7 +49,7 @@ OPTS = [dict(), dict(fixed_modes=[0, 0, 0]), dict(fixed_modes=[2, 2, 3]), dict(b
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_encode_and_decode_agree(oracle, name):
     pcm = CASES[name]
-    for kw in (OPTS if name in ("clicks", "white") else OPTS[:2]):
+    for kw in (OPTS if name in ("clicks", "white", "non_finite") else OPTS[:2]):
         want = oracle.encode_pcm([pcm], oracle.make_options(**kw))
         got, modes = N.encode_mono(pcm, **kw)
         assert got.shape == want.shape, (name, kw)
