@@ -58,7 +58,7 @@ EXPORTED_SYMBOLS = [
     "carta1_ctx_launch_count", "carta1_debug_encode_stages", "carta1_debug_decode_stages",
     "carta1_aea_write_header", "carta1_aea_parse_header", "carta1_kernel_count", "carta1_kernel_name",
     "carta1_ctx_profile", "carta1_ctx_profile_read", "carta1_debug_selftest",
-    "carta1_ctx_set_max_units_per_pass", "carta1_host_alloc", "carta1_host_free",
+    "carta1_ctx_set_max_units_per_pass", "carta1_host_alloc", "carta1_host_free", "carta1_deserialize_units",
 ]
 
 _lib = None
@@ -118,6 +118,7 @@ def load():
     L.carta1_ctx_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
     L.carta1_debug_selftest.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.carta1_ctx_set_max_units_per_pass.argtypes = [vp, sz]
+    L.carta1_deserialize_units.argtypes = [vp, vp, sz, vp, vp, vp, vp, vp]
     L.carta1_host_alloc.argtypes = [sz, C.POINTER(vp)]
     L.carta1_host_free.argtypes = [vp]
     L.carta1_host_free.restype = None
@@ -290,6 +291,16 @@ class Context:
 
     def decode_su_s16_into(self, su: np.ndarray, n_su: int, n_ch: int, out: np.ndarray) -> None:
         self._check(self.L.carta1_decode_su_s16(self.h, _ptr(su), n_su, n_ch, _ptr(out)))
+
+    def deserialize_units(self, su: np.ndarray) -> dict:
+        """Batched deserializeFrame (carta1_deserialize_units): arrays per unit, integers in bitstream order."""
+        su = np.ascontiguousarray(su, np.uint8).reshape(-1, SU_BYTES)
+        n = su.shape[0]
+        out = dict(n_bfu=np.zeros(n, np.uint8), block_modes=np.zeros((n, 3), np.int8), wl=np.zeros((n, 52), np.uint8),
+                   sfi=np.zeros((n, 52), np.uint8), q=np.zeros((n, 512), np.int32))
+        self._check(self.L.carta1_deserialize_units(self.h, _ptr(su), n, _ptr(out["n_bfu"]), _ptr(out["block_modes"]),
+                                                    _ptr(out["wl"]), _ptr(out["sfi"]), _ptr(out["q"])))
+        return out
 
     def selftest(self) -> int:
         bad = C.c_uint64()

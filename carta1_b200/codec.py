@@ -457,3 +457,23 @@ def decodeAeaPcm(data, ctx=None):
         raise ValueError(f"Unsupported channel count: {info['channelCount']}")
     su = np.ascontiguousarray(raw[AEA_HEADER_SIZE:AEA_HEADER_SIZE + n * SOUND_UNIT_SIZE])
     return (ctx or default_context()).decode_su(su, info["channelCount"])
+
+
+def deserializeFrames(units, ctx=None) -> list:
+    """deserializeFrame over many sound units at once on the device (carta1_deserialize_units): the frame
+    objects the `--json` dump of bin/cli.js:567-677 writes, one per 212-byte unit, equal to
+    [deserializeFrame(u) for u in units]."""
+    units = np.ascontiguousarray(units, np.uint8).reshape(-1, SOUND_UNIT_SIZE)
+    d = (ctx or default_context()).deserialize_units(units)
+    starts = np.concatenate([[0], np.cumsum(SPECS_PER_BFU)]).astype(int)
+    frames = []
+    for i in range(units.shape[0]):
+        n = int(d["n_bfu"][i])
+        frames.append({
+            "nBfu": n,
+            "scaleFactorIndices": d["sfi"][i, :n].astype(np.int32),
+            "wordLengthIndices": d["wl"][i, :n].astype(np.int32),
+            "quantizedCoefficients": [d["q"][i, starts[b]:starts[b + 1]].copy() for b in range(n)],
+            "blockModes": [int(m) for m in d["block_modes"][i]],
+        })
+    return frames

@@ -1257,6 +1257,35 @@ int carta1_dec_frames_expanded(carta1_decoder *d, const int32_t *q, const uint8_
   return dec_frames_impl(d, nullptr, q, sfi, bits, modes, n_frames, pcm_out);
 }
 
+// ------------------------------------------------------------------ frame dump
+int carta1_deserialize_units(carta1_ctx *ctx, const uint8_t *su, size_t n_su, uint8_t *n_bfu, int8_t *block_modes,
+                             uint8_t *wl, uint8_t *sfi, int32_t *q) {
+  if (!ctx) return CARTA1_ERR_ARG;
+  if (n_su == 0) return CARTA1_OK;
+  if (!su || !n_bfu || !block_modes || !wl || !sfi || !q) return fail(ctx, CARTA1_ERR_ARG, "carta1_deserialize_units: NULL argument");
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t chunk = std::max<size_t>(1, ctx->max_units_per_pass);
+  const size_t m = std::min(n_su, chunk);
+  // one buffer: units | q | wl | sfi | modes | n_bfu
+  const size_t o_q = (m * CARTA1_SU_BYTES + 255) & ~(size_t)255, o_wl = o_q + m * 2048, o_sfi = o_wl + m * 52,
+               o_modes = o_sfi + m * 52, o_n = o_modes + m * 3;
+  CU(ctx, ctx->dbg.ensure(o_n + m));
+  uint8_t *d = (uint8_t *)ctx->dbg.p;
+  for (size_t a = 0; a < n_su; a += chunk) {
+    const size_t k = std::min(chunk, n_su - a);
+    CU(ctx, cudaMemcpyAsync(d, su + a * CARTA1_SU_BYTES, k * CARTA1_SU_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, launch_deserialize(d, (int)k, ctx->d_tables, d + o_n, (int8_t *)(d + o_modes), d + o_wl, d + o_sfi,
+                               (int32_t *)(d + o_q), ctx->stream, &ctx->prof));
+    CU(ctx, cudaMemcpyAsync(q + a * 512, d + o_q, k * 2048, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(wl + a * 52, d + o_wl, k * 52, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(sfi + a * 52, d + o_sfi, k * 52, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(block_modes + a * 3, d + o_modes, k * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(n_bfu + a, d + o_n, k, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return CARTA1_OK;
+}
+
 // ------------------------------------------------------------------ stage taps
 int carta1_debug_encode_stages(carta1_ctx *ctx, const float *pcm, size_t n_samples, const carta1_enc_opts *opts,
                                float *bands, float *mags, int32_t *modes, float *coefs, uint8_t *su) {

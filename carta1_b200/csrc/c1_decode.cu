@@ -282,6 +282,90 @@ unpack_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_
 }
 
 // ------------------------------------------------------------------------------------
+// deserializeFrame in batches (serialization.js:111-176; the frame dump of bin/cli.js:567-677 runs it over
+// a whole file): one warp per sound unit -> BFU count, block modes, word-length and scale-factor indices
+// and the quantised integers in bitstream order (BFU b's SPECS_PER_BFU[b] values at BFU_START_LONG[b],
+// which is the running sum of the sizes).  Reads past byte 212 follow unpackBits (bitstream.js:55-68).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kUnpackWarps * 32)
+deserialize_kernel(const uint8_t *__restrict__ su, int n_units, const DevTables *__restrict__ T,
+                   uint8_t *__restrict__ n_bfu_out, int8_t *__restrict__ modes_out, uint8_t *__restrict__ wl_out,
+                   uint8_t *__restrict__ sfi_out, int32_t *__restrict__ q_out) {
+  __shared__ uint32_t s_words[kUnpackWarps][56];
+  __shared__ uint32_t s_base[kUnpackWarps][52];  // bit offset | width << 16
+  __shared__ uint16_t s_bj[512];                 // bitstream position -> (BFU << 5) | index inside the BFU
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const FormatTables &F = T->fmt;
+  for (int i = tid; i < 512; i += kUnpackWarps * 32) s_bj[i] = F.bj_long[i];
+  __syncthreads();
+  uint32_t *words = s_words[warp], *base = s_base[warp];
+  const int sz0 = F.specs[lane], sz1 = lane < 20 ? F.specs[lane + 32] : 0;
+  for (int unit = blockIdx.x * kUnpackWarps + warp; unit < n_units; unit += gridDim.x * kUnpackWarps) {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(su + (size_t)unit * kSuBytes);
+    const uint32_t w0 = __ldg(src + lane), w1 = lane < kSuWords - 32 ? __ldg(src + 32 + lane) : 0u;
+    __syncwarp();
+    words[lane] = __byte_perm(w0, 0, 0x0123);
+    if (lane < 24) words[32 + lane] = __byte_perm(w1, 0, 0x0123);
+    __syncwarp();
+    const uint32_t header = words[0] >> 16;
+    const int idx = (header >> 5) & 7;
+    const int n = idx == 0 ? 20 : 24 + 4 * idx;  // BFU_AMOUNTS
+    if (lane == 0) {
+      n_bfu_out[unit] = (uint8_t)n;
+      modes_out[unit * 3 + 0] = (int8_t)(2 - (int)((header >> 14) & 3));
+      modes_out[unit * 3 + 1] = (int8_t)(2 - (int)((header >> 12) & 3));
+      modes_out[unit * 3 + 2] = (int8_t)(3 - (int)((header >> 10) & 3));
+    }
+    int run = 16 + 10 * n;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int b = lane + 32 * h;
+      int wl = 0, sfi = 0;
+      if (b < n) {
+        wl = (int)get_bits(words, 16 + 4 * b, 4);
+        sfi = (int)get_bits(words, 16 + 4 * n + 6 * b, 6);
+      }
+      const int bits = wl_bits(wl);
+      const int cost = bits * (h == 0 ? sz0 : sz1);
+      int incl = cost;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (b < 52) {
+        base[b] = (uint32_t)(run + incl - cost) | ((uint32_t)bits << 16);
+        wl_out[(size_t)unit * 52 + b] = (uint8_t)wl;
+        sfi_out[(size_t)unit * 52 + b] = (uint8_t)sfi;
+      }
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+#pragma unroll 4
+    for (int k = 0; k < 16; k++) {
+      const uint32_t bj = s_bj[lane + 32 * k];
+      const uint32_t r = base[bj >> 5];
+      const int bits = (int)(r >> 16);
+      int q = 0;
+      if (bits > 0) {
+        const int v = (int)get_bits(words, (int)(r & 0xFFFFu) + (int)(bj & 31u) * bits, bits);
+        q = v >= (1 << (bits - 1)) ? v - (1 << bits) : v;  // bitstream.js:78-82
+      }
+      q_out[(size_t)unit * 512 + lane + 32 * k] = q;
+    }
+  }
+}
+
+cudaError_t launch_deserialize(const uint8_t *d_su, int n_units, const DevTables *tables, uint8_t *n_bfu, int8_t *modes,
+                               uint8_t *wl, uint8_t *sfi, int32_t *q, cudaStream_t st, Prof *prof) {
+  if (n_units <= 0) return cudaSuccess;
+  deserialize_kernel<<<std::min((n_units + kUnpackWarps - 1) / kUnpackWarps, persistent_ctas(4)), kUnpackWarps * 32, 0, st>>>(
+      d_su, n_units, tables, n_bfu, modes, wl, sfi, q);
+  prof->launches++;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
 // K6: IMDCT.  Long blocks use the in-thread passes of c1_fft.cuh.  A warp task is a pair of
 // consecutive sound units and a ROLE: role 0 transforms the low and mid bands of both units
 // (4 x IMDCT256), role 1 their high bands (2 x IMDCT512); rows holds the task's coefficients,

@@ -102,6 +102,9 @@ cudaError_t upload_encode_constants(const DevTables *host_tables);
 cudaError_t upload_decode_constants(const DevTables *host_tables);
 cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof);
 cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, Prof *prof);
+// batched deserializeFrame: [n] BFU counts, [n][3] block modes, [n][52] indices, [n][512] integers in bitstream order
+cudaError_t launch_deserialize(const uint8_t *d_su, int n_units, const DevTables *tables, uint8_t *n_bfu, int8_t *modes,
+                               uint8_t *wl, uint8_t *sfi, int32_t *q, cudaStream_t st, Prof *prof);
 cudaError_t launch_selftest(const DevTables *tables, unsigned long long *d_bad, cudaStream_t st);
 
 }  // namespace c1

@@ -409,6 +409,36 @@ static napi_value DecodeSu(napi_env env, napi_callback_info info) {
   return queue_job(env, j, "carta1_b200.decodeSu");
 }
 
+/* deserializeUnits(ctx, su: Uint8Array) -> [nBfu: Uint8Array(n), blockModes: Int8Array(3n), wl: Uint8Array(52n),
+ * sfi: Uint8Array(52n), q: Int32Array(512n)]: deserializeFrame over a whole file (bin/cli.js:567-677), see
+ * carta1_deserialize_units for the layouts. */
+static napi_value DeserializeUnits(napi_env env, napi_callback_info info) {
+  size_t argc = 2, len = 0, n;
+  napi_value argv[2], result, v[5];
+  handle *hc;
+  void *su, *p[5];
+  int rc, i;
+  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+  if (argc < 2 || !(hc = get_handle(env, argv[0], H_CTX))) return NULL;
+  if (!typed(env, argv[1], napi_uint8_array, &su, &len) || len % CARTA1_SU_BYTES) {
+    napi_throw_error(env, NULL, "Frame must be 212 bytes");  /* serialization.js:112-114 */
+    return NULL;
+  }
+  n = len / CARTA1_SU_BYTES;
+  v[0] = new_typed(env, napi_uint8_array, n, 1, &p[0]);
+  v[1] = new_typed(env, napi_int8_array, 3 * n, 1, &p[1]);
+  v[2] = new_typed(env, napi_uint8_array, 52 * n, 1, &p[2]);
+  v[3] = new_typed(env, napi_uint8_array, 52 * n, 1, &p[3]);
+  v[4] = new_typed(env, napi_int32_array, 512 * n, 4, &p[4]);
+  for (i = 0; i < 5; i++) if (!v[i]) return NULL;
+  rc = carta1_deserialize_units((carta1_ctx *)hc->ptr, (const uint8_t *)su, n, (uint8_t *)p[0], (int8_t *)p[1],
+                                (uint8_t *)p[2], (uint8_t *)p[3], (int32_t *)p[4]);
+  if (rc) return throw_abi(env, rc, (carta1_ctx *)hc->ptr);
+  NAPI_OK(napi_create_array_with_length(env, 5, &result));
+  for (i = 0; i < 5; i++) NAPI_OK(napi_set_element(env, result, (uint32_t)i, v[i]));
+  return result;
+}
+
 static napi_value Init(napi_env env, napi_value exports) {
   static const napi_property_descriptor props[] = {
       {"createContext", NULL, CreateContext, NULL, NULL, NULL, napi_default, NULL},
@@ -419,6 +449,7 @@ static napi_value Init(napi_env env, napi_value exports) {
       {"decodeFramesExpanded", NULL, DecodeFramesExpanded, NULL, NULL, NULL, napi_default, NULL},
       {"encodePcm", NULL, EncodePcm, NULL, NULL, NULL, napi_default, NULL},
       {"decodeSu", NULL, DecodeSu, NULL, NULL, NULL, napi_default, NULL},
+      {"deserializeUnits", NULL, DeserializeUnits, NULL, NULL, NULL, napi_default, NULL},
       {"destroy", NULL, Destroy, NULL, NULL, NULL, napi_default, NULL},
   };
   NAPI_OK(napi_define_properties(env, exports, sizeof props / sizeof props[0], props));

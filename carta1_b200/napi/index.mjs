@@ -202,7 +202,34 @@ async function decodeAeaPcm(input) {
   return native.decodeSu(context(), bytes.slice(AEA_HEADER_SIZE, AEA_HEADER_SIZE + units * SOUND_UNIT_SIZE), info.channelCount)
 }
 
+/**
+ * deserializeFrame over many sound units at once (what the CLI's `--json` dump, bin/cli.js:567-677, runs over a
+ * file): frame objects equal to Array.from(units, deserializeFrame).  Not part of the reference's export list.
+ * @param {Uint8Array} bytes - n * 212 bytes
+ */
+function deserializeFrames(bytes) {
+  const [nBfu, modes, wl, sfi, q] = native.deserializeUnits(context(), bytes)
+  const frames = new Array(nBfu.length)
+  for (let i = 0; i < nBfu.length; i++) {
+    const n = nBfu[i]
+    const quantizedCoefficients = new Array(n)
+    for (let b = 0; b < n; b++) {
+      const at = 512 * i + BFU_START_LONG[b]
+      quantizedCoefficients[b] = q.slice(at, at + SPECS_PER_BFU[b])
+    }
+    frames[i] = {
+      nBfu: n,
+      scaleFactorIndices: Int32Array.from(sfi.subarray(52 * i, 52 * i + n)),
+      wordLengthIndices: Int32Array.from(wl.subarray(52 * i, 52 * i + n)),
+      quantizedCoefficients,
+      blockModes: [modes[3 * i], modes[3 * i + 1], modes[3 * i + 2]],
+    }
+  }
+  return frames
+}
+
 export {
+  deserializeFrames,
   pipe, encode, decode, qmfAnalysisStage, mdctStage, serializeFrame, deserializeFrame, quantize, dequantize, AeaFile,
   BufferPool, EncoderOptions, AudioProcessor, decodeAeaPcm, encodeAeaPcm, FFT, WORD_LENGTH_BITS, SPECS_PER_BFU,
   SCALE_FACTORS, BFU_START_LONG,

@@ -202,6 +202,19 @@ int carta1_aea_write_header(const char *title_utf8, uint32_t su_count, int n_ch,
 int carta1_aea_parse_header(const uint8_t *hdr, size_t len, char title_out[257],
                             uint32_t *su_count, int *n_ch);
 
+/* ---- frame dump -------------------------------------------------------------------
+ * deserializeFrame (codec/io/serialization.js:111-176) over n_su sound units at once: what the
+ * `--json` dump of bin/cli.js:567-677 runs over a whole file.  Per unit i:
+ *   n_bfu[i]            nBfu (BFU_AMOUNTS[(header >> 5) & 7])
+ *   block_modes[3 i..]  blockModes as stored: 2 - field, 2 - field, 3 - field (may be negative)
+ *   wl[52 i + b], sfi[52 i + b]   wordLengthIndices / scaleFactorIndices of BFU b (0 for b >= nBfu)
+ *   q[512 i + p]        quantizedCoefficients in bitstream order: BFU b's SPECS_PER_BFU[b] integers
+ *                       at p = BFU_START_LONG[b] + j (the running sum of the sizes); 0 where the
+ *                       BFU carries no bits or b >= nBfu
+ * Units that claim more bits than they have follow unpackBits past the end (bitstream.js:55-68). */
+int carta1_deserialize_units(carta1_ctx *ctx, const uint8_t *su, size_t n_su, uint8_t *n_bfu,
+                             int8_t *block_modes, uint8_t *wl, uint8_t *sfi, int32_t *q);
+
 #ifdef __cplusplus
 }
 #endif

@@ -196,3 +196,28 @@ def test_complete_aea_helpers(K, oracle):  # :94-117
                           oracle.encode_pcm(channels, oracle.make_options(bias=3.0)))
     with pytest.raises(ValueError, match="Value for allocationBias must be between 0 and 5"):
         K.encodeAeaPcm(channels, {"allocationBias": 7})
+
+
+def test_batched_frame_dump_equals_deserialize_frame(K, oracle):
+    """carta1_deserialize_units (the batched deserializeFrame of the CLI's JSON dump, bin/cli.js:567-677):
+    encoder output, every BFU count, and random bytes whose declared payload runs past the 212 bytes."""
+    rng = np.random.default_rng(12)
+    x = S.cfg3_transients(0.4, seed=9, n_ch=1)[0]
+    units = [oracle.encode_pcm([x]), oracle.encode_pcm([x], oracle.make_options(bias=3.0)),
+             rng.integers(0, 256, (40, 212), dtype=np.uint8)]
+    K.default_context().set_max_units_per_pass(16)  # several passes
+    try:
+        for su in units:
+            got = K.deserializeFrames(su)
+            assert len(got) == len(su)
+            for u, g in zip(su, got):
+                w = K.deserializeFrame(u)
+                assert g["nBfu"] == w["nBfu"] and g["blockModes"] == w["blockModes"]
+                assert np.array_equal(g["wordLengthIndices"], w["wordLengthIndices"])
+                assert np.array_equal(g["scaleFactorIndices"], w["scaleFactorIndices"])
+                assert len(g["quantizedCoefficients"]) == w["nBfu"]
+                for a, b in zip(g["quantizedCoefficients"], w["quantizedCoefficients"]):
+                    assert a.dtype == np.int32 and np.array_equal(a, b)
+    finally:
+        K.default_context().set_max_units_per_pass(0)
+
