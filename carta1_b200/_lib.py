@@ -59,6 +59,7 @@ EXPORTED_SYMBOLS = [
     "carta1_aea_write_header", "carta1_aea_parse_header", "carta1_kernel_count", "carta1_kernel_name",
     "carta1_ctx_profile", "carta1_ctx_profile_read", "carta1_debug_selftest",
     "carta1_ctx_set_max_units_per_pass", "carta1_host_alloc", "carta1_host_free", "carta1_deserialize_units",
+    "carta1_debug_transient_scores", "carta1_ctx_near_threshold",
 ]
 
 _lib = None
@@ -124,6 +125,8 @@ def load():
     L.carta1_host_free.restype = None
     L.carta1_debug_encode_stages.argtypes = [vp, vp, sz, C.POINTER(EncOpts), vp, vp, vp, vp, vp]
     L.carta1_debug_decode_stages.argtypes = [vp, vp, sz, vp, vp, vp]
+    L.carta1_debug_transient_scores.argtypes = [vp, vp, sz, C.POINTER(EncOpts), vp]
+    L.carta1_ctx_near_threshold.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int]
     L.carta1_aea_write_header.argtypes = [C.c_char_p, C.c_uint32, C.c_int, vp]
     L.carta1_aea_parse_header.argtypes = [vp, sz, C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
     _lib = L
@@ -320,6 +323,21 @@ class Context:
                                                       C.byref(opts) if opts is not None else None, _ptr(bands),
                                                       _ptr(mags), _ptr(modes), _ptr(coefs), _ptr(su)))
         return dict(bands=bands, mags=mags, modes=modes, coefs=coefs, su=su)
+
+    def debug_transient_scores(self, pcm: np.ndarray, opts: EncOpts | None = None) -> np.ndarray:
+        """[n_frames][3] transient scores (auto block modes) of one row of PCM."""
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        nf = (len(pcm) + FRAME - 1) // FRAME
+        scores = np.zeros((nf, 3), np.float64)
+        self._check(self.L.carta1_debug_transient_scores(self.h, _ptr(pcm), len(pcm),
+                                                         C.byref(opts) if opts is not None else None, _ptr(scores)))
+        return scores
+
+    def near_threshold(self, reset: bool = False) -> dict:
+        """Close calls of `score > threshold` since creation / the last reset (carta1_ctx_near_threshold)."""
+        c = (C.c_uint64 * 3)()
+        self._check(self.L.carta1_ctx_near_threshold(self.h, c, int(reset)))
+        return {"decisions": int(c[0]), "within_1e-9": int(c[1]), "within_1e-12": int(c[2])}
 
     def debug_decode_stages(self, su: np.ndarray):
         su = np.ascontiguousarray(su, np.uint8).reshape(-1, SU_BYTES)

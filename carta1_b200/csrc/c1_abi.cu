@@ -6,6 +6,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -18,7 +20,23 @@ using namespace c1;
 
 namespace {
 
-std::string g_create_error;
+// last error of the calls that have no context to keep it in (carta1_ctx_create, carta1_aea_parse_header):
+// per thread, so that two threads creating contexts do not write one string
+thread_local std::string g_create_error;
+
+// The kernels read the QMF taps and the FFT twiddles of stages 0..2 from __constant__ memory, which is one
+// copy per DEVICE, not per context.  The taps are literals of the format (constants.js:74-107) and never
+// differ; the twiddles derive from carta1_tables::fft_w, which a host may inject.  Contexts on one device
+// therefore have to agree on fft_w: the first context uploads, later ones are refused if theirs differ
+// (CARTA1_ERR_ARG), and the upload only ever happens while no context of the device is alive, i.e. while
+// none of its kernels can be running.
+struct DeviceConstants {
+  int live = 0;                 // contexts alive on the device
+  bool loaded = false;
+  double fft_w[8][2];
+};
+std::mutex g_const_mutex;
+DeviceConstants g_const[64];
 
 // ---------------------------------------------------------------- host tables
 const int kSpecs[52] = {8, 8, 8, 8, 4, 4, 4, 4, 8, 8, 8, 8, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 7, 7,
@@ -250,7 +268,8 @@ struct PassTrace {
 };
 
 // Bumped whenever a device buffer moves: captured launch sequences (GraphCache) hold raw pointers.
-static unsigned long long g_alloc_generation = 0;
+// Process-wide and atomic: contexts are used from different threads at the same time.
+static std::atomic<unsigned long long> g_alloc_generation{0};
 
 struct DevBuf {
   void *p = nullptr;
@@ -343,6 +362,8 @@ struct carta1_ctx {
   carta1_enc_opts params_opts;
   double params_bsf[64];
   DevBuf bands, mags, feats, modes, coefs, sfi, inv, scores, dbg, recs;
+  unsigned long long *d_near = nullptr;  // transient close calls (< 1e-9, < 1e-12), see carta1_ctx_near_threshold
+  uint64_t near_decisions = 0;           // block-mode decisions taken (3 per emitted unit of an auto-mode call)
   // Host entry points: passes rotate through kSlots staging slots so that the H2D copy of pass i+1 and the D2H
   // copy of pass i-1 run while pass i computes (three streams, events between them).
   DevBuf stage_pcm[kSlots], stage_su[kUnitSlots];
@@ -354,6 +375,7 @@ struct carta1_ctx {
   HostBuf bounce_pcm[kSlots], bounce_su[kSlots];
   cudaEvent_t ev_bin[kSlots] = {};  // the H2D that read bounce slot i has finished
   size_t max_units_per_pass = 1u << 16;  // frames*channels per pass of the chunked host entry points
+  bool holds_constants = false;          // counted in g_const[device].live
 };
 
 struct carta1_encoder {
@@ -403,17 +425,18 @@ int upload_params(carta1_ctx *ctx, const carta1_enc_opts *opts, DevEncParams *d_
     if (same && o.biased_scale_factors)
       same = memcmp(ctx->params_bsf, o.biased_scale_factors, sizeof ctx->params_bsf) == 0;
     if (same) return CARTA1_OK;
-    ctx->params_valid = true;
-    ctx->params_opts = o;
-    if (o.biased_scale_factors) memcpy(ctx->params_bsf, o.biased_scale_factors, sizeof ctx->params_bsf);
+    ctx->params_valid = false;  // until the new parameters are on the device
   }
   DevEncParams hp;
-  if (!build_enc_params(ctx->tables, o, &hp)) {
-    if (d_params == ctx->d_params) ctx->params_valid = false;
+  if (!build_enc_params(ctx->tables, o, &hp))
     return fail(ctx, CARTA1_ERR_ARG, "carta1: biased scale factors must be positive, finite and normal in binary32");
-  }
   CU(ctx, cudaMemcpyAsync(d_params, &hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));  // hp lives on this stack frame
+  if (d_params == ctx->d_params) {
+    ctx->params_opts = o;
+    if (o.biased_scale_factors) memcpy(ctx->params_bsf, o.biased_scale_factors, sizeof ctx->params_bsf);
+    ctx->params_valid = true;
+  }
   return CARTA1_OK;
 }
 
@@ -540,10 +563,37 @@ int carta1_ctx_create(int device, const carta1_tables *tables, carta1_ctx **out)
   }
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_tables, sizeof(DevTables));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_params, sizeof(DevEncParams));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_near, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(ctx->d_near, 0, 2 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tables, ht, sizeof(DevTables), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = upload_encode_constants(ht);
-  if (e == cudaSuccess) e = upload_decode_constants(ht);
+  bool tables_clash = false;
+  if (e == cudaSuccess) {
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    DeviceConstants &dc = g_const[device & 63];
+    const bool same = dc.loaded && memcmp(dc.fft_w, ctx->tables.fft_w, sizeof dc.fft_w) == 0;
+    if (dc.live > 0 && !same) {
+      tables_clash = true;
+    } else {
+      if (!same) {  // no context of this device is alive: nothing of ours is running on it
+        dc.loaded = false;
+        e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = upload_encode_constants(ht);
+        if (e == cudaSuccess) e = upload_decode_constants(ht);
+        if (e == cudaSuccess) {
+          memcpy(dc.fft_w, ctx->tables.fft_w, sizeof dc.fft_w);
+          dc.loaded = true;
+        }
+      }
+      if (e == cudaSuccess) { dc.live++; ctx->holds_constants = true; }
+    }
+  }
   delete ht;
+  if (tables_clash) {
+    carta1_ctx_destroy(ctx);
+    return fail(nullptr, CARTA1_ERR_ARG,
+                "carta1_ctx_create: a live context on this device was created with different fft_w tables "
+                "(the FFT twiddles live in per-device constant memory)");
+  }
   if (e != cudaSuccess) {
     cuda_fail(nullptr, e, "carta1_ctx_create");
     carta1_ctx_destroy(ctx);
@@ -580,7 +630,12 @@ void carta1_ctx_destroy(carta1_ctx *ctx) {
   if (ctx->small) cudaStreamDestroy(ctx->small);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_params) cudaFree(ctx->d_params);
+  if (ctx->d_near) cudaFree(ctx->d_near);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->holds_constants) {
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    g_const[ctx->device & 63].live--;
+  }
   delete ctx;
 }
 
@@ -646,7 +701,7 @@ static int encode_device_impl(carta1_ctx *ctx, const void *d_pcm, int pcm_fmt, s
                               int n_ch_interleave, int n_streams, size_t valid_samples, size_t halo_frames,
                               size_t n_frames, const DevEncParams *d_params, bool use_fixed, uint8_t *d_su,
                               size_t su_frame_stride, size_t su_stream_stride, float *dbg_bands,
-                              float *dbg_mags, uint8_t *dbg_modes, float *dbg_coefs) {
+                              float *dbg_mags, uint8_t *dbg_modes, float *dbg_coefs, double *dbg_scores = nullptr) {
   const size_t frames_total = halo_frames + n_frames;
   const size_t units = frames_total * (size_t)n_streams;
   if (units == 0) return CARTA1_OK;
@@ -665,7 +720,9 @@ static int encode_device_impl(carta1_ctx *ctx, const void *d_pcm, int pcm_fmt, s
   L.mags = dbg_mags ? dbg_mags : (float *)ctx->mags.p;
   L.modes = dbg_modes ? dbg_modes : (uint8_t *)ctx->modes.p;
   L.coefs = dbg_coefs ? dbg_coefs : (float *)ctx->coefs.p;
-  L.scores = nullptr;
+  L.scores = dbg_scores;
+  L.near_counts = ctx->d_near;
+  if (!use_fixed) ctx->near_decisions += 3ull * (uint64_t)n_streams * n_frames;
   L.feats = ctx->feats.p;
   L.sfi = (uint8_t *)ctx->sfi.p;
   L.alloc_recs = ctx->recs.p;
@@ -785,11 +842,10 @@ static void *mapped_alias(const void *host) {
 // Development switch CARTA1_SMALL_COPY: 0 copy engines on the h2d/d2h streams, 1 copy engines on the
 // priority stream, 2 copy kernel in both directions, 3 (default) copy kernel for writes to the host only.
 static int small_copy_mode() {
-  static int mode = -1;
-  if (mode < 0) {
+  static const int mode = [] {  // initialised once, thread-safe
     const char *v = getenv("CARTA1_SMALL_COPY");
-    mode = v && *v ? atoi(v) : 3;
-  }
+    return v && *v ? atoi(v) : 3;
+  }();
   return mode;
 }
 
@@ -810,7 +866,18 @@ static cudaError_t small_copy(void *dst, const void *src, size_t bytes, cudaMemc
   return cudaGetLastError();
 }
 
-static int encode_host_impl(carta1_ctx *ctx, const float *const *channels, const int16_t *interleaved,
+// A pipelined host call that fails half-way returns while earlier passes may still be copying into or out of
+// the caller's buffers and the context's slots: wait for all four streams before the caller gets the error.
+static void quiesce(carta1_ctx *ctx) {
+  if (!ctx || cudaSetDevice(ctx->device) != cudaSuccess) return;
+  if (ctx->h2d) cudaStreamSynchronize(ctx->h2d);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->small) cudaStreamSynchronize(ctx->small);
+  if (ctx->d2h) cudaStreamSynchronize(ctx->d2h);
+  cudaGetLastError();
+}
+
+static int encode_host_body(carta1_ctx *ctx, const float *const *channels, const int16_t *interleaved,
                             int n_ch, size_t n_samples, const carta1_enc_opts *opts, uint8_t *su_out,
                             size_t su_capacity_bytes, size_t *n_su_out) {
   if (!ctx) return CARTA1_ERR_ARG;
@@ -947,6 +1014,14 @@ static int encode_host_impl(carta1_ctx *ctx, const float *const *channels, const
   return CARTA1_OK;
 }
 
+static int encode_host_impl(carta1_ctx *ctx, const float *const *channels, const int16_t *interleaved,
+                            int n_ch, size_t n_samples, const carta1_enc_opts *opts, uint8_t *su_out,
+                            size_t su_capacity_bytes, size_t *n_su_out) {
+  const int rc = encode_host_body(ctx, channels, interleaved, n_ch, n_samples, opts, su_out, su_capacity_bytes, n_su_out);
+  if (rc != CARTA1_OK) quiesce(ctx);
+  return rc;
+}
+
 int carta1_encode_pcm(carta1_ctx *ctx, const float *const *channels, int n_ch, size_t n_samples,
                       const carta1_enc_opts *opts, uint8_t *su_out, size_t su_capacity_bytes,
                       size_t *n_su_out) {
@@ -959,7 +1034,7 @@ int carta1_encode_pcm_s16(carta1_ctx *ctx, const int16_t *interleaved, int n_ch,
   return encode_host_impl(ctx, nullptr, interleaved, n_ch, n_samples, opts, su_out, su_capacity_bytes, n_su_out);
 }
 
-static int decode_host_impl(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch,
+static int decode_host_body(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch,
                             float *const *channels_out, int16_t *interleaved_out) {
   if (!ctx) return CARTA1_ERR_ARG;
   if (n_ch != 1 && n_ch != 2) {  // processor.js:147-157
@@ -1073,6 +1148,13 @@ static int decode_host_impl(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   tr.report();
   return CARTA1_OK;
+}
+
+static int decode_host_impl(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch,
+                            float *const *channels_out, int16_t *interleaved_out) {
+  const int rc = decode_host_body(ctx, su, n_su, n_ch, channels_out, interleaved_out);
+  if (rc != CARTA1_OK) quiesce(ctx);
+  return rc;
 }
 
 int carta1_decode_su(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch, float *const *channels_out) {
@@ -1339,6 +1421,45 @@ int carta1_debug_decode_stages(carta1_ctx *ctx, const uint8_t *su, size_t n_su, 
   if (bands) CU(ctx, cudaMemcpyAsync(bands, base + o_bands, n_su * 512 * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (pcm) CU(ctx, cudaMemcpyAsync(pcm, base + o_pcm, n_su * 512 * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return CARTA1_OK;
+}
+
+int carta1_debug_transient_scores(carta1_ctx *ctx, const float *pcm, size_t n_samples, const carta1_enc_opts *opts,
+                                  double *scores) {
+  if (!ctx) return CARTA1_ERR_ARG;
+  const size_t frames = carta1_frame_count(n_samples);
+  if (frames == 0) return CARTA1_OK;
+  if (!pcm || !scores) return fail(ctx, CARTA1_ERR_ARG, "carta1_debug_transient_scores: NULL argument");
+  if (opts && opts->use_fixed_block_modes)
+    return fail(ctx, CARTA1_ERR_ARG, "carta1_debug_transient_scores: fixed block modes compute no score");
+  CU(ctx, cudaSetDevice(ctx->device));
+  int rc = upload_params(ctx, opts, ctx->d_params);
+  if (rc) return rc;
+  // layout: pcm | scores (doubles, 8-byte aligned)
+  const size_t o_scores = (frames * 512 + 1) & ~(size_t)1;
+  CU(ctx, ctx->dbg.ensure(o_scores * sizeof(float) + frames * 3 * sizeof(double)));
+  float *base = (float *)ctx->dbg.p;
+  CU(ctx, cudaMemsetAsync(base, 0, o_scores * sizeof(float), ctx->stream));
+  CU(ctx, cudaMemcpyAsync(base, pcm, n_samples * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  rc = encode_device_impl(ctx, base, 0, frames * 512, 1, 1, n_samples, 0, frames, ctx->d_params, false, nullptr, 1, frames,
+                          nullptr, nullptr, nullptr, nullptr, (double *)(base + o_scores));
+  if (rc) return rc;
+  CU(ctx, cudaMemcpyAsync(scores, base + o_scores, frames * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return CARTA1_OK;
+}
+
+int carta1_ctx_near_threshold(carta1_ctx *ctx, uint64_t counts[3], int reset) {
+  if (!ctx || !counts) return CARTA1_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  unsigned long long near[2] = {0, 0};
+  CU(ctx, cudaMemcpyAsync(near, ctx->d_near, sizeof near, cudaMemcpyDeviceToHost, ctx->stream));
+  if (reset) CU(ctx, cudaMemsetAsync(ctx->d_near, 0, sizeof near, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  counts[0] = ctx->near_decisions;
+  counts[1] = near[0];
+  counts[2] = near[1];
+  if (reset) ctx->near_decisions = 0;
   return CARTA1_OK;
 }
 

@@ -15,6 +15,8 @@
 #include "c1_launch.h"
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 
 namespace c1 {
 
@@ -527,9 +529,9 @@ constexpr int kTmWarps = 4, kTmUnits = 8, kTmRow = 273;
 __device__ __forceinline__ int tm_off(int band) { return band == 0 ? 0 : band == 1 ? 64 + 8 : 128 + 16; }
 
 __global__ void __launch_bounds__(kTmWarps * 32)
-transient_modes_kernel(const float *__restrict__ mags, const SpectrumFeatures *__restrict__ feats, int frames,
+transient_modes_kernel(const float *__restrict__ mags, const SpectrumFeatures *__restrict__ feats, int frames, int halo,
                        int n_su, const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
-                       uint8_t *__restrict__ modes, double *__restrict__ scores) {
+                       uint8_t *__restrict__ modes, double *__restrict__ scores, unsigned long long *__restrict__ near) {
   __shared__ float s_rows[kTmWarps][(kTmUnits + 1) * kTmRow];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float *rows = s_rows[warp];
@@ -588,6 +590,14 @@ transient_modes_kernel(const float *__restrict__ mags, const SpectrumFeatures *_
       const int transient = score > P->threshold;
       modes[(size_t)su * 4 + band] = (uint8_t)(transient ? (band == 2 ? 3 : 2) : 0);
       if (scores) scores[(size_t)su * 3 + band] = score;
+      // Close calls of `score > threshold` (transient.js:54): the score goes through log / exp / log10 / log1p, the one
+      // place where a libm that is not V8's could flip a decision; counted for emitted frames so
+      // the risk is observable (carta1_ctx_near_threshold).
+      const double gap = fabs(score - P->threshold);
+      if (near && frame >= halo && gap < 1e-9) {
+        atomicAdd(near, 1ull);
+        if (gap < 1e-12) atomicAdd(near + 1, 1ull);
+      }
     }
   }
 }
@@ -1490,10 +1500,12 @@ int pick_run_len(int frames, int n_streams, int warps) {
 // partly empty wave; the kernels stride over their work lists).  Cached per kernel.
 int resident_ctas(const void *kernel, int threads, size_t dyn_smem) {
   struct Entry { const void *k; int dev; int ctas; };
-  static Entry cache[32];
+  static std::mutex mu;  // contexts launch from different threads at the same time
+  static Entry cache[64];
   static int n_cache = 0;
   int dev = 0;
   cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
   for (int i = 0; i < n_cache; i++)
     if (cache[i].k == kernel && cache[i].dev == dev) return cache[i].ctas;
   int per_sm = 0;
@@ -1502,17 +1514,19 @@ int resident_ctas(const void *kernel, int threads, size_t dyn_smem) {
     per_sm = 1;
   }
   const int ctas = persistent_ctas(per_sm);
-  if (n_cache < 32) cache[n_cache++] = {kernel, dev, ctas};
+  if (n_cache < 64) cache[n_cache++] = {kernel, dev, ctas};
   return ctas;
 }
 
-// CTAs of a persistent kernel: every SM filled to `per_sm` resident CTAs.
+// CTAs of a persistent kernel: every SM of the current device filled to `per_sm` resident CTAs.
 int persistent_ctas(int per_sm) {
-  static int sms = 0;
+  static std::atomic<int> sms_of[64];  // per device; 0 = not queried yet (a racing double query stores the same value)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int sms = sms_of[dev & 63].load(std::memory_order_relaxed);
   if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    sms_of[dev & 63].store(sms, std::memory_order_relaxed);
   }
   return sms * per_sm;
 }
@@ -1559,7 +1573,8 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
     transient_modes_kernel<<<std::min((n_tm_groups + kTmWarps - 1) / kTmWarps,
                                       resident_ctas((const void *)transient_modes_kernel, kTmWarps * 32, 0)),
                              kTmWarps * 32, 0, st>>>(L.mags, static_cast<const SpectrumFeatures *>(L.feats),
-                                                                  frames, n_su, L.tables, L.params, L.modes, L.scores);
+                                                                  frames, L.halo_frames, n_su, L.tables, L.params, L.modes, L.scores,
+                                                                  L.near_counts);
     prof->end(K_TRANSIENT_MODES, st);
   }
   prof->begin(K_MDCT, st);

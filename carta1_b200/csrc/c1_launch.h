@@ -33,6 +33,7 @@ struct EncodeLaunch {
   void *feats;              // 3 x {flatness, hf ratio, energy} doubles per unit (auto modes only)
   uint8_t *modes;           // 4 per unit   (auto modes only)
   double *scores;           // 3 per unit, optional
+  unsigned long long *near_counts;  // optional: [0] decisions with |score - threshold| < 1e-9, [1] < 1e-12 (emitted frames)
   float *coefs;             // 512 per unit
   uint8_t *sfi;             // 64 per unit: scale-factor index per BFU (52 used)
   void *alloc_recs;         // alloc_rec_bytes() per emitted unit

@@ -190,6 +190,18 @@ int carta1_debug_encode_stages(carta1_ctx *ctx, const float *pcm, size_t n_sampl
 int carta1_debug_decode_stages(carta1_ctx *ctx, const uint8_t *su, size_t n_su, float *coefs,
                                float *bands, float *pcm);
 
+/* Transient scores [n_frames][3] (low, mid, high) of one row of PCM with auto block modes: the value
+ * detectTransient compares with the threshold (codec/analysis/transient.js:44-55,197-226). */
+int carta1_debug_transient_scores(carta1_ctx *ctx, const float *pcm, size_t n_samples,
+                                  const carta1_enc_opts *opts, double *scores);
+
+/* Close calls of the block-mode decision `score > threshold` (codec/analysis/transient.js:54), the one
+ * place where a libm that differs from V8's by an ulp could change emitted bytes:
+ * counts[0] = decisions taken (3 per emitted sound unit of every auto-block-mode call), counts[1] = those
+ * with |score - threshold| < 1e-9, counts[2] = those with |score - threshold| < 1e-12, since the context
+ * was created or last reset.  Synchronises the context's stream.  No counterpart in the reference. */
+int carta1_ctx_near_threshold(carta1_ctx *ctx, uint64_t counts[3], int reset);
+
 /* Device self-test of the kernels' exact arithmetic shortcuts (reciprocal-based division,
  * in-FP64 rounding to binary32) against the IEEE operations they replace; *mismatches must
  * come back 0. */

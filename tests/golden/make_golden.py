@@ -7,7 +7,12 @@ JavaScript engine exists in the build image, so the reference cannot be executed
 against drift, and are the file a maintainer with Node diffs first: encode the `pcm_s16`
 arrays with carta1 (scaled by 1/32768 as bin/cli.js:395 does) and compare `su`.
 
-    python tests/golden/make_golden.py        # rewrites the fixtures in place
+    python tests/golden/make_golden.py                       # rewrites the fixtures in place
+    python tests/golden/make_golden.py --export-ref-inputs   # writes tests/golden/ref/inputs/ for tools/ref_dump.mjs
+
+The second form does not touch the fixtures: it unpacks their `pcm_s16` inputs as raw little-endian int16
+files plus a cases.json (channels, options), the form tools/ref_dump.mjs feeds to the real carta1 under Node;
+tests/test_reference_pin.py then compares oracle and CUDA path with what the reference wrote.
 """
 import os
 import sys
@@ -32,7 +37,30 @@ CASES = {
 }
 
 
+def export_ref_inputs():
+    import glob
+    import json
+
+    out = os.path.join(HERE, "ref", "inputs")
+    os.makedirs(out, exist_ok=True)
+    cases = []
+    for path in sorted(glob.glob(os.path.join(HERE, "*.npz"))):
+        z = np.load(path)
+        name = os.path.basename(path)[:-4]
+        s16 = np.ascontiguousarray(z["pcm_s16"], "<i2")  # [samples][channels]: interleaved
+        s16.tofile(os.path.join(out, name + ".s16"))
+        fixed = None if z["fixed_modes"][0] < 0 else [int(v) for v in z["fixed_modes"]]
+        cases.append(dict(name=name, channels=int(s16.shape[1]), samples=int(s16.shape[0]),
+                          threshold=float(z["threshold"]), bias=float(z["bias"]), fixed_modes=fixed))
+    with open(os.path.join(out, "cases.json"), "w") as f:
+        json.dump(cases, f, indent=1)
+    print("wrote %d cases to %s" % (len(cases), out))
+
+
 def main():
+    if "--export-ref-inputs" in sys.argv[1:]:
+        export_ref_inputs()
+        return
     O.build()
     for name, (make, kw) in CASES.items():
         chans = make()
