@@ -60,6 +60,7 @@ EXPORTED_SYMBOLS = [
     "carta1_ctx_profile", "carta1_ctx_profile_read", "carta1_debug_selftest",
     "carta1_ctx_set_max_units_per_pass", "carta1_host_alloc", "carta1_host_free", "carta1_deserialize_units",
     "carta1_debug_transient_scores", "carta1_ctx_near_threshold",
+    "carta1_encode_pcm_shard", "carta1_decode_su_shard",
 ]
 
 _lib = None
@@ -94,6 +95,8 @@ def load():
     L.carta1_decode_su.argtypes = [vp, vp, sz, C.c_int, fpp]
     L.carta1_encode_pcm_s16.argtypes = [vp, vp, C.c_int, sz, C.POINTER(EncOpts), vp, sz, C.POINTER(sz)]
     L.carta1_decode_su_s16.argtypes = [vp, vp, sz, C.c_int, vp]
+    L.carta1_encode_pcm_shard.argtypes = [vp, fpp, C.c_int, sz, sz, C.POINTER(EncOpts), vp, sz, C.POINTER(sz)]
+    L.carta1_decode_su_shard.argtypes = [vp, vp, sz, C.c_int, sz, fpp]
     L.carta1_enc_create.argtypes = [vp, C.POINTER(EncOpts), C.c_int, C.POINTER(vp)]
     L.carta1_enc_destroy.argtypes = [vp]
     L.carta1_enc_destroy.restype = None
@@ -284,6 +287,23 @@ class Context:
     def decode_su_into(self, su: np.ndarray, n_su: int, n_ch: int, outs) -> None:
         ptrs = (C.POINTER(C.c_float) * len(outs))(*[c.ctypes.data_as(C.POINTER(C.c_float)) for c in outs])
         self._check(self.L.carta1_decode_su(self.h, _ptr(su), n_su, n_ch, ptrs))
+
+    def encode_pcm_shard_into(self, chans, halo_frames: int, su_out: np.ndarray, opts: EncOpts | None = None) -> int:
+        """One shard of a longer stream (carta1_encode_pcm_shard): chans start halo_frames frames before the first
+        emitted frame."""
+        n = len(chans[0])
+        ptrs = (C.POINTER(C.c_float) * len(chans))(*[c.ctypes.data_as(C.POINTER(C.c_float)) for c in chans])
+        n_su = C.c_size_t()
+        self._check(self.L.carta1_encode_pcm_shard(self.h, ptrs, len(chans), n, int(halo_frames),
+                                                   C.byref(opts) if opts is not None else None, _ptr(su_out), su_out.nbytes,
+                                                   C.byref(n_su)))
+        return n_su.value
+
+    def decode_su_shard_into(self, su: np.ndarray, n_su: int, n_ch: int, halo_frames: int, outs) -> None:
+        """One shard of a longer file (carta1_decode_su_shard): su starts halo_frames frames before the first
+        emitted frame."""
+        ptrs = (C.POINTER(C.c_float) * len(outs))(*[c.ctypes.data_as(C.POINTER(C.c_float)) for c in outs])
+        self._check(self.L.carta1_decode_su_shard(self.h, _ptr(su), n_su, n_ch, int(halo_frames), ptrs))
 
     def encode_pcm_s16_into(self, interleaved: np.ndarray, n_ch: int, su_out: np.ndarray, opts: EncOpts | None = None) -> int:
         n = interleaved.size // n_ch

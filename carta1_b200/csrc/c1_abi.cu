@@ -877,8 +877,10 @@ static void quiesce(carta1_ctx *ctx) {
   cudaGetLastError();
 }
 
+// halo0: frames of real history at the head of the caller's PCM that are not emitted (0, or >= 2: a shard of a
+// longer stream); the whole-buffer entry points pass 0.
 static int encode_host_body(carta1_ctx *ctx, const float *const *channels, const int16_t *interleaved,
-                            int n_ch, size_t n_samples, const carta1_enc_opts *opts, uint8_t *su_out,
+                            int n_ch, size_t n_samples, size_t halo0, const carta1_enc_opts *opts, uint8_t *su_out,
                             size_t su_capacity_bytes, size_t *n_su_out) {
   if (!ctx) return CARTA1_ERR_ARG;
   // processor.js:598-604
@@ -888,8 +890,9 @@ static int encode_host_body(carta1_ctx *ctx, const float *const *channels, const
     for (int c = 0; c < n_ch; c++)
       if (!channels[c] && n_samples)
         return fail(ctx, CARTA1_ERR_ARG, "ATRAC1 encoding requires one or two Float32 channels");
-  const size_t frames = carta1_frame_count(n_samples);
-  const size_t n_su = frames * (size_t)n_ch;
+  const size_t frames = carta1_frame_count(n_samples);  // halo included
+  if (halo0 == 1) return fail(ctx, CARTA1_ERR_ARG, "carta1_encode_pcm_shard: halo_frames must be 0 or >= 2");
+  const size_t n_su = (frames > halo0 ? frames - halo0 : 0) * (size_t)n_ch;
   if (n_su_out) *n_su_out = n_su;
   if (n_su == 0) return CARTA1_OK;
   if (!su_out || su_capacity_bytes < n_su * CARTA1_SU_BYTES)
@@ -939,10 +942,10 @@ static int encode_host_body(carta1_ctx *ctx, const float *const *channels, const
   };
   PassTrace tr;
   tr.start("encode", ctx->h2d);
-  for (size_t a = 0; a < frames; a += chunk, pass++) {
+  for (size_t a = halo0; a < frames; a += chunk, pass++) {
     const int sl = (int)(pass % kSlots);
     const size_t b = std::min(frames, a + chunk);
-    const size_t halo = a >= 2 ? 2 : 0;  // a is 0 or >= chunk
+    const size_t halo = a >= 2 ? 2 : 0;  // a is 0, halo0 (>= 2) or >= chunk (>= 2)
     const size_t first = a - halo;
     const size_t span = (b - first) * 512;                       // samples staged per row
     const size_t have = std::min(n_samples - first * 512, span); // samples that exist
@@ -991,7 +994,7 @@ static int encode_host_body(carta1_ctx *ctx, const float *const *channels, const
     tr.mark(ctx->stream);
     CU(ctx, cudaStreamWaitEvent(s_out, ctx->ev_comp[sl], 0));
     tr.mark(s_out);
-    const size_t off = a * (size_t)n_ch * CARTA1_SU_BYTES;
+    const size_t off = (a - halo0) * (size_t)n_ch * CARTA1_SU_BYTES;
     if (bounce_out) {
       uint8_t *bs = (uint8_t *)ctx->bounce_su[sl].p;  // drained (pass - 1 at the latest) before it is reused
       CU(ctx, small_copy(bs, ctx->stage_su[sl].p, out_units * CARTA1_SU_BYTES, cudaMemcpyDeviceToHost,
@@ -1016,8 +1019,8 @@ static int encode_host_body(carta1_ctx *ctx, const float *const *channels, const
 
 static int encode_host_impl(carta1_ctx *ctx, const float *const *channels, const int16_t *interleaved,
                             int n_ch, size_t n_samples, const carta1_enc_opts *opts, uint8_t *su_out,
-                            size_t su_capacity_bytes, size_t *n_su_out) {
-  const int rc = encode_host_body(ctx, channels, interleaved, n_ch, n_samples, opts, su_out, su_capacity_bytes, n_su_out);
+                            size_t su_capacity_bytes, size_t *n_su_out, size_t halo0 = 0) {
+  const int rc = encode_host_body(ctx, channels, interleaved, n_ch, n_samples, halo0, opts, su_out, su_capacity_bytes, n_su_out);
   if (rc != CARTA1_OK) quiesce(ctx);
   return rc;
 }
@@ -1034,7 +1037,15 @@ int carta1_encode_pcm_s16(carta1_ctx *ctx, const int16_t *interleaved, int n_ch,
   return encode_host_impl(ctx, nullptr, interleaved, n_ch, n_samples, opts, su_out, su_capacity_bytes, n_su_out);
 }
 
-static int decode_host_body(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch,
+int carta1_encode_pcm_shard(carta1_ctx *ctx, const float *const *channels, int n_ch, size_t n_samples,
+                            size_t halo_frames, const carta1_enc_opts *opts, uint8_t *su_out,
+                            size_t su_capacity_bytes, size_t *n_su_out) {
+  return encode_host_impl(ctx, channels, nullptr, n_ch, n_samples, opts, su_out, su_capacity_bytes, n_su_out, halo_frames);
+}
+
+// halo0: frames of sound units at the head of `su` that are history only (a shard of a longer file); their
+// PCM is not written, channels_out[c] starts at the first emitted frame.
+static int decode_host_body(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch, size_t halo0,
                             float *const *channels_out, int16_t *interleaved_out) {
   if (!ctx) return CARTA1_ERR_ARG;
   if (n_ch != 1 && n_ch != 2) {  // processor.js:147-157
@@ -1043,13 +1054,13 @@ static int decode_host_body(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int
     return fail(ctx, CARTA1_ERR_ARG, msg);
   }
   if (n_su && !su) return fail(ctx, CARTA1_ERR_ARG, "ATRAC1 decoding requires AEA bytes or a Blob");
-  const size_t frames = (n_su + (size_t)n_ch - 1) / (size_t)n_ch;
-  if (frames == 0) return CARTA1_OK;
+  const size_t frames = (n_su + (size_t)n_ch - 1) / (size_t)n_ch;  // halo included
+  if (frames <= halo0) return CARTA1_OK;
   CU(ctx, cudaSetDevice(ctx->device));
   const size_t chunk = std::max<size_t>(2, ctx->max_units_per_pass / (size_t)n_ch);
-  const size_t max_frames = std::min(frames, chunk);
+  const size_t max_frames = std::min(frames - halo0, chunk);
   const size_t out_elem = channels_out ? sizeof(float) : sizeof(int16_t);
-  const size_t n_passes = (frames + chunk - 1) / chunk;
+  const size_t n_passes = (frames - halo0 + chunk - 1) / chunk;
   for (int sl = 0; sl < kSlots; sl++) CU(ctx, ctx->stage_pcm[sl].ensure((size_t)n_ch * max_frames * 512 * out_elem));
   for (size_t us = 0; us < std::min<size_t>(n_passes, kUnitSlots); us++)
     CU(ctx, ctx->stage_su[us].ensure((max_frames + 1) * (size_t)n_ch * CARTA1_SU_BYTES));
@@ -1061,7 +1072,7 @@ static int decode_host_body(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int
   // pageable caller arrays go through the pinned bounce slots (see encode_host_impl)
   const size_t kBounceMinBytes = bounce_min_bytes();
   const bool bounce_in = !su_alias && n_su * CARTA1_SU_BYTES >= kBounceMinBytes / 8;
-  const size_t pcm_bytes = frames * 512 * (size_t)n_ch * out_elem;
+  const size_t pcm_bytes = (frames - halo0) * 512 * (size_t)n_ch * out_elem;
   bool bounce_out = pcm_bytes >= kBounceMinBytes;
   if (bounce_out) {
     bool pinned = true;
@@ -1081,9 +1092,9 @@ static int decode_host_body(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int
       const char *bb = (const char *)ctx->bounce_pcm[pend.sl].p;
       if (channels_out) {
         for (int c = 0; c < n_ch; c++)
-          parallel_memcpy(channels_out[c] + pend.a * 512, bb + (size_t)c * pend.span * sizeof(float), pend.span * sizeof(float));
+          parallel_memcpy(channels_out[c] + (pend.a - halo0) * 512, bb + (size_t)c * pend.span * sizeof(float), pend.span * sizeof(float));
       } else {
-        parallel_memcpy(interleaved_out + pend.a * 512 * (size_t)n_ch, bb, (size_t)n_ch * pend.span * sizeof(int16_t));
+        parallel_memcpy(interleaved_out + (pend.a - halo0) * 512 * (size_t)n_ch, bb, (size_t)n_ch * pend.span * sizeof(int16_t));
       }
     }
     pend.on = false;
@@ -1091,7 +1102,7 @@ static int decode_host_body(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int
   };
   PassTrace tr;
   tr.start("decode", s_in);
-  for (size_t a = 0; a < frames; a += chunk, pass++) {
+  for (size_t a = halo0; a < frames; a += chunk, pass++) {
     const int sl = (int)(pass % kSlots), us = (int)(pass % kUnitSlots);
     const size_t b = std::min(frames, a + chunk);
     const size_t halo = a >= 1 ? 1 : 0;
@@ -1130,10 +1141,10 @@ static int decode_host_body(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int
                               cudaMemcpyDeviceToHost, ctx->d2h));
     } else if (channels_out) {
       for (int c = 0; c < n_ch; c++)
-        CU(ctx, cudaMemcpyAsync(channels_out[c] + a * 512, (float *)ctx->stage_pcm[sl].p + (size_t)c * span,
+        CU(ctx, cudaMemcpyAsync(channels_out[c] + (a - halo0) * 512, (float *)ctx->stage_pcm[sl].p + (size_t)c * span,
                                 span * sizeof(float), cudaMemcpyDeviceToHost, ctx->d2h));
     } else {
-      CU(ctx, cudaMemcpyAsync(interleaved_out + a * 512 * (size_t)n_ch, ctx->stage_pcm[sl].p,
+      CU(ctx, cudaMemcpyAsync(interleaved_out + (a - halo0) * 512 * (size_t)n_ch, ctx->stage_pcm[sl].p,
                               (size_t)n_ch * span * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->d2h));
     }
     CU(ctx, cudaEventRecord(ctx->ev_out[sl], ctx->d2h));
@@ -1151,8 +1162,8 @@ static int decode_host_body(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int
 }
 
 static int decode_host_impl(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch,
-                            float *const *channels_out, int16_t *interleaved_out) {
-  const int rc = decode_host_body(ctx, su, n_su, n_ch, channels_out, interleaved_out);
+                            float *const *channels_out, int16_t *interleaved_out, size_t halo0 = 0) {
+  const int rc = decode_host_body(ctx, su, n_su, n_ch, halo0, channels_out, interleaved_out);
   if (rc != CARTA1_OK) quiesce(ctx);
   return rc;
 }
@@ -1160,6 +1171,11 @@ static int decode_host_impl(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int
 int carta1_decode_su(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch, float *const *channels_out) {
   if (ctx && !channels_out) return fail(ctx, CARTA1_ERR_ARG, "carta1_decode_su: channels_out is NULL");
   return decode_host_impl(ctx, su, n_su, n_ch, channels_out, nullptr);
+}
+int carta1_decode_su_shard(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch, size_t halo_frames,
+                           float *const *channels_out) {
+  if (ctx && !channels_out) return fail(ctx, CARTA1_ERR_ARG, "carta1_decode_su_shard: channels_out is NULL");
+  return decode_host_impl(ctx, su, n_su, n_ch, channels_out, nullptr, halo_frames);
 }
 int carta1_decode_su_s16(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch, int16_t *interleaved_out) {
   if (ctx && !interleaved_out) return fail(ctx, CARTA1_ERR_ARG, "carta1_decode_su_s16: output is NULL");

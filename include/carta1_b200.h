@@ -118,6 +118,20 @@ int carta1_encode_pcm_s16(carta1_ctx *ctx, const int16_t *interleaved, int n_ch,
 int carta1_decode_su_s16(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch,
                          int16_t *interleaved_out);
 
+/* One shard of a longer stream through host memory (BASELINE configs[4]: a rank's contiguous frame range of
+ * a stream; the loop being cut is codec/io/processor.js:97-136).  channels[c] holds
+ * n_samples samples of which the first halo_frames * 512 are history that is read but not emitted:
+ * halo_frames is 0 (the shard starts the stream) or >= 2.  Writes (frame_count(n_samples) - halo_frames)
+ * * n_ch units; they equal the corresponding units of the whole-stream call bit for bit. */
+int carta1_encode_pcm_shard(carta1_ctx *ctx, const float *const *channels, int n_ch, size_t n_samples,
+                            size_t halo_frames, const carta1_enc_opts *opts, uint8_t *su_out,
+                            size_t su_capacity_bytes, size_t *n_su_out);
+/* su holds n_su interleaved units of which the first halo_frames * n_ch are history (0: the shard starts
+ * the file, else >= 1; the loop being cut is processor.js:159-237).  channels_out[c] receives
+ * (ceil(n_su / n_ch) - halo_frames) * 512 samples, equal to that span of the whole-file call. */
+int carta1_decode_su_shard(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch, size_t halo_frames,
+                           float *const *channels_out);
+
 /* ---- stateful, batched frame closures --------------------------------------------
  * n_streams independent encode() closures (codec/pipeline/encoder.js:438-450) advanced
  * together: pcm is [n_streams][n_frames][512] f32, su_out is [n_streams][n_frames][212].

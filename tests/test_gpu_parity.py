@@ -430,6 +430,43 @@ def test_sharded_device_path(ctx, oracle, world):
             assert np.array_equal(bits(pcm_out[i][c]), bits(ref[c])), (i, c)
 
 
+@pytest.mark.parametrize("world", [2, 5])
+@pytest.mark.parametrize("units_per_pass", [0, 24])
+def test_sharded_host_path(ctx, oracle, world, units_per_pass):
+    """The same shards through the host entry points carta1_encode_pcm_shard / carta1_decode_su_shard (what a
+    rank of the multi-GPU bench calls with its slice of the PCM / of the AEA file), with whole-call and with
+    multi-pass staging: byte-identical to the whole-stream result."""
+    from carta1_b200 import sharding
+
+    streams = [S.cfg3_transients(sec, seed=60 + i, n_ch=2) for i, sec in enumerate((0.5, 0.27))]
+    frames = [oracle.frame_count(len(ch[0])) for ch in streams]
+    plan = sharding.plan(frames, world)
+    sharding.check_plan(plan, frames)
+    wants = [oracle.encode_pcm(ch) for ch in streams]
+    refs = [oracle.decode_su(w, 2) for w in wants]
+    ctx.set_max_units_per_pass(units_per_pass)
+    try:
+        for shards in plan:
+            for sh in shards:
+                ch = streams[sh.stream]
+                first, last = sh.pcm_span()
+                part = [np.ascontiguousarray(ch[c][first:last]) for c in range(2)]  # the last shard is ragged
+                su = np.zeros((sh.frames * 2, 212), np.uint8)
+                got = ctx.encode_pcm_shard_into(part, sh.enc_halo, su, None)
+                assert got == sh.frames * 2
+                assert np.array_equal(su, wants[sh.stream][sh.begin * 2:sh.end * 2]), sh
+                ua, ub = sh.unit_span(2)
+                src = np.ascontiguousarray(wants[sh.stream][ua:ub])
+                outs = [np.zeros(sh.frames * 512, np.float32) for _ in range(2)]
+                ctx.decode_su_shard_into(src, ub - ua, 2, sh.dec_halo, outs)
+                for c in range(2):
+                    assert np.array_equal(bits(outs[c]), bits(refs[sh.stream][c][sh.begin * 512:sh.end * 512])), (sh, c)
+        with pytest.raises(ValueError, match="halo_frames must be 0 or >= 2"):
+            ctx.encode_pcm_shard_into([np.zeros(2048, np.float32)], 1, np.zeros((3, 212), np.uint8), None)
+    finally:
+        ctx.set_max_units_per_pass(0)
+
+
 def test_arithmetic_shortcuts_selftest(ctx):
     """Exhaustive device check: reciprocal division == IEEE division for every (q, R, SF);
     in-FP64 rounding == cvt.rn.f32.f64 on 3e8 values around rounding ties."""
