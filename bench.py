@@ -334,6 +334,7 @@ class ShardWork:
         self.su_in = torch.zeros((end - e0) * 2 * 212, dtype=torch.uint8, device=dev)
         self.su_out = torch.zeros(self.frames * 2 * 212, dtype=torch.uint8, device=dev)
         self.out = torch.zeros((2, self.frames * 512), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()  # the PCM was written on torch's stream, the library launches on the context's
         # the decode input (with its halo unit): the same encoder over [e0, end), outside the timed region
         ctx.encode_device(self.pcm.data_ptr() + 4 * (e0 - (2 if e0 else 0) - s0) * 512, span, 2,
                           self.valid - (e0 - (2 if e0 else 0) - s0) * 512, 2 if e0 else 0, end - e0, opts,
@@ -421,6 +422,7 @@ def run_configs(torch, np, carta1_b200, ctx, dev, args):
         opts = carta1_b200.make_enc_opts()
         d_su = torch.zeros(n_su * 212, dtype=torch.uint8, device=dev)
         d_out = torch.zeros((2, frames * 512), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()  # torch's stream wrote the PCM, the context's stream reads it
         enc = lambda: ctx.encode_device(pcm.data_ptr(), n, 2, n, 0, frames, opts, d_su.data_ptr(), 2, 1)  # noqa: E731
         dec = lambda: ctx.decode_device(d_su.data_ptr(), 2, 1, n_su, 2, 0, frames, d_out.data_ptr(), frames * 512)  # noqa: E731
         ctx.near_threshold(reset=True)
@@ -580,7 +582,11 @@ def run_ours(args, rank, local_rank, world):
     sharding.check_plan(plan, stream_frames)
     my = plan[rank]
     opts = carta1_b200.make_enc_opts(fixed_block_modes=None if args.auto_modes else [0, 0, 0])
-    works = [ShardWork(torch, ctx, sh, 0xCA27A2 + sh.stream, lens[sh.stream], n_samples[sh.stream], opts, dev) for sh in my]
+    # one context (own stream and scratch) per shard of this rank: the launch sequences of a rank's shards are
+    # independent, so they run on different streams and one shard's kernels fill the tail of the other's
+    ctxs = [ctx] + [carta1_b200.Context(local_rank) for _ in my[1:]]
+    streams = [stream] + [torch.cuda.ExternalStream(c.stream, device=dev) for c in ctxs[1:]]
+    works = [ShardWork(torch, c, sh, 0xCA27A2 + sh.stream, lens[sh.stream], n_samples[sh.stream], opts, dev) for c, sh in zip(ctxs, my)]
     my_frames = sum(w.frames for w in works)
     n_su = 2 * my_frames                      # this rank's sound units per pass
     total_seconds = sum(n_samples) / SR       # whole job
@@ -595,11 +601,19 @@ def run_ours(args, rank, local_rank, world):
             w.decode()
 
     def timed(fn, steps):
+        """CUDA events on the first context's stream; the other shards' streams fork after the first event and join
+        before the second, so the interval covers every launch of every shard."""
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        for s in streams[1:]:
+            s.wait_event(e0)
         for _ in range(steps):
             fn()
+        for s in streams[1:]:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            stream.wait_event(ev)
         e1.record(stream)
         e1.synchronize()
         return e0.elapsed_time(e1)
@@ -612,24 +626,31 @@ def run_ours(args, rank, local_rank, world):
     sampler.start()
     for _ in range(max(args.warmup, 3)):
         both()
-    ctx.sync()
+    for c in ctxs:
+        c.sync()
     # ---- the timed region: K steps, device-resident inputs (1.27 GB PCM per pass >> 126 MB L2)
     barrier()
-    launches0 = ctx.launch_count
+    launches0 = sum(c.launch_count for c in ctxs)
     t_start = time.perf_counter()
     ms = timed(both, args.steps)
     t_end = time.perf_counter()
-    launches = ctx.launch_count - launches0
+    launches = sum(c.launch_count for c in ctxs) - launches0
     barrier()
     ms_enc = timed(encode, args.steps)
     ms_dec = timed(decode, args.steps)
     # ---- per-kernel durations with CUDA events on the launching stream (separate pass so the
-    # event records do not sit inside the headline region)
-    ctx.profile(True)
-    for _ in range(args.steps):
-        both()
-    prof = ctx.profile_read()
-    ctx.profile(False)
+    # event records do not sit inside the headline region); shard by shard, so that the events of one
+    # shard's kernels do not include the other's
+    prof = {}
+    for c, w in zip(ctxs, works):
+        c.profile(True)
+        for _ in range(args.steps):
+            w.encode()
+            w.decode()
+        for k, v in c.profile_read().items():
+            a = prof.get(k, (0.0, 0))
+            prof[k] = (a[0] + v[0], a[1] + v[1])
+        c.profile(False)
     # the timed encode reproduces the decode input it was derived from (same encoder, one frame further back)
     local_ok = all(bool(torch.equal(w.su_out, w.su_in[w.dec_halo * 2 * 212:])) for w in works)
 
@@ -781,8 +802,10 @@ def run_ours(args, rank, local_rank, world):
     # gathered shard outputs with it byte for byte (the gather is verification traffic, not part of the data path)
     sharded_identical = None
     cuts = sum(1 for shards in plan for sh in shards if sh.begin > 0)
+    check_detail = None
     if world > 1:
         ok = True
+        bad = []
         for si, (sec_i, n_i, fr_i) in enumerate(zip(lens, n_samples, stream_frames)):
             ref_su = ref_out = None
             if rank == 0:
@@ -790,6 +813,7 @@ def run_ours(args, rank, local_rank, world):
                 whole[:, :n_i] = synth_cfg2_span(torch, 0xCA27A2 + si, sec_i, 0, n_i, dev)
                 ref_su = torch.zeros(fr_i * 2 * 212, dtype=torch.uint8, device=dev)
                 ref_out = torch.zeros((2, fr_i * 512), dtype=torch.float32, device=dev)
+                torch.cuda.synchronize()  # torch's stream wrote the PCM, the context's stream reads it
                 ctx.encode_device(whole.data_ptr(), fr_i * 512, 2, n_i, 0, fr_i, opts, ref_su.data_ptr(), 2, 1)
                 ctx.decode_device(ref_su.data_ptr(), 2, 1, fr_i * 2, 2, 0, fr_i, ref_out.data_ptr(), fr_i * 512, sync=True)
                 del whole
@@ -806,16 +830,23 @@ def run_ours(args, rank, local_rank, world):
                             out_part = torch.empty((2, sh.frames * 512), dtype=torch.float32, device=dev)
                             dist.recv(su_part, src=r)
                             dist.recv(out_part, src=r)
-                        ok = ok and bool(torch.equal(su_part, ref_su[sh.begin * 2 * 212:sh.end * 2 * 212]))
-                        ok = ok and bool(torch.equal(out_part.view(torch.int32), ref_out[:, sh.begin * 512:sh.end * 512].view(torch.int32)))
+                        ok_su = bool(torch.equal(su_part, ref_su[sh.begin * 2 * 212:sh.end * 2 * 212]))
+                        ok_pcm = bool(torch.equal(out_part.view(torch.int32), ref_out[:, sh.begin * 512:sh.end * 512].contiguous().view(torch.int32)))
+                        if not (ok_su and ok_pcm):
+                            ne = (su_part != ref_su[sh.begin * 2 * 212:sh.end * 2 * 212]).nonzero()
+                            bad.append({"rank": r, "stream": si, "begin": sh.begin, "end": sh.end, "su": ok_su, "pcm": ok_pcm,
+                                        "first_su_byte": int(ne[0].item()) if ne.numel() else None, "su_bytes_differing": int(ne.numel())})
+                        ok = ok and ok_su and ok_pcm
                     elif r == rank:
-                        torch.cuda.current_stream().wait_stream(stream)
+                        torch.cuda.synchronize()
                         dist.send(w.su_out, dst=0)
                         dist.send(w.out, dst=0)
             del ref_su, ref_out
-        flags = torch.tensor([1 if (local_ok and host_ok) else 0], dtype=torch.int64, device=dev)
+        flags = torch.tensor([1 if local_ok else 0, 1 if host_ok else 0], dtype=torch.int64, device=dev)
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
-        sharded_identical = bool(ok) and bool(flags.item() == 1) if rank == 0 else None
+        sharded_identical = bool(ok) and bool(flags.min().item() == 1) if rank == 0 else None
+        check_detail = {"gathered_shards_equal_unsharded": bool(ok), "timed_encode_equals_decode_input_on_every_rank": bool(flags[0].item() == 1),
+                        "host_api_equals_device_on_every_rank": bool(flags[1].item() == 1), "mismatches": bad[:8]}
 
     if dist is not None:
         t = torch.tensor([ms, ms_enc, ms_dec, ms_e2e, ms_e2e_seq], dtype=torch.float64, device=dev)
@@ -868,6 +899,7 @@ def run_ours(args, rank, local_rank, world):
             "sharded_check": ("rank 0 encodes+decodes every stream unsharded and compares the gathered shard outputs (sound units and PCM) "
                               "byte for byte; host-API shard outputs equal the device ones on every rank") if world > 1
                              else "single shard (N = 1): the plan is the whole stream",
+            "sharded_check_detail": check_detail,
             "encode_only": {"value": total_seconds / (ms_enc / args.steps / 1000.0), "unit": UNIT},
             "decode_only": {"value": total_seconds / (ms_dec / args.steps / 1000.0), "unit": UNIT},
             "roofline": {
@@ -935,7 +967,8 @@ def run_ours(args, rank, local_rank, world):
     if rank == 0:
         print(json.dumps(line), flush=True)
     barrier()
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if dist is not None:
         dist.destroy_process_group()
 

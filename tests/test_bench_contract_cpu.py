@@ -42,6 +42,50 @@ def test_our_arm_line_has_every_contract_key():
     for k in ("sm_mhz", "sm_max_mhz", "reasons"):
         assert k in d["clocks"], k
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    # the link ceiling the end-to-end number is read against
+    assert e["link_ceiling_gbs"]["duplex"] > 0 and 0 < e["frac_of_link_ceiling"] <= 1.05
+    assert e["host_output_identical_to_device_run"] is True
+    # the other BASELINE configs ride in the same line, each with value, e2e and a parity flag
+    for name in ("cfg1", "cfg3", "cfg4"):
+        c = d["configs"][name]
+        assert c["value"] > 0 and c["e2e"]["value"] > 0 and c["bit_exact_vs_oracle"] is True, name
+    assert "whole stream: 620158 sound units" in d["configs"]["cfg3"]["parity_span"]
+    assert d["configs"]["cfg3"]["short_block_frames"]["any_band"] > 0.01
+    assert set(d["configs"]["cfg4"]["frames_per_call"]) == {"1", "8", "64"}
+    for name in ("cfg1", "cfg3"):
+        nt = d["configs"][name]["near_threshold"]
+        assert nt["decisions"] > 0 and nt["within_1e-12"] <= nt["within_1e-9"] <= nt["decisions"]
+
+
+def test_multi_gpu_lines_run_the_sharded_partition():
+    """N > 1: the plan cuts frame ranges inside streams, the gathered shards equal the unsharded bytes."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_bench_*gpu_v*.json")))
+    assert files
+    for f in files:
+        d = json.loads([ln for ln in open(f).read().splitlines() if ln.startswith("{")][-1])
+        assert d["n_gpus"] > 1 and d["scaling"] == "weak"
+        assert d["sharded_output_identical"] is True and d["config"]["frame_range_cuts"] >= 1
+        assert max(d["config"]["shards_per_rank"]) >= 2
+        det = d["sharded_check_detail"]
+        assert det["gathered_shards_equal_unsharded"] and det["host_api_equals_device_on_every_rank"] and not det["mismatches"]
+        assert abs(d["config"]["audio_seconds_per_gpu"] - 3600.0) < 1.0
+
+
+def test_committed_ncu_capture_describes_this_build():
+    """roofline.traffic and the FP64 instruction count come from a committed ncu launch list; that list must have been
+    taken from the kernel sources as they are now (tools/gpu_check.sh + tools/traffic_from_launches.py refresh it)."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    doc, path, fresh = bench.ncu_capture()
+    assert doc is not None, "no profiles/r*_dram_traffic_*.json"
+    assert fresh, "%s was captured from other kernel sources (source_sha %s, build %s): refresh it" % (
+        path, doc.get("source_sha"), bench.kernel_source_sha())
+    assert doc["sound_units"] == 620158
+    names = {bench_name for bench_name in doc["kernels"]}
+    assert {"alloc", "quant_pack", "unpack_dequant"} <= names
+    per_unit, src = bench.fp64_per_unit(doc, fresh)
+    assert "smsp__inst_executed_pipe_fp64" in src and 800 < per_unit < 2000
 
 
 def test_reference_arm_line():
