@@ -713,20 +713,28 @@ __device__ __noinline__ void mdct_band_exact(int band, bool is_long, const doubl
 // odd j, edge values only for j == 0 / j == 7 (every lane of FFT64; even t / odd t of FFT128).
 // Adding the +0 of an outside tap is kept where it can turn a -0 into +0 (x + 0), dropped
 // where it cannot (x - 0).
-//   pr = &a[n34 - 1 - ws - 2 rev_t], pm = &a[n4 - ws + 2 rev_t]  (a: buffer, index 0 == windowStart)
+//
+// Shared-memory layout (bank conflicts, profiles/r02_mdct_shared_conflicts.txt): the pre-twiddle reads every
+// other element of the buffer (the first tap only odd elements, the second only even ones), so the buffer is kept
+// de-interleaved: element k of [overlap 32 | samples kSize] (index 0 == windowStart) lives in plane k & 1 at index
+// k >> 1, and a warp's loads are unit-stride.  The pre/post table is an array of (cos, sin) pairs whose pair s sits
+// at slot s + (s >> 3): the bit-reversed lanes of a quarter-warp then touch 8 different 16-byte bank groups.
+//   pr = &O[(n34 - 2 - ws) / 2 - rev_t], pm = &E[(n4 - ws) / 2 + rev_t], ptab = &tab2[pad(rev_t)]
+__host__ __device__ constexpr int pad8(int s) { return s + (s >> 3); }
+
 template <int kRole, int kJ, typename R>
-__device__ __forceinline__ Cplx mdct_pre_long(const double *pr, const double *pm, const double *ptab, bool edge,
+__device__ __forceinline__ Cplx mdct_pre_long(const double *pr, const double *pm, const double2 *ptab, bool edge,
                                               R &rnd) {
   using G = LongGeom<kRole>;
-  constexpr int i0 = 2 * G::q_step(kJ);  // i = i0 + 2 rev_t
-  constexpr int n4 = G::kN / 4;
-  double r = pr[-i0], m = pm[i0];
+  constexpr int q = G::q_step(kJ);  // FFT input q + rev_t, i.e. i = 2 (q + rev_t)
+  constexpr int n8 = G::kN / 8;     // n4 elements = n8 plane entries
+  double r = pr[-q], m = pm[q];
   if (kJ == 0) {         // r = in(n34-1-i) + in(n34+i), m = in(n4+i) - in(n4-1-i): taps n34+i, n4-1-i
-    const double r1 = edge ? pm[i0 + 2 * n4] : 0.0, m1 = edge ? pr[-i0 - 2 * n4] : 0.0;
+    const double r1 = edge ? pm[q + 2 * n8] : 0.0, m1 = edge ? pr[-q - 2 * n8] : 0.0;
     r = r + r1;
     m = m - m1;
   } else if (kJ == 7) {  // r = in(n34-1-i) - in(i-n4), m = in(n4+i) + in(5*n4-1-i): taps i-n4, 5*n4-1-i
-    const double r1 = edge ? pm[i0 - 2 * n4] : 0.0, m1 = edge ? pr[-i0 + 2 * n4] : 0.0;
+    const double r1 = edge ? pm[q - 2 * n8] : 0.0, m1 = edge ? pr[-q + 2 * n8] : 0.0;
     r = r - r1;
     m = m + m1;
   } else if ((kJ & 1) == 0) {
@@ -734,7 +742,7 @@ __device__ __forceinline__ Cplx mdct_pre_long(const double *pr, const double *pm
   } else {
     m = m + 0.0;
   }
-  const double2 cs = *reinterpret_cast<const double2 *>(ptab + i0);
+  const double2 cs = ptab[pad8(q)];
   Cplx z;
   z.re = rnd.r0(r * cs.x + m * cs.y);
   z.im = rnd.r1(m * cs.x - r * cs.y);
@@ -742,7 +750,7 @@ __device__ __forceinline__ Cplx mdct_pre_long(const double *pr, const double *pm
 }
 
 template <int kRole, int kJ, typename R>
-__device__ __forceinline__ void mdct_pre_all(Cplx (&v)[8], const double *pr, const double *pm, const double *ptab,
+__device__ __forceinline__ void mdct_pre_all(Cplx (&v)[8], const double *pr, const double *pm, const double2 *ptab,
                                              int t, R &rnd) {
   if constexpr (kJ < 8) {
     // FFT128: q < 8 needs brev4(t) < 8 (t even), q >= 120 needs t odd
@@ -752,73 +760,93 @@ __device__ __forceinline__ void mdct_pre_all(Cplx (&v)[8], const double *pr, con
   }
 }
 
-// The transforms of one warp task.  arr: kPerWarp buffers of [overlap 32 | samples kSize] doubles
-// (each doubles as its transform's transpose buffer once the pre-twiddle has read it); out:
-// kPerWarp x kSize coefficients.  Transforms whose bit in long_mask is clear (short mode) run the
-// same instructions on whatever their buffer holds and do not store.
+// Shared-memory geometry of a role's warp task.
+template <int kRole>
+struct MdctLayout {
+  static constexpr int kSize = LongGeom<kRole>::kSize;
+  // doubles per plane: (kSize + 32) / 2 used, + 4 so that the buffers of the two transforms a half-warp of role 0
+  // reads together start 64 bytes apart modulo 128
+  static constexpr int kPlane = (kSize + 32) / 2 + 4;      // 84 / 148
+  static constexpr int kBuf = 2 * kPlane;                  // doubles per transform: 168 / 296
+  // coefficient rows, de-interleaved the same way (even positions | odd positions); the row stride spreads the
+  // transforms of a warp over the banks (role 0: 8 floats apart modulo 32, role 1: 16)
+  static constexpr int kRow = kSize + (kRole == 0 ? 8 : 16);  // floats: 136 / 272
+};
+
+// The transforms of one warp task.  arr: kPerWarp de-interleaved buffers (MdctLayout; each doubles as its
+// transform's transpose buffer once the pre-twiddle has read it); out: kPerWarp de-interleaved coefficient rows.
+// Transforms whose bit in long_mask is clear (short mode) run the same instructions on whatever their buffer
+// holds and do not store.
 template <int kRole, typename R>
-__device__ __forceinline__ void mdct_long_task(unsigned long_mask, double *arr, float *out, const double *tab,
+__device__ __forceinline__ void mdct_long_task(unsigned long_mask, double *arr, float *out, const double2 *tab2,
                                                const double2 *tw, int lane) {
   using G = LongGeom<kRole>;
+  using L = MdctLayout<kRole>;
   constexpr int kWs = kRole == 0 ? 48 : 112;  // constants.js:115-119
-  constexpr int kN = G::kN, kBuf = G::kSize + 32;
+  constexpr int kN = G::kN;
   R rnd;
   const G g(lane);
-  double *a = arr + g.x * kBuf;
+  double *a = arr + g.x * L::kBuf;
   Cplx v[8];
-  mdct_pre_all<kRole, 0>(v, a + (3 * kN / 4 - 1 - kWs) - 2 * g.rev_t, a + (kN / 4 - kWs) + 2 * g.rev_t,
-                         tab + 2 * g.rev_t, g.t, rnd);
+  mdct_pre_all<kRole, 0>(v, a + L::kPlane + (3 * kN / 4 - 2 - kWs) / 2 - g.rev_t, a + (kN / 4 - kWs) / 2 + g.rev_t,
+                         tab2 + pad8(g.rev_t), g.t, rnd);
   fft_long_inthread<kRole>(v, g, reinterpret_cast<double2 *>(a), tw, rnd);
   if ((long_mask >> g.x) & 1) {
-    // mdct.js:111-119; spectrum reversed for the mid and high bands (utils.js:42-48)
+    // mdct.js:111-119: FFT output i gives coefficients 2i and size-1-2i; spectrum reversed for the mid and high
+    // bands (utils.js:42-48), which swaps the two.  Even positions live in the first half of the row, odd ones in
+    // the second: position 2i at E[i], position size-1-2i at O[size/2-1-i].
     const bool reverse = kRole == 1 || (g.x & 1);
     const int ib = g.out_base();
-    float *o = out + g.x * G::kSize;
-    const double2 *pt = reinterpret_cast<const double2 *>(tab) + ib;
-    float *o0 = reverse ? o + (G::kSize - 1 - 2 * ib) : o + 2 * ib;
-    float *o1 = reverse ? o + 2 * ib : o + (G::kSize - 1 - 2 * ib);
+    float *row = out + g.x * L::kRow;
+    const double2 *pt = tab2 + pad8(ib);
+    float *pe = row + ib, *po = row + (G::kSize - 1) - ib;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int st = G::out_step(k);
-      const double2 cs = pt[st];
+      const double2 cs = pt[pad8(st)];
       const float c0 = (float)(-v[k].re * cs.x - v[k].im * cs.y);
       const float c1 = (float)(-v[k].re * cs.y + v[k].im * cs.x);
-      if (reverse) { o0[-2 * st] = c0; o1[2 * st] = c1; }
-      else { o0[2 * st] = c0; o1[-2 * st] = c1; }
+      pe[st] = reverse ? c1 : c0;
+      po[-st] = reverse ? c0 : c1;
     }
   }
 }
-static_assert(LongGeom<0>::kSlots * 2 <= 160 && LongGeom<1>::kSlots * 2 <= 288, "transpose buffers alias the input buffers");
+static_assert(LongGeom<0>::kSlots * 2 <= MdctLayout<0>::kBuf && LongGeom<1>::kSlots * 2 <= MdctLayout<1>::kBuf,
+              "transpose buffers alias the input buffers");
 
 template <int kRole>
-__device__ __noinline__ void mdct_long_task_exact(unsigned long_mask, double *arr, float *out, const double *tab,
+__device__ __noinline__ void mdct_long_task_exact(unsigned long_mask, double *arr, float *out, const double2 *tab2,
                                                   const double2 *tw, int lane) {
-  mdct_long_task<kRole, ExactRound>(long_mask, arr, out, tab, tw, lane);
+  mdct_long_task<kRole, ExactRound>(long_mask, arr, out, tab2, tw, lane);
 }
 
 constexpr int kMdctWarps = 8, kMdctCtasPerSm = 3;
 struct MdctWarpSmem {
-  double guard[16]; // the two edge taps of mdct_pre_long are loaded (and discarded) up to 16 doubles
-                    // outside a buffer on lanes where they fall into the zero padding
-  double arr[640];  // role 0: 4 x 160, role 1: 2 x 288; short blocks: up to 512
-  float out[512];   // role 0: 4 x 128, role 1: 2 x 256 (also absorbs the overshoot past arr)
+  double guard[16]; // the two edge taps of mdct_pre_long are loaded (and discarded) up to 8 doubles in front of a
+                    // buffer on lanes where they fall into the zero padding
+  double arr[672];  // role 0: 4 x 168, role 1: 2 x 296 (MdctLayout); short blocks: 512 + a 256-float staging row
+  float out[544];   // role 0: 4 x 136, role 1: 2 x 272, de-interleaved rows
 };
-// twiddle tables of the role, staged once per CTA: pre/post table (N/2 doubles) and the FFT
-// recurrence twiddles of stages 3.. (indices below 128)
+static_assert(4 * MdctLayout<0>::kBuf <= 672 && 2 * MdctLayout<1>::kBuf <= 672 && 4 * MdctLayout<0>::kRow <= 544 &&
+              2 * MdctLayout<1>::kRow <= 544, "MdctWarpSmem");
+// twiddle tables of the role, staged once per CTA: pre/post table (N/4 (cos, sin) pairs, pair s at slot pad8(s)) and
+// the FFT recurrence twiddles of stages 3.. (indices below 128)
 struct MdctTables {
-  double tab[256];
+  double2 tab2[144];
   double2 tw[128];
 };
 constexpr size_t kMdctSmemBytes = sizeof(MdctWarpSmem) * kMdctWarps + sizeof(MdctTables);
 
 // Short blocks of one band (encoder.js:279-304): block b transforms
 // [WIN * previous block (32) | block * reversed WIN (32)].  c: the band's samples of this frame
-// (c - 512: the previous frame's).
+// (c - 512: the previous frame's).  The coefficients are produced in natural order in a staging row behind the
+// transform inputs and then scattered into the de-interleaved row `row` (even positions | odd positions).
 __device__ __noinline__ void mdct_short_band(int band, const float *__restrict__ c, bool has_prev, bool fast,
-                                             double *arr, float *out, const DevTables *__restrict__ T, int lane,
+                                             double *arr, float *row, const DevTables *__restrict__ T, int lane,
                                              double w_fwd, double w_rev) {
   ExactRound xr;
   const int size = band == 2 ? 256 : 128;
+  float *stage = reinterpret_cast<float *>(arr + 512);
   for (int b = 0; b < (size >> 5); b++) {
     float src_prev = 0.0f;
     bool have_prev = true;
@@ -828,8 +856,10 @@ __device__ __noinline__ void mdct_short_band(int band, const float *__restrict__
     arr[64 * b + 32 + lane] = xr((double)c[32 * b + lane] * w_rev);
   }
   __syncwarp();
-  if (fast) mdct_band<FastRound>(band, false, arr, out, T, lane);
-  else mdct_band<ExactRound>(band, false, arr, out, T, lane);
+  if (fast) mdct_band<FastRound>(band, false, arr, stage, T, lane);
+  else mdct_band<ExactRound>(band, false, arr, stage, T, lane);
+  __syncwarp();
+  for (int p = lane; p < size; p += 32) row[(p & 1) * (size >> 1) + (p >> 1)] = stage[p];
   __syncwarp();
 }
 
@@ -857,11 +887,12 @@ __device__ __forceinline__ void mdct_warp_task(int pair, const float *__restrict
                                                const uint8_t *__restrict__ modes, int frames, int n_su,
                                                const DevTables *__restrict__ T, const DevEncParams *__restrict__ P,
                                                float *__restrict__ coefs, uint8_t *__restrict__ sfi_out,
-                                               MdctWarpSmem &S, const double *s_tab, const double2 *s_tw, int lane,
+                                               MdctWarpSmem &S, const double2 *s_tab2, const double2 *s_tw, int lane,
                                                double w_fwd, double w_rev) {
   using G = LongGeom<kRole>;
-  constexpr int kSize = G::kSize, kBuf = kSize + 32, kPer = G::kPerWarp / 2;  // transforms per unit
-  constexpr int kOff = kRole == 0 ? 0 : 256;                                // first band sample of the role
+  using L = MdctLayout<kRole>;
+  constexpr int kSize = G::kSize, kPer = G::kPerWarp / 2;  // transforms per unit
+  constexpr int kOff = kRole == 0 ? 0 : 256;              // first band sample of the role
   double *arr = S.arr;
   float *out = S.out;
   const int su0 = 2 * pair;
@@ -895,25 +926,27 @@ __device__ __forceinline__ void mdct_warp_task(int pair, const float *__restrict
     for (int b = 0; b < kPer; b++) pv[b] = frame0 > 0 ? __ldg(cur0 - 512 + b * kSize + kSize - 32 + lane) : 0.0f;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      // role 0: k = transform (unit k>>1, band k&1), sample 4*lane; role 1: transform k>>1, sample 128*(k&1) + 4*lane
-      const int at = kRole == 0 ? k * kBuf + 32 + 4 * lane : (k >> 1) * kBuf + 32 + 128 * (k & 1) + 4 * lane;
-      double2 *d = reinterpret_cast<double2 *>(arr + at);
-      d[0] = make_double2((double)x[k].x, (double)x[k].y);
-      d[1] = make_double2((double)x[k].z, (double)x[k].w);
+      // role 0: k = transform (unit k>>1, band k&1), samples 4*lane ..; role 1: transform k>>1, samples 128*(k&1) + 4*lane ..
+      // sample s is buffer element 32 + s: even samples at E[16 + s/2], odd ones at O[16 + s/2]
+      const int at = kRole == 0 ? k * L::kBuf + 16 + 2 * lane : (k >> 1) * L::kBuf + 16 + 64 * (k & 1) + 2 * lane;
+      *reinterpret_cast<double2 *>(arr + at) = make_double2((double)x[k].x, (double)x[k].z);
+      *reinterpret_cast<double2 *>(arr + at + L::kPlane) = make_double2((double)x[k].y, (double)x[k].w);
       big = max(big, max(max(__float_as_uint(x[k].x) & 0x7FFFFFFFu, __float_as_uint(x[k].y) & 0x7FFFFFFFu),
                          max(__float_as_uint(x[k].z) & 0x7FFFFFFFu, __float_as_uint(x[k].w) & 0x7FFFFFFFu)));
     }
     __syncwarp();
     // tail windowing (encoder.js:309-316): the last 32 samples v of a frame become v * WIN[31-i] in
-    // this frame's buffer and WIN[i] * v in the overlap slot of the next frame's
+    // this frame's buffer and WIN[i] * v in the overlap slot of the next frame's.  Lane i owns buffer elements
+    // i (overlap slot) and kSize + i (tail): plane i & 1, indices i >> 1 and kSize / 2 + (i >> 1).
+    const int pl = (lane & 1) * L::kPlane, lo = lane >> 1, hi = kSize / 2 + (lane >> 1);
 #pragma unroll
     for (int b = 0; b < kPer; b++) {
-      double *a0 = arr + b * kBuf, *a1 = arr + (kPer + b) * kBuf;
-      const double v0 = a0[kSize + lane], v1 = a1[kSize + lane];
-      a0[lane] = frame0 > 0 ? xr(w_fwd * (double)pv[b]) : 0.0;
-      a0[kSize + lane] = xr(v0 * w_rev);
-      a1[lane] = cont1 ? xr(w_fwd * v0) : 0.0;
-      a1[kSize + lane] = xr(v1 * w_rev);
+      double *a0 = arr + b * L::kBuf + pl, *a1 = arr + (kPer + b) * L::kBuf + pl;
+      const double v0 = a0[hi], v1 = a1[hi];
+      a0[lo] = frame0 > 0 ? xr(w_fwd * (double)pv[b]) : 0.0;
+      a0[hi] = xr(v0 * w_rev);
+      a1[lo] = cont1 ? xr(w_fwd * v0) : 0.0;
+      a1[hi] = xr(v1 * w_rev);
       big = max(big, __float_as_uint(pv[b]) & 0x7FFFFFFFu);
     }
     __syncwarp();
@@ -922,8 +955,8 @@ __device__ __forceinline__ void mdct_warp_task(int pair, const float *__restrict
   // threshold, the one case FastRound cannot round
   const bool fast = __reduce_max_sync(0xffffffffu, big) < 0x71800000u;
   if (long_mask) {
-    if (fast) mdct_long_task<kRole, FastRound>(long_mask, arr, out, s_tab, s_tw, lane);
-    else mdct_long_task_exact<kRole>(long_mask, arr, out, s_tab, s_tw, lane);
+    if (fast) mdct_long_task<kRole, FastRound>(long_mask, arr, out, s_tab2, s_tw, lane);
+    else mdct_long_task_exact<kRole>(long_mask, arr, out, s_tab2, s_tw, lane);
     __syncwarp();
   }
   // ---- short blocks, one band at a time (rare: out of line)
@@ -932,7 +965,7 @@ __device__ __forceinline__ void mdct_warp_task(int pair, const float *__restrict
       const int unit = x / kPer, bsel = x % kPer;
       if (((long_mask >> x) & 1) || (unit == 1 && !have1)) continue;
       mdct_short_band(kRole == 0 ? bsel : 2, cur0 + 512 * unit + bsel * kSize, unit == 0 ? frame0 > 0 : cont1, fast,
-                      arr, out + x * kSize, T, lane, w_fwd, w_rev);
+                      arr, out + x * L::kRow, T, lane, w_fwd, w_rev);
     }
   }
   // scale-factor index of every BFU of the role (groupIntoBFUs, quantization.js:106-149 +
@@ -945,23 +978,32 @@ __device__ __forceinline__ void mdct_warp_task(int pair, const float *__restrict
       if (unit == 1 && !have1) break;
       const int x = kRole == 0 ? unit * 2 + (b >= 20) : unit;
       const int start = (mode[x] == 0 ? F.start_long[b] : F.start_short[b]) - (kRole == 0 ? (b >= 20 ? 128 : 0) : 256);
-      const float *c = out + x * kSize + start;
       const int sz = F.specs[b];
+      // positions start .. start + sz - 1 of the row: the even ones are E[(start + 1) >> 1 ..], the odd ones
+      // O[start >> 1 ..]
+      const float *ce = out + x * L::kRow + ((start + 1) >> 1);
+      const float *co = out + x * L::kRow + kSize / 2 + (start >> 1);
+      const int ne = ((start + sz + 1) >> 1) - ((start + 1) >> 1), no = ((start + sz) >> 1) - (start >> 1);
       // max |c| (NaN never wins, as with the reference's `if (a > max)`): one FMNMX per coefficient
-      constexpr int kMaxSz = kRole == 0 ? 10 : 20;
+      constexpr int kMaxHalf = kRole == 0 ? 5 : 10;
       float mx = 0.0f;
 #pragma unroll
-      for (int j = 0; j < kMaxSz; j++)
-        if (j < sz) mx = fmaxf(mx, fabsf(c[j]));
+      for (int j = 0; j < kMaxHalf; j++) {
+        if (j < ne) mx = fmaxf(mx, fabsf(ce[j]));
+        if (j < no) mx = fmaxf(mx, fabsf(co[j]));
+      }
       sfi_out[(size_t)(su0 + unit) * 64 + b] = (uint8_t)scale_factor_index(mx, T);
     }
   }
-  // 256 coefficients of the role per unit
-  const float4 *src = reinterpret_cast<const float4 *>(out);
+  // 256 coefficients of the role per unit, back to natural order: positions 4 lane .. 4 lane + 3 of a row are
+  // E[2 lane], O[2 lane], E[2 lane + 1], O[2 lane + 1]
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    if (k < 2 || have1)
-      reinterpret_cast<float4 *>(coefs + (size_t)(su0 + (k >> 1)) * 512 + kOff)[lane + 32 * (k & 1)] = src[lane + 32 * k];
+    if (k < 2 || have1) {
+      const float *row = kRole == 0 ? out + k * L::kRow + 2 * lane : out + (k >> 1) * L::kRow + 64 * (k & 1) + 2 * lane;
+      const float2 e = *reinterpret_cast<const float2 *>(row), o = *reinterpret_cast<const float2 *>(row + kSize / 2);
+      reinterpret_cast<float4 *>(coefs + (size_t)(su0 + (k >> 1)) * 512 + kOff)[lane + 32 * (k & 1)] = make_float4(e.x, o.x, e.y, o.y);
+    }
   }
   __syncwarp();
 }
@@ -979,7 +1021,7 @@ mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, 
   MdctTables &ST = *reinterpret_cast<MdctTables *>(smem_raw + sizeof(MdctWarpSmem) * kMdctWarps);
   {
     const double *tab = kRole == 0 ? T->mdct_fwd256 : T->mdct_fwd512;
-    for (int i = threadIdx.x; i < LongGeom<kRole>::kN / 2; i += blockDim.x) ST.tab[i] = tab[i];
+    for (int i = threadIdx.x; i < LongGeom<kRole>::kN / 4; i += blockDim.x) ST.tab2[pad8(i)] = make_double2(tab[2 * i], tab[2 * i + 1]);
     for (int i = threadIdx.x; i < 128; i += blockDim.x) ST.tw[i] = T->fft_tw[i];
   }
   __syncthreads();
@@ -992,7 +1034,7 @@ mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, 
       const int su = 2 * next + (lane >> 3);
       if (lane < 16 && su < n_su) prefetch_l2(bands + (size_t)su * 512 + (kRole == 0 ? 0 : 256) + 32 * (lane & 7));
     }
-    mdct_warp_task<kRole>(pair, bands, modes, frames, n_su, T, P, coefs, sfi_out, S, ST.tab, ST.tw, lane, w_fwd, w_rev);
+    mdct_warp_task<kRole>(pair, bands, modes, frames, n_su, T, P, coefs, sfi_out, S, ST.tab2, ST.tw, lane, w_fwd, w_rev);
   }
 }
 
