@@ -380,25 +380,36 @@ cudaError_t launch_deserialize(const uint8_t *d_su, int n_units, const DevTables
 // the first transpose, every output written after the last).  Transforms whose bit in
 // long_mask is clear run the same instructions and do not store.
 // ------------------------------------------------------------------------------------
+// Shared-memory rows (bank conflicts, profiles/r02_mdct_shared_conflicts.txt): the pre-twiddle reads x[2q] and
+// x[size-1-2q], the post-twiddle writes record positions of one parity per store, so a row is kept de-interleaved:
+// position p at plane p & 1 (even positions first, odd ones kSize / 2 further), index p >> 1, both for the
+// coefficients read and for the record written over them.  The row stride spreads the transforms of a warp over
+// the banks; the pre/post table holds (cos, sin) pair s at slot s + (s >> 3) (as in the MDCT kernels).
+template <int kRole>
+struct ImdctLayout {
+  static constexpr int kSize = LongGeom<kRole>::kSize;
+  static constexpr int kRow = kSize + (kRole == 0 ? 8 : 16);  // floats: 136 / 272
+};
+
 template <int kRole, typename R>
 __device__ __forceinline__ void imdct_long_task(unsigned long_mask, float *rows, double2 *xbuf_all,
-                                                const double *tab, const double2 *tw, int lane) {
+                                                const double2 *tab2, const double2 *tw, int lane) {
   using G = LongGeom<kRole>;
   constexpr int kSize = G::kSize;
   R rnd;
   const G g(lane);
-  float *xb = rows + g.x * kSize;
+  float *xb = rows + g.x * ImdctLayout<kRole>::kRow;
   const bool rev = kRole == 1 || (g.x & 1);  // utils.js:42-48: un-reverse mid / high spectra
-  const float *pa = xb + 2 * g.rev_t, *pb = xb + (kSize - 1) - 2 * g.rev_t;
-  const double *ptab = tab + 2 * g.rev_t;
+  const float *pa = xb + g.rev_t, *pb = xb + (kSize - 1) - g.rev_t;  // x[2q] = E[q], x[size-1-2q] = O[size/2-1-q]
+  const double2 *ptab = tab2 + pad8(g.rev_t);
   Cplx v[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) {  // mdct.js:161-170 for FFT input q = q_step(j) + rev_t
-    const int i0 = 2 * G::q_step(j);
-    const float fa = pa[i0], fb = pb[-i0];  // x[2q], x[size - 1 - 2q]
+    const int q = G::q_step(j);
+    const float fa = pa[q], fb = pb[-q];
     const double r = -(double)(rev ? fb : fa);
     const double m = -(double)(rev ? fa : fb);
-    const double2 cs = *reinterpret_cast<const double2 *>(ptab + i0);
+    const double2 cs = ptab[pad8(q)];
     v[j].re = rnd.r0(m * cs.y + r * cs.x);
     v[j].im = rnd.r1(m * cs.x - r * cs.y);
   }
@@ -407,38 +418,43 @@ __device__ __forceinline__ void imdct_long_task(unsigned long_mask, float *rows,
     // mdct.js:177-208 restricted to output[n/4 .. 3n/4): FFT output i gives y[2i] and y[size-1-2i].
     // Record position of y[q]: q + 16, except q < 16 -> q (head) and q >= size - 16 -> q - size + 32
     // (tail).  2i < 16 only for k == 0 and 2i >= size - 16 only for k == 7 (role 1: on the lanes
-    // with b6 == 0 / b6 == 1 respectively).
+    // with b6 == 0 / b6 == 1 respectively).  y[2i] lands on an even position P (stored at E[P / 2]),
+    // y[size-1-2i] on an odd one (O[(P - 1) / 2]).
     const int ib = g.out_base();
-    const double2 *pt = reinterpret_cast<const double2 *>(tab) + ib;
-    float *o0 = xb + 2 * ib + 16, *o1 = xb + (kSize - 1) - 2 * ib + 16;
+    const double2 *pt = tab2 + pad8(ib);
+    float *pe = xb + ib + 8, *po = xb + kSize + 7 - ib;
     const bool first = kRole == 0 || g.b6 == 0, last = kRole == 0 || g.b6 == 1;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int st = G::out_step(k);
-      const double2 cs = pt[st];
+      const double2 cs = pt[pad8(st)];
       const float y1 = (float)(v[k].re * cs.x + v[k].im * cs.y);  // y[size - 1 - 2i]
       const float y0 = (float)(v[k].re * cs.y - v[k].im * cs.x);  // y[2i]
-      int d0 = 2 * st, d1 = -2 * st;
-      if (k == 0 && first) { d0 -= 16; d1 += 16 - kSize; }  // y[2i] is head, y[size-1-2i] is tail
-      if (k == 7 && last) { d0 += 16 - kSize; d1 -= 16; }   // y[2i] is tail, y[size-1-2i] is head
-      o0[d0] = y0;
-      o1[d1] = y1;
+      int d0 = st, d1 = -st;
+      if (k == 0 && first) { d0 -= 8; d1 += 8 - kSize / 2; }  // y[2i] is head, y[size-1-2i] is tail
+      if (k == 7 && last) { d0 += 8 - kSize / 2; d1 -= 8; }   // y[2i] is tail, y[size-1-2i] is head
+      pe[d0] = y0;
+      po[d1] = y1;
     }
   }
 }
 
 template <int kRole>
 __device__ __noinline__ void imdct_long_task_exact(unsigned long_mask, float *rows, double2 *xbuf_all,
-                                                   const double *tab, const double2 *tw, int lane) {
-  imdct_long_task<kRole, ExactRound>(long_mask, rows, xbuf_all, tab, tw, lane);
+                                                   const double2 *tab2, const double2 *tw, int lane) {
+  imdct_long_task<kRole, ExactRound>(long_mask, rows, xbuf_all, tab2, tw, lane);
 }
 
-// Short blocks of one band (rare: out of line): transform in place, then assemble the record
-// through `stage` (block-to-block overlap-add, mdct.js:230-245 with prev = second half of the
-// previous block).
-__device__ __noinline__ void imdct_short_band(int band, float *x, float *stage, bool fast,
+// Short blocks of one band (rare: out of line): the coefficients are gathered from the de-interleaved row into
+// natural order (scratch[0 .. size)), transformed in place, the record is assembled in scratch[256 ..)
+// (block-to-block overlap-add, mdct.js:230-245 with prev = second half of the previous block) and scattered back
+// into the row.
+__device__ __noinline__ void imdct_short_band(int band, float *row, float *scratch, bool fast,
                                               const DevTables *__restrict__ T, int lane) {
   const int size = band == 2 ? 256 : 128;
+  float *x = scratch, *stage = scratch + 256;
+  for (int p = lane; p < size; p += 32) x[p] = row[(p & 1) * (size >> 1) + (p >> 1)];
+  __syncwarp();
   if (fast) imdct_band<FastRound>(band, false, x, x, T, lane);
   else imdct_band<ExactRound>(band, false, x, x, T, lane);
   __syncwarp();
@@ -453,18 +469,19 @@ __device__ __noinline__ void imdct_short_band(int band, float *x, float *stage, 
     stage[p] = q < 16 ? (float)(pv * w2 - cv * w1) : (float)(pv * w1 + cv * w2);
   }
   __syncwarp();
-  for (int p = lane; p < size; p += 32) x[p] = stage[p];
+  for (int p = lane; p < size; p += 32) row[(p & 1) * (size >> 1) + (p >> 1)] = stage[p];
   __syncwarp();
 }
 
 constexpr int kImdctWarps = 8, kImdctCtasPerSm = 3;
 struct ImdctWarpSmem {
-  double2 xbuf[4 * LongGeom<0>::kSlots];  // transposes of the long-block FFTs (also the short-block stage)
-  float rows[512];                         // role 0: 4 x 128, role 1: 2 x 256
+  double2 xbuf[4 * LongGeom<0>::kSlots];  // transposes of the long-block FFTs (also the short-block scratch)
+  float rows[544];                         // role 0: 4 x 136, role 1: 2 x 272, de-interleaved (ImdctLayout)
 };
 static_assert(4 * LongGeom<0>::kSlots == 2 * LongGeom<1>::kSlots, "xbuf");
-struct ImdctTables {  // staged once per CTA: pre/post table (N/2 doubles), FFT twiddles of stages 3..
-  double tab[256];
+static_assert(4 * ImdctLayout<0>::kRow <= 544 && 2 * ImdctLayout<1>::kRow <= 544, "rows");
+struct ImdctTables {  // staged once per CTA: pre/post table (N/4 pairs, pair s at slot pad8(s)), FFT twiddles of stages 3..
+  double2 tab2[144];
   double2 tw[128];
 };
 constexpr size_t kImdctSmemBytes = sizeof(ImdctWarpSmem) * kImdctWarps + sizeof(ImdctTables);
@@ -483,7 +500,7 @@ imdct_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes,
   ImdctTables &ST = *reinterpret_cast<ImdctTables *>(smem_raw + sizeof(ImdctWarpSmem) * kImdctWarps);
   {
     const double *tab = kRole == 0 ? T->mdct_inv256 : T->mdct_inv512;
-    for (int i = threadIdx.x; i < G::kN / 2; i += blockDim.x) ST.tab[i] = tab[i];
+    for (int i = threadIdx.x; i < G::kN / 4; i += blockDim.x) ST.tab2[pad8(i)] = make_double2(tab[2 * i], tab[2 * i + 1]);
     for (int i = threadIdx.x; i < 128; i += blockDim.x) ST.tw[i] = T->fft_tw[i];
   }
   __syncthreads();
@@ -512,14 +529,18 @@ imdct_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes,
       }
     }
     if (!live[0] && !live[1]) continue;
-    // 256 coefficients of the role per unit = 2 float4 per lane and unit
+    // 256 coefficients of the role per unit = 2 float4 per lane and unit; positions 4 lane .. 4 lane + 3 of a row go
+    // to E[2 lane], O[2 lane], E[2 lane + 1], O[2 lane + 1]
+    constexpr int kRow = ImdctLayout<kRole>::kRow;
     unsigned big = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const float4 x = live[k >> 1]
                            ? __ldg(reinterpret_cast<const float4 *>(coefs + (size_t)(u0 + (k >> 1)) * 512 + kOff) + lane + 32 * (k & 1))
                            : make_float4(0.f, 0.f, 0.f, 0.f);
-      reinterpret_cast<float4 *>(S.rows)[lane + 32 * k] = x;
+      float *row = kRole == 0 ? S.rows + k * kRow + 2 * lane : S.rows + (k >> 1) * kRow + 64 * (k & 1) + 2 * lane;
+      *reinterpret_cast<float2 *>(row) = make_float2(x.x, x.z);
+      *reinterpret_cast<float2 *>(row + kSize / 2) = make_float2(x.y, x.w);
       big = max(big, max(max(__float_as_uint(x.x) & 0x7FFFFFFFu, __float_as_uint(x.y) & 0x7FFFFFFFu),
                          max(__float_as_uint(x.z) & 0x7FFFFFFFu, __float_as_uint(x.w) & 0x7FFFFFFFu)));
     }
@@ -527,20 +548,22 @@ imdct_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes,
     // 0x71800000 is 2^100 as binary32: below it FastRound is exact for every transform value
     const bool fast = __reduce_max_sync(0xffffffffu, big) < 0x71800000u;
     if (long_mask) {
-      if (fast) imdct_long_task<kRole, FastRound>(long_mask, S.rows, S.xbuf, ST.tab, ST.tw, lane);
-      else imdct_long_task_exact<kRole>(long_mask, S.rows, S.xbuf, ST.tab, ST.tw, lane);
+      if (fast) imdct_long_task<kRole, FastRound>(long_mask, S.rows, S.xbuf, ST.tab2, ST.tw, lane);
+      else imdct_long_task_exact<kRole>(long_mask, S.rows, S.xbuf, ST.tab2, ST.tw, lane);
       __syncwarp();
     }
     if (short_mask) {
       for (int x = 0; x < G::kPerWarp; x++)
         if ((short_mask >> x) & 1)
-          imdct_short_band(kRole == 0 ? x % kPer : 2, S.rows + x * kSize, reinterpret_cast<float *>(S.xbuf), fast, T, lane);
+          imdct_short_band(kRole == 0 ? x % kPer : 2, S.rows + x * kRow, reinterpret_cast<float *>(S.xbuf), fast, T, lane);
     }
 #pragma unroll
     for (int k = 0; k < 4; k++)
-      if (live[k >> 1])
-        reinterpret_cast<float4 *>(inv + (size_t)(u0 + (k >> 1)) * 512 + kOff)[lane + 32 * (k & 1)] =
-            reinterpret_cast<const float4 *>(S.rows)[lane + 32 * k];
+      if (live[k >> 1]) {
+        const float *row = kRole == 0 ? S.rows + k * kRow + 2 * lane : S.rows + (k >> 1) * kRow + 64 * (k & 1) + 2 * lane;
+        const float2 e = *reinterpret_cast<const float2 *>(row), o = *reinterpret_cast<const float2 *>(row + kSize / 2);
+        reinterpret_cast<float4 *>(inv + (size_t)(u0 + (k >> 1)) * 512 + kOff)[lane + 32 * (k & 1)] = make_float4(e.x, o.x, e.y, o.y);
+      }
   }
 }
 

@@ -720,7 +720,6 @@ __device__ __noinline__ void mdct_band_exact(int band, bool is_long, const doubl
 // k >> 1, and a warp's loads are unit-stride.  The pre/post table is an array of (cos, sin) pairs whose pair s sits
 // at slot s + (s >> 3): the bit-reversed lanes of a quarter-warp then touch 8 different 16-byte bank groups.
 //   pr = &O[(n34 - 2 - ws) / 2 - rev_t], pm = &E[(n4 - ws) / 2 + rev_t], ptab = &tab2[pad(rev_t)]
-__host__ __device__ constexpr int pad8(int s) { return s + (s >> 3); }
 
 template <int kRole, int kJ, typename R>
 __device__ __forceinline__ Cplx mdct_pre_long(const double *pr, const double *pm, const double2 *ptab, bool edge,

@@ -148,6 +148,10 @@ __device__ __forceinline__ int brev_bits(int x, int bits) { return (int)(__brev(
 // Transpose buffer: complex position p lives at 16-byte slot p + (p >> 3); every quarter-warp
 // access of the three layouts above then touches 8 distinct 16-byte bank groups.
 // ------------------------------------------------------------------------------------
+// slot of (cos, sin) pair s in the padded pre/post-twiddle tables of the MDCT / IMDCT kernels: one empty slot after
+// every eight, so that the bit-reversed lanes of a quarter-warp touch 8 different 16-byte bank groups
+__host__ __device__ constexpr int pad8(int s) { return s + (s >> 3); }
+
 static __constant__ double2 c_fft_tw[255];  // DevTables::fft_tw, one copy per translation unit
 
 template <typename R>
