@@ -653,19 +653,25 @@ __device__ __forceinline__ void fir_synthesis(const double *__restrict__ seq, in
   }
 }
 
-// Band record of one unit -> time-domain frame in S.td (first 32 samples of a band: overlap-add
-// with the previous unit's tail, mdct.js:230-245), merged low/mid -> S/D ring (elements 24..151),
-// high -> hd ring (40..295); the unit's tails replace the previous ones.
-__device__ __forceinline__ void sy_load_unit(SyWarpSmem &S, const float *__restrict__ rec, const double w1,
-                                             const double w2, int lane) {
-  const float4 *r4 = reinterpret_cast<const float4 *>(rec);
-  float4 x[4];
+// The band record of a unit (512 floats) is fetched straight into S.td with cp.async while the frame before it is being
+// filtered: lane l copies 16-byte chunks l + 32k.  S.td is free from the moment the previous unit's merge has read it
+// (the caller's warp barrier after sy_load_unit) until sy_load_unit of this unit waits for the copy.
+__device__ __forceinline__ void sy_prefetch(SyWarpSmem &S, const float *__restrict__ rec, int lane) {
+  const float *src = rec + 4 * lane;
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(S.td + 4 * lane);
 #pragma unroll
-  for (int k = 0; k < 4; k++) x[k] = __ldg(r4 + lane + 32 * k);
+  for (int k = 0; k < 4; k++)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 512 * k), "l"(src + 128 * k) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// Band record of one unit (already on its way into S.td, sy_prefetch) -> time-domain frame in S.td (first 32 samples
+// of a band: overlap-add with the previous unit's tail, mdct.js:230-245), merged low/mid -> S/D ring (elements
+// 24..151), high -> hd ring (40..295); the unit's tails replace the previous ones.
+__device__ __forceinline__ void sy_load_unit(SyWarpSmem &S, const double w1, const double w2, int lane) {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   // lane p finishes sample p of each band: i = p < 16 ? p : 31 - p, w1 = WIN[i], w2 = WIN[31 - i]
   const int i = lane < 16 ? lane : 31 - lane;
-#pragma unroll
-  for (int k = 0; k < 4; k++) reinterpret_cast<float4 *>(S.td)[lane + 32 * k] = x[k];
   __syncwarp();
   float ola[3], tl[3];
 #pragma unroll
@@ -730,14 +736,14 @@ __device__ __forceinline__ void sy_stage2(SyWarpSmem &S, int lane) {
   }
 }
 
-__device__ __forceinline__ void sy_shift(SyWarpSmem &S, int lane) {
+__device__ __forceinline__ void sy_shift(SyWarpSmem &S, int lane, int keep_a_at, int keep_b_at) {
+  // element `lane` of the a / b rings sits at keep_a_at / keep_b_at; elements 128 + lane / 256 + lane 32 columns further
   double keep_a[2], keep_b[2];
   if (lane < 24) {
 #pragma unroll
     for (int p = 0; p < 2; p++) {
-      const int ea = 128 + lane, eb = 256 + lane;
-      keep_a[p] = S.a[p][(ea & 3) * kSyStrideA + (ea >> 2)];
-      keep_b[p] = S.b[p][(eb & 7) * kSyStrideB + (eb >> 3)];
+      keep_a[p] = S.a[p][keep_a_at + 32];
+      keep_b[p] = S.b[p][keep_b_at + 32];
     }
   }
   const float h0 = S.hd[256 + lane], h1 = lane < 8 ? S.hd[288 + lane] : 0.0f;
@@ -745,8 +751,8 @@ __device__ __forceinline__ void sy_shift(SyWarpSmem &S, int lane) {
   if (lane < 24) {
 #pragma unroll
     for (int p = 0; p < 2; p++) {
-      S.a[p][(lane & 3) * kSyStrideA + (lane >> 2)] = keep_a[p];
-      S.b[p][(lane & 7) * kSyStrideB + (lane >> 3)] = keep_b[p];
+      S.a[p][keep_a_at] = keep_a[p];
+      S.b[p][keep_b_at] = keep_b[p];
     }
   }
   S.hd[lane] = h0;
@@ -762,6 +768,7 @@ synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams,
   SyWarpSmem &S = reinterpret_cast<SyWarpSmem *>(smem_raw)[warp];
   const int wi = lane < 16 ? lane : 31 - lane;
   const double w1 = T->win[wi], w2 = T->win[31 - wi];
+  const int keep_a_at = (lane & 3) * kSyStrideA + (lane >> 2), keep_b_at = (lane & 7) * kSyStrideB + (lane >> 3);
   const int out_frames = frames - halo;
   const int runs_per_row = (out_frames + run_len - 1) / run_len;
   const int n_runs = runs_per_row * n_streams;
@@ -771,12 +778,13 @@ synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams,
     const int f1 = min(f0 + run_len, frames);
     const float *inv_row = inv + (size_t)stream * frames * 512;
     __syncwarp();
+    sy_prefetch(S, inv_row + (size_t)(f0 > 0 ? f0 - 1 : f0) * 512, lane);
     // silent state (new BufferPool, buffers.js:31-35,67-72)
     if (lane < 24) {
 #pragma unroll
       for (int p = 0; p < 2; p++) {
-        S.a[p][(lane & 3) * kSyStrideA + (lane >> 2)] = 0.0;
-        S.b[p][(lane & 7) * kSyStrideB + (lane >> 3)] = 0.0;
+        S.a[p][keep_a_at] = 0.0;
+        S.b[p][keep_b_at] = 0.0;
       }
     }
     S.hd[lane] = 0.0f;
@@ -787,16 +795,18 @@ synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams,
     if (f0 > 0) {
       // prime from unit f0 - 1: only samples >= 32 of its bands reach the state (they do not depend
       // on the tails before it), so the zero state above is as good as the true one
-      sy_load_unit(S, inv_row + (size_t)(f0 - 1) * 512, w1, w2, lane);
+      sy_load_unit(S, w1, w2, lane);
       __syncwarp();
+      sy_prefetch(S, inv_row + (size_t)f0 * 512, lane);
       sy_stage2(S, lane);
       __syncwarp();
-      sy_shift(S, lane);
+      sy_shift(S, lane, keep_a_at, keep_b_at);
     }
     for (int f = f0; f < f1; f++) {
       __syncwarp();
-      sy_load_unit(S, inv_row + (size_t)f * 512, w1, w2, lane);
+      sy_load_unit(S, w1, w2, lane);
       __syncwarp();
+      if (f + 1 < f1) sy_prefetch(S, inv_row + (size_t)(f + 1) * 512, lane);
       sy_stage2(S, lane);
       __syncwarp();
       {  // stage 1 -> PCM: lane covers samples [16 lane, 16 lane + 16) of the frame
@@ -828,7 +838,7 @@ synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams,
         }
       }
       __syncwarp();
-      sy_shift(S, lane);
+      sy_shift(S, lane, keep_a_at, keep_b_at);
     }
   }
 }

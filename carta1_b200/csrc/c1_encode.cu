@@ -122,6 +122,14 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 // [16 l + 512 k, +16) only, so no warp barrier is needed around the staging buffer.
 __device__ __forceinline__ void qa_prefetch(QaWarpSmem &S, const float *__restrict__ row, long long first,
                                             long long valid_samples, int lane) {
+  if (first + 512 <= valid_samples) {  // the whole frame exists (every frame but a row's last): no per-chunk bounds
+    const float *src = row + first + 4 * lane;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(S.raw + 4 * lane);
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 512 * k), "l"(src + 128 * k) : "memory");
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const long long g = first + 4 * lane + 128 * k;
@@ -131,11 +139,22 @@ __device__ __forceinline__ void qa_prefetch(QaWarpSmem &S, const float *__restri
   }
 }
 
+// Per-lane ring positions, computed once per kernel (the compiler otherwise re-derives them every frame).
+struct QaLane {
+  int fill;   // sample 4 lane of a frame in its polyphase ring: element 24 + 2 lane -> ((2 lane) & 7) * stride + 3 + (2 lane >> 3)
+  int keep_x; // element `lane` of the x rings (element 256 + lane is 32 columns further)
+  int keep_s; // element `lane` of the s rings (element 128 + lane is 32 columns further)
+  __device__ __forceinline__ explicit QaLane(int lane)
+      : fill(((2 * lane) & 7) * kQaStride1 + 3 + ((2 * lane) >> 3)),
+        keep_x((lane & 7) * kQaStride1 + (lane >> 3)),
+        keep_s((lane & 3) * kQaStride2 + (lane >> 2)) {}
+};
+
 // PCM frame -> polyphase ring (elements 24..279).  Lane l owns samples 4l + 128k + c.
 template <int kFmt>
 __device__ __forceinline__ void qa_fill(QaWarpSmem &S, const void *__restrict__ pcm_v, size_t row_off, int n_ch,
                                         int stream, long long first, long long valid_samples, bool vec_ok, int lane,
-                                        long long next_first) {
+                                        long long next_first, const QaLane &Q) {
   float v[4][4];
   if (kFmt == 0 && vec_ok) {
     cp_async_commit_wait_all();
@@ -161,13 +180,14 @@ __device__ __forceinline__ void qa_fill(QaWarpSmem &S, const void *__restrict__ 
       }
     }
   }
+  // sample 4l + 128k + c is element e = 24 + 2l + 64k + (c >> 1) of polyphase (c & 1 ? 0 : 1); its ring position
+  // (e & 7) * stride + (e >> 3) is Q.fill + stride * (c >> 1) + 8k
+  double *xb = S.x[0] + Q.fill;
 #pragma unroll
   for (int k = 0; k < 4; k++)
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-      const int e = 24 + 2 * lane + 64 * k + (c >> 1);  // sample 4l + 128k + c: polyphase index (g >> 1) + 24
-      S.x[(c & 1) ? 0 : 1][(e & 7) * kQaStride1 + (e >> 3)] = (double)v[k][c];
-    }
+    for (int c = 0; c < 4; c++)
+      xb[((c & 1) ? 0 : 8 * kQaStride1) + kQaStride1 * (c >> 1) + 8 * k] = (double)v[k][c];
 }
 
 // stage 1 of the frame in the ring: S1lo -> stage-2 ring (elements 24..151), S1hi -> hi ring (40..295)
@@ -189,15 +209,14 @@ __device__ __forceinline__ void qa_stage1(QaWarpSmem &S, int lane) {
 }
 
 // frame end: the last 24 polyphase entries / 40 S1hi values become the history of the next frame
-__device__ __forceinline__ void qa_shift(QaWarpSmem &S, int lane) {
+__device__ __forceinline__ void qa_shift(QaWarpSmem &S, int lane, const QaLane &Q) {
   double keep_x[2], keep_s[2];
   float keep_h[2];
   if (lane < 24) {
 #pragma unroll
     for (int p = 0; p < 2; p++) {
-      const int ex = 256 + lane, es = 128 + lane;
-      keep_x[p] = S.x[p][(ex & 7) * kQaStride1 + (ex >> 3)];
-      keep_s[p] = S.s[p][(es & 3) * kQaStride2 + (es >> 2)];
+      keep_x[p] = S.x[p][Q.keep_x + 32];
+      keep_s[p] = S.s[p][Q.keep_s + 32];
     }
   }
   keep_h[0] = S.hi[256 + lane];
@@ -206,8 +225,8 @@ __device__ __forceinline__ void qa_shift(QaWarpSmem &S, int lane) {
   if (lane < 24) {
 #pragma unroll
     for (int p = 0; p < 2; p++) {
-      S.x[p][(lane & 7) * kQaStride1 + (lane >> 3)] = keep_x[p];
-      S.s[p][(lane & 3) * kQaStride2 + (lane >> 2)] = keep_s[p];
+      S.x[p][Q.keep_x] = keep_x[p];
+      S.s[p][Q.keep_s] = keep_s[p];
     }
   }
   S.hi[lane] = keep_h[0];
@@ -221,6 +240,7 @@ qmf_analysis_kernel(const void *__restrict__ pcm_v, size_t row_stride, int n_ch,
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   QaWarpSmem &S = reinterpret_cast<QaWarpSmem *>(smem_raw)[warp];
+  const QaLane Q(lane);
   const int runs_per_row = (frames + run_len - 1) / run_len;
   const int n_runs = runs_per_row * n_streams;
   for (int run = blockIdx.x * kQaWarps + warp; run < n_runs; run += gridDim.x * kQaWarps) {
@@ -237,23 +257,23 @@ qmf_analysis_kernel(const void *__restrict__ pcm_v, size_t row_stride, int n_ch,
       if (lane < 24) {
 #pragma unroll
         for (int p = 0; p < 2; p++) {
-          S.x[p][(lane & 7) * kQaStride1 + (lane >> 3)] = 0.0;
-          S.s[p][(lane & 3) * kQaStride2 + (lane >> 2)] = 0.0;
+          S.x[p][Q.keep_x] = 0.0;
+          S.s[p][Q.keep_s] = 0.0;
         }
       }
       S.hi[lane] = 0.0f;
       if (lane < 8) S.hi[32 + lane] = 0.0f;
     } else {        // prime the state from the frame before the run (only its last 64 S1 outputs matter)
-      qa_fill<kFmt>(S, pcm_v, row_off, n_ch, stream, 512ll * (f0 - 1), valid_samples, vec_ok, lane, 512ll * f0);
+      qa_fill<kFmt>(S, pcm_v, row_off, n_ch, stream, 512ll * (f0 - 1), valid_samples, vec_ok, lane, 512ll * f0, Q);
       __syncwarp();
       qa_stage1(S, lane);
       __syncwarp();
-      qa_shift(S, lane);
+      qa_shift(S, lane, Q);
     }
     for (int f = f0; f < f1; f++) {
       __syncwarp();
       qa_fill<kFmt>(S, pcm_v, row_off, n_ch, stream, 512ll * f, valid_samples, vec_ok, lane,
-                    f + 1 < f1 ? 512ll * (f + 1) : -1);
+                    f + 1 < f1 ? 512ll * (f + 1) : -1, Q);
       __syncwarp();
       qa_stage1(S, lane);
       __syncwarp();
@@ -267,11 +287,17 @@ qmf_analysis_kernel(const void *__restrict__ pcm_v, size_t row_stride, int n_ch,
         reinterpret_cast<float4 *>(out + 128)[lane] = make_float4((float)(e[0] - o[0]), (float)(e[1] - o[1]),
                                                                   (float)(e[2] - o[2]), (float)(e[3] - o[3]));
       }
-      // high band delayed by 39 (encoder.js:84-90): H[n] = S1hi[n - 39] = ring[n + 1]
-#pragma unroll
-      for (int r = 0; r < 8; r++) out[256 + lane + 32 * r] = S.hi[lane + 32 * r + 1];
+      // high band delayed by 39 (encoder.js:84-90): H[n] = S1hi[n - 39] = ring[n + 1]; lane l emits
+      // H[8l .. 8l + 7] = ring[8l + 1 .. 8l + 8] from three aligned 16-byte reads
+      {
+        const float4 *hp = reinterpret_cast<const float4 *>(S.hi) + 2 * lane;
+        const float4 a = hp[0], b = hp[1], c = hp[2];
+        float4 *o4 = reinterpret_cast<float4 *>(out + 256) + 2 * lane;
+        o4[0] = make_float4(a.y, a.z, a.w, b.x);
+        o4[1] = make_float4(b.y, b.z, b.w, c.x);
+      }
       __syncwarp();
-      qa_shift(S, lane);
+      qa_shift(S, lane, Q);
     }
   }
 }
