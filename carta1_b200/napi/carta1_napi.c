@@ -287,6 +287,7 @@ typedef struct {
   size_t su_cap, n_su_out;
   float *pcm_out[2];
   size_t frames;
+  size_t halo_frames;     /* > 0: a shard of a longer stream (carta1_encode_pcm_shard / carta1_decode_su_shard) */
   int rc;
   char err[256];
 } job;
@@ -294,7 +295,10 @@ typedef struct {
 static void job_execute(napi_env env, void *data) {
   job *j = (job *)data;
   (void)env;
-  if (j->encode) j->rc = carta1_encode_pcm(j->ctx, j->chan, j->n_ch, j->n_samples, &j->opts, j->su_out, j->su_cap, &j->n_su_out);
+  if (j->encode && j->halo_frames)
+    j->rc = carta1_encode_pcm_shard(j->ctx, j->chan, j->n_ch, j->n_samples, j->halo_frames, &j->opts, j->su_out, j->su_cap, &j->n_su_out);
+  else if (j->encode) j->rc = carta1_encode_pcm(j->ctx, j->chan, j->n_ch, j->n_samples, &j->opts, j->su_out, j->su_cap, &j->n_su_out);
+  else if (j->halo_frames) j->rc = carta1_decode_su_shard(j->ctx, j->su, j->n_su, j->n_ch, j->halo_frames, j->pcm_out);
   else j->rc = carta1_decode_su(j->ctx, j->su, j->n_su, j->n_ch, j->pcm_out);
   if (j->rc) { strncpy(j->err, carta1_last_error(j->ctx), sizeof j->err - 1); j->err[sizeof j->err - 1] = 0; }
 }
@@ -336,10 +340,12 @@ static napi_value queue_job(napi_env env, job *j, const char *name) {
   return promise;
 }
 
-/* encodePcm(ctx, channels: Float32Array[1|2] (equal lengths; index.mjs zero-pads), opts) */
+/* encodePcm(ctx, channels: Float32Array[1|2] (equal lengths; index.mjs zero-pads), opts[, haloFrames])
+ * haloFrames (0 or >= 2): the channels start that many frames before the first frame to emit -- one shard of a
+ * longer stream (carta1_encode_pcm_shard). */
 static napi_value EncodePcm(napi_env env, napi_callback_info info) {
-  size_t argc = 3;
-  napi_value argv[3];
+  size_t argc = 4;
+  napi_value argv[4];
   handle *hc;
   uint32_t n_ch = 0, c;
   bool is_arr = false;
@@ -367,10 +373,15 @@ static napi_value EncodePcm(napi_env env, napi_callback_info info) {
     napi_create_reference(env, e, 1, &j->keep[j->n_keep++]);
   }
   if (argc < 3 || !read_opts(env, argv[2], &j->opts, j->bsf)) carta1_default_enc_opts(&j->opts);
+  if (argc >= 4) {
+    uint32_t halo = 0;
+    if (napi_get_value_uint32(env, argv[3], &halo) == napi_ok) j->halo_frames = halo;
+  }
   {
     napi_value out;
     void *dst;
-    j->su_cap = carta1_frame_count(j->n_samples) * (size_t)n_ch * CARTA1_SU_BYTES;
+    const size_t all = carta1_frame_count(j->n_samples);
+    j->su_cap = (all > j->halo_frames ? all - j->halo_frames : 0) * (size_t)n_ch * CARTA1_SU_BYTES;
     out = new_typed(env, napi_uint8_array, j->su_cap, 1, &dst);
     if (!out || napi_create_reference(env, out, 1, &j->out_ref[0]) != napi_ok) { free(j); return NULL; }
     j->su_out = (uint8_t *)dst;
@@ -378,9 +389,11 @@ static napi_value EncodePcm(napi_env env, napi_callback_info info) {
   return queue_job(env, j, "carta1_b200.encodePcm");
 }
 
+/* decodeSu(ctx, su: Uint8Array, channelCount[, haloFrames]); haloFrames >= 1: the units start that many frames before
+ * the first frame to emit (carta1_decode_su_shard). */
 static napi_value DecodeSu(napi_env env, napi_callback_info info) {
-  size_t argc = 3, len = 0;
-  napi_value argv[3];
+  size_t argc = 4, len = 0;
+  napi_value argv[4];
   handle *hc;
   void *data;
   int32_t n_ch = 1;
@@ -397,6 +410,11 @@ static napi_value DecodeSu(napi_env env, napi_callback_info info) {
   j->ctx = (carta1_ctx *)hc->ptr; j->n_ch = n_ch; j->su = (const uint8_t *)data; j->n_su = len / CARTA1_SU_BYTES;
   napi_create_reference(env, argv[1], 1, &j->keep[j->n_keep++]);
   j->frames = (j->n_su + (size_t)n_ch - 1) / (size_t)n_ch;
+  if (argc >= 4) {
+    uint32_t halo = 0;
+    if (napi_get_value_uint32(env, argv[3], &halo) == napi_ok) j->halo_frames = halo;
+    j->frames = j->frames > j->halo_frames ? j->frames - j->halo_frames : 0;
+  }
   {
     int c;
     for (c = 0; c < n_ch; c++) {

@@ -203,6 +203,21 @@ async function decodeAeaPcm(input) {
 }
 
 /**
+ * One shard of a longer stream (no counterpart in the reference, whose loop processor.js:97-136 is sequential): the
+ * channels start `haloFrames` frames (0, or >= 2) before the first frame to encode; resolves to the sound units of the
+ * frames after the halo, identical to that span of encodeAeaPcm's body.  A host that spreads a long recording over
+ * several GPUs (one context per GPU, CARTA1_B200_DEVICE) calls this per (stream, frame range).
+ */
+async function encodePcmShard(channels, haloFrames, options = {}) {
+  return native.encodePcm(context(), channels, abiOptions(new EncoderOptions(options)), haloFrames)
+}
+
+/** The decode counterpart: `units` start `haloFrames` frames (0, or >= 1) before the first frame to decode. */
+async function decodeUnitsShard(units, channelCount, haloFrames) {
+  return native.decodeSu(context(), units, channelCount, haloFrames)
+}
+
+/**
  * deserializeFrame over many sound units at once (what the CLI's `--json` dump, bin/cli.js:567-677, runs over a
  * file): frame objects equal to Array.from(units, deserializeFrame).  Not part of the reference's export list.
  * @param {Uint8Array} bytes - n * 212 bytes
@@ -229,7 +244,7 @@ function deserializeFrames(bytes) {
 }
 
 export {
-  deserializeFrames,
+  deserializeFrames, encodePcmShard, decodeUnitsShard,
   pipe, encode, decode, qmfAnalysisStage, mdctStage, serializeFrame, deserializeFrame, quantize, dequantize, AeaFile,
   BufferPool, EncoderOptions, AudioProcessor, decodeAeaPcm, encodeAeaPcm, FFT, WORD_LENGTH_BITS, SPECS_PER_BFU,
   SCALE_FACTORS, BFU_START_LONG,

@@ -66,6 +66,7 @@ napi_status napi_typeof(napi_env, napi_value, napi_valuetype *result);
 napi_status napi_get_undefined(napi_env, napi_value *result);
 napi_status napi_get_value_double(napi_env, napi_value, double *result);
 napi_status napi_get_value_int32(napi_env, napi_value, int32_t *result);
+napi_status napi_get_value_uint32(napi_env, napi_value, uint32_t *result);
 napi_status napi_get_value_bool(napi_env, napi_value, bool *result);
 napi_status napi_create_double(napi_env, double value, napi_value *result);
 napi_status napi_create_string_utf8(napi_env, const char *str, size_t length, napi_value *result);
