@@ -311,6 +311,16 @@ def stream_seconds(world, seconds):
     return lens
 
 
+def shard_staging(begin, enc_halo):
+    """Frame arithmetic of one shard [begin, end) of a stream.  Returns (s0, e0, enc_off_frames, dec_halo):
+    PCM is staged from frame s0 (two frames of encode halo, plus one more so that the unit before `begin`, the decode
+    halo, can be produced on the same rank); the decode input starts at unit frame e0; the timed encode starts
+    enc_off_frames after s0 and skips enc_halo frames; the decode skips dec_halo frames."""
+    s0 = begin - 3 if begin >= 5 else 0
+    e0 = begin - 1 if s0 > 0 else 0
+    return s0, e0, begin - enc_halo - s0, begin - e0
+
+
 class ShardWork:
     """Device buffers of one (stream, frame range) shard and the launches over them."""
 
@@ -318,10 +328,7 @@ class ShardWork:
         self.sh, self.ctx, self.opts = sh, ctx, opts
         begin, end = sh.begin, sh.end
         self.frames = end - begin
-        # PCM staged from frame s0: two frames of encode halo, plus one more so that the unit before `begin`
-        # (the decode halo) can be produced here as well
-        s0 = begin - 3 if begin >= 5 else 0
-        e0 = begin - 1 if s0 > 0 else 0                       # first unit of the decode input
+        s0, e0, enc_off_frames, dec_halo = shard_staging(begin, sh.enc_halo)
         self.s0, self.e0 = s0, e0
         span = (end - s0) * 512
         self.span = span
@@ -329,8 +336,8 @@ class ShardWork:
         self.pcm = torch.zeros((2, span), dtype=torch.float32, device=dev)
         self.pcm[:, :last - s0 * 512] = synth_cfg2_span(torch, stream_key, stream_s, s0 * 512, last, dev)
         self.valid = last - s0 * 512
-        self.enc_off = (begin - sh.enc_halo - s0) * 512       # floats from the row start to the encode halo
-        self.dec_halo = begin - e0
+        self.enc_off = enc_off_frames * 512                   # floats from the row start to the encode halo
+        self.dec_halo = dec_halo
         self.su_in = torch.zeros((end - e0) * 2 * 212, dtype=torch.uint8, device=dev)
         self.su_out = torch.zeros(self.frames * 2 * 212, dtype=torch.uint8, device=dev)
         self.out = torch.zeros((2, self.frames * 512), dtype=torch.float32, device=dev)
@@ -569,6 +576,10 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.lib:  # development aid: a variant build of the library (tools/onchip_experiment.sh)
+        from carta1_b200 import _lib as lib_mod
+
+        lib_mod.LIB_PATH = os.path.abspath(args.lib)
     ctx = carta1_b200.Context(local_rank)
     if args.units_per_pass:
         ctx.set_max_units_per_pass(args.units_per_pass)
@@ -933,6 +944,8 @@ def run_ours(args, rank, local_rank, world):
             "gpu_launches": launches,
             "clocks": sampler.summary(t_start, t_end),
         }
+        if args.lib:
+            line["experiment_library"] = args.lib  # not a bench line: a variant build was timed
         line["e2e"].update(extra)
         # ---- CPU baseline leg (rank 0, N=1): the oracle on the same data, doubling as the in-bench parity check
         if world == 1 and not args.no_cpu_baseline:
@@ -987,6 +1000,7 @@ def main():
     ap.add_argument("--cfg3-seconds", type=float, default=3600.0, help="development aid: length of the cfg3 stream (default: its 1 h)")
     ap.add_argument("--units-per-pass", type=int, default=0,
                     help="development aid: sound units per pipelined pass of the host entry points (default: the library's)")
+    ap.add_argument("--lib", default="", help="development aid: time a variant build of the library (its output is not checked)")
     ap.add_argument("--auto-modes", action="store_true",
                     help="development aid: transient-driven block modes instead of the headline fixed [0,0,0] (not a bench line)")
     args = ap.parse_args()

@@ -92,4 +92,14 @@ __device__ __forceinline__ int wl_bits(int wl) { return wl == 0 ? 0 : wl + 1; } 
 // item's first loads pay an L2 hit instead of a DRAM round trip.
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// Experiment build only (tools/onchip_experiment.sh, -DC1_EXPERIMENT_ONCHIP_INTERMEDIATES; never the shipped library): the
+// band rows between K1 and K3 and the band records between K6 and K7 are aliased onto 64 rows that stay in L1 / L2.
+// The results are garbage; the kernel times bound from above what keeping those intermediates on chip (a K1->K3 /
+// K6->K7 fusion) could save.
+#ifdef C1_EXPERIMENT_ONCHIP_INTERMEDIATES
+__device__ __forceinline__ size_t onchip_row(size_t u) { return 64 + (u & 63); }
+#else
+__device__ __forceinline__ size_t onchip_row(size_t u) { return u; }
+#endif
+
 }  // namespace c1

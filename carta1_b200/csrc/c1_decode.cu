@@ -562,7 +562,7 @@ imdct_kernel(const float *__restrict__ coefs, const uint8_t *__restrict__ modes,
       if (live[k >> 1]) {
         const float *row = kRole == 0 ? S.rows + k * kRow + 2 * lane : S.rows + (k >> 1) * kRow + 64 * (k & 1) + 2 * lane;
         const float2 e = *reinterpret_cast<const float2 *>(row), o = *reinterpret_cast<const float2 *>(row + kSize / 2);
-        reinterpret_cast<float4 *>(inv + (size_t)(u0 + (k >> 1)) * 512 + kOff)[lane + 32 * (k & 1)] = make_float4(e.x, o.x, e.y, o.y);
+        reinterpret_cast<float4 *>(inv + onchip_row((size_t)(u0 + (k >> 1))) * 512 + kOff)[lane + 32 * (k & 1)] = make_float4(e.x, o.x, e.y, o.y);
       }
   }
 }
@@ -776,9 +776,9 @@ synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams,
     const int stream = run / runs_per_row;
     const int f0 = halo + (run - stream * runs_per_row) * run_len;
     const int f1 = min(f0 + run_len, frames);
-    const float *inv_row = inv + (size_t)stream * frames * 512;
+    const size_t row0 = (size_t)stream * frames;  // unit index of the row's frame 0
     __syncwarp();
-    sy_prefetch(S, inv_row + (size_t)(f0 > 0 ? f0 - 1 : f0) * 512, lane);
+    sy_prefetch(S, inv + onchip_row(row0 + (f0 > 0 ? f0 - 1 : f0)) * 512, lane);
     // silent state (new BufferPool, buffers.js:31-35,67-72)
     if (lane < 24) {
 #pragma unroll
@@ -797,7 +797,7 @@ synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams,
       // on the tails before it), so the zero state above is as good as the true one
       sy_load_unit(S, w1, w2, lane);
       __syncwarp();
-      sy_prefetch(S, inv_row + (size_t)f0 * 512, lane);
+      sy_prefetch(S, inv + onchip_row(row0 + f0) * 512, lane);
       sy_stage2(S, lane);
       __syncwarp();
       sy_shift(S, lane, keep_a_at, keep_b_at);
@@ -806,7 +806,7 @@ synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams,
       __syncwarp();
       sy_load_unit(S, w1, w2, lane);
       __syncwarp();
-      if (f + 1 < f1) sy_prefetch(S, inv_row + (size_t)(f + 1) * 512, lane);
+      if (f + 1 < f1) sy_prefetch(S, inv + onchip_row(row0 + f + 1) * 512, lane);
       sy_stage2(S, lane);
       __syncwarp();
       {  // stage 1 -> PCM: lane covers samples [16 lane, 16 lane + 16) of the frame

@@ -277,7 +277,7 @@ qmf_analysis_kernel(const void *__restrict__ pcm_v, size_t row_stride, int n_ch,
       __syncwarp();
       qa_stage1(S, lane);
       __syncwarp();
-      float *out = bands + ((size_t)stream * frames + f) * 512;
+      float *out = bands + onchip_row((size_t)stream * frames + f) * 512;
       {  // stage 2: low / mid samples 4 lane .. 4 lane + 3
         double e[4], o[4];
         fir_analysis<4, kQaStride2>(S.s[0], lane, c_qmf_even, e);
@@ -924,7 +924,7 @@ __device__ __forceinline__ void mdct_warp_task(int pair, const float *__restrict
   const bool have1 = su0 + 1 < n_su;
   const int frame0 = su0 % frames;
   const bool cont1 = have1 && frame0 + 1 < frames;  // unit 1 continues unit 0's row
-  const float *cur0 = bands + (size_t)su0 * 512 + kOff;
+  const float *cur0 = bands + onchip_row((size_t)su0) * 512 + kOff;
   ExactRound xr;
   // block modes of this role's bands: transform x = unit * kPer + band
   int mode[G::kPerWarp];
@@ -1057,7 +1057,7 @@ mdct_kernel(const float *__restrict__ bands, const uint8_t *__restrict__ modes, 
     {  // the next pair's 2 x 1 KB of band samples (this role's half of each unit): 16 lines, one per lane
       const int next = pair + gridDim.x * kMdctWarps;
       const int su = 2 * next + (lane >> 3);
-      if (lane < 16 && su < n_su) prefetch_l2(bands + (size_t)su * 512 + (kRole == 0 ? 0 : 256) + 32 * (lane & 7));
+      if (lane < 16 && su < n_su) prefetch_l2(bands + onchip_row((size_t)su) * 512 + (kRole == 0 ? 0 : 256) + 32 * (lane & 7));
     }
     mdct_warp_task<kRole>(pair, bands, modes, frames, n_su, T, P, coefs, sfi_out, S, ST.tab2, ST.tw, lane, w_fwd, w_rev);
   }

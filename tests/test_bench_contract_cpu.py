@@ -105,3 +105,46 @@ def test_bench_parses_without_a_gpu():
     # no CUDA device here: our arm must refuse loudly instead of falling back to the CPU
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_synthetic_streams_are_pure_functions_of_the_sample_index():
+    """A rank that holds only a frame range of a stream has to generate exactly the samples the unsharded run sees."""
+    import torch
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    whole = bench.synth_cfg2_span(torch, 0xCA27A2 + 1, 37.5, 0, 60000, torch.device("cpu"))
+    for a, b in ((0, 60000), (1, 513), (12345, 54321), (59999, 60000)):
+        part = bench.synth_cfg2_span(torch, 0xCA27A2 + 1, 37.5, a, b, torch.device("cpu"))
+        assert torch.equal(part, whole[:, a:b]), (a, b)
+    other = bench.synth_cfg2_span(torch, 0xCA27A2 + 2, 37.5, 0, 4096, torch.device("cpu"))
+    assert not torch.equal(other, whole[:, :4096])          # another stream, another signal
+    z = bench.hashed_normal(torch, torch.arange(0, 1 << 18, dtype=torch.int64), 7)
+    assert abs(z.mean().item()) < 0.01 and abs(z.std().item() - 1.0) < 0.01
+
+
+def test_stream_list_and_shard_staging_of_the_multi_gpu_run():
+    sys.path.insert(0, ROOT)
+    import bench
+    from carta1_b200 import sharding
+
+    for world in (1, 2, 3, 4, 8):
+        lens = bench.stream_seconds(world, 3600.0)
+        assert abs(sum(lens) - 3600.0 * world) < 1e-6 and len(lens) == world
+        frames = [(int(round(s * 44100)) + 511) // 512 for s in lens]
+        plan = sharding.plan(frames, world)
+        sharding.check_plan(plan, frames)
+        if world > 1:
+            assert sum(1 for p in plan for sh in p if sh.begin > 0) >= world // 2   # frame-range cuts inside streams
+            per_rank = [sum(sh.frames for sh in p) for p in plan]
+            assert max(per_rank) - min(per_rank) <= 4                                   # balanced: 1 h each
+    for begin in range(0, 12):
+        if begin == 1:
+            continue  # the plan never cuts at frame 1
+        halo = 2 if begin else 0
+        s0, e0, off, dec_halo = bench.shard_staging(begin, halo)
+        assert 0 <= s0 <= e0 <= begin and (s0 == 0 or s0 == begin - 3)
+        assert off == begin - halo - s0 and off >= 0
+        assert dec_halo == begin - e0 and (dec_halo >= 1 if begin else dec_halo == 0)
+        assert e0 - s0 in (0, 2)                                                        # the set-up encode's own halo
