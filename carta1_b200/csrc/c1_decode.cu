@@ -665,6 +665,24 @@ __device__ __forceinline__ void sy_prefetch(SyWarpSmem &S, const float *__restri
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// f32(0.5 * ((double)a +- (double)b)) (qmf.js:77-83, decoder.js:362-367) without leaving binary32.  The reference's value is
+// RN24(RN53(0.5 a +- 0.5 b)); rounding first to 53 and then to 24 bits is innocuous for a sum of two 24-bit numbers
+// (53 >= 2 * 24 + 2), so it equals RN24(0.5 a +- 0.5 b), which is what one FMA computes when 0.5 b is exact: b zero, or
+// |b| >= 2^-125 (also true for infinities and NaN).  merge_exact_in_f32 says whether that holds; the caller falls back to the
+// binary64 expression otherwise.  Saves four conversions per pair on the XU pipe (16 lanes per clock per SM).
+__device__ __forceinline__ unsigned merge_key(float b) { return (__float_as_uint(b) & 0x7FFFFFFFu) - 1u; }  // 0 -> 0xFFFFFFFF
+__device__ __forceinline__ bool merge_exact_in_f32(unsigned min_key) { return min_key >= 0x00FFFFFFu; }
+__device__ __forceinline__ void merge_f32(float a, float b, float &sum, float &dif) {
+  const float hb = 0.5f * b;
+  sum = fmaf(0.5f, a, hb);
+  dif = fmaf(0.5f, a, -hb);
+}
+
+struct SyWarpSmem;
+__device__ __noinline__ void sy_merge_lm_f64(SyWarpSmem &S, int lane);
+__device__ __noinline__ void sy_merge_hd_f64(SyWarpSmem &S, int lane, float x0, float x1, float x2, float x3, float x4, float x5,
+                                             float x6, float x7);
+
 // Band record of one unit (already on its way into S.td, sy_prefetch) -> time-domain frame in S.td (first 32 samples
 // of a band: overlap-add with the previous unit's tail, mdct.js:230-245), merged low/mid -> S/D ring (elements
 // 24..151), high -> hd ring (40..295); the unit's tails replace the previous ones.
@@ -694,12 +712,17 @@ __device__ __forceinline__ void sy_load_unit(SyWarpSmem &S, const double w1, con
   {
     const float4 l4 = reinterpret_cast<const float4 *>(S.td)[lane], m4 = reinterpret_cast<const float4 *>(S.td + 128)[lane];
     const float l[4] = {l4.x, l4.y, l4.z, l4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w};
+    const bool f32_ok = merge_exact_in_f32(min(min(merge_key(m[0]), merge_key(m[1])), min(merge_key(m[2]), merge_key(m[3]))));
+    if (__all_sync(0xffffffffu, f32_ok)) {
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const float sum = (float)(0.5 * ((double)l[r] + (double)m[r]));
-      const float dif = (float)(0.5 * ((double)l[r] - (double)m[r]));
-      S.a[0][r * kSyStrideA + lane + 6] = (double)dif;
-      S.a[1][r * kSyStrideA + lane + 6] = (double)sum;
+      for (int r = 0; r < 4; r++) {
+        float sum, dif;
+        merge_f32(l[r], m[r], sum, dif);
+        S.a[0][r * kSyStrideA + lane + 6] = (double)dif;
+        S.a[1][r * kSyStrideA + lane + 6] = (double)sum;
+      }
+    } else {
+      sy_merge_lm_f64(S, lane);  // binary32-subnormal mid-band samples somewhere in the warp: rare, out of line
     }
   }
   // high band into its delay ring
@@ -720,19 +743,48 @@ __device__ __forceinline__ void sy_stage2(SyWarpSmem &S, int lane) {
   const float4 ha = reinterpret_cast<const float4 *>(S.hd)[2 * lane], hb = reinterpret_cast<const float4 *>(S.hd)[2 * lane + 1],
                hc = reinterpret_cast<const float4 *>(S.hd)[2 * lane + 2];
   const float hv[8] = {ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w, hc.x};
+  unsigned key = merge_key(hv[0]);
 #pragma unroll
-  for (int r = 0; r < 4; r++) {
+  for (int c = 1; c < 8; c++) key = min(key, merge_key(hv[c]));
+  float x[8];
 #pragma unroll
-    for (int par = 0; par < 2; par++) {
-      const int c = 2 * r + par;  // n = 8 lane + c
-      const float x = (float)(par ? ev[r] : od[r]);
-      const float h = hv[c];
-      const float s1 = (float)(0.5 * ((double)x + (double)h));
-      const float d1 = (float)(0.5 * ((double)x - (double)h));
+  for (int c = 0; c < 8; c++) x[c] = (float)((c & 1) ? ev[c >> 1] : od[c >> 1]);  // n = 8 lane + c
+  if (__all_sync(0xffffffffu, merge_exact_in_f32(key))) {
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      float s1, d1;
+      merge_f32(x[c], hv[c], s1, d1);
       // element 24 + n = 8 (lane + 3) + c
       S.b[0][c * kSyStrideB + lane + 3] = (double)d1;
       S.b[1][c * kSyStrideB + lane + 3] = (double)s1;
     }
+  } else {
+    sy_merge_hd_f64(S, lane, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);  // rare, out of line
+  }
+}
+
+// The two merges as the reference writes them (binary64), for warps that hold binary32-subnormal samples.
+__device__ __noinline__ void sy_merge_lm_f64(SyWarpSmem &S, int lane) {
+  const float4 l4 = reinterpret_cast<const float4 *>(S.td)[lane], m4 = reinterpret_cast<const float4 *>(S.td + 128)[lane];
+  const float l[4] = {l4.x, l4.y, l4.z, l4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const float sum = (float)(0.5 * ((double)l[r] + (double)m[r]));
+    const float dif = (float)(0.5 * ((double)l[r] - (double)m[r]));
+    S.a[0][r * kSyStrideA + lane + 6] = (double)dif;
+    S.a[1][r * kSyStrideA + lane + 6] = (double)sum;
+  }
+}
+__device__ __noinline__ void sy_merge_hd_f64(SyWarpSmem &S, int lane, float x0, float x1, float x2, float x3, float x4, float x5,
+                                             float x6, float x7) {
+  const float x[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const float h = S.hd[8 * lane + c + 1];
+    const float s1 = (float)(0.5 * ((double)x[c] + (double)h));
+    const float d1 = (float)(0.5 * ((double)x[c] - (double)h));
+    S.b[0][c * kSyStrideB + lane + 3] = (double)d1;
+    S.b[1][c * kSyStrideB + lane + 3] = (double)s1;
   }
 }
 
