@@ -459,6 +459,35 @@ def decodeAeaPcm(data, ctx=None):
     return (ctx or default_context()).decode_su(su, info["channelCount"])
 
 
+def encodePcmShard(channels, haloFrames, options=None, ctx=None) -> np.ndarray:
+    """One (stream, frame range) shard of encodeAeaPcm's body (no counterpart in the reference, whose loop
+    codec/io/processor.js:97-136 is sequential): `channels` start `haloFrames` frames (0, or >= 2) before the first
+    frame to encode.  Returns the sound units [n, 212] of the frames after the halo, bit-identical to that span of
+    the whole-stream result (carta1_encode_pcm_shard)."""
+    if (not isinstance(channels, (list, tuple)) or len(channels) not in (1, 2) or
+            any(not (isinstance(c, np.ndarray) and c.dtype == np.float32 and c.ndim == 1) for c in channels)):
+        raise TypeError("ATRAC1 encoding requires one or two Float32 channels")
+    n = max(len(c) for c in channels)
+    chans = [np.ascontiguousarray(c if len(c) == n else np.concatenate([c, np.zeros(n - len(c), np.float32)])) for c in channels]
+    frames = max((n + 511) // 512 - int(haloFrames), 0)
+    su = np.zeros((frames * len(chans), SOUND_UNIT_SIZE), np.uint8)
+    got = (ctx or default_context()).encode_pcm_shard_into(chans, int(haloFrames), su, EncoderOptions(dict(options or {})).to_abi())
+    return su[:got]
+
+
+def decodeUnitsShard(units, channelCount, haloFrames, ctx=None):
+    """The decode counterpart (carta1_decode_su_shard): `units` start `haloFrames` frames (0, or >= 1) before the
+    first frame to decode; returns one Float32 array per channel for the frames after the halo."""
+    if channelCount not in (1, 2):
+        raise ValueError(f"Unsupported channel count: {channelCount}")
+    units = np.ascontiguousarray(units, np.uint8).reshape(-1, SOUND_UNIT_SIZE)
+    frames = max((units.shape[0] + channelCount - 1) // channelCount - int(haloFrames), 0)
+    outs = [np.zeros(frames * 512, np.float32) for _ in range(channelCount)]
+    if frames:
+        (ctx or default_context()).decode_su_shard_into(units, units.shape[0], channelCount, int(haloFrames), outs)
+    return outs
+
+
 def deserializeFrames(units, ctx=None) -> list:
     """deserializeFrame over many sound units at once on the device (carta1_deserialize_units): the frame
     objects the `--json` dump of bin/cli.js:567-677 writes, one per 212-byte unit, equal to

@@ -461,6 +461,18 @@ def test_sharded_host_path(ctx, oracle, world, units_per_pass):
                 ctx.decode_su_shard_into(src, ub - ua, 2, sh.dec_halo, outs)
                 for c in range(2):
                     assert np.array_equal(bits(outs[c]), bits(refs[sh.stream][c][sh.begin * 512:sh.end * 512])), (sh, c)
+        # the same through the mirror of the JS layer (index.mjs: encodePcmShard / decodeUnitsShard)
+        from carta1_b200 import codec
+
+        sh = plan[-1][-1]
+        ch = streams[sh.stream]
+        first, last = sh.pcm_span()
+        su = codec.encodePcmShard([np.ascontiguousarray(ch[c][first:last]) for c in range(2)], sh.enc_halo, ctx=ctx)
+        assert np.array_equal(su, wants[sh.stream][sh.begin * 2:sh.end * 2])
+        ua, ub = sh.unit_span(2)
+        outs = codec.decodeUnitsShard(wants[sh.stream][ua:ub], 2, sh.dec_halo, ctx=ctx)
+        for c in range(2):
+            assert np.array_equal(bits(outs[c]), bits(refs[sh.stream][c][sh.begin * 512:sh.end * 512]))
         with pytest.raises(ValueError, match="halo_frames must be 0 or >= 2"):
             ctx.encode_pcm_shard_into([np.zeros(2048, np.float32)], 1, np.zeros((3, 212), np.uint8), None)
     finally:

@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""ref_run_qjs.py -- runs the REAL carta1 (aynik/carta1, JavaScript, /root/reference) in this image.
+
+The image has no Node, but NVIDIA Nsight Compute ships Qt 6.6.3, and libQt6Qml.so.6 contains Qt's own
+ECMAScript engine (QJSEngine, "V4": ES2016 + `?.` / `??`, typed arrays, classes, generators, ES modules,
+baseline JIT).  This script drives that engine through ctypes (no Qt headers exist here: the six C++ entry
+points it needs are called by their mangled names, QString values are laid out by hand) and lets it import
+the reference's own modules FROM WHERE THEY LIE.  Nothing of the reference is copied into this repository;
+a scratch mirror is made under a temporary directory at run time because two of the reference's files use
+syntax newer than the engine:
+
+    codec/core/options.js   three object spreads `{ ...x }`            -> Object.assign({}, x)
+    codec/io/processor.js   async / await / `for await` / object rest  -> the synchronous equivalents
+                            (every awaited value in that file is computed synchronously; Blob is a host shim)
+
+Every rewritten line is printed and recorded in tests/golden/ref/provenance.json.  All files that hold codec
+arithmetic -- constants, buffers, qmf, fft, mdct, transient, bitallocation, quantization, encoder, decoder,
+bitstream, serialization, utils -- are loaded byte for byte as the reference ships them (their sha256 is
+recorded too).
+
+What it writes (tests/golden/ref/, the layout tools/ref_dump.mjs writes under Node; tests/test_reference_pin.py
+reads either):
+    tables.json        every libm-derived table as THIS engine computed it (V4 calls the host's glibc)
+    <case>.aea         encodeAeaPcm(channels, options)        codec/io/processor.js:597-617
+    <case>.pcm.f32     decodeAeaPcm(that)                     codec/io/processor.js:628-654
+    stages.npz         per-stage outputs of the reference's own stage functions on the same inputs
+                       (qmfAnalysisStage bands, performFFT magnitudes, transient scores, block modes,
+                       mdctStage coefficients, the frame object; dequantised coefficients, IMDCT bands, PCM)
+    kat.json           known answers of single functions (FFT.fft, MDCT/IMDCT transform, qmfAnalysis /
+                       qmfSynthesis, findScaleFactor, quantize / dequantize, allocateBits, packBits)
+
+usage:  python tests/golden/make_golden.py --export-ref-inputs
+        python tools/ref_run_qjs.py [/root/reference] [outdir]
+"""
+import ctypes
+import glob
+import hashlib
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+QT_CANDIDATES = sorted(glob.glob("/opt/nvidia/nsight-compute/*/host/linux-desktop-glibc_*-x64"), reverse=True)
+
+GLIB_SYMBOLS = """g_main_context_default g_main_context_iteration g_main_context_new g_main_context_pop_thread_default
+g_main_context_push_thread_default g_main_context_ref g_main_context_unref g_main_context_wakeup g_source_add_poll
+g_source_attach g_source_destroy g_source_new g_source_remove_poll g_source_set_can_recurse g_source_set_name
+g_source_unref""".split()
+
+
+def find_qt():
+    for d in QT_CANDIDATES:
+        if os.path.exists(os.path.join(d, "libQt6Qml.so.6")) and os.path.exists(os.path.join(d, "libQt6Core.so.6")):
+            return d
+    return None
+
+
+class QString(ctypes.Structure):
+    # Qt 6: QArrayDataPointer<char16_t> { Data *d; char16_t *ptr; qsizetype size; }; d == nullptr is a
+    # legal non-owning string (QString::fromRawData builds exactly that)
+    _fields_ = [("d", ctypes.c_void_p), ("ptr", ctypes.c_void_p), ("size", ctypes.c_longlong)]
+
+
+class Engine:
+    """QCoreApplication + QJSEngine of the Qt that ships with Nsight Compute, by mangled name."""
+
+    def __init__(self, scratch):
+        qt = find_qt()
+        if qt is None:
+            raise RuntimeError("no Qt 6 (libQt6Qml.so.6) found under /opt/nvidia/nsight-compute")
+        self.qt_dir = qt
+        # libQt6Core wants libglib-2.0.so.0 / libgthread-2.0.so.0 (its optional event dispatcher); the image
+        # has neither.  QT_NO_GLIB=1 keeps Qt off them; empty stand-ins satisfy the loader.
+        os.environ["QT_NO_GLIB"] = "1"
+        stub_c = os.path.join(scratch, "glibstub.c")
+        with open(stub_c, "w") as f:
+            f.write("#include <stdlib.h>\n" + "".join("void %s(void){abort();}\n" % s for s in GLIB_SYMBOLS))
+        for name in ("libglib-2.0.so.0", "libgthread-2.0.so.0"):
+            out = os.path.join(scratch, name)
+            subprocess.check_call(["gcc", "-shared", "-fPIC", "-o", out, stub_c, "-Wl,-soname," + name])
+            ctypes.CDLL(out, mode=ctypes.RTLD_GLOBAL)
+        self.core = ctypes.CDLL(os.path.join(qt, "libQt6Core.so.6"), mode=ctypes.RTLD_GLOBAL)
+        self.qml = ctypes.CDLL(os.path.join(qt, "libQt6Qml.so.6"), mode=ctypes.RTLD_GLOBAL)
+        self._keep = []
+        self._argc = ctypes.c_int(1)
+        self._argv = (ctypes.c_char_p * 2)(b"ref_run_qjs", None)
+        self._app = ctypes.create_string_buffer(64)
+        # QCoreApplication::QCoreApplication(int &argc, char **argv, int flags = QT_VERSION)
+        self.core._ZN16QCoreApplicationC1ERiPPci(self._app, ctypes.byref(self._argc), self._argv, ctypes.c_int(0x060603))
+        self._eng = ctypes.create_string_buffer(64)
+        self.qml._ZN9QJSEngineC1Ev(self._eng)  # QJSEngine::QJSEngine()
+        self.qml._ZNK8QJSValue7isErrorEv.restype = ctypes.c_bool
+        self.version = ctypes.cast(self._call_c("qVersion"), ctypes.c_char_p).value.decode()
+
+    def _call_c(self, name):
+        fn = getattr(self.core, name)
+        fn.restype = ctypes.c_void_p
+        return fn()
+
+    def _qs(self, s):
+        b = s.encode("utf-16-le")
+        buf = ctypes.create_string_buffer(b + b"\0\0")
+        self._keep.append(buf)  # never freed: a QString with d == nullptr is taken for immortal raw data and V4 keeps pointers into it
+        return QString(None, ctypes.addressof(buf), len(b) // 2)
+
+    def to_string(self, v):
+        r = QString()
+        self.qml._ZNK8QJSValue8toStringEv(ctypes.byref(r), v)  # QString QJSValue::toString() const (sret)
+        return ctypes.string_at(r.ptr, r.size * 2).decode("utf-16-le") if r.size else ""
+
+    def is_error(self, v):
+        return bool(self.qml._ZNK8QJSValue7isErrorEv(v))
+
+    def _check(self, v, what):
+        if self.is_error(v):
+            p = ctypes.create_string_buffer(16)
+            info = []
+            for k in ("fileName", "lineNumber", "stack"):
+                self.qml._ZNK8QJSValue8propertyERK7QString(p, v, ctypes.byref(self._qs(k)))
+                info.append("%s=%s" % (k, self.to_string(p)))
+            raise RuntimeError("%s: %s (%s)" % (what, self.to_string(v), ", ".join(info)))
+        return v
+
+    def evaluate(self, src, name="<driver>"):
+        v = ctypes.create_string_buffer(16)
+        # QJSValue QJSEngine::evaluate(const QString &program, const QString &fileName, int line, QStringList *)
+        self.qml._ZN9QJSEngine8evaluateERK7QStringS2_iP5QListIS0_E(v, self._eng, ctypes.byref(self._qs(src)),
+                                                                 ctypes.byref(self._qs(name)), ctypes.c_int(1), None)
+        return self.to_string(self._check(v, name))
+
+    def import_module(self, path, as_global):
+        v = ctypes.create_string_buffer(16)
+        self.qml._ZN9QJSEngine12importModuleERK7QString(v, self._eng, ctypes.byref(self._qs(path)))
+        self._check(v, "import " + path)
+        g = ctypes.create_string_buffer(16)
+        self.qml._ZNK9QJSEngine12globalObjectEv(g, self._eng)
+        self.qml._ZN8QJSValue11setPropertyERK7QStringRKS_(g, ctypes.byref(self._qs(as_global)), v)
+
+
+# ---------------------------------------------------------------------------------------------------
+# The scratch mirror and the two downlevelled files
+UNTOUCHED = ["core/constants.js", "core/buffers.js", "transforms/qmf.js", "transforms/fft.js", "transforms/mdct.js",
+             "analysis/transient.js", "coding/bitallocation.js", "coding/quantization.js", "pipeline/encoder.js",
+             "pipeline/decoder.js", "io/bitstream.js", "io/serialization.js", "utils.js", "index.js"]
+
+OPTIONS_RULES = [(r"\{ \.\.\.(this\.\w+) \}", r"Object.assign({}, \1)")]
+PROCESSOR_RULES = [
+    (r"\bstatic async \*", "static *"),
+    (r"\bstatic async ", "static "),
+    (r"\bexport async function ", "export function "),
+    (r"= async function\* \(", "= function* ("),
+    (r"\bfor await \(", "for ("),
+    (r"\bawait ", ""),
+    (r"const \{ title = 'encoded by carta1', \.\.\.encoderValues \} = options",
+     "const title = options.title === undefined ? 'encoded by carta1' : options.title; "
+     "const encoderValues = Object.assign({}, options); delete encoderValues.title"),
+]
+
+
+def downlevel(text, rules, log, rel):
+    out = []
+    for no, line in enumerate(text.split("\n"), 1):
+        new = line
+        for pat, rep in rules:
+            new = re.sub(pat, rep, new)
+        if new != line:
+            log.append({"file": rel, "line": no, "from": line.strip(), "to": new.strip()})
+        out.append(new)
+    return "\n".join(out)
+
+
+def stage_reference(ref_root, scratch):
+    """Mirror <ref_root>/codec (without browser/ and the fs reader) under scratch, downlevelling two files."""
+    src = os.path.join(ref_root, "codec")
+    dst = os.path.join(scratch, "carta1", "codec")
+    log, hashes = [], {}
+    for rel in UNTOUCHED + ["core/options.js", "io/processor.js"]:
+        s = open(os.path.join(src, rel), encoding="utf-8").read()
+        hashes["codec/" + rel] = hashlib.sha256(s.encode()).hexdigest()
+        if rel == "core/options.js":
+            s = downlevel(s, OPTIONS_RULES, log, "codec/" + rel)
+        elif rel == "io/processor.js":
+            s = downlevel(s, PROCESSOR_RULES, log, "codec/" + rel)
+        os.makedirs(os.path.dirname(os.path.join(dst, rel)), exist_ok=True)
+        with open(os.path.join(dst, rel), "w", encoding="utf-8") as f:
+            f.write(s)
+    return dst, log, hashes
+
+
+# ---------------------------------------------------------------------------------------------------
+def hex_of(a):
+    return np.ascontiguousarray(a).tobytes().hex()
+
+
+def main():
+    ref_root = os.path.abspath(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
+    out_dir = os.path.abspath(sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "tests", "golden", "ref"))
+    in_dir = os.path.join(out_dir, "inputs")
+    if not os.path.exists(os.path.join(in_dir, "cases.json")):
+        raise SystemExit("run `python tests/golden/make_golden.py --export-ref-inputs` first")
+    scratch = tempfile.mkdtemp(prefix="carta1_qjs_")
+    try:
+        eng = Engine(scratch)
+        codec, log, hashes = stage_reference(ref_root, scratch)
+        for e in log:
+            print("downlevel %s:%d\n    - %s\n    + %s" % (e["file"], e["line"], e["from"], e["to"]))
+        eng.evaluate(open(os.path.join(HERE, "ref_run_qjs_shims.js")).read(), "ref_run_qjs_shims.js")
+        mods = {"carta1": "index.js", "C": "core/constants.js", "M": "transforms/mdct.js", "ENC": "pipeline/encoder.js",
+                "DEC": "pipeline/decoder.js", "QMF": "transforms/qmf.js", "TR": "analysis/transient.js",
+                "BA": "coding/bitallocation.js", "QZ": "coding/quantization.js", "BS": "io/bitstream.js",
+                "SER": "io/serialization.js", "BUF": "core/buffers.js", "OPT": "core/options.js", "FFTM": "transforms/fft.js"}
+        for g, rel in mods.items():
+            eng.import_module(os.path.join(codec, rel), g)
+        eng.evaluate(open(os.path.join(HERE, "ref_run_qjs_driver.js")).read(), "ref_run_qjs_driver.js")
+
+        cases = json.load(open(os.path.join(in_dir, "cases.json")))
+        biases = sorted({c["bias"] for c in cases})
+        tables = json.loads(eng.evaluate("JSON.stringify(dumpTables(%s))" % json.dumps(biases)))
+        pkg = json.load(open(os.path.join(ref_root, "package.json")))
+        tables["versions"] = {"engine": "Qt QJSEngine (V4)", "qt": eng.version, "libm": "host glibc (V4 calls std::sin/cos/pow/log/exp)",
+                              "from": eng.qt_dir}
+        tables["carta1"] = pkg["version"]
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, "tables.json"), "w") as f:
+            json.dump(tables, f, indent=1)
+
+        stages = {}
+        for c in cases:
+            s16 = np.fromfile(os.path.join(in_dir, c["name"] + ".s16"), "<i2").reshape(-1, c["channels"])
+            opts = {"transientThresholdLow": c["threshold"], "allocationBias": c["bias"]}
+            if c["fixed_modes"]:
+                opts["fixedBlockModes"] = c["fixed_modes"]
+            # bin/cli.js:394-396: readInt16LE / 32768.0 into a Float32Array, done in the engine
+            eng.evaluate("setInput(%s, %d)" % (json.dumps(hex_of(s16)), c["channels"]))
+            aea_hex = eng.evaluate("runEncode(%s)" % json.dumps(opts))
+            aea = np.frombuffer(bytes.fromhex(aea_hex), np.uint8)
+            aea.tofile(os.path.join(out_dir, c["name"] + ".aea"))
+            pcm = np.frombuffer(bytes.fromhex(eng.evaluate("runDecode()")), "<f4")
+            pcm.tofile(os.path.join(out_dir, c["name"] + ".pcm.f32"))
+            doc = json.loads(eng.evaluate("JSON.stringify(runStages(%s))" % json.dumps(opts)))
+            for k, v in doc.items():
+                dt = {"f32": "<f4", "f64": "<f8", "u8": np.uint8, "i32": "<i4"}[v["type"]]
+                stages[c["name"] + "/" + k] = np.frombuffer(bytes.fromhex(v["hex"]), dt).reshape(v["shape"])
+            print("%-32s %d ch, %d samples, %d sound units" % (c["name"], c["channels"], s16.shape[0], (len(aea) - 2048) // 212))
+        np.savez_compressed(os.path.join(out_dir, "stages.npz"), **stages)
+
+        kat = json.loads(eng.evaluate("JSON.stringify(runKats())"))
+        with open(os.path.join(out_dir, "kat.json"), "w") as f:
+            json.dump(kat, f)
+        with open(os.path.join(out_dir, "provenance.json"), "w") as f:
+            json.dump({"engine": tables["versions"], "carta1": pkg["version"], "reference_sha256": hashes,
+                       "loaded_unmodified": ["codec/" + r for r in UNTOUCHED], "downlevelled_lines": log,
+                       "host_shims": ["Blob", "TextEncoder", "TextDecoder"],
+                       "generator": "tools/ref_run_qjs.py + ref_run_qjs_driver.js + ref_run_qjs_shims.js"}, f, indent=1)
+        print("wrote %s (Qt %s QJSEngine)" % (out_dir, eng.version))
+    finally:
+        shutil.rmtree(scratch, ignore_errors=True)
+    sys.stdout.flush()
+    os._exit(0)  # no QCoreApplication teardown: the objects live in ctypes buffers
+
+
+if __name__ == "__main__":
+    main()
