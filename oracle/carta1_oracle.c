@@ -588,6 +588,16 @@ static double spectral_flux(const float *cur, const float *prev, int n) { /* :92
   return flux / norm;
 }
 
+/* Which libm the transient detector's log / exp / log10 / log1p use: 0 (default) the fdlibm port above, which is
+ * what V8 carries; 1 the host's libm, which is what Qt's QJSEngine (the engine that wrote tests/golden/ref) calls.
+ * Test-only switch, process-wide. */
+static int g_host_libm = 0;
+void c1o_set_host_libm(int on) { g_host_libm = on; }
+static double m_log(double x) { return g_host_libm ? log(x) : c1o_log(x); }
+static double m_exp(double x) { return g_host_libm ? exp(x) : c1o_exp(x); }
+static double m_log10(double x) { return g_host_libm ? log10(x) : c1o_log10(x); }
+static double m_log1p(double x) { return g_host_libm ? log1p(x) : c1o_log1p(x); }
+
 static double spectral_flatness(const float *x, int n) { /* :120-141 */
   const double EPS = 1e-10;
   double sum_log = 0, sum_lin = 0;
@@ -595,13 +605,13 @@ static double spectral_flatness(const float *x, int n) { /* :120-141 */
   for (int i = 0; i < n; i++) {
     const double m = fabs((double)x[i]);
     if (m > EPS) {
-      sum_log += c1o_log(m);
+      sum_log += m_log(m);
       sum_lin += m;
       valid++;
     }
   }
   if (valid == 0) return 0;
-  const double geo = c1o_exp(sum_log / valid);
+  const double geo = m_exp(sum_log / valid);
   const double arith = sum_lin / valid;
   return arith > EPS ? geo / arith : 0;
 }
@@ -623,7 +633,7 @@ static double energy_change(const float *cur, const float *prev, int n) { /* :17
   }
   ce = js_max(ce, 1e-10);
   pe = js_max(pe, 1e-10);
-  const double db = 10 * c1o_log10(ce / pe);
+  const double db = 10 * m_log10(ce / pe);
   return js_max(0, db);
 }
 
@@ -634,7 +644,7 @@ double c1o_transient_score(const float *cur, const float *prev, int n) {
   const double hf_change = fabs(hf_ratio(cur, n) - hf_ratio(prev, n));
   const double e_change = energy_change(cur, prev, n);
   const double flat_c = sqrt(flat_change);
-  const double hf_c = c1o_log1p(hf_change * 10) / c1o_log1p(10);
+  const double hf_c = m_log1p(hf_change * 10) / m_log1p(10);
   const double e_c = js_min(e_change / 30, 1);
   return (flux + flat_c + hf_c + e_c) / 4;
 }

@@ -130,6 +130,7 @@ int c1o_unpack_bits(const uint8_t *buf, size_t buf_len, int bit_pos, int bit_cou
 int c1o_unpack_signed_bits(const uint8_t *buf, size_t buf_len, int bit_pos, int bit_count);
 void c1o_serialize_frame(const c1o_frame *f, uint8_t out[C1O_SU_BYTES]);
 void c1o_deserialize_frame(const uint8_t in[C1O_SU_BYTES], c1o_frame *f);
+void c1o_set_host_libm(int on); /* transient detector: 1 = host libm (the dump's engine), 0 = fdlibm port (V8), default */
 double c1o_log(double x);
 double c1o_exp(double x);
 double c1o_log10(double x);

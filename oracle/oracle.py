@@ -258,6 +258,11 @@ def perform_fft(samples: np.ndarray, fft_size: int, tables=None) -> np.ndarray:
     return mag
 
 
+def set_host_libm(on: bool) -> None:
+    """Transient detector libm: True = the host's (what Qt's QJSEngine calls), False = fdlibm port (V8; default)."""
+    lib().c1o_set_host_libm(int(bool(on)))
+
+
 def transient_score(cur: np.ndarray, prev: np.ndarray) -> float:
     cur = np.ascontiguousarray(cur, np.float32)
     prev = np.ascontiguousarray(prev, np.float32)

@@ -130,3 +130,263 @@ def test_gpu_equals_reference(c):
         assert np.array_equal(pcm.view(np.uint32), pcm_ref.view(np.uint32)), "GPU PCM differs from the reference's decodeAeaPcm"
     finally:
         ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Stage by stage: what the reference's own stage closures hand to each other (tools/ref_run_qjs_driver.js
+# runStages), and single-function known answers (runKats).  Present when the dump came from tools/ref_run_qjs.py.
+HAVE_STAGES = HAVE and os.path.exists(os.path.join(REF, "stages.npz")) and os.path.exists(os.path.join(REF, "kat.json"))
+needs_stages = pytest.mark.skipif(not HAVE_STAGES, reason="tests/golden/ref/stages.npz absent (written by tools/ref_run_qjs.py)")
+
+
+def f32bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def unhex_arr(h, dtype):
+    return np.frombuffer(bytes.fromhex(h), dtype).copy()
+
+
+def ulp_distance(a, b):
+    a = np.asarray(a, np.float64).view(np.int64)
+    b = np.asarray(b, np.float64).view(np.int64)
+    return np.abs(a - b)
+
+
+@needs_stages
+@pytest.mark.parametrize("c", cases(), ids=[c["name"] for c in cases()])
+def test_oracle_stages_equal_reference(oracle, c):
+    O = oracle
+    doc = ref_tables()
+    t = fill_tables(O.Tables(), doc)
+    z = np.load(os.path.join(REF, "stages.npz"))
+    ref = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(c["name"] + "/")}
+    s16, _, _ = load_case(c)
+    n_frames = ref["su"].shape[1]
+    worst_score, exact_with_host_libm = 0, True
+    for ch in range(c["channels"]):
+        x = np.zeros(n_frames * 512, np.float32)
+        x[:s16.shape[0]] = O.int16_to_pcm(s16[:, ch].copy())
+        opts = O.make_options(threshold=c["threshold"], bias=c["bias"], fixed_modes=c["fixed_modes"], tables=t)
+        for i, v in enumerate(biased(doc, c["bias"])):
+            opts.biased_sf[i] = float(v)
+        enc, dec = O.FrameEncoder(opts, t), O.FrameDecoder(t)
+        for f in range(n_frames):
+            fr, dbg = enc(x[512 * f:512 * f + 512], debug=True)
+            where = (c["name"], ch, f)
+            assert np.array_equal(f32bits(dbg.bands), f32bits(ref["enc_bands"][ch, f])), (where, "qmfAnalysisStage bands")
+            if not c["fixed_modes"]:
+                assert np.array_equal(f32bits(dbg.mags), f32bits(ref["enc_mags"][ch, f])), (where, "performFFT magnitudes")
+                # the score passes through log / exp / log10 / log1p: the engine that wrote the dump used the host's
+                # glibc, the oracle uses the fdlibm port V8 carries; both are faithfully rounded, not identical
+                worst_score = max(worst_score, int(ulp_distance(list(dbg.score), ref["enc_scores"][ch, f]).max()))
+                if f:  # with the engine's libm the score itself is bit-identical
+                    O.set_host_libm(True)
+                    try:
+                        off = 0
+                        for b, nb in enumerate((64, 64, 128)):
+                            s = O.transient_score(np.array(dbg.mags[off:off + nb], np.float32), ref["enc_mags"][ch, f - 1][off:off + nb])
+                            exact_with_host_libm &= bool(ulp_distance([s], [ref["enc_scores"][ch, f][b]])[0] == 0)
+                            off += nb
+                    finally:
+                        O.set_host_libm(False)
+            assert list(fr.modes) == list(ref["enc_modes"][ch, f]), (where, "block modes")
+            assert np.array_equal(f32bits(dbg.coefs), f32bits(ref["enc_coefs"][ch, f])), (where, "mdctStage coefficients")
+            n = fr.n_bfu
+            assert n == int(ref["n_bfu"][ch, f]), (where, "nBfu")
+            assert list(fr.sfi)[:n] == list(ref["sfi"][ch, f][:n]), (where, "scaleFactorIndices")
+            assert list(fr.wl)[:n] == list(ref["wl"][ch, f][:n]), (where, "wordLengthIndices")
+            q = np.array([list(row) for row in fr.q], np.int32)[:n]
+            assert np.array_equal(q, ref["q"][ch, f][:n]), (where, "quantizedCoefficients")
+            su = O.serialize_frame(fr)
+            assert np.array_equal(su, ref["su"][ch, f]), (where, "serializeFrame")
+            pcm, ddbg = dec(O.deserialize_frame(su), debug=True)
+            assert np.array_equal(f32bits(ddbg.coefs), f32bits(ref["dec_coefs"][ch, f])), (where, "dequantizationStage")
+            assert np.array_equal(f32bits(ddbg.bands), f32bits(ref["dec_bands"][ch, f])), (where, "imdctStage")
+            assert np.array_equal(f32bits(pcm), f32bits(ref["dec_pcm"][ch, f])), (where, "qmfSynthesisStage")
+    assert exact_with_host_libm, "transient score differs from the engine's even with the engine's libm"
+    assert worst_score <= 64, "transient score (fdlibm) differs from the engine's (glibc) by %d ulp" % worst_score
+
+
+@needs_stages
+def test_oracle_function_kats(oracle):
+    """FFT.fft, MDCT / IMDCT.transform, qmfAnalysis / qmfSynthesis, overlapAdd, findScaleFactor, quantize, dequantize,
+    groupIntoBFUs + allocateBits, packBits, performFFT, detectTransient: each called alone inside the engine."""
+    O = oracle
+    doc = ref_tables()
+    t = fill_tables(O.Tables(), doc)
+    kat = json.load(open(os.path.join(REF, "kat.json")))
+    f4 = "<f4"
+    for k in kat["fft"]:
+        re, im = O.fft(unhex_arr(k["re_in"], f4), unhex_arr(k["im_in"], f4), t)
+        assert np.array_equal(f32bits(re), f32bits(unhex_arr(k["re"], f4))) and np.array_equal(f32bits(im), f32bits(unhex_arr(k["im"], f4))), ("fft", k["n"])
+    for k in kat["mdct"]:
+        assert np.array_equal(f32bits(O.mdct(unhex_arr(k["x"], f4), t)), f32bits(unhex_arr(k["y"], f4))), ("mdct", k["n"])
+    for k in kat["imdct"]:
+        assert np.array_equal(f32bits(O.imdct(unhex_arr(k["x"], f4), t)), f32bits(unhex_arr(k["y"], f4))), ("imdct", k["n"])
+    for k in kat["qmf_analysis"]:
+        lo, hi, d = O.qmf_analysis(unhex_arr(k["x"], f4), unhex_arr(k["delay"], f4))
+        for got, want in ((lo, "low"), (hi, "high"), (d, "new_delay")):
+            assert np.array_equal(f32bits(got), f32bits(unhex_arr(k[want], f4))), ("qmfAnalysis", want)
+    for k in kat["qmf_synthesis"]:
+        out, d = O.qmf_synthesis(unhex_arr(k["low"], f4), unhex_arr(k["high"], f4), unhex_arr(k["delay"], f4))
+        assert np.array_equal(f32bits(out), f32bits(unhex_arr(k["out"], f4))) and np.array_equal(f32bits(d), f32bits(unhex_arr(k["new_delay"], f4))), "qmfSynthesis"
+    for k in kat["overlap_add"]:
+        got = O.overlap_add(unhex_arr(k["prev"], f4), unhex_arr(k["curr"], f4), unhex_arr(k["window"], "<f8"))
+        assert np.array_equal(f32bits(got), f32bits(unhex_arr(k["out"], f4))), "overlapAdd"
+    for k in kat["find_scale_factor"]:
+        x = unhex_arr(k["x"], f4)
+        assert O.find_scale_factor(x) == k["sfi"], ("findScaleFactor", x.tolist())
+    for k in kat["quantize"]:
+        assert np.array_equal(O.quantize(unhex_arr(k["x"], f4), k["sfi"], k["bits"], t), unhex_arr(k["q"], "<i4")), ("quantize", k["sfi"], k["bits"])
+    for k in kat["dequantize"]:
+        got = O.dequantize(unhex_arr(k["q"], "<i4"), k["sfi"], k["bits"], t)
+        assert np.array_equal(f32bits(got), f32bits(unhex_arr(k["x"], f4))), ("dequantize", k["sfi"], k["bits"])
+    for k in kat["allocate_bits"]:
+        opts = O.make_options(bias=k["bias"], tables=t)
+        n, sfi, wl = O.allocate_bits(unhex_arr(k["coefs"], f4), k["modes"], opts)
+        assert n == k["n_bfu"], ("allocateBits bfuCount", k["modes"], k["bias"])
+        assert np.array_equal(wl[:n], unhex_arr(k["wl"], "<i4")[:n]), ("allocateBits allocation", k["modes"], k["bias"])
+        assert np.array_equal(sfi[:n], unhex_arr(k["sfi"], "<i4")[:n]), ("allocateBits scaleFactorIndices", k["modes"], k["bias"])
+    for k in kat["perform_fft"]:
+        x = unhex_arr(k["x"], f4)
+        assert np.array_equal(f32bits(O.perform_fft(x, k["size"], t)), f32bits(unhex_arr(k["mag"], f4))), "performFFT"
+    # detectTransient: the decision, and the score itself (recovered from the unmodified function by bisection over the
+    # threshold).  With the libm of the engine that wrote the dump the score is bit-identical; with the fdlibm port
+    # (V8's libm, the oracle's default and what the CUDA path carries) it is the same to rounding noise, which the
+    # sqrt of a near-zero flatness change amplifies (the `cur = 1.01 * prev` cases)
+    for k in kat["detect_transient"]:
+        cur, prev = unhex_arr(k["cur"], f4), unhex_arr(k["prev"], f4)
+        want = np.array([int(k["score"], 16)], np.uint64).view(np.float64)[0]
+        O.set_host_libm(True)
+        try:
+            assert ulp_distance([O.transient_score(cur, prev)], [want])[0] == 0, "transient score with the engine's libm"
+            assert int(O.detect_transient(cur, prev, k["threshold"])) == k["transient"], "detectTransient"
+        finally:
+            O.set_host_libm(False)
+        got = O.transient_score(cur, prev)
+        assert abs(got - want) <= 1e-10 * max(abs(want), 1e-300), "transient score with fdlibm: %r vs %r" % (got, want)
+        if abs(got - k["threshold"]) > 1e-9:
+            assert int(O.detect_transient(cur, prev, k["threshold"])) == k["transient"], "detectTransient"
+
+
+def test_pack_bits_kats(oracle):
+    if not HAVE_STAGES:
+        pytest.skip("no kat.json")
+    import ctypes as C
+
+    kat = json.load(open(os.path.join(REF, "kat.json")))
+    L = oracle.lib()
+    for k in kat["pack_bits"]:
+        buf = np.zeros(16, np.uint8)
+        for pos, val, cnt in k["ops"]:
+            L.c1o_pack_bits(buf.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_size_t(16), C.c_int(pos), C.c_int(val), C.c_int(cnt))
+        assert buf.tobytes().hex() == k["bytes"], k["ops"]
+
+
+# ---------------------------------------------------------------------------------------------------
+# The parity suite's own inputs (tests/test_gpu_parity.py: mono_signals x OPTION_SETS, non-finite PCM, random bytes
+# as sound units, ragged stereo) through the reference's encodeAeaPcm / decodeAeaPcm.
+HAVE_BATTERY = HAVE and os.path.exists(os.path.join(REF, "battery.npz"))
+needs_battery = pytest.mark.skipif(not HAVE_BATTERY, reason="tests/golden/ref/battery.npz absent (written by tools/ref_run_qjs.py)")
+
+
+def battery_inputs():
+    """Rebuilds the inputs tools/ref_run_qjs.py fed to the reference and checks them against the recorded hashes."""
+    import hashlib
+    import importlib.util
+    import sys
+
+    spec = importlib.util.spec_from_file_location("ref_run_qjs", os.path.join(HERE, "..", "tools", "ref_run_qjs.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules.setdefault("ref_run_qjs", mod)
+    spec.loader.exec_module(mod)
+    meta = json.load(open(os.path.join(REF, "battery.json")))
+    out = mod.battery_cases()
+    assert set(out) == set(meta)
+    for name, (chans, kw, units, n_ch) in out.items():
+        blobs = [np.ascontiguousarray(c, np.float32).tobytes() for c in chans] if chans is not None else [units.tobytes()]
+        assert [hashlib.sha256(b).hexdigest() for b in blobs] == meta[name]["input_sha256"], "input of %s is not what the reference was fed" % name
+    return out
+
+
+@needs_battery
+def test_oracle_battery_equals_reference(oracle):
+    O = oracle
+    doc = ref_tables()
+    t = fill_tables(O.Tables(), doc)
+    z = np.load(os.path.join(REF, "battery.npz"))
+    n_checked = 0
+    for name, (chans, kw, units, n_ch) in battery_inputs().items():
+        if chans is not None:
+            opts = O.make_options(threshold=kw.get("threshold", 1.0), bias=kw.get("bias", 1.0), fixed_modes=kw.get("fixed_modes"), tables=t)
+            su = O.encode_pcm(chans, opts, tables=t)
+            assert np.array_equal(su, z[name + "/su"]), (name, "sound units")
+        else:
+            su = units
+        pcm = np.stack(O.decode_su(su, n_ch, tables=t))
+        assert np.array_equal(f32bits(pcm), f32bits(z[name + "/pcm"])), (name, "pcm")
+        n_checked += 1
+    assert n_checked >= 100
+
+
+@pytest.mark.gpu
+@needs_battery
+def test_gpu_battery_equals_reference():
+    import carta1_b200
+    from carta1_b200._lib import Tables
+
+    doc = ref_tables()
+    t = fill_tables(Tables(), doc)
+    z = np.load(os.path.join(REF, "battery.npz"))
+    ctx = carta1_b200.Context(0, t)
+    try:
+        for name, (chans, kw, units, n_ch) in battery_inputs().items():
+            if chans is not None:
+                opts = carta1_b200.make_enc_opts(kw.get("threshold", 1.0), kw.get("bias", 1.0), kw.get("fixed_modes"))
+                su = ctx.encode_pcm(chans, opts)
+                assert np.array_equal(su, z[name + "/su"]), (name, "sound units")
+            else:
+                su = units
+            pcm = np.stack(ctx.decode_su(su, n_ch))
+            assert np.array_equal(f32bits(pcm), f32bits(z[name + "/pcm"])), (name, "pcm")
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+@needs_stages
+@pytest.mark.parametrize("c", cases(), ids=[c["name"] for c in cases()])
+def test_gpu_stages_equal_reference(c):
+    """Every f32 intermediate of the CUDA path against what the reference's stage closures produced."""
+    import carta1_b200
+    from carta1_b200._lib import Tables
+
+    doc = ref_tables()
+    t = fill_tables(Tables(), doc)
+    z = np.load(os.path.join(REF, "stages.npz"))
+    ref = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(c["name"] + "/")}
+    s16, _, _ = load_case(c)
+    ctx = carta1_b200.Context(0, t)
+    try:
+        opts = carta1_b200.make_enc_opts(c["threshold"], c["bias"], c["fixed_modes"], biased_scale_factors=biased(doc, c["bias"]))
+        for ch in range(c["channels"]):
+            pcm = (s16[:, ch].astype(np.float64) / 32768.0).astype(np.float32)
+            got = ctx.debug_encode_stages(pcm, opts)
+            assert np.array_equal(f32bits(got["bands"]), f32bits(ref["enc_bands"][ch])), (ch, "bands")
+            if not c["fixed_modes"]:
+                assert np.array_equal(f32bits(got["mags"]), f32bits(ref["enc_mags"][ch])), (ch, "mags")
+                scores = ctx.debug_transient_scores(pcm, opts)
+                assert ulp_distance(scores, ref["enc_scores"][ch]).max() <= 64, (ch, "scores")
+            assert np.array_equal(got["modes"], ref["enc_modes"][ch]), (ch, "modes")
+            assert np.array_equal(f32bits(got["coefs"]), f32bits(ref["enc_coefs"][ch])), (ch, "coefs")
+            assert np.array_equal(got["su"], ref["su"][ch]), (ch, "su")
+            fr = ctx.deserialize_units(ref["su"][ch])
+            n = ref["n_bfu"][ch]
+            assert np.array_equal(fr["n_bfu"], n), (ch, "nBfu")
+            dec = ctx.debug_decode_stages(ref["su"][ch])
+            assert np.array_equal(f32bits(dec["coefs"]), f32bits(ref["dec_coefs"][ch])), (ch, "dequantised")
+            assert np.array_equal(f32bits(dec["bands"]), f32bits(ref["dec_bands"][ch])), (ch, "imdct bands")
+            assert np.array_equal(f32bits(dec["pcm"]), f32bits(ref["dec_pcm"][ch])), (ch, "pcm")
+    finally:
+        ctx.close()

@@ -196,6 +196,61 @@ def stage_reference(ref_root, scratch):
 
 
 # ---------------------------------------------------------------------------------------------------
+def battery_cases():
+    """The inputs of tests/test_gpu_parity.py (mono_signals x OPTION_SETS, the non-finite injections, random
+    sound units): name -> (channels or None, option dict or None, raw units or None, channel count)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_gpu_parity as T
+
+    out = {}
+    for si, (name, pcm) in enumerate(T.mono_signals().items()):
+        for oi, kw in enumerate(T.OPTION_SETS):
+            out["%s|%d" % (name, oi)] = ([pcm], kw, None, 1)
+    rng = np.random.default_rng(3)  # test_non_finite_input
+    for ii, inject in enumerate(((np.inf,), (-np.inf,), (np.nan,), (3e38, -3e38), (np.inf, np.nan, -3e38, 3e38, -np.inf))):
+        pcm = (0.3 * rng.standard_normal(512 * 8)).astype(np.float32)
+        for i, v in enumerate(inject):
+            pcm[700 + 611 * i] = v
+        for oi, kw in enumerate([dict(), dict(fixed_modes=[0, 0, 0]), dict(fixed_modes=[2, 2, 3]), dict(bias=2.5)]):
+            out["nonfinite%d|%d" % (ii, oi)] = ([pcm], kw, None, 1)
+    rng = np.random.default_rng(5)
+    out["random_units_mono"] = (None, None, rng.integers(0, 256, (48, 212), dtype=np.uint8), 1)
+    out["random_units_stereo_odd"] = (None, None, rng.integers(0, 256, (33, 212), dtype=np.uint8), 2)
+    st = [T.S.cfg1_stereo(0.12)[0], T.S.cfg1_stereo(0.12)[1][:3000]]  # ragged stereo: the shorter channel is padded
+    out["stereo_ragged|0"] = (st, dict(), None, 2)
+    return out
+
+
+def js_options(kw):
+    o = {}
+    if "threshold" in kw:
+        o["transientThresholdLow"] = kw["threshold"]
+    if "bias" in kw:
+        o["allocationBias"] = kw["bias"]
+    if kw.get("fixed_modes"):
+        o["fixedBlockModes"] = kw["fixed_modes"]
+    return o
+
+
+def battery(eng, out_dir):
+    res, meta = {}, {}
+    for name, (chans, kw, units, n_ch) in battery_cases().items():
+        if chans is not None:
+            chans = [np.ascontiguousarray(c, np.float32) for c in chans]
+            eng.evaluate("setInputF32(%s)" % json.dumps([hex_of(c) for c in chans]))
+            aea = np.frombuffer(bytes.fromhex(eng.evaluate("runEncode(%s)" % json.dumps(js_options(kw)))), np.uint8)
+            res[name + "/su"] = aea[2048:].reshape(-1, 212).copy()
+            meta[name] = {"input_sha256": [hashlib.sha256(c.tobytes()).hexdigest() for c in chans], "options": kw, "channels": n_ch}
+        else:
+            eng.evaluate("aeaOf(%s, %d)" % (json.dumps(hex_of(units)), n_ch))
+            meta[name] = {"input_sha256": [hashlib.sha256(units.tobytes()).hexdigest()], "channels": n_ch}
+        res[name + "/pcm"] = np.frombuffer(bytes.fromhex(eng.evaluate("runDecode()")), "<f4").reshape(n_ch, -1).copy()
+    np.savez_compressed(os.path.join(out_dir, "battery.npz"), **res)
+    with open(os.path.join(out_dir, "battery.json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print("battery: %d runs of the parity suite's inputs through encodeAeaPcm / decodeAeaPcm" % len(meta))
+
+
 def hex_of(a):
     return np.ascontiguousarray(a).tobytes().hex()
 
@@ -251,6 +306,8 @@ def main():
                 stages[c["name"] + "/" + k] = np.frombuffer(bytes.fromhex(v["hex"]), dt).reshape(v["shape"])
             print("%-32s %d ch, %d samples, %d sound units" % (c["name"], c["channels"], s16.shape[0], (len(aea) - 2048) // 212))
         np.savez_compressed(os.path.join(out_dir, "stages.npz"), **stages)
+
+        battery(eng, out_dir)
 
         kat = json.loads(eng.evaluate("JSON.stringify(runKats())"))
         with open(os.path.join(out_dir, "kat.json"), "w") as f:

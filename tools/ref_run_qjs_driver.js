@@ -87,6 +87,49 @@ function setInput(hex, nCh) {
   for (var i = 0; i < n; i++) for (var c = 0; c < nCh; c++) channels[c][i] = dv.getInt16((i * nCh + c) * 2, true) / 32768.0
   return n
 }
+function setInputF32(hexes) {
+  channels = hexes.map(function (hx) { var b = fromHex(hx); return new Float32Array(b.buffer) })
+  return channels.length
+}
+function setAea(hex) {
+  lastAea = fromHex(hex)
+  return lastAea.length
+}
+function aeaOf(unitsHex, nCh) {
+  // a complete AEA image around caller-supplied sound units: the reference's own header writer
+  var units = fromHex(unitsHex)
+  var header = SER.AeaFile.createHeader('arbitrary', units.length / 212, nCh)
+  var all = new Uint8Array(header.length + units.length)
+  all.set(header, 0)
+  all.set(units, header.length)
+  lastAea = all
+  return all.length
+}
+// detectTransient returns only `score > threshold` (transient.js:54) and the score function is not exported;
+// the exact binary64 score is recovered from the unmodified function by bisection over the threshold's bit pattern.
+function scoreOf(cur, prev) {
+  if (!TR.detectTransient(cur, prev, 0)) return TR.detectTransient(cur, prev, -1) ? 0 : -1
+  var dv = new DataView(new ArrayBuffer(8))
+  function f(hiWord, loWord) { dv.setUint32(0, hiWord, false); dv.setUint32(4, loWord, false); return dv.getFloat64(0, false) }
+  if (TR.detectTransient(cur, prev, f(0x7ff00000, 0))) return Infinity
+  // the smallest bit pattern t (as a 64-bit integer, positive doubles are ordered like their patterns) with
+  // !(score > f(t)) is the score itself; 32 steps for the high word, 32 for the low one
+  var lo = 0, hi = 0x7ff00000 // score > f(lo, 0), !(score > f(hi, 0))
+  while (hi - lo > 1) {
+    var mid = Math.floor((lo + hi) / 2)
+    if (TR.detectTransient(cur, prev, f(mid, 0))) lo = mid
+    else hi = mid
+  }
+  // score lies in (f(lo,0), f(hi,0)] : either f(hi,0) itself or f(lo, x) for the smallest x with !(score > f(lo,x))
+  if (TR.detectTransient(cur, prev, f(lo, 0xffffffff))) return f(hi, 0)
+  var a = 0, b = 0xffffffff // score > f(lo,a), !(score > f(lo,b))
+  while (b - a > 1) {
+    var m = Math.floor((a + b) / 2)
+    if (TR.detectTransient(cur, prev, f(lo, m))) a = m
+    else b = m
+  }
+  return f(lo, b)
+}
 function runEncode(options) {
   lastAea = carta1.encodeAeaPcm(channels, options) // codec/io/processor.js:597-617
   return hexOfBytes(lastAea)
@@ -116,7 +159,7 @@ function runStages(optionValues) {
   var nBfu = new Int32Array(nCh * nFrames), sfi = new Int32Array(nCh * nFrames * 52), wl = new Int32Array(nCh * nFrames * 52)
   var q = new Int32Array(nCh * nFrames * 52 * 20), su = new Uint8Array(nCh * nFrames * 212)
   var dcoefs = new Float32Array(nCh * nFrames * 512), dbands = new Float32Array(nCh * nFrames * 512)
-  var dpcm = new Float32Array(nCh * nFrames * 512)
+  var dpcm = new Float32Array(nCh * nFrames * 512), scores = new Float64Array(nCh * nFrames * 3)
   for (var ch = 0; ch < nCh; ch++) {
     var ectx = { options: new OPT.EncoderOptions(optionValues), bufferPool: new BUF.BufferPool() }
     var s1 = ENC.qmfAnalysisStage(ectx), s2 = ENC.blockSelectorStage(ectx), s3 = ENC.mdctStage(ectx), s4 = ENC.quantizationStage(ectx)
@@ -132,7 +175,12 @@ function runStages(optionValues) {
       if (!ectx.options.fixedBlockModes) {
         // performFFT is a pure function of the band (transient.js:17-35): calling it again changes nothing
         var off = 0
-        for (var b = 0; b < 3; b++) { mags.set(TR.performFFT(a.bands[b], fftSizes[b]), u * 256 + off); off += fftSizes[b] / 2 }
+        for (var b = 0; b < 3; b++) {
+          var mg = TR.performFFT(a.bands[b], fftSizes[b])
+          mags.set(mg, u * 256 + off)
+          off += fftSizes[b] / 2
+          scores[u * 3 + b] = scoreOf(mg, ectx.bufferPool.transientDetection[b])
+        }
       }
       var bsel = s2(a)
       for (var b2 = 0; b2 < 3; b2++) modes[u * 3 + b2] = bsel.blockModes[b2]
@@ -161,7 +209,7 @@ function runStages(optionValues) {
     n_bfu: packed('i32', [nCh, nFrames], nBfu), sfi: packed('i32', [nCh, nFrames, 52], sfi), wl: packed('i32', [nCh, nFrames, 52], wl),
     q: packed('i32', [nCh, nFrames, 52, 20], q), su: packed('u8', [nCh, nFrames, 212], su),
     dec_coefs: packed('f32', [nCh, nFrames, 512], dcoefs), dec_bands: packed('f32', [nCh, nFrames, 512], dbands),
-    dec_pcm: packed('f32', [nCh, nFrames, 512], dpcm),
+    dec_pcm: packed('f32', [nCh, nFrames, 512], dpcm), enc_scores: packed('f64', [nCh, nFrames, 3], scores),
   }
 }
 
@@ -272,7 +320,8 @@ function runKats() {
       var m1 = TR.performFFT(x1, t[1]), m2 = TR.performFFT(x2, t[1])
       out.perform_fft.push({ x: h(x1), size: t[1], mag: h(m1) })
       var thr = [0.05, 0.3, 1, 3][r % 4]
-      out.detect_transient.push({ prev: h(m1), cur: h(m2), threshold: thr, transient: TR.detectTransient(m2, m1, thr) ? 1 : 0 })
+      out.detect_transient.push({ prev: h(m1), cur: h(m2), threshold: thr, transient: TR.detectTransient(m2, m1, thr) ? 1 : 0,
+                                  score: f64hex(scoreOf(m2, m1)) })
     }
   })
   return out
