@@ -291,16 +291,24 @@ HAVE_BATTERY = HAVE and os.path.exists(os.path.join(REF, "battery.npz"))
 needs_battery = pytest.mark.skipif(not HAVE_BATTERY, reason="tests/golden/ref/battery.npz absent (written by tools/ref_run_qjs.py)")
 
 
-def battery_inputs():
-    """Rebuilds the inputs tools/ref_run_qjs.py fed to the reference and checks them against the recorded hashes."""
-    import hashlib
+def ref_tool():
+    """tools/ref_run_qjs.py as a module: the input builders and checksum helpers the dump was made with."""
     import importlib.util
     import sys
 
-    spec = importlib.util.spec_from_file_location("ref_run_qjs", os.path.join(HERE, "..", "tools", "ref_run_qjs.py"))
-    mod = importlib.util.module_from_spec(spec)
-    sys.modules.setdefault("ref_run_qjs", mod)
-    spec.loader.exec_module(mod)
+    if "ref_run_qjs" not in sys.modules:
+        spec = importlib.util.spec_from_file_location("ref_run_qjs", os.path.join(HERE, "..", "tools", "ref_run_qjs.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["ref_run_qjs"] = mod
+        spec.loader.exec_module(mod)
+    return sys.modules["ref_run_qjs"]
+
+
+def battery_inputs():
+    """Rebuilds the inputs tools/ref_run_qjs.py fed to the reference and checks them against the recorded hashes."""
+    import hashlib
+
+    mod = ref_tool()
     meta = json.load(open(os.path.join(REF, "battery.json")))
     out = mod.battery_cases()
     assert set(out) == set(meta)
@@ -325,7 +333,7 @@ def test_oracle_battery_equals_reference(oracle):
         else:
             su = units
         pcm = np.stack(O.decode_su(su, n_ch, tables=t))
-        assert np.array_equal(f32bits(pcm), f32bits(z[name + "/pcm"])), (name, "pcm")
+        assert np.array_equal(ref_tool().frame_crcs(pcm), z[name + "/pcm_crc"]), (name, "pcm")
         n_checked += 1
     assert n_checked >= 100
 
@@ -349,7 +357,7 @@ def test_gpu_battery_equals_reference():
             else:
                 su = units
             pcm = np.stack(ctx.decode_su(su, n_ch))
-            assert np.array_equal(f32bits(pcm), f32bits(z[name + "/pcm"])), (name, "pcm")
+            assert np.array_equal(ref_tool().frame_crcs(pcm), z[name + "/pcm_crc"]), (name, "pcm")
     finally:
         ctx.close()
 
@@ -388,5 +396,76 @@ def test_gpu_stages_equal_reference(c):
             assert np.array_equal(f32bits(dec["coefs"]), f32bits(ref["dec_coefs"][ch])), (ch, "dequantised")
             assert np.array_equal(f32bits(dec["bands"]), f32bits(ref["dec_bands"][ch])), (ch, "imdct bands")
             assert np.array_equal(f32bits(dec["pcm"]), f32bits(ref["dec_pcm"][ch])), (ch, "pcm")
+    finally:
+        ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Seconds-long runs (BASELINE configs[0] is 10 s stereo with auto block modes): the golden inputs tiled, the
+# reference's output kept as checksums (sha256 of the whole image, CRC-32 per sound unit and per PCM frame).
+HAVE_LONG = HAVE and os.path.exists(os.path.join(REF, "long.npz"))
+needs_long = pytest.mark.skipif(not HAVE_LONG, reason="tests/golden/ref/long.npz absent (written by tools/ref_run_qjs.py)")
+
+
+def long_list():
+    if not HAVE_LONG:
+        return []
+    meta = json.load(open(os.path.join(REF, "long.json")))
+    return [c for c in cases() if c["name"] in meta]
+
+
+def check_long(c, su, pcm):
+    import hashlib
+
+    T = ref_tool()
+    meta = json.load(open(os.path.join(REF, "long.json")))[c["name"]]
+    z = np.load(os.path.join(REF, "long.npz"))
+    bad = np.nonzero(T.unit_crcs(su) != z[c["name"] + "/su_crc"])[0]
+    assert bad.size == 0, "sound units %r differ from the reference's" % bad[:8].tolist()
+    assert su.shape[0] == meta["sound_units"]
+    hdr = np.fromfile(os.path.join(REF, c["name"] + ".aea"), np.uint8)[:2048].copy()
+    hdr[260:264] = np.frombuffer(np.uint32(su.shape[0]).tobytes(), np.uint8)  # frame count field of the AEA header
+    assert hashlib.sha256(hdr.tobytes() + su.tobytes()).hexdigest() == meta["aea_sha256"], "AEA image"
+    bad = np.argwhere(T.frame_crcs(pcm) != z[c["name"] + "/pcm_crc"])
+    assert bad.size == 0, "PCM frames %r differ from the reference's" % bad[:8].tolist()
+    assert hashlib.sha256(np.ascontiguousarray(pcm, "<f4").tobytes()).hexdigest() == meta["pcm_sha256"], "PCM"
+
+
+@needs_long
+@pytest.mark.parametrize("c", long_list(), ids=[c["name"] for c in long_list()])
+def test_oracle_long_runs_equal_reference(oracle, c):
+    import hashlib
+
+    O, T = oracle, ref_tool()
+    doc = ref_tables()
+    t = fill_tables(O.Tables(), doc)
+    meta = json.load(open(os.path.join(REF, "long.json")))[c["name"]]
+    s16 = T.long_input(os.path.join(REF, "inputs"), c, meta["seconds"])
+    assert hashlib.sha256(s16.tobytes()).hexdigest() == meta["input_sha256"]
+    chans = [O.int16_to_pcm(s16[:, ch].copy()) for ch in range(c["channels"])]
+    opts = O.make_options(threshold=c["threshold"], bias=c["bias"], fixed_modes=c["fixed_modes"], tables=t)
+    su = O.encode_pcm(chans, opts, tables=t, threads=4, chunk_frames=64)
+    pcm = np.stack(O.decode_su(su, c["channels"], tables=t, threads=4, chunk_frames=64))
+    check_long(c, su, pcm)
+
+
+@pytest.mark.gpu
+@needs_long
+@pytest.mark.parametrize("c", long_list(), ids=[c["name"] for c in long_list()])
+def test_gpu_long_runs_equal_reference(c):
+    import carta1_b200
+    from carta1_b200._lib import Tables
+
+    T = ref_tool()
+    doc = ref_tables()
+    t = fill_tables(Tables(), doc)
+    meta = json.load(open(os.path.join(REF, "long.json")))[c["name"]]
+    s16 = T.long_input(os.path.join(REF, "inputs"), c, meta["seconds"])
+    ctx = carta1_b200.Context(0, t)
+    try:
+        opts = carta1_b200.make_enc_opts(c["threshold"], c["bias"], c["fixed_modes"], biased_scale_factors=biased(doc, c["bias"]))
+        su = ctx.encode_pcm_s16(s16, c["channels"], opts)
+        pcm = np.stack(ctx.decode_su(su, c["channels"]))
+        check_long(c, su, pcm)
     finally:
         ctx.close()

@@ -244,11 +244,66 @@ def battery(eng, out_dir):
         else:
             eng.evaluate("aeaOf(%s, %d)" % (json.dumps(hex_of(units)), n_ch))
             meta[name] = {"input_sha256": [hashlib.sha256(units.tobytes()).hexdigest()], "channels": n_ch}
-        res[name + "/pcm"] = np.frombuffer(bytes.fromhex(eng.evaluate("runDecode()")), "<f4").reshape(n_ch, -1).copy()
+        pcm = np.frombuffer(bytes.fromhex(eng.evaluate("runDecode()")), "<f4").reshape(n_ch, -1)
+        res[name + "/pcm_crc"] = frame_crcs(pcm)  # [channel][frame] CRC-32 of the frame's 2048 bytes
+        meta[name]["pcm_sha256"] = hashlib.sha256(pcm.tobytes()).hexdigest()
     np.savez_compressed(os.path.join(out_dir, "battery.npz"), **res)
     with open(os.path.join(out_dir, "battery.json"), "w") as f:
         json.dump(meta, f, indent=1)
     print("battery: %d runs of the parity suite's inputs through encodeAeaPcm / decodeAeaPcm" % len(meta))
+
+
+def frame_crcs(pcm):
+    """pcm [channels][frames * 512] f32 -> uint32 [channels][frames], CRC-32 of each frame's bytes."""
+    import zlib
+
+    pcm = np.ascontiguousarray(pcm, "<f4")
+    return np.array([[zlib.crc32(row[f * 512:(f + 1) * 512].tobytes()) for f in range(row.shape[0] // 512)] for row in pcm], np.uint32)
+
+
+def unit_crcs(su):
+    import zlib
+
+    su = np.ascontiguousarray(su, np.uint8).reshape(-1, 212)
+    return np.array([zlib.crc32(u.tobytes()) for u in su], np.uint32)
+
+
+LONG_CASES = {  # golden input (tests/golden/ref/inputs/<name>.s16) repeated to this many seconds
+    "cfg1_sine_noise_auto": 10.0,      # BASELINE configs[0]: 10 s stereo, default bias, auto block modes
+    "cfg3_transients_auto": 10.0,
+    "cfg2_chirp_fixed_long": 5.0,
+}
+
+
+def long_input(in_dir, c, seconds):
+    """The case's int16 input tiled to `seconds` (a seam every repetition: a few more transients, nothing else)."""
+    s16 = np.fromfile(os.path.join(in_dir, c["name"] + ".s16"), "<i2").reshape(-1, c["channels"])
+    reps = int(np.ceil(seconds * 44100 / s16.shape[0]))
+    return np.ascontiguousarray(np.tile(s16, (reps, 1))[:int(round(seconds * 44100))])
+
+
+def long_cases(eng, out_dir, in_dir, cases):
+    """Seconds-long runs: only checksums are kept (sha256 of the whole output, CRC-32 per sound unit / PCM frame)."""
+    res, meta = {}, {}
+    for c in cases:
+        if c["name"] not in LONG_CASES:
+            continue
+        s16 = long_input(in_dir, c, LONG_CASES[c["name"]])
+        opts = {"transientThresholdLow": c["threshold"], "allocationBias": c["bias"]}
+        if c["fixed_modes"]:
+            opts["fixedBlockModes"] = c["fixed_modes"]
+        eng.evaluate("setInput(%s, %d)" % (json.dumps(hex_of(s16)), c["channels"]))
+        aea = np.frombuffer(bytes.fromhex(eng.evaluate("runEncode(%s)" % json.dumps(opts))), np.uint8)
+        pcm = np.frombuffer(bytes.fromhex(eng.evaluate("runDecode()")), "<f4").reshape(c["channels"], -1)
+        res[c["name"] + "/su_crc"] = unit_crcs(aea[2048:])
+        res[c["name"] + "/pcm_crc"] = frame_crcs(pcm)
+        meta[c["name"]] = {"seconds": LONG_CASES[c["name"]], "samples": int(s16.shape[0]), "channels": c["channels"],
+                           "input_sha256": hashlib.sha256(s16.tobytes()).hexdigest(), "sound_units": int((len(aea) - 2048) // 212),
+                           "aea_sha256": hashlib.sha256(aea.tobytes()).hexdigest(), "pcm_sha256": hashlib.sha256(pcm.tobytes()).hexdigest()}
+        print("long %-28s %.0f s, %d sound units" % (c["name"], LONG_CASES[c["name"]], meta[c["name"]]["sound_units"]))
+    np.savez_compressed(os.path.join(out_dir, "long.npz"), **res)
+    with open(os.path.join(out_dir, "long.json"), "w") as f:
+        json.dump(meta, f, indent=1)
 
 
 def hex_of(a):
@@ -308,6 +363,7 @@ def main():
         np.savez_compressed(os.path.join(out_dir, "stages.npz"), **stages)
 
         battery(eng, out_dir)
+        long_cases(eng, out_dir, in_dir, cases)
 
         kat = json.loads(eng.evaluate("JSON.stringify(runKats())"))
         with open(os.path.join(out_dir, "kat.json"), "w") as f:
