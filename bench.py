@@ -288,8 +288,9 @@ def run_reference(args, rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample, "threads": threads,
-                   "note": "reference = C restatement of carta1's JS algorithm (oracle/): no JavaScript engine "
-                           "exists in this image, so the JS reference itself cannot run"},
+                   "note": "reference = C restatement of carta1's JS algorithm (oracle/), bit-identical to the output of the "
+                           "JavaScript itself on the pinned inputs (tests/golden/ref); the JavaScript cannot travel to "
+                           "the GPU box (no reference sources in the repo, no Node there)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -966,10 +967,24 @@ def run_ours(args, rank, local_rank, world):
                                             pcm_ref[c][: (k // 2) * 512].view(np.uint32)) for c in range(2))
             line["cpu_baseline"] = {
                 "value": (ns / SR) / (te + td), "unit": UNIT, "cores": threads, "kind": "port",
-                "sample": "first %.0f s of the same stereo PCM, encode+decode, %d threads (C restatement; no JS engine in the image)" % (ns / SR, threads),
+                "sample": "first %.0f s of the same stereo PCM, encode+decode, %d threads (C restatement of the reference, itself pinned to the reference's output: reference_pin)" % (ns / SR, threads),
                 "encode_only": (ns / SR) / te, "decode_only": (ns / SR) / td,
                 "gpu_output_bit_exact_on_sample": parity and gpu_pcm_ok and local_ok and host_ok,
             }
+            # ---- and against the reference itself: the bytes carta1's own JavaScript wrote for the golden inputs
+            # (tests/golden/ref, produced by tools/ref_run_qjs.py in the build image; /root/reference does not exist
+            # on this box, so the committed output is what the CUDA path is held to)
+            from oracle import refpin
+
+            if refpin.available():
+                from carta1_b200._lib import Tables
+
+                try:
+                    line["reference_pin"] = refpin.check_context(
+                        lambda t: carta1_b200.Context(torch.cuda.current_device(), t),
+                        lambda thr, bias, fixed, bsf: carta1_b200.make_enc_opts(thr, bias, fixed, biased_scale_factors=bsf), Tables)
+                except AssertionError as ex:
+                    line["reference_pin"] = {"equal_to_reference_output": False, "first_difference": str(ex)}
     del works, hosts
     torch.cuda.empty_cache()
     # ---- the other BASELINE configs, rank 0 only (the other ranks wait at the barrier)

@@ -6,12 +6,23 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may build, load or call it.  The product path (carta1_b200/) never does.
  *
- * PARITY STATUS: "parity unpinned" for AEA bytes and decoded PCM.  The reference ships
- * no golden vectors and no JavaScript engine exists in this image,
- * so the reference cannot be executed here.  The oracle is pinned against every exact
- * known-answer value the reference's tests do hold (tests/bitstream.test.js:6-71,
- * tests/mdct.test.js:22-33) and against all structural / tolerance assertions of the
- * reference test-suite (tests/test_oracle_reference_suite.py restates them).
+ * PARITY STATUS: PINNED against outputs of the reference itself, run in the build image.
+ * The reference ships no golden vectors and the image has no Node, but
+ * Nsight Compute ships Qt 6.6.3, whose QJSEngine is a complete ECMAScript engine:
+ * tools/ref_run_qjs.py lets it import the reference's own modules from /root/reference
+ * (every file that holds codec arithmetic byte for byte as shipped) and records, under
+ * tests/golden/ref/, the AEA bytes and decoded PCM of encodeAeaPcm / decodeAeaPcm for the
+ * golden inputs, what the reference's stage closures hand to each other, known answers of
+ * each function alone, the parity suite's 122 inputs and seconds-long runs.  This oracle
+ * equals every one of them bit for bit (tests/test_reference_pin.py), and so does the CUDA
+ * path.  What the engine does not pin is V8's libm: Qt's engine calls the host's glibc, V8
+ * carries fdlibm ports.  libm enters in two places only: the sin/cos/pow tables, which are
+ * inputs (c1o_tables; the dump's are used for the comparison), and the transient score's
+ * log/exp/log10/log1p, where this file carries the fdlibm port by default and the host's
+ * libm behind c1o_set_host_libm(1) (bit-identical scores with the dump's engine).
+ * It is also pinned against every exact known-answer value the reference's tests hold
+ * (tests/bitstream.test.js:6-71, tests/mdct.test.js:22-33) and against all structural /
+ * tolerance assertions of the reference test-suite (tests/test_oracle_reference_suite.py).
  *
  * Numerical contract: every typed-array store is a round to
  * binary32, every expression between stores is IEEE binary64 evaluated one operator at a

@@ -1,7 +1,9 @@
 """oracle_np.py -- a SECOND, independent restatement of carta1's ATRAC1 encode/decode hot path.
 
-TEST INFRASTRUCTURE ONLY (tests/ may import it; the product never does).  Parity unpinned: no JavaScript
-engine exists in this image, so neither restatement has been run against the reference itself.
+TEST INFRASTRUCTURE ONLY (tests/ may import it; the product never does).  It predates the reference pin
+(tests/golden/ref, tools/ref_run_qjs.py: the reference's own JavaScript under Qt's QJSEngine), which now pins
+oracle/carta1_oracle.c directly; it stays as a cross-check and as the glibc-libm twin of the transient score
+(its scores equal the engine's bit for bit).
 
 Why it exists: oracle/carta1_oracle.c is what every GPU parity test compares against, and it was written
 by reading the reference.  This module was written separately, again from the reference's JavaScript, in

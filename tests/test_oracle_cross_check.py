@@ -1,6 +1,6 @@
 """The C oracle against the second, independent restatement (oracle/oracle_np.py): two transcriptions of the
-reference's JavaScript must agree bit for bit on sound units, block modes and decoded PCM.  (Neither has run
-against the reference itself: no JavaScript engine in this image -- DESIGN.md section 3.)"""
+reference's JavaScript must agree bit for bit on sound units, block modes and decoded PCM.  (The pin against
+the reference itself is tests/test_reference_pin.py -- DESIGN.md section 3.)"""
 import numpy as np
 import pytest
 

@@ -1,17 +1,17 @@
-"""The reference-side pin: oracle (CPU) and CUDA path against what the REAL carta1 wrote under Node.
+"""The reference-side pin: oracle (CPU) and CUDA path against what the REAL carta1 produced.
 
-tools/ref_dump.mjs runs aynik/carta1's own encodeAeaPcm / decodeAeaPcm (codec/io/processor.js:597-654) on
-the inputs of tests/golden/*.npz and dumps V8's libm-derived tables.  No JavaScript engine exists in the
-build image, so the dump cannot be produced there and every test below is SKIPPED until a maintainer
-with Node >= 20.16 has run (see README.md, "Pinning against the reference"):
+tests/golden/ref/ holds output of aynik/carta1's own JavaScript: tools/ref_run_qjs.py runs it in the build image under
+Qt's QJSEngine (shipped inside Nsight Compute; there is no Node), tools/ref_dump.mjs does the file-level part under
+Node >= 20.16 for whoever has one.  The dump carries the tables its engine computed; they are injected (the C ABI takes
+them as input: include/carta1_b200.h carta1_tables), so the comparison is independent of the engine's libm, and
+test_default_tables_against_v8 reports separately whether the library's built-in default tables equal the dump's.
 
     python tests/golden/make_golden.py --export-ref-inputs
-    node tools/ref_dump.mjs /path/to/carta1
+    python tools/ref_run_qjs.py                 # or: node tools/ref_dump.mjs /path/to/carta1
     python -m pytest tests/test_reference_pin.py            # add -m gpu on a B200 box
 
-With the dump present the tests demand byte equality of the AEA image and bit equality of the decoded
-PCM, with V8's tables injected (the C ABI takes them as input: include/carta1_b200.h carta1_tables) --
-and report separately whether the library's built-in default tables (glibc sin/cos/pow) equal V8's.
+Every comparison is bit for bit: AEA bytes and decoded PCM of encodeAeaPcm / decodeAeaPcm, every stage's output,
+single-function known answers, the parity suite's inputs, seconds-long runs.
 """
 import glob
 import json
@@ -24,7 +24,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(HERE, "golden", "ref")
 HAVE = os.path.exists(os.path.join(REF, "tables.json")) and os.path.exists(os.path.join(REF, "inputs", "cases.json"))
-pytestmark = pytest.mark.skipif(not HAVE, reason="tests/golden/ref/ absent: run tools/ref_dump.mjs under Node (unrunnable in the build image)")
+pytestmark = pytest.mark.skipif(not HAVE, reason="tests/golden/ref/ absent: run tools/ref_run_qjs.py (or tools/ref_dump.mjs under Node)")
 
 TABLE_FIELDS = ["window_short", "scale_factors", "mdct_fwd64", "mdct_fwd256", "mdct_fwd512", "mdct_inv64", "mdct_inv256",
                 "mdct_inv512"]
@@ -137,6 +137,12 @@ def test_gpu_equals_reference(c):
 # runStages), and single-function known answers (runKats).  Present when the dump came from tools/ref_run_qjs.py.
 HAVE_STAGES = HAVE and os.path.exists(os.path.join(REF, "stages.npz")) and os.path.exists(os.path.join(REF, "kat.json"))
 needs_stages = pytest.mark.skipif(not HAVE_STAGES, reason="tests/golden/ref/stages.npz absent (written by tools/ref_run_qjs.py)")
+
+
+def frame_crcs(pcm):
+    from oracle import refpin
+
+    return refpin.frame_crcs(pcm)
 
 
 def f32bits(a):
@@ -333,7 +339,7 @@ def test_oracle_battery_equals_reference(oracle):
         else:
             su = units
         pcm = np.stack(O.decode_su(su, n_ch, tables=t))
-        assert np.array_equal(ref_tool().frame_crcs(pcm), z[name + "/pcm_crc"]), (name, "pcm")
+        assert np.array_equal(frame_crcs(pcm), z[name + "/pcm_crc"]), (name, "pcm")
         n_checked += 1
     assert n_checked >= 100
 
@@ -357,7 +363,7 @@ def test_gpu_battery_equals_reference():
             else:
                 su = units
             pcm = np.stack(ctx.decode_su(su, n_ch))
-            assert np.array_equal(ref_tool().frame_crcs(pcm), z[name + "/pcm_crc"]), (name, "pcm")
+            assert np.array_equal(frame_crcs(pcm), z[name + "/pcm_crc"]), (name, "pcm")
     finally:
         ctx.close()
 
@@ -415,20 +421,9 @@ def long_list():
 
 
 def check_long(c, su, pcm):
-    import hashlib
+    from oracle import refpin
 
-    T = ref_tool()
-    meta = json.load(open(os.path.join(REF, "long.json")))[c["name"]]
-    z = np.load(os.path.join(REF, "long.npz"))
-    bad = np.nonzero(T.unit_crcs(su) != z[c["name"] + "/su_crc"])[0]
-    assert bad.size == 0, "sound units %r differ from the reference's" % bad[:8].tolist()
-    assert su.shape[0] == meta["sound_units"]
-    hdr = np.fromfile(os.path.join(REF, c["name"] + ".aea"), np.uint8)[:2048].copy()
-    hdr[260:264] = np.frombuffer(np.uint32(su.shape[0]).tobytes(), np.uint8)  # frame count field of the AEA header
-    assert hashlib.sha256(hdr.tobytes() + su.tobytes()).hexdigest() == meta["aea_sha256"], "AEA image"
-    bad = np.argwhere(T.frame_crcs(pcm) != z[c["name"] + "/pcm_crc"])
-    assert bad.size == 0, "PCM frames %r differ from the reference's" % bad[:8].tolist()
-    assert hashlib.sha256(np.ascontiguousarray(pcm, "<f4").tobytes()).hexdigest() == meta["pcm_sha256"], "PCM"
+    refpin.check_long(c, su, pcm)
 
 
 @needs_long
