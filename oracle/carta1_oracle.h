@@ -111,6 +111,11 @@ typedef struct c1o_dec_debug {
 
 /* ---- tables / options ---- */
 void c1o_default_tables(c1o_tables *t);          /* glibc libm */
+void c1o_fdlibm_tables(c1o_tables *t);           /* the same with fdlibm's sin / cos / pow (V8 <= 11.3): fdlibm_trig_pow.c */
+double c1o_fd_sin(double x);
+double c1o_fd_cos(double x);
+double c1o_fd_pow(double x, double y);
+int c1o_fd_selfcheck(void);                      /* 0 = every fdlibm constant's decimal and bit pattern agree */
 const float *c1o_qmf_even(void);                 /* 24 taps */
 const float *c1o_qmf_odd(void);
 const int *c1o_specs_per_bfu(void);

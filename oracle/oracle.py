@@ -23,8 +23,9 @@ AEA_HEADER = 2048
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "carta1_oracle.c")
     hdr = os.path.join(_HERE, "carta1_oracle.h")
+    fd = os.path.join(_HERE, "fdlibm_trig_pow.c")
     stale = (not os.path.exists(_SO)) or any(
-        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr)
+        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr, fd)
     )
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
@@ -113,6 +114,12 @@ def lib():
         ip = C.POINTER(C.c_int)
         u8 = C.POINTER(C.c_uint8)
         L.c1o_default_tables.argtypes = [C.POINTER(Tables)]
+        L.c1o_fdlibm_tables.argtypes = [C.POINTER(Tables)]
+        for name in ("c1o_fd_sin", "c1o_fd_cos"):
+            getattr(L, name).argtypes = [C.c_double]
+            getattr(L, name).restype = C.c_double
+        L.c1o_fd_pow.argtypes = [C.c_double, C.c_double]
+        L.c1o_fd_pow.restype = C.c_double
         L.c1o_qmf_even.restype = fp
         L.c1o_qmf_odd.restype = fp
         L.c1o_specs_per_bfu.restype = ip
@@ -185,6 +192,17 @@ def default_tables() -> Tables:
         lib().c1o_default_tables(C.byref(t))
         _default_tables = t
     return _default_tables
+
+
+def fdlibm_tables() -> Tables:
+    """default_tables() with fdlibm's sin / cos / pow (what V8 <= 11.3 computes) instead of the host libm's."""
+    t = Tables()
+    lib().c1o_fdlibm_tables(C.byref(t))
+    return t
+
+
+def fd_pow(x: float, y: float) -> float:
+    return lib().c1o_fd_pow(C.c_double(x), C.c_double(y))
 
 
 def make_options(threshold=1.0, bias=1.0, fixed_modes=None, tables=None) -> Options:

@@ -464,3 +464,56 @@ def test_gpu_long_runs_equal_reference(c):
         check_long(c, su, pcm)
     finally:
         ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# V8's libm.  The dump's engine (Qt's) calls glibc; V8 <= 11.3 (Node 20) carries fdlibm's sin / cos / pow, restated in
+# oracle/fdlibm_trig_pow.c.  How much of the output depends on which of the two built the tables?
+def test_fdlibm_restatement_selfcheck(oracle):
+    import math
+
+    L = oracle.lib()
+    assert L.c1o_fd_selfcheck() == 0, "a fdlibm constant's decimal and bit pattern disagree"
+    rng = np.random.default_rng(1)
+    xs = rng.uniform(-7, 7, 20000)
+    for fd, ref in ((L.c1o_fd_sin, math.sin), (L.c1o_fd_cos, math.cos)):
+        assert max(ulp_distance([fd(float(x))], [ref(float(x))])[0] for x in xs) <= 1
+    for x, y in zip(rng.uniform(1e-7, 2, 20000), rng.uniform(-6, 6, 20000)):
+        assert ulp_distance([oracle.fd_pow(float(x), float(y))], [math.pow(float(x), float(y))])[0] <= 1
+    for i in range(64):  # Math.pow(2.0, i / 3.0 - 21): fdlibm and glibc agree on every scale factor
+        assert oracle.fd_pow(2.0, i / 3.0 - 21) == math.pow(2.0, i / 3.0 - 21)
+
+
+@needs_long
+def test_table_flavours(oracle):
+    """glibc-built tables (the library's default, and the dump's engine) against fdlibm-built ones (V8 <= 11.3): a few
+    dozen of the ~930 entries differ in the last bit or two, and no emitted byte or decoded sample of the pinned runs
+    (4,480 sound units, 2.3 M samples) changes.  (30 minutes of cfg1 / cfg2 / cfg3 material: none either)"""
+    from oracle import refpin as R
+
+    O = oracle
+    d, f = O.default_tables(), O.fdlibm_tables()
+    differing = 0
+    for name in R.TABLE_FIELDS:
+        a, b = np.array(list(getattr(d, name))), np.array(list(getattr(f, name)))
+        dist = ulp_distance(a, b)
+        assert dist.max() <= 2, name
+        differing += int((dist != 0).sum())
+    assert 0 < differing < 64  # the two libms are not identical, and nearly so
+    for c in R.cases():
+        runs = [R.load_case(c)[0]]
+        if c["name"] in R.long_meta():
+            runs.append(R.long_input(c, R.long_meta()[c["name"]]["seconds"]))
+        for s16 in runs:
+            ch = [O.int16_to_pcm(s16[:, k].copy()) for k in range(c["channels"])]
+            og = O.make_options(threshold=c["threshold"], bias=c["bias"], fixed_modes=c["fixed_modes"], tables=d)
+            of = O.make_options(threshold=c["threshold"], bias=c["bias"], fixed_modes=c["fixed_modes"], tables=f)
+            if c["bias"] != 1:
+                for i in range(64):
+                    of.biased_sf[i] = O.fd_pow(f.scale_factors[i], c["bias"])
+            su_g = O.encode_pcm(ch, og, tables=d, threads=4, chunk_frames=64)
+            su_f = O.encode_pcm(ch, of, tables=f, threads=4, chunk_frames=64)
+            assert np.array_equal(su_g, su_f), (c["name"], "sound units depend on the libm that built the tables")
+            p_g = np.stack(O.decode_su(su_g, c["channels"], tables=d, threads=4, chunk_frames=64))
+            p_f = np.stack(O.decode_su(su_g, c["channels"], tables=f, threads=4, chunk_frames=64))
+            assert np.array_equal(f32bits(p_g), f32bits(p_f)), (c["name"], "PCM depends on the libm that built the tables")
