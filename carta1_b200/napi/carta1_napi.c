@@ -7,9 +7,11 @@
  * AudioProcessor streams through the functions below.  No arithmetic happens here or in the
  * JS wrapper: typed arrays in, typed arrays out.
  *
- * Node is not present in the build image, so this file is syntax-checked against
- * node_api_min.h (hand-declared Node-API subset) by __graft_entry__.build() and has never been
- * loaded into a JS engine; binding.gyp builds it against Node's own headers.
+ * Node is not present in the build image.  __graft_entry__.build() compiles this file, unchanged, against
+ * node_api_min.h (hand-declared Node-API subset) and links it with tests/napi_host/napi_host.c, a minimal
+ * Node-API host; tests/test_napi_host.py then calls every export the way index.mjs does (on a B200 against
+ * the reference's own bytes).  It has never been loaded into Node itself; binding.gyp builds it against
+ * Node's own headers.
  *
  * Exports (all synchronous unless noted):
  *   createContext(device, tables|null)                        -> ctx

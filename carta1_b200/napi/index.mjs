@@ -9,7 +9,7 @@
  *   encodeAeaPcm / decodeAeaPcm          one GPU pass over the whole buffer
  *   AudioProcessor.encodeStream / decodeStream / encodeAeaPcm / decodeAeaPcm
  *
- * NOTE: never executed in the build image (no Node there); see INTEGRATION.md.
+ * NOTE: never executed in the build image (no Node there); the addon below it is (tests/test_napi_host.py); see INTEGRATION.md.
  */
 import { createRequire } from 'node:module'
 import * as ref from 'carta1'

@@ -3,7 +3,7 @@
  * carta1_napi.c uses, declared by hand.
  *
  * Node is not installed in the build image, so there is no node_api.h to
- * compile against.  build() syntax-checks the shim against these declarations; a real build
+ * compile against.  build() compiles the shim against these declarations (and links it with tests/napi_host); a real build
  * (binding.gyp) uses Node's own header instead (CARTA1_NAPI_USE_NODE_HEADERS).
  * Names, enum values and signatures follow the stable Node-API ABI.
  */
