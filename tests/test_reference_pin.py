@@ -517,3 +517,148 @@ def test_table_flavours(oracle):
             p_g = np.stack(O.decode_su(su_g, c["channels"], tables=d, threads=4, chunk_frames=64))
             p_f = np.stack(O.decode_su(su_g, c["channels"], tables=f, threads=4, chunk_frames=64))
             assert np.array_equal(f32bits(p_g), f32bits(p_f)), (c["name"], "PCM depends on the libm that built the tables")
+
+
+# ---------------------------------------------------------------------------------------------------
+# WAV int16 emit: the reference's createWavBlob (processor.js:349-447: clip to [-1, 1], scale by 32768
+# below zero and 32767 above, DataView.setInt16 = ToInt16) on decoded frames, incl. samples far beyond +-1.
+HAVE_WAV = HAVE and os.path.exists(os.path.join(REF, "wav.npz"))
+needs_wav = pytest.mark.skipif(not HAVE_WAV, reason="tests/golden/ref/wav.npz absent (written by tools/ref_run_qjs.py)")
+
+
+def wav_inputs():
+    """name -> (sound units [n][212], channel count) of every run whose WAV the reference wrote."""
+    meta = json.load(open(os.path.join(REF, "wav.json")))
+    bat = np.load(os.path.join(REF, "battery.npz"))
+    units = None
+    out = {}
+    for name, m in meta.items():
+        if os.path.exists(os.path.join(REF, name + ".aea")):
+            su = np.fromfile(os.path.join(REF, name + ".aea"), np.uint8)[2048:].reshape(-1, 212)
+        elif name + "/su" in bat.files:
+            su = bat[name + "/su"]
+        else:
+            units = units or battery_inputs()
+            su = units[name][2]
+        out[name] = (np.ascontiguousarray(su), m["channels"])
+    return out
+
+
+def check_wav(name, s16):
+    import hashlib
+
+    meta = json.load(open(os.path.join(REF, "wav.json")))[name]
+    z = np.load(os.path.join(REF, "wav.npz"))
+    data = np.ascontiguousarray(s16, "<i2").tobytes()
+    got = ref_tool().wav_frame_crcs(data, meta["channels"])
+    bad = np.nonzero(got != z[name + "/crc"])[0]
+    assert bad.size == 0, (name, "WAV frames %r differ from the reference's" % bad[:8].tolist())
+    assert hashlib.sha256(data).hexdigest() == meta["data_sha256"], name
+
+
+@needs_wav
+def test_oracle_wav_int16_equals_reference(oracle):
+    O = oracle
+    t = fill_tables(O.Tables(), ref_tables())
+    clipped = 0
+    for name, (su, n_ch) in wav_inputs().items():
+        pcm = O.decode_su(su, n_ch, tables=t)
+        s16 = np.stack([O.pcm_to_int16(p) for p in pcm], axis=1)
+        clipped += int((np.abs(np.stack(pcm)) > 1).sum())
+        check_wav(name, s16)
+    assert clipped > 1000  # the clipping branch is exercised (random bytes as sound units, the loud signal)
+
+
+@pytest.mark.gpu
+@needs_wav
+def test_gpu_wav_int16_equals_reference():
+    import carta1_b200
+    from carta1_b200._lib import Tables
+
+    t = fill_tables(Tables(), ref_tables())
+    ctx = carta1_b200.Context(0, t)
+    try:
+        for name, (su, n_ch) in wav_inputs().items():
+            check_wav(name, ctx.decode_su_s16(su, n_ch))
+    finally:
+        ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# The public surface as a caller uses it: encodeAeaPcm(channels, {title, per-band thresholds, unknown keys ...}) -> a
+# whole AEA file, header included; and what `new EncoderOptions(x)` holds or throws (codec/core/options.js:67-109).
+HAVE_API = HAVE and os.path.exists(os.path.join(REF, "api.npz"))
+needs_api = pytest.mark.skipif(not HAVE_API, reason="tests/golden/ref/api.npz absent (written by tools/ref_run_qjs.py)")
+
+
+def api_inputs():
+    import hashlib
+
+    import test_gpu_parity as T
+
+    doc = json.load(open(os.path.join(REF, "api.json")))
+    z = np.load(os.path.join(REF, "api.npz"))
+    sig = T.mono_signals()
+    out = {}
+    for name, m in doc["cases"].items():
+        pcm = np.ascontiguousarray(sig[m["signal"]][:m["samples"]], np.float32)
+        assert hashlib.sha256(pcm.tobytes()).hexdigest() == m["input_sha256"], name
+        out[name] = (pcm, m["options"], z[name + "/aea"])
+    return out
+
+
+@needs_api
+def test_option_trials_match_reference():
+    from carta1_b200 import codec
+
+    doc = json.load(open(os.path.join(REF, "api.json")))
+    checked = 0
+    for t in doc["option_trials"]:
+        if any(isinstance(v, str) for v in t["options"].values()):
+            continue  # JavaScript's string-to-number coercion in `<` is not mirrored
+        want = t["result"]
+        try:
+            got = codec.EncoderOptions(t["options"]).toObject()["values"]
+        except ValueError as ex:
+            assert "error" in want and str(ex) == want["error"], (t["options"], str(ex), want)
+        else:
+            assert "values" in want and got == want["values"], (t["options"], got, want)
+        checked += 1
+    assert checked >= 12
+
+
+@needs_api
+def test_oracle_api_files_equal_reference(oracle):
+    from carta1_b200 import codec
+
+    O = oracle
+    t = fill_tables(O.Tables(), ref_tables())
+    for name, (pcm, options, aea) in api_inputs().items():
+        title = options.get("title", "encoded by carta1")
+        fixed = options.get("fixedBlockModes")
+        opts = O.make_options(threshold=options.get("transientThresholdLow", 1.0), bias=options.get("allocationBias", 1.0),
+                              fixed_modes=fixed, tables=t)  # Mid / High thresholds are never read (encoder.js:137-141)
+        su = O.encode_pcm([pcm], opts, tables=t)
+        assert np.array_equal(O.aea_header(title, su.shape[0], 1), aea[:2048]), (name, "AEA header (oracle)")
+        assert np.array_equal(np.asarray(codec.AeaFile.createHeader(title, su.shape[0], 1)), aea[:2048]), (name, "AEA header (C ABI)")
+        assert np.array_equal(su.reshape(-1), aea[2048:]), (name, "sound units")
+        info = codec.AeaFile.parseHeader(aea[:2048])
+        assert (info["title"], info["frameCount"], info["channelCount"]) == (title, su.shape[0], 1), name
+
+
+@pytest.mark.gpu
+@needs_api
+def test_gpu_mirror_api_files_equal_reference():
+    """carta1_b200.codec (the mirror of carta1's index.js) called the way a user of carta1 calls it."""
+    import carta1_b200
+    from carta1_b200 import codec
+    from carta1_b200._lib import Tables
+
+    t = fill_tables(Tables(), ref_tables())
+    ctx = carta1_b200.Context(0, t)
+    try:
+        for name, (pcm, options, aea) in api_inputs().items():
+            got = codec.encodeAeaPcm([pcm], dict(options), ctx=ctx)
+            assert np.array_equal(np.asarray(got, np.uint8), aea), (name, "AEA file")
+    finally:
+        ctx.close()

@@ -26,6 +26,9 @@ reads either):
     stages.npz         per-stage outputs of the reference's own stage functions on the same inputs
                        (qmfAnalysisStage bands, performFFT magnitudes, transient scores, block modes,
                        mdctStage coefficients, the frame object; dequantised coefficients, IMDCT bands, PCM)
+    wav.npz, wav.json  the CLI's decode-to-WAV route (createWavBlob: clip, scale by 32767 / 32768, ToInt16): CRC-32 per frame
+    api.npz, api.json  whole AEA files (header included) for caller-shaped options (title, per-band thresholds, unknown keys),
+                       and what `new EncoderOptions(x)` holds or throws for a list of trials
     kat.json           known answers of single functions (FFT.fft, MDCT/IMDCT transform, qmfAnalysis /
                        qmfSynthesis, findScaleFactor, quantize / dequantize, allocateBits, packBits)
 
@@ -221,6 +224,40 @@ def battery_cases():
     return out
 
 
+API_CASES = {  # options exactly as a caller of carta1's index.js passes them (title included): name -> (signal, options)
+    "api_title_and_band_thresholds": ("transients", {"title": "hello B200", "transientThresholdLow": 0.3, "transientThresholdMid": 0.01,
+                                                     "transientThresholdHigh": 4.0}),
+    "api_bias_fixed_modes": ("chirp", {"allocationBias": 2.5, "fixedBlockModes": [0, 2, 0]}),
+    "api_defaults": ("sine_noise", {}),
+    "api_unknown_keys_ignored": ("white", {"notAnOption": 7, "title": ""}),
+}
+OPTION_TRIALS = [
+    {}, {"transientThresholdLow": 0.01}, {"transientThresholdLow": 2}, {"transientThresholdLow": 2.5}, {"transientThresholdLow": 0.001},
+    {"transientThresholdMid": 3.5}, {"transientThresholdHigh": 4.01}, {"allocationBias": -0.1}, {"allocationBias": 5}, {"allocationBias": 5.5},
+    {"fixedBlockModes": [2, 2, 3]}, {"fixedBlockModes": None}, {"bogus": 1}, {"transientThresholdLow": "1.5"},
+]
+
+
+def api_cases(eng, out_dir):
+    """Whole AEA files (header included) for caller-shaped options, and EncoderOptions validation trials."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_gpu_parity as T
+
+    sig = T.mono_signals()
+    files, meta = {}, {}
+    for name, (signal, options) in API_CASES.items():
+        pcm = np.ascontiguousarray(sig[signal][:512 * 9 + 100], np.float32)
+        eng.evaluate("setInputF32(%s)" % json.dumps([hex_of(pcm)]))
+        aea = np.frombuffer(bytes.fromhex(eng.evaluate("runEncode(%s)" % json.dumps(options))), np.uint8)
+        files[name + "/aea"] = aea.copy()
+        meta[name] = {"signal": signal, "samples": int(pcm.size), "options": options, "input_sha256": hashlib.sha256(pcm.tobytes()).hexdigest()}
+    trials = json.loads(eng.evaluate("JSON.stringify(runOptionTrials(%s))" % json.dumps(OPTION_TRIALS)))
+    np.savez_compressed(os.path.join(out_dir, "api.npz"), **files)
+    with open(os.path.join(out_dir, "api.json"), "w") as f:
+        json.dump({"cases": meta, "option_trials": [{"options": t, "result": r} for t, r in zip(OPTION_TRIALS, trials)]}, f, indent=1)
+    print("api: %d whole-file cases, %d option trials" % (len(meta), len(trials)))
+
+
 def js_options(kw):
     o = {}
     if "threshold" in kw:
@@ -232,7 +269,7 @@ def js_options(kw):
     return o
 
 
-def battery(eng, out_dir):
+def battery(eng, out_dir, wavs, wav_meta):
     res, meta = {}, {}
     for name, (chans, kw, units, n_ch) in battery_cases().items():
         if chans is not None:
@@ -247,6 +284,11 @@ def battery(eng, out_dir):
         pcm = np.frombuffer(bytes.fromhex(eng.evaluate("runDecode()")), "<f4").reshape(n_ch, -1)
         res[name + "/pcm_crc"] = frame_crcs(pcm)  # [channel][frame] CRC-32 of the frame's 2048 bytes
         meta[name]["pcm_sha256"] = hashlib.sha256(pcm.tobytes()).hexdigest()
+        if name.startswith("random_units") or name.startswith("loud|") or name.startswith("nonfinite4|"):
+            # decoded samples beyond +-1 (and whatever non-finite input left behind): the WAV writer's clipping and ToInt16
+            wav = bytes.fromhex(eng.evaluate("runWav()"))
+            wavs[name + "/crc"] = wav_frame_crcs(wav[44:], n_ch)
+            wav_meta[name] = {"header": wav[:44].hex(), "data_sha256": hashlib.sha256(wav[44:]).hexdigest(), "channels": n_ch}
     np.savez_compressed(os.path.join(out_dir, "battery.npz"), **res)
     with open(os.path.join(out_dir, "battery.json"), "w") as f:
         json.dump(meta, f, indent=1)
@@ -306,6 +348,14 @@ def long_cases(eng, out_dir, in_dir, cases):
         json.dump(meta, f, indent=1)
 
 
+def wav_frame_crcs(data_bytes, n_ch):
+    """CRC-32 of every 512-sample frame of a WAV data section (interleaved int16)."""
+    import zlib
+
+    step = 512 * 2 * n_ch
+    return np.array([zlib.crc32(data_bytes[i:i + step]) for i in range(0, len(data_bytes), step)], np.uint32)
+
+
 def hex_of(a):
     return np.ascontiguousarray(a).tobytes().hex()
 
@@ -342,7 +392,7 @@ def main():
         with open(os.path.join(out_dir, "tables.json"), "w") as f:
             json.dump(tables, f, indent=1)
 
-        stages = {}
+        stages, wavs, wav_meta = {}, {}, {}
         for c in cases:
             s16 = np.fromfile(os.path.join(in_dir, c["name"] + ".s16"), "<i2").reshape(-1, c["channels"])
             opts = {"transientThresholdLow": c["threshold"], "allocationBias": c["bias"]}
@@ -355,6 +405,9 @@ def main():
             aea.tofile(os.path.join(out_dir, c["name"] + ".aea"))
             pcm = np.frombuffer(bytes.fromhex(eng.evaluate("runDecode()")), "<f4")
             pcm.tofile(os.path.join(out_dir, c["name"] + ".pcm.f32"))
+            wav = bytes.fromhex(eng.evaluate("runWav()"))
+            wavs[c["name"] + "/crc"] = wav_frame_crcs(wav[44:], c["channels"])
+            wav_meta[c["name"]] = {"header": wav[:44].hex(), "data_sha256": hashlib.sha256(wav[44:]).hexdigest(), "channels": c["channels"]}
             doc = json.loads(eng.evaluate("JSON.stringify(runStages(%s))" % json.dumps(opts)))
             for k, v in doc.items():
                 dt = {"f32": "<f4", "f64": "<f8", "u8": np.uint8, "i32": "<i4"}[v["type"]]
@@ -362,8 +415,12 @@ def main():
             print("%-32s %d ch, %d samples, %d sound units" % (c["name"], c["channels"], s16.shape[0], (len(aea) - 2048) // 212))
         np.savez_compressed(os.path.join(out_dir, "stages.npz"), **stages)
 
-        battery(eng, out_dir)
+        battery(eng, out_dir, wavs, wav_meta)
+        np.savez_compressed(os.path.join(out_dir, "wav.npz"), **wavs)
+        with open(os.path.join(out_dir, "wav.json"), "w") as f:
+            json.dump(wav_meta, f, indent=1)
         long_cases(eng, out_dir, in_dir, cases)
+        api_cases(eng, out_dir)
 
         kat = json.loads(eng.evaluate("JSON.stringify(runKats())"))
         with open(os.path.join(out_dir, "kat.json"), "w") as f:

@@ -144,6 +144,29 @@ function runDecode() {
   return hexOf(flat)
 }
 
+// the CLI's decode-to-WAV route: parseAeaBlob -> deserializedFrameStream -> decodeStream -> collectFrames ->
+// createWavBlob (processor.js:147-215, 286-293, 349-447, 511-536); returns the WAV file
+function runWav() {
+  var AP = carta1.AudioProcessor
+  var parsed = AP.parseAeaBlob(new Blob([lastAea]))
+  var frames = AP.deserializedFrameStream(parsed.frameData)
+  var decoded = AP.collectFrames(AP.decodeStream(frames, { channelCount: parsed.info.channelCount }))
+  var wav = AP.createWavBlob(decoded, parsed.info.channelCount)
+  return hexOfBytes(new Uint8Array(wav.arrayBuffer()))
+}
+
+// EncoderOptions as the reference validates them: for each trial either the resulting values or the error text
+function runOptionTrials(trials) {
+  return trials.map(function (t) {
+    try {
+      var o = new OPT.EncoderOptions(t)
+      return { values: o.toObject().values }
+    } catch (e) {
+      return { error: String(e.message), name: e.name }
+    }
+  })
+}
+
 // ---- the same run stage by stage -----------------------------------------------------------------------
 // encode(options) is pipe(context, qmfAnalysisStage, blockSelectorStage, mdctStage, quantizationStage)
 // (codec/pipeline/encoder.js:438-450) and decode() is pipe(context, dequantizationStage, imdctStage,
