@@ -662,3 +662,37 @@ def test_gpu_mirror_api_files_equal_reference():
             assert np.array_equal(np.asarray(got, np.uint8), aea), (name, "AEA file")
     finally:
         ctx.close()
+
+
+@needs_api
+def test_error_texts_and_classes_match_reference():
+    """What carta1 throws for bad input (name and message, recorded from the reference itself) against the Python mirror:
+    Error -> ValueError, TypeError -> TypeError.  All of these are raised before any device work."""
+    from carta1_b200 import codec
+
+    f32 = np.zeros(512, np.float32)
+    calls = {
+        "encodeAeaPcm: no channels": lambda: codec.encodeAeaPcm([]),
+        "encodeAeaPcm: three channels": lambda: codec.encodeAeaPcm([f32, f32, f32]),
+        "encodeAeaPcm: Float64Array channel": lambda: codec.encodeAeaPcm([np.zeros(512, np.float64)]),
+        "encodeAeaPcm: not an array": lambda: codec.encodeAeaPcm(f32),
+        "encodeAeaPcm: option out of range": lambda: codec.encodeAeaPcm([f32], {"allocationBias": 9}),
+        "decodeAeaPcm: string": lambda: codec.decodeAeaPcm("abc"),
+        "decodeAeaPcm: short buffer": lambda: codec.decodeAeaPcm(np.zeros(100, np.uint8)),
+        "decodeAeaPcm: bad magic": lambda: codec.decodeAeaPcm(np.zeros(2048 + 212, np.uint8)),
+        "deserializeFrame: 211 bytes": lambda: codec.deserializeFrame(np.zeros(211, np.uint8)),
+        "deserializeFrame: 213 bytes": lambda: codec.deserializeFrame(np.zeros(213, np.uint8)),
+        "parseHeader: 2047 bytes": lambda: codec.AeaFile.parseHeader(np.zeros(2047, np.uint8)),
+        "parseHeader: bad magic": lambda: codec.AeaFile.parseHeader(np.zeros(2048, np.uint8)),
+        "setValue: unknown option": lambda: codec.EncoderOptions().setValue("x", 1),
+        "getValue: unknown option": lambda: codec.EncoderOptions().getValue("x"),
+        "encodeStream: three channels": lambda: list(codec.AudioProcessor.encodeStream([f32], {"channelCount": 3})),
+        "decodeStream: zero channels": lambda: list(codec.AudioProcessor.decodeStream([], {"channelCount": 0})),
+    }
+    trials = json.load(open(os.path.join(REF, "api.json")))["error_trials"]
+    assert {t[0] for t in trials} == set(calls)
+    for label, name, message in trials:
+        want = {"Error": ValueError, "TypeError": TypeError}[name]
+        with pytest.raises(want) as e:
+            calls[label]()
+        assert type(e.value) is want and str(e.value) == message, (label, type(e.value).__name__, str(e.value), message)

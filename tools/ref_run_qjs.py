@@ -252,9 +252,11 @@ def api_cases(eng, out_dir):
         files[name + "/aea"] = aea.copy()
         meta[name] = {"signal": signal, "samples": int(pcm.size), "options": options, "input_sha256": hashlib.sha256(pcm.tobytes()).hexdigest()}
     trials = json.loads(eng.evaluate("JSON.stringify(runOptionTrials(%s))" % json.dumps(OPTION_TRIALS)))
+    errors = json.loads(eng.evaluate("JSON.stringify(runErrorTrials())"))
     np.savez_compressed(os.path.join(out_dir, "api.npz"), **files)
     with open(os.path.join(out_dir, "api.json"), "w") as f:
-        json.dump({"cases": meta, "option_trials": [{"options": t, "result": r} for t, r in zip(OPTION_TRIALS, trials)]}, f, indent=1)
+        json.dump({"cases": meta, "option_trials": [{"options": t, "result": r} for t, r in zip(OPTION_TRIALS, trials)],
+                   "error_trials": errors}, f, indent=1)
     print("api: %d whole-file cases, %d option trials" % (len(meta), len(trials)))
 
 

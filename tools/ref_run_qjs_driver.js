@@ -167,6 +167,33 @@ function runOptionTrials(trials) {
   })
 }
 
+// what the reference throws for bad input: [label, error name, message] per trial
+function runErrorTrials() {
+  var AP = carta1.AudioProcessor, f32 = new Float32Array(512)
+  function drain(g) { var n = 0; for (var x of g) n++; return n }
+  var trials = [
+    ['encodeAeaPcm: no channels', function () { carta1.encodeAeaPcm([]) }],
+    ['encodeAeaPcm: three channels', function () { carta1.encodeAeaPcm([f32, f32, f32]) }],
+    ['encodeAeaPcm: Float64Array channel', function () { carta1.encodeAeaPcm([new Float64Array(512)]) }],
+    ['encodeAeaPcm: not an array', function () { carta1.encodeAeaPcm(f32) }],
+    ['encodeAeaPcm: option out of range', function () { carta1.encodeAeaPcm([f32], { allocationBias: 9 }) }],
+    ['decodeAeaPcm: string', function () { carta1.decodeAeaPcm('abc') }],
+    ['decodeAeaPcm: short buffer', function () { carta1.decodeAeaPcm(new Uint8Array(100)) }],
+    ['decodeAeaPcm: bad magic', function () { carta1.decodeAeaPcm(new Uint8Array(2048 + 212)) }],
+    ['deserializeFrame: 211 bytes', function () { SER.deserializeFrame(new Uint8Array(211)) }],
+    ['deserializeFrame: 213 bytes', function () { SER.deserializeFrame(new Uint8Array(213)) }],
+    ['parseHeader: 2047 bytes', function () { SER.AeaFile.parseHeader(new Uint8Array(2047)) }],
+    ['parseHeader: bad magic', function () { SER.AeaFile.parseHeader(new Uint8Array(2048)) }],
+    ['setValue: unknown option', function () { new OPT.EncoderOptions().setValue('x', 1) }],
+    ['getValue: unknown option', function () { new OPT.EncoderOptions().getValue('x') }],
+    ['encodeStream: three channels', function () { drain(AP.encodeStream([f32], { channelCount: 3 })) }],
+    ['decodeStream: zero channels', function () { drain(AP.decodeStream([], { channelCount: 0 })) }],
+  ]
+  return trials.map(function (t) {
+    try { t[1](); return [t[0], null, null] } catch (e) { return [t[0], e.name, String(e.message)] }
+  })
+}
+
 // ---- the same run stage by stage -----------------------------------------------------------------------
 // encode(options) is pipe(context, qmfAnalysisStage, blockSelectorStage, mdctStage, quantizationStage)
 // (codec/pipeline/encoder.js:438-450) and decode() is pipe(context, dequantizationStage, imdctStage,
