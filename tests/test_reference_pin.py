@@ -696,3 +696,20 @@ def test_error_texts_and_classes_match_reference():
         with pytest.raises(want) as e:
             calls[label]()
         assert type(e.value) is want and str(e.value) == message, (label, type(e.value).__name__, str(e.value), message)
+
+
+def test_committed_dump_reproduces_from_the_reference():
+    """Where the reference checkout and Qt's engine exist (the build container; not the GPU box), run carta1's own
+    JavaScript again on the file-level cases and require the committed tests/golden/ref bytes: the fixtures are the
+    reference's output, not the oracle's."""
+    import subprocess
+    import sys
+
+    tool = ref_tool()
+    if not os.path.isdir("/root/reference/codec") or tool.find_qt() is None:
+        pytest.skip("no /root/reference or no Qt (libQt6Qml) in this environment")
+    if not HAVE:
+        pytest.skip("tests/golden/ref absent")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "..", "tools", "ref_run_qjs.py"), "--verify"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "verified: carta1" in r.stdout

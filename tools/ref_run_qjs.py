@@ -33,7 +33,8 @@ reads either):
                        qmfSynthesis, findScaleFactor, quantize / dequantize, allocateBits, packBits)
 
 usage:  python tests/golden/make_golden.py --export-ref-inputs
-        python tools/ref_run_qjs.py [/root/reference] [outdir]
+        python tools/ref_run_qjs.py [/root/reference] [outdir]            # writes the dump
+        python tools/ref_run_qjs.py --verify [/root/reference] [outdir]   # re-runs the file-level cases, compares, writes nothing
 """
 import ctypes
 import glob
@@ -362,9 +363,35 @@ def hex_of(a):
     return np.ascontiguousarray(a).tobytes().hex()
 
 
+def verify(eng, out_dir, in_dir, cases, hashes):
+    """--verify: run the reference again on the file-level cases and compare with what is committed; writes nothing."""
+    prov = json.load(open(os.path.join(out_dir, "provenance.json")))
+    bad = [k for k, v in hashes.items() if prov["reference_sha256"].get(k) != v]
+    if bad:
+        print("reference sources differ from the ones the committed dump was made from: %s" % bad)
+        return 1
+    for c in cases:
+        s16 = np.fromfile(os.path.join(in_dir, c["name"] + ".s16"), "<i2").reshape(-1, c["channels"])
+        opts = {"transientThresholdLow": c["threshold"], "allocationBias": c["bias"]}
+        if c["fixed_modes"]:
+            opts["fixedBlockModes"] = c["fixed_modes"]
+        eng.evaluate("setInput(%s, %d)" % (json.dumps(hex_of(s16)), c["channels"]))
+        aea = bytes.fromhex(eng.evaluate("runEncode(%s)" % json.dumps(opts)))
+        pcm = bytes.fromhex(eng.evaluate("runDecode()"))
+        same = (aea == open(os.path.join(out_dir, c["name"] + ".aea"), "rb").read() and
+                pcm == open(os.path.join(out_dir, c["name"] + ".pcm.f32"), "rb").read())
+        print("%-32s %s" % (c["name"], "reproduced" if same else "DIFFERS from the committed dump"))
+        if not same:
+            return 1
+    print("verified: carta1 %s under Qt %s QJSEngine reproduces tests/golden/ref" % (prov["carta1"], eng.version))
+    return 0
+
+
 def main():
-    ref_root = os.path.abspath(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
-    out_dir = os.path.abspath(sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "tests", "golden", "ref"))
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    only_verify = "--verify" in sys.argv[1:]
+    ref_root = os.path.abspath(args[0] if len(args) > 0 else "/root/reference")
+    out_dir = os.path.abspath(args[1] if len(args) > 1 else os.path.join(ROOT, "tests", "golden", "ref"))
     in_dir = os.path.join(out_dir, "inputs")
     if not os.path.exists(os.path.join(in_dir, "cases.json")):
         raise SystemExit("run `python tests/golden/make_golden.py --export-ref-inputs` first")
@@ -384,6 +411,11 @@ def main():
         eng.evaluate(open(os.path.join(HERE, "ref_run_qjs_driver.js")).read(), "ref_run_qjs_driver.js")
 
         cases = json.load(open(os.path.join(in_dir, "cases.json")))
+        if only_verify:
+            rc = verify(eng, out_dir, in_dir, cases, hashes)
+            shutil.rmtree(scratch, ignore_errors=True)
+            sys.stdout.flush()
+            os._exit(rc)
         biases = sorted({c["bias"] for c in cases})
         tables = json.loads(eng.evaluate("JSON.stringify(dumpTables(%s))" % json.dumps(biases)))
         pkg = json.load(open(os.path.join(ref_root, "package.json")))
