@@ -9,7 +9,9 @@
  *   encodeAeaPcm / decodeAeaPcm          one GPU pass over the whole buffer
  *   AudioProcessor.encodeStream / decodeStream / encodeAeaPcm / decodeAeaPcm
  *
- * NOTE: never executed in the build image (no Node there); the addon below it is (tests/test_napi_host.py); see INTEGRATION.md.
+ * NOTE: no Node in the build image.  This file runs there inside Qt's QJSEngine next to the reference, with the addon
+ * replaced by tests/js_layer/mock_native.js (tools/ref_run_qjs.py --check-js-layer); the addon itself runs against
+ * tests/napi_host on the GPU (tests/test_napi_host.py).  See INTEGRATION.md.
  */
 import { createRequire } from 'node:module'
 import * as ref from 'carta1'

@@ -343,3 +343,22 @@ def test_shard_calls_and_finalizer(host):
     host.collect(ctx)
     with pytest.raises(JsError, match="bad or destroyed handle"):
         host.call("createDecoder", ctx, 1)
+
+
+def test_js_layer_runs_next_to_the_reference():
+    """carta1_b200/napi/index.mjs executed: inside Qt's QJSEngine (where the reference itself runs, tools/ref_run_qjs.py)
+    with the addon replaced by tests/js_layer/mock_native.js, i.e. the addon's documented contract implemented over the
+    reference's own functions.  Every public call of the drop-in (encodeAeaPcm, decodeAeaPcm, encode / decode closures,
+    AudioProcessor.encodeStream / decodeStream across a batch boundary, deserializeFrames, the shard calls, error
+    classes, hostTables) must return what the reference returns.  Needs /root/reference and Qt: skipped elsewhere."""
+    import importlib.util
+    import sys
+
+    spec = importlib.util.spec_from_file_location("ref_run_qjs_probe", os.path.join(HERE, "..", "tools", "ref_run_qjs.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    if not os.path.isdir("/root/reference/codec") or tool.find_qt() is None:
+        pytest.skip("no /root/reference or no Qt (libQt6Qml) in this environment")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "..", "tools", "ref_run_qjs.py"), "--check-js-layer"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "js layer: 15 checks, 0 failed" in r.stdout

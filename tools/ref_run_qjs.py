@@ -35,6 +35,7 @@ reads either):
 usage:  python tests/golden/make_golden.py --export-ref-inputs
         python tools/ref_run_qjs.py [/root/reference] [outdir]            # writes the dump
         python tools/ref_run_qjs.py --verify [/root/reference] [outdir]   # re-runs the file-level cases, compares, writes nothing
+        python tools/ref_run_qjs.py --check-js-layer                      # runs carta1_b200/napi/index.mjs next to the reference
 """
 import ctypes
 import glob
@@ -363,6 +364,37 @@ def hex_of(a):
     return np.ascontiguousarray(a).tobytes().hex()
 
 
+INDEX_MJS_RULES = PROCESSOR_RULES + [
+    (r"^import \{ createRequire \} from 'node:module'$", "// (no node:module here)"),
+    (r"^import \* as ref from 'carta1'$", "import * as ref from './carta1/codec/index.js'"),
+    (r"^const native = createRequire\(import\.meta\.url\)\('\./build/Release/carta1_b200\.node'\)$",
+     "const native = __carta1_native  // tests/js_layer/mock_native.js: the addon contract over the reference's functions"),
+    (r"^async function\* ", "function* "),
+    (r"^async function ", "function "),
+]
+
+
+def check_js_layer(eng, scratch, codec_dir):
+    """--check-js-layer: run carta1_b200/napi/index.mjs (the drop-in's JavaScript layer) inside the engine, with the
+    addon replaced by tests/js_layer/mock_native.js, and compare it call by call with the reference."""
+    log = []
+    src = open(os.path.join(ROOT, "carta1_b200", "napi", "index.mjs"), encoding="utf-8").read()
+    with open(os.path.join(scratch, "index_b200.js"), "w", encoding="utf-8") as f:
+        f.write(downlevel(src, INDEX_MJS_RULES, log, "carta1_b200/napi/index.mjs"))
+    print("index.mjs: %d lines downlevelled (async / await / object rest / the two Node imports)" % len(log))
+    js = os.path.join(ROOT, "tests", "js_layer")
+    eng.evaluate(open(os.path.join(js, "mock_native.js")).read(), "mock_native.js")
+    eng.import_module(os.path.join(scratch, "index_b200.js"), "B200")
+    eng.evaluate(open(os.path.join(js, "js_layer_check.js")).read(), "js_layer_check.js")
+    doc = json.loads(eng.evaluate("JSON.stringify(runJsLayerChecks())"))
+    bad = 0
+    for name, ok, detail in doc["results"]:
+        print("%-4s %s%s" % ("ok" if ok else "FAIL", name, "" if ok else "  -- " + detail[:400]))
+        bad += not ok
+    print("js layer: %d checks, %d failed, %d addon calls" % (len(doc["results"]), bad, doc["calls"]))
+    return 1 if bad else 0
+
+
 def verify(eng, out_dir, in_dir, cases, hashes):
     """--verify: run the reference again on the file-level cases and compare with what is committed; writes nothing."""
     prov = json.load(open(os.path.join(out_dir, "provenance.json")))
@@ -390,6 +422,7 @@ def verify(eng, out_dir, in_dir, cases, hashes):
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     only_verify = "--verify" in sys.argv[1:]
+    only_js_layer = "--check-js-layer" in sys.argv[1:]
     ref_root = os.path.abspath(args[0] if len(args) > 0 else "/root/reference")
     out_dir = os.path.abspath(args[1] if len(args) > 1 else os.path.join(ROOT, "tests", "golden", "ref"))
     in_dir = os.path.join(out_dir, "inputs")
@@ -410,6 +443,11 @@ def main():
             eng.import_module(os.path.join(codec, rel), g)
         eng.evaluate(open(os.path.join(HERE, "ref_run_qjs_driver.js")).read(), "ref_run_qjs_driver.js")
 
+        if only_js_layer:
+            rc = check_js_layer(eng, scratch, codec)
+            shutil.rmtree(scratch, ignore_errors=True)
+            sys.stdout.flush()
+            os._exit(rc)
         cases = json.load(open(os.path.join(in_dir, "cases.json")))
         if only_verify:
             rc = verify(eng, out_dir, in_dir, cases, hashes)

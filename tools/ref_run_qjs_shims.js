@@ -42,4 +42,5 @@
       return s
     }
   }
+  if (!g.process) g.process = { env: {} }   // index.mjs reads process.env.CARTA1_B200_DEVICE
 })(this)
