@@ -1,6 +1,6 @@
 """Host-side mirror of carta1's public surface (codec/index.js:26-47) over the C ABI.
 
-The reference's host language is JavaScript; no JavaScript engine exists in this image, so the
+The reference's host language is JavaScript and this image has no Node, so the
 host side above libcarta1_b200.so is written in Python with the reference's own names, argument
 meaning and error behaviour (the N-API shim a Node host would load instead lives in
 carta1_b200/napi/).  Everything numerical happens on the GPU behind the C

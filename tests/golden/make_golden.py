@@ -1,17 +1,17 @@
 #!/usr/bin/env python
 """Regenerates tests/golden/*.npz from the CPU oracle.
 
-PROVENANCE: these vectors come from oracle/ (the C restatement), NOT from carta1 itself -- no
-JavaScript engine exists in the build image, so the reference cannot be executed (SURVEY.md
-8c; "parity unpinned" in oracle/carta1_oracle.h).  They pin the oracle and the CUDA path
-against drift, and are the file a maintainer with Node diffs first: encode the `pcm_s16`
-arrays with carta1 (scaled by 1/32768 as bin/cli.js:395 does) and compare `su`.
+PROVENANCE: these vectors come from oracle/ (the C restatement), NOT from carta1 itself.  They pin the
+oracle and the CUDA path against drift.  Their inputs are also what the reference itself is run on
+(--export-ref-inputs, then tools/ref_run_qjs.py under Qt's QJSEngine in the build image, or
+tools/ref_dump.mjs under Node): tests/golden/ref holds the reference's output, which the `su` and
+`pcm_out` stored here equal byte for byte (tests/test_reference_pin.py).
 
     python tests/golden/make_golden.py                       # rewrites the fixtures in place
     python tests/golden/make_golden.py --export-ref-inputs   # writes tests/golden/ref/inputs/ for tools/ref_dump.mjs
 
 The second form does not touch the fixtures: it unpacks their `pcm_s16` inputs as raw little-endian int16
-files plus a cases.json (channels, options), the form tools/ref_dump.mjs feeds to the real carta1 under Node;
+files plus a cases.json (channels, options), the form tools/ref_run_qjs.py / tools/ref_dump.mjs feed to the real carta1;
 tests/test_reference_pin.py then compares oracle and CUDA path with what the reference wrote.
 """
 import os

@@ -1,5 +1,5 @@
-"""Golden vectors (tests/golden/*.npz, generated from the oracle by make_golden.py; the
-reference itself cannot run in this image): the oracle must keep reproducing them on CPU, the
+"""Golden vectors (tests/golden/*.npz, generated from the oracle by make_golden.py; the same
+inputs run through the reference itself are tests/golden/ref, see test_reference_pin.py): the oracle must keep reproducing them on CPU, the
 CUDA path must reproduce them on the GPU."""
 import glob
 import os

@@ -713,3 +713,14 @@ def test_committed_dump_reproduces_from_the_reference():
     r = subprocess.run([sys.executable, os.path.join(HERE, "..", "tools", "ref_run_qjs.py"), "--verify"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "verified: carta1" in r.stdout
+
+
+@pytest.mark.parametrize("c", cases(), ids=[c["name"] for c in cases()])
+def test_oracle_generated_goldens_equal_the_reference(c):
+    """tests/golden/<case>.npz was generated from the oracle (make_golden.py) before the reference could be run; what it
+    stores equals what the reference wrote for the same input."""
+    z = np.load(os.path.join(HERE, "golden", c["name"] + ".npz"))
+    s16, aea, pcm_ref = load_case(c)
+    assert np.array_equal(z["pcm_s16"], s16)
+    assert np.array_equal(z["su"].reshape(-1), aea[2048:])
+    assert np.array_equal(f32bits(z["pcm_out"]), f32bits(pcm_ref))

@@ -3,7 +3,8 @@
 //
 // Runs the REAL carta1 (aynik/carta1, JavaScript) on the inputs of tests/golden/*.npz and writes what its
 // own code produces, so that the CPU oracle and the CUDA path can be compared with the reference itself
-// instead of with each other.  It cannot run in the build image (no JavaScript engine there); a maintainer
+// instead of with each other.  The build image has no Node (tools/ref_run_qjs.py does the same job there under Qt's
+// QJSEngine and writes the same layout, plus stage dumps and known answers); a maintainer
 // with Node >= 20.16 (the version the reference's CI pins, .github/workflows/ci.yml:24-26) runs:
 //
 //     python tests/golden/make_golden.py --export-ref-inputs      # writes tests/golden/ref/inputs/
