@@ -92,6 +92,31 @@ __device__ __forceinline__ int wl_bits(int wl) { return wl == 0 ? 0 : wl + 1; } 
 // item's first loads pay an L2 hit instead of a DRAM round trip.
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// TMA bulk copy (cp.async.bulk, SASS UBLKCP) of a contiguous, 16-byte aligned block from global into shared memory,
+// completion signalled on an mbarrier: one lane arms the barrier with the byte count and issues one instruction for
+// the whole block; the data goes through the TMA unit, not through the warp's LSU / L1 path.  The streaming QMF
+// kernels stage the next frame (K1: 2 KB of PCM, K7: the 2 KB band record) this way while the current one is
+// filtered.  A warp owns its barrier (arrival count 1); `parity` is the phase bit the caller flips after every wait.
+__device__ __forceinline__ void mbar_init(uint32_t mbar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy (the TMA unit)
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint32_t mbar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+               "l"(gsrc), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra W_%=;\n\t}" ::"r"(mbar),
+      "r"(parity)
+      : "memory");
+}
+
 // Experiment build only (tools/onchip_experiment.sh, -DC1_EXPERIMENT_ONCHIP_INTERMEDIATES; never the shipped library): the
 // band rows between K1 and K3 and the band records between K6 and K7 are aliased onto 64 rows that stay in L1 / L2.
 // The results are garbage; the kernel times bound from above what keeping those intermediates on chip (a K1->K3 /

@@ -622,6 +622,7 @@ struct SyWarpSmem {
   float hd[40 + 256];            // high band with 40 entries of history (39 used)
   float td[512];                 // time-domain band frame: low 128 | mid 128 | high 256
   float tail[48];                // tail16 of the previous unit's three band records
+  unsigned long long mbar, pad;  // the warp's mbarrier: completion of the copy into td
 };
 constexpr size_t kSySmemBytes = sizeof(SyWarpSmem) * kSyWarps;
 
@@ -653,16 +654,15 @@ __device__ __forceinline__ void fir_synthesis(const double *__restrict__ seq, in
   }
 }
 
-// The band record of a unit (512 floats) is fetched straight into S.td with cp.async while the frame before it is being
-// filtered: lane l copies 16-byte chunks l + 32k.  S.td is free from the moment the previous unit's merge has read it
-// (the caller's warp barrier after sy_load_unit) until sy_load_unit of this unit waits for the copy.
+// The band record of a unit (512 floats, 2 KB, 16-byte aligned: context scratch) is fetched straight into S.td with one
+// TMA bulk copy issued by lane 0 while the frame before it is being filtered; completion is a phase of the warp's
+// mbarrier.  S.td is free from the moment the previous unit's merge has read it (the caller's warp barrier after
+// sy_load_unit) until sy_load_unit of this unit waits for the copy.
 __device__ __forceinline__ void sy_prefetch(SyWarpSmem &S, const float *__restrict__ rec, int lane) {
-  const float *src = rec + 4 * lane;
-  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(S.td + 4 * lane);
-#pragma unroll
-  for (int k = 0; k < 4; k++)
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 512 * k), "l"(src + 128 * k) : "memory");
-  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (lane == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the lanes' accesses to td, before the TMA unit rewrites it
+    bulk_g2s((uint32_t)__cvta_generic_to_shared(S.td), rec, 2048u, (uint32_t)__cvta_generic_to_shared(&S.mbar));
+  }
 }
 
 // f32(0.5 * ((double)a +- (double)b)) (qmf.js:77-83, decoder.js:362-367) without leaving binary32.  The reference's value is
@@ -686,8 +686,9 @@ __device__ __noinline__ void sy_merge_hd_f64(SyWarpSmem &S, int lane, float x0, 
 // Band record of one unit (already on its way into S.td, sy_prefetch) -> time-domain frame in S.td (first 32 samples
 // of a band: overlap-add with the previous unit's tail, mdct.js:230-245), merged low/mid -> S/D ring (elements
 // 24..151), high -> hd ring (40..295); the unit's tails replace the previous ones.
-__device__ __forceinline__ void sy_load_unit(SyWarpSmem &S, const double w1, const double w2, int lane) {
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+__device__ __forceinline__ void sy_load_unit(SyWarpSmem &S, const double w1, const double w2, int lane, uint32_t &parity) {
+  mbar_wait((uint32_t)__cvta_generic_to_shared(&S.mbar), parity);
+  parity ^= 1u;
   // lane p finishes sample p of each band: i = p < 16 ? p : 31 - p, w1 = WIN[i], w2 = WIN[31 - i]
   const int i = lane < 16 ? lane : 31 - lane;
   __syncwarp();
@@ -818,6 +819,9 @@ synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams,
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   SyWarpSmem &S = reinterpret_cast<SyWarpSmem *>(smem_raw)[warp];
+  uint32_t parity = 0;
+  if (lane == 0) mbar_init((uint32_t)__cvta_generic_to_shared(&S.mbar));
+  __syncwarp();
   const int wi = lane < 16 ? lane : 31 - lane;
   const double w1 = T->win[wi], w2 = T->win[31 - wi];
   const int keep_a_at = (lane & 3) * kSyStrideA + (lane >> 2), keep_b_at = (lane & 7) * kSyStrideB + (lane >> 3);
@@ -847,7 +851,7 @@ synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams,
     if (f0 > 0) {
       // prime from unit f0 - 1: only samples >= 32 of its bands reach the state (they do not depend
       // on the tails before it), so the zero state above is as good as the true one
-      sy_load_unit(S, w1, w2, lane);
+      sy_load_unit(S, w1, w2, lane, parity);
       __syncwarp();
       sy_prefetch(S, inv + onchip_row(row0 + f0) * 512, lane);
       sy_stage2(S, lane);
@@ -856,7 +860,7 @@ synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams,
     }
     for (int f = f0; f < f1; f++) {
       __syncwarp();
-      sy_load_unit(S, w1, w2, lane);
+      sy_load_unit(S, w1, w2, lane, parity);
       __syncwarp();
       if (f + 1 < f1) sy_prefetch(S, inv + onchip_row(row0 + f + 1) * 512, lane);
       sy_stage2(S, lane);

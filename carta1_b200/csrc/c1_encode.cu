@@ -75,7 +75,8 @@ struct QaWarpSmem {
   double x[2][8 * kQaStride1];   // odd, even polyphase of the PCM frame
   double s[2][4 * kQaStride2];   // odd, even polyphase of S1lo
   float hi[40 + 256];            // S1hi with 40 entries of history (39 used)
-  float raw[512];                // the next PCM frame, in flight (cp.async) while this one is filtered
+  float raw[512];                // the next PCM frame, in flight (TMA bulk copy) while this one is filtered
+  unsigned long long mbar, pad;  // the warp's mbarrier: completion of the copy into raw
 };
 static_assert(sizeof(QaWarpSmem) % 16 == 0 && (sizeof(double) * (2 * 8 * kQaStride1 + 2 * 4 * kQaStride2) + 4 * 296) % 16 == 0, "raw is 16-byte aligned");
 constexpr size_t kQaSmemBytes = sizeof(QaWarpSmem) * kQaWarps;
@@ -113,22 +114,20 @@ __device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gsr
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
                "l"(gsrc), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
 
-// f32 planar, 16-byte aligned rows: the frame starting at sample `first` is fetched into the warp's raw
-// staging buffer while the previous frame is being filtered.  Lane l copies, and later reads, bytes
-// [16 l + 512 k, +16) only, so no warp barrier is needed around the staging buffer.
-__device__ __forceinline__ void qa_prefetch(QaWarpSmem &S, const float *__restrict__ row, long long first,
-                                            long long valid_samples, int lane) {
-  if (first + 512 <= valid_samples) {  // the whole frame exists (every frame but a row's last): no per-chunk bounds
-    const float *src = row + first + 4 * lane;
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(S.raw + 4 * lane);
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 512 * k), "l"(src + 128 * k) : "memory");
-    return;
+// f32 planar, 16-byte aligned rows: the frame starting at sample `first` is fetched into the warp's raw staging
+// buffer while the previous frame is being filtered.  A whole frame (every frame but a row's last) is one TMA bulk
+// copy of 2 KB issued by lane 0, completion on the warp's mbarrier; a partial frame takes 16-byte cp.async chunks
+// with zero fill.  The caller issues it after the warp barrier that follows qa_fill (every lane has read raw).
+// Returns how the fetch completes: 2 = mbarrier phase, 1 = cp.async group.
+__device__ __forceinline__ int qa_prefetch(QaWarpSmem &S, const float *__restrict__ row, long long first,
+                                           long long valid_samples, int lane) {
+  if (first + 512 <= valid_samples) {
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the lanes' reads of raw, before the TMA unit rewrites it
+      bulk_g2s((uint32_t)__cvta_generic_to_shared(S.raw), row + first, 2048u, (uint32_t)__cvta_generic_to_shared(&S.mbar));
+    }
+    return 2;
   }
 #pragma unroll
   for (int k = 0; k < 4; k++) {
@@ -137,6 +136,8 @@ __device__ __forceinline__ void qa_prefetch(QaWarpSmem &S, const float *__restri
     const int bytes = left >= 4 ? 16 : (left > 0 ? (int)left * 4 : 0);
     cp_async16_zfill(S.raw + 4 * lane + 128 * k, row + (bytes ? g : 0), bytes);
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  return 1;
 }
 
 // Per-lane ring positions, computed once per kernel (the compiler otherwise re-derives them every frame).
@@ -150,20 +151,25 @@ struct QaLane {
         keep_s((lane & 3) * kQaStride2 + (lane >> 2)) {}
 };
 
-// PCM frame -> polyphase ring (elements 24..279).  Lane l owns samples 4l + 128k + c.
+// PCM frame -> polyphase ring (elements 24..279).  Lane l owns samples 4l + 128k + c.  pending: how the frame's
+// fetch into S.raw completes (qa_prefetch), 0 = not prefetched (unaligned rows, int16); parity: the mbarrier's phase.
 template <int kFmt>
 __device__ __forceinline__ void qa_fill(QaWarpSmem &S, const void *__restrict__ pcm_v, size_t row_off, int n_ch,
-                                        int stream, long long first, long long valid_samples, bool vec_ok, int lane,
-                                        long long next_first, const QaLane &Q) {
+                                        int stream, long long first, long long valid_samples, int pending, uint32_t &parity,
+                                        int lane, const QaLane &Q) {
   float v[4][4];
-  if (kFmt == 0 && vec_ok) {
-    cp_async_commit_wait_all();
+  if (kFmt == 0 && pending) {
+    if (pending == 2) {
+      mbar_wait((uint32_t)__cvta_generic_to_shared(&S.mbar), parity);
+      parity ^= 1u;
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const float4 q = *reinterpret_cast<const float4 *>(S.raw + 4 * lane + 128 * k);
       v[k][0] = q.x; v[k][1] = q.y; v[k][2] = q.z; v[k][3] = q.w;
     }
-    if (next_first >= 0) qa_prefetch(S, static_cast<const float *>(pcm_v) + row_off, next_first, valid_samples, lane);
   } else {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -241,6 +247,9 @@ qmf_analysis_kernel(const void *__restrict__ pcm_v, size_t row_stride, int n_ch,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   QaWarpSmem &S = reinterpret_cast<QaWarpSmem *>(smem_raw)[warp];
   const QaLane Q(lane);
+  uint32_t parity = 0;
+  if (lane == 0) mbar_init((uint32_t)__cvta_generic_to_shared(&S.mbar));
+  __syncwarp();
   const int runs_per_row = (frames + run_len - 1) / run_len;
   const int n_runs = runs_per_row * n_streams;
   for (int run = blockIdx.x * kQaWarps + warp; run < n_runs; run += gridDim.x * kQaWarps) {
@@ -248,11 +257,11 @@ qmf_analysis_kernel(const void *__restrict__ pcm_v, size_t row_stride, int n_ch,
     const int f0 = (run - stream * runs_per_row) * run_len;
     const int f1 = min(f0 + run_len, frames);
     const size_t row_off = kFmt == 0 ? (size_t)stream * row_stride : 0;
-    const bool vec_ok = kFmt == 0 && ((reinterpret_cast<uintptr_t>(static_cast<const float *>(pcm_v) + row_off) & 15) == 0);
+    const float *row = static_cast<const float *>(pcm_v) + row_off;  // kFmt == 0 only
+    const bool async_ok = kFmt == 0 && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
     __syncwarp();
-    const bool async_ok = kFmt == 0 && vec_ok;
-    if (async_ok)
-      qa_prefetch(S, static_cast<const float *>(pcm_v) + row_off, 512ll * (f0 > 0 ? f0 - 1 : f0), valid_samples, lane);
+    int pending = 0;
+    if (async_ok) pending = qa_prefetch(S, row, 512ll * (f0 > 0 ? f0 - 1 : f0), valid_samples, lane);
     if (f0 == 0) {  // row start: silent history (new BufferPool, buffers.js:31-42)
       if (lane < 24) {
 #pragma unroll
@@ -264,17 +273,18 @@ qmf_analysis_kernel(const void *__restrict__ pcm_v, size_t row_stride, int n_ch,
       S.hi[lane] = 0.0f;
       if (lane < 8) S.hi[32 + lane] = 0.0f;
     } else {        // prime the state from the frame before the run (only its last 64 S1 outputs matter)
-      qa_fill<kFmt>(S, pcm_v, row_off, n_ch, stream, 512ll * (f0 - 1), valid_samples, vec_ok, lane, 512ll * f0, Q);
+      qa_fill<kFmt>(S, pcm_v, row_off, n_ch, stream, 512ll * (f0 - 1), valid_samples, pending, parity, lane, Q);
       __syncwarp();
+      if (async_ok) pending = qa_prefetch(S, row, 512ll * f0, valid_samples, lane);
       qa_stage1(S, lane);
       __syncwarp();
       qa_shift(S, lane, Q);
     }
     for (int f = f0; f < f1; f++) {
       __syncwarp();
-      qa_fill<kFmt>(S, pcm_v, row_off, n_ch, stream, 512ll * f, valid_samples, vec_ok, lane,
-                    f + 1 < f1 ? 512ll * (f + 1) : -1, Q);
+      qa_fill<kFmt>(S, pcm_v, row_off, n_ch, stream, 512ll * f, valid_samples, pending, parity, lane, Q);
       __syncwarp();
+      if (async_ok && f + 1 < f1) pending = qa_prefetch(S, row, 512ll * (f + 1), valid_samples, lane);
       qa_stage1(S, lane);
       __syncwarp();
       float *out = bands + onchip_row((size_t)stream * frames + f) * 512;
