@@ -473,7 +473,11 @@ __device__ __noinline__ void imdct_short_band(int band, float *row, float *scrat
   __syncwarp();
 }
 
-constexpr int kImdctWarps = 8, kImdctCtasPerSm = 3;
+#ifndef C1_IMDCT_WARPS
+#define C1_IMDCT_WARPS 8
+#define C1_IMDCT_CTAS 3
+#endif
+constexpr int kImdctWarps = C1_IMDCT_WARPS, kImdctCtasPerSm = C1_IMDCT_CTAS;
 struct ImdctWarpSmem {
   double2 xbuf[4 * LongGeom<0>::kSlots];  // transposes of the long-block FFTs (also the short-block scratch)
   float rows[544];                         // role 0: 4 x 136, role 1: 2 x 272, de-interleaved (ImdctLayout)

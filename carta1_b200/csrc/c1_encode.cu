@@ -351,7 +351,11 @@ __device__ __forceinline__ void fft8_pass_a_real(Cplx (&v)[8], R &rnd) {
   for (int j = 0; j < 4; j++) butterfly(v[j], v[j + 4], c_fft_tw[3 + j], rnd);  // stage 2
 }
 
-constexpr int kTsWarps = 8, kTsCtasPerSm = 3;
+#ifndef C1_TS_WARPS
+#define C1_TS_WARPS 8
+#define C1_TS_CTAS 3
+#endif
+constexpr int kTsWarps = C1_TS_WARPS, kTsCtasPerSm = C1_TS_CTAS;
 struct TsWarpSmem {
   double2 xbuf[256 + 32];  // transpose buffer (slot p + p/8)
   double logm[256 + 12];   // log(magnitude) where magnitude > 1e-10 (term arrays are skewed, see ts_skew)
@@ -855,7 +859,11 @@ __device__ __noinline__ void mdct_long_task_exact(unsigned long_mask, double *ar
   mdct_long_task<kRole, ExactRound>(long_mask, arr, out, tab2, tw, lane);
 }
 
-constexpr int kMdctWarps = 8, kMdctCtasPerSm = 3;
+#ifndef C1_MDCT_WARPS
+#define C1_MDCT_WARPS 8
+#define C1_MDCT_CTAS 3
+#endif
+constexpr int kMdctWarps = C1_MDCT_WARPS, kMdctCtasPerSm = C1_MDCT_CTAS;
 struct MdctWarpSmem {
   double guard[16]; // the two edge taps of mdct_pre_long are loaded (and discarded) up to 8 doubles in front of a
                     // buffer on lanes where they fall into the zero padding

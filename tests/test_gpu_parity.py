@@ -430,6 +430,40 @@ def test_sharded_device_path(ctx, oracle, world):
             assert np.array_equal(bits(pcm_out[i][c]), bits(ref[c])), (i, c)
 
 
+@pytest.mark.parametrize("shift,stride_pad", [(0, 0), (1, 0), (0, 3), (3, 1)])
+@pytest.mark.parametrize("ragged", [0, 1, 137])
+def test_device_rows_any_alignment(ctx, oracle, shift, stride_pad, ragged):
+    """K1 stages whole frames of 16-byte aligned rows with one TMA bulk copy each, a row's partial last frame with
+    zero-filling cp.async chunks, and rows that are only 4-byte aligned with plain loads (qa_prefetch / qa_fill,
+    c1_encode.cu); K7 stores float4 where the output row is aligned and scalars otherwise.  All of them have to
+    give the reference's bytes: device rows at every alignment (base shifted by `shift` floats, row stride not a
+    multiple of four floats) and lengths that end inside a frame."""
+    import torch
+
+    ch = S.cfg3_transients(0.31, seed=77, n_ch=2)
+    n = len(ch[0]) - ragged
+    ch = [c[:n] for c in ch]
+    frames = oracle.frame_count(n)
+    want = oracle.encode_pcm(ch)
+    stride = frames * 512 + stride_pad
+    buf = torch.zeros(shift + 2 * stride + 8, dtype=torch.float32, device="cuda")
+    for c in range(2):
+        buf[shift + c * stride:shift + c * stride + n] = torch.from_numpy(np.ascontiguousarray(ch[c])).cuda()
+    d_su = torch.zeros(frames * 2 * 212, dtype=torch.uint8, device="cuda")
+    ctx.encode_device(buf.data_ptr() + 4 * shift, stride, 2, n, 0, frames, None, d_su.data_ptr(), 2, 1, sync=True)
+    assert np.array_equal(d_su.cpu().numpy().reshape(-1, 212), want)
+    out = torch.full((shift + 2 * stride + 8,), 7.0, dtype=torch.float32, device="cuda")
+    ctx.decode_device(d_su.data_ptr(), 2, 1, frames * 2, 2, 0, frames, out.data_ptr() + 4 * shift, stride, sync=True)
+    ref = oracle.decode_su(want, 2)
+    got = out.cpu().numpy()
+    for c in range(2):
+        a = shift + c * stride
+        assert np.array_equal(bits(got[a:a + frames * 512]), bits(ref[c])), c
+    assert np.all(got[:shift] == 7.0) and np.all(got[shift + 2 * stride:] == 7.0)  # nothing written outside the rows
+    if stride_pad:
+        assert np.all(got[shift + frames * 512:shift + stride] == 7.0)
+
+
 @pytest.mark.parametrize("world", [2, 5])
 @pytest.mark.parametrize("units_per_pass", [0, 24])
 def test_sharded_host_path(ctx, oracle, world, units_per_pass):
