@@ -612,17 +612,22 @@ bands_time_kernel(const float *__restrict__ inv, const uint8_t *__restrict__ mod
 //   pcm[2n]      = f32(sum_j D1[n-23+j] * ODD[j]), pcm[2n+1]  = f32(sum_j S1[n-23+j] * EVEN[j])
 // A run that does not start at the row start is primed from the band record of the unit
 // before it: the state after a frame depends on that unit alone.
-// Rings: S/D with 24 entries of history, 4 rows (element e at row e&3, column e>>2; a lane
-// produces 4 consecutive i); S1/D1 with 24, 8 rows (8 consecutive n per lane); the delayed
-// high band with 40.
+// Rings: S/D with 24 entries of history, a lane produces 4 consecutive i; S1/D1 with 24, 8 consecutive n
+// per lane; the delayed high band with 40.  A ring whose lanes produce kR outputs each keeps element e at
+// index e + 2 (e / kR): groups of kR doubles, 2 doubles of padding after each.  Lane t's register window
+// (elements kR t .. kR t + kR + 23) then starts at (kR + 2) t, its even/odd element pairs are 16-byte aligned
+// (one LDS.128 per pair: 14 / 16 loads per window instead of 27 / 31), and a quarter-warp's loads touch eight
+// different 16-byte bank groups ((kR + 2) / 2 = 3 / 5 is odd).  A lane's kR fresh elements are one whole group.
 // ------------------------------------------------------------------------------------
 constexpr int kSyWarps = 8, kSyCtasPerSm = 2;
-constexpr int kSyStrideA = 40;    // >= (24 + 128) / 4
-constexpr int kSyStrideB = 50;    // >= (24 + 256) / 8, == 2 mod 16
-static_assert(kSyStrideA * 4 >= 152 && kSyStrideB * 8 >= 280 && kSyStrideB % 16 == 2, "ring strides");
+template <int kR>
+__host__ __device__ constexpr int ring_at(int e) { return e + 2 * (e / kR); }
+constexpr int kSyRingA = 228;     // > ring_at<4>(24 + 128 - 1), even
+constexpr int kSyRingB = 348;     // > ring_at<8>(24 + 256 - 1), even
+static_assert(ring_at<4>(151) < kSyRingA && ring_at<8>(279) < kSyRingB && kSyRingA % 2 == 0 && kSyRingB % 2 == 0, "ring sizes");
 struct SyWarpSmem {
-  double a[2][4 * kSyStrideA];   // D, S of stage 2
-  double b[2][8 * kSyStrideB];   // D1, S1 of stage 1
+  double a[2][kSyRingA];         // D, S of stage 2
+  double b[2][kSyRingB];         // D1, S1 of stage 1
   float hd[40 + 256];            // high band with 40 entries of history (39 used)
   float td[512];                 // time-domain band frame: low 128 | mid 128 | high 256
   float tail[48];                // tail16 of the previous unit's three band records
@@ -640,21 +645,26 @@ cudaError_t upload_decode_constants(const DevTables *host_tables) {
   return e;
 }
 
-// acc[r] = sum_j seq[kR*t + 1 + r + j] * taps[j], j ascending, r = 0..kR-1: element kR*t + i
-// sits at row i & (kR-1), column t + i / kR of a kR-row ring
-template <int kR, int kStride>
+// acc[r] = sum_j seq[kR*t + 1 + r + j] * taps[j], j ascending, r = 0..kR-1: window element i = r + j + 1 of
+// lane t sits at (kR + 2) t + ring_at<kR>(i); the window is loaded as (even, odd) pairs
+template <int kR>
 __device__ __forceinline__ void fir_synthesis(const double *__restrict__ seq, int t, const double *taps,
                                               double (&acc)[kR]) {
+  const double *base = seq + (kR + 2) * t;
+  double w[kR + 24];
+#pragma unroll
+  for (int i = 0; i < kR + 24; i += 2) {
+    const double2 v = *reinterpret_cast<const double2 *>(base + ring_at<kR>(i));
+    w[i] = v.x;
+    w[i + 1] = v.y;
+  }
 #pragma unroll
   for (int r = 0; r < kR; r++) acc[r] = 0.0;
 #pragma unroll
   for (int j = 0; j < 24; j++) {
     const double c = taps[j];
 #pragma unroll
-    for (int r = 0; r < kR; r++) {
-      const int i = r + j + 1;
-      acc[r] = fma(seq[(i & (kR - 1)) * kStride + t + i / kR], c, acc[r]);
-    }
+    for (int r = 0; r < kR; r++) acc[r] = fma(w[r + j + 1], c, acc[r]);
   }
 }
 
@@ -719,31 +729,34 @@ __device__ __forceinline__ void sy_load_unit(SyWarpSmem &S, const double w1, con
     const float l[4] = {l4.x, l4.y, l4.z, l4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w};
     const bool f32_ok = merge_exact_in_f32(min(min(merge_key(m[0]), merge_key(m[1])), min(merge_key(m[2]), merge_key(m[3]))));
     if (__all_sync(0xffffffffu, f32_ok)) {
+      float sum[4], dif[4];
 #pragma unroll
-      for (int r = 0; r < 4; r++) {
-        float sum, dif;
-        merge_f32(l[r], m[r], sum, dif);
-        S.a[0][r * kSyStrideA + lane + 6] = (double)dif;
-        S.a[1][r * kSyStrideA + lane + 6] = (double)sum;
-      }
+      for (int r = 0; r < 4; r++) merge_f32(l[r], m[r], sum[r], dif[r]);
+      // elements 24 + 4 lane + r: the whole group lane + 6
+      double2 *da = reinterpret_cast<double2 *>(S.a[0] + 6 * (lane + 6)), *sa = reinterpret_cast<double2 *>(S.a[1] + 6 * (lane + 6));
+      da[0] = make_double2((double)dif[0], (double)dif[1]);
+      da[1] = make_double2((double)dif[2], (double)dif[3]);
+      sa[0] = make_double2((double)sum[0], (double)sum[1]);
+      sa[1] = make_double2((double)sum[2], (double)sum[3]);
     } else {
       sy_merge_lm_f64(S, lane);  // binary32-subnormal mid-band samples somewhere in the warp: rare, out of line
     }
   }
   // high band into its delay ring
   {
-    const float4 h0 = reinterpret_cast<const float4 *>(S.td + 256)[2 * lane], h1 = reinterpret_cast<const float4 *>(S.td + 256)[2 * lane + 1];
-    float4 *d = reinterpret_cast<float4 *>(S.hd + 40 + 8 * lane);
-    d[0] = h0;
-    d[1] = h1;
+    // (a plain copy of 256 floats: lane l moves 16-byte chunks l and l + 32, unit stride across the warp)
+    const float4 h0 = reinterpret_cast<const float4 *>(S.td + 256)[lane], h1 = reinterpret_cast<const float4 *>(S.td + 256)[lane + 32];
+    float4 *d = reinterpret_cast<float4 *>(S.hd + 40);
+    d[lane] = h0;
+    d[lane + 32] = h1;
   }
 }
 
 // stage 2 + merge with the delayed high band -> D1/S1 ring (elements 24..279)
 __device__ __forceinline__ void sy_stage2(SyWarpSmem &S, int lane) {
   double ev[4], od[4];
-  fir_synthesis<4, kSyStrideA>(S.a[0], lane, c_syn_odd, od);   // out2[2i],   i = 4 lane + r
-  fir_synthesis<4, kSyStrideA>(S.a[1], lane, c_syn_even, ev);  // out2[2i+1]
+  fir_synthesis<4>(S.a[0], lane, c_syn_odd, od);   // out2[2i],   i = 4 lane + r
+  fir_synthesis<4>(S.a[1], lane, c_syn_even, ev);  // out2[2i+1]
   // H[n - 39] = hd[8 lane + c + 1], c = 0..7: three aligned 16-byte reads instead of eight 8-way conflicting ones
   const float4 ha = reinterpret_cast<const float4 *>(S.hd)[2 * lane], hb = reinterpret_cast<const float4 *>(S.hd)[2 * lane + 1],
                hc = reinterpret_cast<const float4 *>(S.hd)[2 * lane + 2];
@@ -755,13 +768,15 @@ __device__ __forceinline__ void sy_stage2(SyWarpSmem &S, int lane) {
 #pragma unroll
   for (int c = 0; c < 8; c++) x[c] = (float)((c & 1) ? ev[c >> 1] : od[c >> 1]);  // n = 8 lane + c
   if (__all_sync(0xffffffffu, merge_exact_in_f32(key))) {
+    float s1[8], d1[8];
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
-      float s1, d1;
-      merge_f32(x[c], hv[c], s1, d1);
-      // element 24 + n = 8 (lane + 3) + c
-      S.b[0][c * kSyStrideB + lane + 3] = (double)d1;
-      S.b[1][c * kSyStrideB + lane + 3] = (double)s1;
+    for (int c = 0; c < 8; c++) merge_f32(x[c], hv[c], s1[c], d1[c]);
+    // elements 24 + n = 8 (lane + 3) + c: the whole group lane + 3
+    double2 *db = reinterpret_cast<double2 *>(S.b[0] + 10 * (lane + 3)), *sb = reinterpret_cast<double2 *>(S.b[1] + 10 * (lane + 3));
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      db[q] = make_double2((double)d1[2 * q], (double)d1[2 * q + 1]);
+      sb[q] = make_double2((double)s1[2 * q], (double)s1[2 * q + 1]);
     }
   } else {
     sy_merge_hd_f64(S, lane, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);  // rare, out of line
@@ -776,8 +791,8 @@ __device__ __noinline__ void sy_merge_lm_f64(SyWarpSmem &S, int lane) {
   for (int r = 0; r < 4; r++) {
     const float sum = (float)(0.5 * ((double)l[r] + (double)m[r]));
     const float dif = (float)(0.5 * ((double)l[r] - (double)m[r]));
-    S.a[0][r * kSyStrideA + lane + 6] = (double)dif;
-    S.a[1][r * kSyStrideA + lane + 6] = (double)sum;
+    S.a[0][6 * (lane + 6) + r] = (double)dif;
+    S.a[1][6 * (lane + 6) + r] = (double)sum;
   }
 }
 __device__ __noinline__ void sy_merge_hd_f64(SyWarpSmem &S, int lane, float x0, float x1, float x2, float x3, float x4, float x5,
@@ -788,19 +803,19 @@ __device__ __noinline__ void sy_merge_hd_f64(SyWarpSmem &S, int lane, float x0, 
     const float h = S.hd[8 * lane + c + 1];
     const float s1 = (float)(0.5 * ((double)x[c] + (double)h));
     const float d1 = (float)(0.5 * ((double)x[c] - (double)h));
-    S.b[0][c * kSyStrideB + lane + 3] = (double)d1;
-    S.b[1][c * kSyStrideB + lane + 3] = (double)s1;
+    S.b[0][10 * (lane + 3) + c] = (double)d1;
+    S.b[1][10 * (lane + 3) + c] = (double)s1;
   }
 }
 
 __device__ __forceinline__ void sy_shift(SyWarpSmem &S, int lane, int keep_a_at, int keep_b_at) {
-  // element `lane` of the a / b rings sits at keep_a_at / keep_b_at; elements 128 + lane / 256 + lane 32 columns further
+  // element `lane` of the a / b rings sits at keep_a_at / keep_b_at; elements 128 + lane / 256 + lane 32 groups further
   double keep_a[2], keep_b[2];
   if (lane < 24) {
 #pragma unroll
     for (int p = 0; p < 2; p++) {
-      keep_a[p] = S.a[p][keep_a_at + 32];
-      keep_b[p] = S.b[p][keep_b_at + 32];
+      keep_a[p] = S.a[p][keep_a_at + 32 * 6];
+      keep_b[p] = S.b[p][keep_b_at + 32 * 10];
     }
   }
   const float h0 = S.hd[256 + lane], h1 = lane < 8 ? S.hd[288 + lane] : 0.0f;
@@ -828,7 +843,7 @@ synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams,
   __syncwarp();
   const int wi = lane < 16 ? lane : 31 - lane;
   const double w1 = T->win[wi], w2 = T->win[31 - wi];
-  const int keep_a_at = (lane & 3) * kSyStrideA + (lane >> 2), keep_b_at = (lane & 7) * kSyStrideB + (lane >> 3);
+  const int keep_a_at = ring_at<4>(lane), keep_b_at = ring_at<8>(lane);
   const int out_frames = frames - halo;
   const int runs_per_row = (out_frames + run_len - 1) / run_len;
   const int n_runs = runs_per_row * n_streams;
@@ -871,8 +886,8 @@ synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams,
       __syncwarp();
       {  // stage 1 -> PCM: lane covers samples [16 lane, 16 lane + 16) of the frame
         double ev[8], od[8];
-        fir_synthesis<8, kSyStrideB>(S.b[0], lane, c_syn_odd, od);
-        fir_synthesis<8, kSyStrideB>(S.b[1], lane, c_syn_even, ev);
+        fir_synthesis<8>(S.b[0], lane, c_syn_odd, od);
+        fir_synthesis<8>(S.b[1], lane, c_syn_even, ev);
         const size_t sample = (size_t)(f - halo) * 512 + 16 * lane;
         if (kFmt == 0) {
           float *dstf = static_cast<float *>(pcm_v) + (size_t)stream * row_stride + sample;
