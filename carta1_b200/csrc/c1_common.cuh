@@ -117,6 +117,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
       : "memory");
 }
 
+// Rings of the streaming QMF kernels (K1 / K7): a ring whose lanes produce kR outputs each keeps element e at index
+// e + 2 (e / kR), i.e. groups of kR doubles with 2 doubles of padding after each.
+template <int kR>
+__host__ __device__ constexpr int ring_at(int e) { return e + 2 * (e / kR); }
+
 // Experiment build only (tools/onchip_experiment.sh, -DC1_EXPERIMENT_ONCHIP_INTERMEDIATES; never the shipped library): the
 // band rows between K1 and K3 and the band records between K6 and K7 are aliased onto 64 rows that stay in L1 / L2.
 // The results are garbage; the kernel times bound from above what keeping those intermediates on chip (a K1->K3 /

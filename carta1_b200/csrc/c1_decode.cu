@@ -620,8 +620,6 @@ bands_time_kernel(const float *__restrict__ inv, const uint8_t *__restrict__ mod
 // different 16-byte bank groups ((kR + 2) / 2 = 3 / 5 is odd).  A lane's kR fresh elements are one whole group.
 // ------------------------------------------------------------------------------------
 constexpr int kSyWarps = 8, kSyCtasPerSm = 2;
-template <int kR>
-__host__ __device__ constexpr int ring_at(int e) { return e + 2 * (e / kR); }
 constexpr int kSyRingA = 228;     // > ring_at<4>(24 + 128 - 1), even
 constexpr int kSyRingB = 348;     // > ring_at<8>(24 + 256 - 1), even
 static_assert(ring_at<4>(151) < kSyRingA && ring_at<8>(279) < kSyRingB && kSyRingA % 2 == 0 && kSyRingB % 2 == 0, "ring sizes");
