@@ -619,7 +619,11 @@ bands_time_kernel(const float *__restrict__ inv, const uint8_t *__restrict__ mod
 // (one LDS.128 per pair: 14 / 16 loads per window instead of 27 / 31), and a quarter-warp's loads touch eight
 // different 16-byte bank groups ((kR + 2) / 2 = 3 / 5 is odd).  A lane's kR fresh elements are one whole group.
 // ------------------------------------------------------------------------------------
-constexpr int kSyWarps = 8, kSyCtasPerSm = 2;
+#ifndef C1_SY_WARPS
+#define C1_SY_WARPS 8
+#define C1_SY_CTAS 2
+#endif
+constexpr int kSyWarps = C1_SY_WARPS, kSyCtasPerSm = C1_SY_CTAS;
 constexpr int kSyRingA = 228;     // > ring_at<4>(24 + 128 - 1), even
 constexpr int kSyRingB = 348;     // > ring_at<8>(24 + 256 - 1), even
 static_assert(ring_at<4>(151) < kSyRingA && ring_at<8>(279) < kSyRingB && kSyRingA % 2 == 0 && kSyRingB % 2 == 0, "ring sizes");
