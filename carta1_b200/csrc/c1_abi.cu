@@ -369,6 +369,8 @@ struct carta1_ctx {
   DevBuf stage_pcm[kSlots], stage_su[kUnitSlots];
   cudaStream_t h2d = nullptr, d2h = nullptr;
   cudaStream_t small = nullptr;  // highest priority: the sound-unit side of a host call (see small_copy)
+  ForkJoin fj;                   // small launches run the two role kernels of a transform side by side (c1_launch.h)
+  cudaEvent_t ev_hist = nullptr; // carta1_enc_frames: the history rows of the next call have been saved (on fj.aux)
   cudaEvent_t ev_in[kSlots] = {}, ev_comp[kSlots] = {}, ev_out[kSlots] = {};
   cudaEvent_t ev_uin[kUnitSlots] = {}, ev_ucomp[kUnitSlots] = {};
   // pageable caller buffers are staged through these (filled / drained by parallel_memcpy, one pass behind)
@@ -546,6 +548,10 @@ int carta1_ctx_create(int device, const carta1_tables *tables, carta1_ctx **out)
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->fj.aux, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->fj.fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->fj.join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_hist, cudaEventDisableTiming);
   if (e == cudaSuccess) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -625,6 +631,10 @@ void carta1_ctx_destroy(carta1_ctx *ctx) {
     if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
     if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
   }
+  if (ctx->ev_hist) cudaEventDestroy(ctx->ev_hist);
+  if (ctx->fj.fork) cudaEventDestroy(ctx->fj.fork);
+  if (ctx->fj.join) cudaEventDestroy(ctx->fj.join);
+  if (ctx->fj.aux) cudaStreamDestroy(ctx->fj.aux);
   if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
   if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
   if (ctx->small) cudaStreamDestroy(ctx->small);
@@ -727,6 +737,7 @@ static int encode_device_impl(carta1_ctx *ctx, const void *d_pcm, int pcm_fmt, s
   L.sfi = (uint8_t *)ctx->sfi.p;
   L.alloc_recs = ctx->recs.p;
   L.su_out = d_su; L.su_frame_stride = su_frame_stride; L.su_stream_stride = su_stream_stride;
+  L.fj = &ctx->fj;
   CU(ctx, launch_encode(L, ctx->stream, &ctx->prof));
   return CARTA1_OK;
 }
@@ -755,6 +766,7 @@ static int decode_device_impl(carta1_ctx *ctx, const uint8_t *d_su, size_t su_fr
   L.prev_rec = prev_rec;
   L.x_q = x_q; L.x_sfi = x_sfi; L.x_bits = x_bits; L.x_modes = x_modes;
   L.pcm = d_pcm; L.pcm_fmt = pcm_fmt; L.row_stride = row_stride; L.n_ch_interleave = n_ch_interleave;
+  L.fj = &ctx->fj;
   CU(ctx, launch_decode(L, ctx->stream, &ctx->prof));
   return CARTA1_OK;
 }
@@ -1242,11 +1254,17 @@ int carta1_enc_frames(carta1_encoder *e, const float *pcm, int n_frames, uint8_t
                             (size_t)n_frames * 512 * sizeof(float), ns, cudaMemcpyHostToDevice, ctx->stream));
   int rc = run_graphed(ctx, e->graph, n_frames, [&]() -> int {
     CU(ctx, copy_rows(w, row, e->d_hist, 1024, 1024, ns, ctx->stream, &ctx->prof));
+    // the history of the next call (the last two frames of w) is saved beside the kernels, not behind them: it only
+    // reads w, as they do; the handle's second stream carries it and joins before the call returns
+    CU(ctx, fork_begin(&ctx->fj, ctx->stream));
+    CU(ctx, copy_rows(e->d_hist, 1024, w + (size_t)n_frames * 512, row, 1024, ns, ctx->fj.aux, &ctx->prof));
+    cudaEvent_t hist_saved = ctx->ev_hist;
+    CU(ctx, cudaEventRecord(hist_saved, ctx->fj.aux));
     const int r = encode_device_impl(ctx, w, 0, row, 1, e->n_streams, row, 2, (size_t)n_frames, e->d_params,
                                      e->opts.use_fixed_block_modes != 0, (uint8_t *)e->su.p, 1, (size_t)n_frames,
                                      nullptr, nullptr, nullptr, nullptr);
+    CU(ctx, cudaStreamWaitEvent(ctx->stream, hist_saved, 0));  // joins the second stream (also after a failed launch)
     if (r) return r;
-    CU(ctx, copy_rows(e->d_hist, 1024, w + (size_t)n_frames * 512, row, 1024, ns, ctx->stream, &ctx->prof));
     return CARTA1_OK;
   });
   if (rc) return rc;

@@ -997,8 +997,11 @@ cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, Prof *prof) {
     const int n_pairs = (n_units + 1) / 2;
     const int grid = std::min((n_pairs + kImdctWarps - 1) / kImdctWarps, persistent_ctas(kImdctCtasPerSm));
     prof->begin(K_IMDCT, st);
+    const bool fork = fork_roles(L.fj, grid, persistent_ctas(kImdctCtasPerSm));
+    if (fork && (e1 = fork_begin(L.fj, st)) != cudaSuccess) return e1;
     imdct_kernel<0><<<grid, kImdctWarps * 32, kImdctSmemBytes, st>>>(L.coefs, L.modes, n_units, L.tables, L.inv);
-    imdct_kernel<1><<<grid, kImdctWarps * 32, kImdctSmemBytes, st>>>(L.coefs, L.modes, n_units, L.tables, L.inv);
+    imdct_kernel<1><<<grid, kImdctWarps * 32, kImdctSmemBytes, fork ? L.fj->aux : st>>>(L.coefs, L.modes, n_units, L.tables, L.inv);
+    if (fork && (e1 = fork_end(L.fj, st)) != cudaSuccess) return e1;
     prof->launches++;
     prof->end(K_IMDCT, st);
   }

@@ -1568,11 +1568,12 @@ const char *kernel_name(int id) {
 // run that does not start its row first re-derives that state from the frame before it (about 0.6 of
 // a frame's work).  With `warps` persistent warps the kernel lasts waves x (run + 0.6) frame times,
 // waves = ceil(runs / warps): pick the run length that minimises it (e.g. 33 instead of 32 for the
-// 1 h stereo workload: 8 full waves instead of 8.2, i.e. 9).
+// 1 h stereo workload: 8 full waves instead of 8.2, i.e. 9).  A launch that fits one wave whatever the run length
+// (the stateful handles' few frames per call) gets runs of one frame: the call waits for the longest run.
 int pick_run_len(int frames, int n_streams, int warps) {
   int best = 32;
   double best_cost = 1e300;
-  for (int len = 4; len <= 96; len++) {
+  for (int len = 1; len <= 96; len++) {
     const long long runs = (long long)((frames + len - 1) / len) * n_streams;
     const long long waves = (runs + warps - 1) / warps;
     const double cost = (double)waves * (std::min(len, frames) + 0.6);
@@ -1604,6 +1605,13 @@ int resident_ctas(const void *kernel, int threads, size_t dyn_smem) {
 }
 
 // CTAs of a persistent kernel: every SM of the current device filled to `per_sm` resident CTAs.
+// Role kernels side by side when both grids together leave the machine room (see ForkJoin); CARTA1_NO_FORK=1 keeps
+// everything on one stream (an A/B switch for measurements).
+bool fork_roles(const ForkJoin *fj, int grid, int resident) {
+  static const bool off = getenv("CARTA1_NO_FORK") != nullptr;
+  return fj && fj->aux && !off && 2 * grid <= resident;
+}
+
 int persistent_ctas(int per_sm) {
   static std::atomic<int> sms_of[64];  // per device; 0 = not queried yet (a racing double query stores the same value)
   int dev = 0;
@@ -1646,10 +1654,13 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
     {
       const int n_ts_pairs = (n_su + 1) / 2;
       const int grid = std::min((n_ts_pairs + kTsWarps - 1) / kTsWarps, persistent_ctas(kTsCtasPerSm));
+      const bool fork = fork_roles(L.fj, grid, persistent_ctas(kTsCtasPerSm));
+      if (fork && (e2 = fork_begin(L.fj, st)) != cudaSuccess) return e2;
       transient_spectrum_kernel<0><<<grid, kTsWarps * 32, kTsSmemBytes, st>>>(L.bands, n_su, L.tables, L.mags,
                                                                               static_cast<SpectrumFeatures *>(L.feats));
-      transient_spectrum_kernel<1><<<grid, kTsWarps * 32, kTsSmemBytes, st>>>(L.bands, n_su, L.tables, L.mags,
-                                                                              static_cast<SpectrumFeatures *>(L.feats));
+      transient_spectrum_kernel<1><<<grid, kTsWarps * 32, kTsSmemBytes, fork ? L.fj->aux : st>>>(
+          L.bands, n_su, L.tables, L.mags, static_cast<SpectrumFeatures *>(L.feats));
+      if (fork && (e2 = fork_end(L.fj, st)) != cudaSuccess) return e2;
       prof->launches++;
     }
     prof->end(K_BAND_MAGS, st);
@@ -1670,8 +1681,12 @@ cudaError_t launch_encode(const EncodeLaunch &L, cudaStream_t st, Prof *prof) {
     if (e1 != cudaSuccess) return e1;
     const int n_pairs = (n_su + 1) / 2;
     const int grid = std::min((n_pairs + kMdctWarps - 1) / kMdctWarps, persistent_ctas(kMdctCtasPerSm));
+    const bool fork = fork_roles(L.fj, grid, persistent_ctas(kMdctCtasPerSm));
+    if (fork && (e1 = fork_begin(L.fj, st)) != cudaSuccess) return e1;
     mdct_kernel<0><<<grid, kMdctWarps * 32, kMdctSmemBytes, st>>>(L.bands, L.modes, frames, n_su, L.tables, L.params, L.coefs, L.sfi);
-    mdct_kernel<1><<<grid, kMdctWarps * 32, kMdctSmemBytes, st>>>(L.bands, L.modes, frames, n_su, L.tables, L.params, L.coefs, L.sfi);
+    mdct_kernel<1><<<grid, kMdctWarps * 32, kMdctSmemBytes, fork ? L.fj->aux : st>>>(L.bands, L.modes, frames, n_su, L.tables,
+                                                                                   L.params, L.coefs, L.sfi);
+    if (fork && (e1 = fork_end(L.fj, st)) != cudaSuccess) return e1;
     prof->launches++;
   }
   prof->end(K_MDCT, st);

@@ -13,6 +13,24 @@ namespace c1 {
 struct DevTables;
 struct DevEncParams;
 
+// A second stream and two events: the two role kernels of a transform (low + mid bands / high band) are independent
+// of each other, so a launch that leaves most of the machine idle (the stateful handles' few frames per call) runs
+// them side by side: fork from the launching stream, join back (also inside a stream capture, where this becomes a
+// fork in the graph).  Large launches fill the machine with one role and stay on one stream.
+struct ForkJoin {
+  cudaStream_t aux = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+bool fork_roles(const ForkJoin *fj, int grid, int resident);  // true: role 1 goes to fj->aux
+inline cudaError_t fork_begin(const ForkJoin *fj, cudaStream_t st) {
+  cudaError_t e = cudaEventRecord(fj->fork, st);
+  return e != cudaSuccess ? e : cudaStreamWaitEvent(fj->aux, fj->fork, 0);
+}
+inline cudaError_t fork_end(const ForkJoin *fj, cudaStream_t st) {
+  cudaError_t e = cudaEventRecord(fj->join, fj->aux);
+  return e != cudaSuccess ? e : cudaStreamWaitEvent(st, fj->join, 0);
+}
+
 // One encode pass over `n_streams` rows of (halo_frames + n_out_frames) frames each.
 struct EncodeLaunch {
   const void *pcm;          // f32 planar rows (pcm_fmt 0) or s16 interleaved (pcm_fmt 1)
@@ -40,6 +58,7 @@ struct EncodeLaunch {
   // output
   uint8_t *su_out;          // may be NULL (stage taps only)
   size_t su_frame_stride, su_stream_stride;
+  const ForkJoin *fj;       // optional
 };
 
 struct DecodeLaunch {
@@ -67,6 +86,7 @@ struct DecodeLaunch {
   int pcm_fmt;
   size_t row_stride;
   int n_ch_interleave;
+  const ForkJoin *fj;       // optional
 };
 
 // Launch accounting and optional per-kernel CUDA-event timing (bench.py's roofline leg).
