@@ -747,7 +747,7 @@ static int decode_device_impl(carta1_ctx *ctx, const uint8_t *d_su, size_t su_fr
                               size_t n_frames, void *d_pcm, int pcm_fmt, size_t row_stride, int n_ch_interleave,
                               float *dbg_coefs, float *dbg_bands, const float *prev_rec = nullptr,
                               const int32_t *x_q = nullptr, const uint8_t *x_sfi = nullptr,
-                              const uint8_t *x_bits = nullptr, const uint8_t *x_modes = nullptr) {
+                              const uint8_t *x_bits = nullptr, const uint8_t *x_modes = nullptr, float *save_rec = nullptr) {
   const size_t frames_total = halo_frames + n_frames;
   const size_t units = frames_total * (size_t)n_streams;
   if (units == 0) return CARTA1_OK;
@@ -764,6 +764,7 @@ static int decode_device_impl(carta1_ctx *ctx, const uint8_t *d_su, size_t su_fr
   L.inv = (float *)ctx->inv.p;
   L.bands_dbg = dbg_bands;
   L.prev_rec = prev_rec;
+  L.save_rec = save_rec;
   L.x_q = x_q; L.x_sfi = x_sfi; L.x_bits = x_bits; L.x_modes = x_modes;
   L.pcm = d_pcm; L.pcm_fmt = pcm_fmt; L.row_stride = row_stride; L.n_ch_interleave = n_ch_interleave;
   L.fj = &ctx->fj;
@@ -1313,7 +1314,6 @@ static int dec_frames_impl(carta1_decoder *d, const uint8_t *su, const int32_t *
   const size_t ns = (size_t)d->n_streams;
   const size_t nf = (size_t)n_frames;
   const size_t halo = d->has_prev ? 1 : 0;
-  const size_t fr = nf + halo;
   CU(ctx, d->pcm.ensure(ns * nf * 512 * sizeof(float)));
   const uint8_t *d_su = nullptr;
   const int32_t *dq = nullptr;
@@ -1337,11 +1337,9 @@ static int dec_frames_impl(carta1_decoder *d, const uint8_t *su, const int32_t *
     dq = (const int32_t *)w; dsfi = w + n * 2048; dbits = w + n * 2560; dmodes = w + n * 3072;
   }
   auto body = [&]() -> int {
-    const int r = decode_device_impl(ctx, d_su, 1, nf, ns * nf, d->n_streams, halo, nf, d->pcm.p, 0, nf * 512, 1,
-                                     nullptr, nullptr, halo ? d->d_rec : nullptr, dq, dsfi, dbits, dmodes);
-    if (r) return r;
-    CU(ctx, copy_rows(d->d_rec, 512, (const float *)ctx->inv.p + (fr - 1) * 512, fr * 512, 512, ns, ctx->stream, &ctx->prof));
-    return CARTA1_OK;
+    // K7 leaves the band record of every stream's last unit in d_rec (DecodeLaunch::save_rec): no row copy behind it
+    return decode_device_impl(ctx, d_su, 1, nf, ns * nf, d->n_streams, halo, nf, d->pcm.p, 0, nf * 512, 1,
+                              nullptr, nullptr, halo ? d->d_rec : nullptr, dq, dsfi, dbits, dmodes, d->d_rec);
   };
   // sound units with a previous unit in the handle: the steady state of a stream, worth a graph
   const int rc = su && halo ? run_graphed(ctx, d->graph, n_frames, body) : body();

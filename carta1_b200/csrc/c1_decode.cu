@@ -836,7 +836,8 @@ __device__ __forceinline__ void sy_shift(SyWarpSmem &S, int lane, int keep_a_at,
 template <int kFmt>  // 0: f32 planar rows, 1: s16 interleaved (processor.js:382-389)
 __global__ void __launch_bounds__(kSyWarps * 32, kSyCtasPerSm)
 synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams, int run_len,
-             const DevTables *__restrict__ T, void *__restrict__ pcm_v, size_t row_stride, int n_ch) {
+             const DevTables *__restrict__ T, void *__restrict__ pcm_v, size_t row_stride, int n_ch,
+             float *__restrict__ save_rec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   SyWarpSmem &S = reinterpret_cast<SyWarpSmem *>(smem_raw)[warp];
@@ -916,6 +917,12 @@ synth_kernel(const float *__restrict__ inv, int frames, int halo, int n_streams,
       }
       __syncwarp();
       sy_shift(S, lane, keep_a_at, keep_b_at);
+    }
+    if (save_rec && f1 == frames) {  // the row's last unit: its band record is the decoder state of the next call
+      const float4 *src = reinterpret_cast<const float4 *>(inv + (row0 + frames - 1) * 512);
+      float4 *dst = reinterpret_cast<float4 *>(save_rec + (size_t)stream * 512);
+#pragma unroll
+      for (int k = 0; k < 4; k++) dst[lane + 32 * k] = src[lane + 32 * k];
     }
   }
 }
@@ -1021,10 +1028,10 @@ cudaError_t launch_decode(const DecodeLaunch &L, cudaStream_t st, Prof *prof) {
     prof->begin(K_SYNTH, st);
     if (L.pcm_fmt == 0)
       synth_kernel<0><<<grid, kSyWarps * 32, kSySmemBytes, st>>>(L.inv, L.frames_total, L.halo_frames, L.n_streams, run_len,
-                                                                  L.tables, L.pcm, L.row_stride, L.n_ch_interleave);
+                                                                  L.tables, L.pcm, L.row_stride, L.n_ch_interleave, L.save_rec);
     else
       synth_kernel<1><<<grid, kSyWarps * 32, kSySmemBytes, st>>>(L.inv, L.frames_total, L.halo_frames, L.n_streams, run_len,
-                                                                  L.tables, L.pcm, L.row_stride, L.n_ch_interleave);
+                                                                  L.tables, L.pcm, L.row_stride, L.n_ch_interleave, L.save_rec);
     prof->end(K_SYNTH, st);
   }
   return cudaGetLastError();

@@ -71,6 +71,9 @@ struct DecodeLaunch {
   // stateful handles: [n_streams][512] band records of the unit before the call; when set,
   // frame 0 of every row is that record and the su / expanded arrays start at frame 1
   const float *prev_rec;
+  // stateful handles: when set, K7 also stores the band record of every row's LAST unit here ([n_streams][512]), the
+  // prev_rec of the next call (K5 has read this call's prev_rec long before)
+  float *save_rec;
   int n_streams;
   int frames_total;         // halo_frames + n_out_frames
   int halo_frames;
