@@ -350,6 +350,10 @@ struct GraphCache {
 }  // namespace
 
 struct carta1_ctx {
+  // Every compute entry point holds this for the duration of the call: the context's stream, scratch buffers, graph
+  // caches and error text are shared by the handles created from it, so calls on one context (from any number of
+  // threads, on any of its handles) run one after the other; concurrency is one context per thread.
+  std::recursive_mutex call_mu;
   int device = 0;
   cudaStream_t stream = nullptr;
   carta1_tables tables;
@@ -401,6 +405,14 @@ struct carta1_decoder {
 };
 
 namespace {
+
+struct CtxLock {
+  std::recursive_mutex *m;
+  explicit CtxLock(carta1_ctx *ctx) : m(ctx ? &ctx->call_mu : nullptr) { if (m) m->lock(); }
+  ~CtxLock() { if (m) m->unlock(); }
+  CtxLock(const CtxLock &) = delete;
+  CtxLock &operator=(const CtxLock &) = delete;
+};
 
 int fail(carta1_ctx *ctx, int code, const std::string &msg) {
   if (ctx) ctx->err = msg; else g_create_error = msg;
@@ -651,6 +663,7 @@ void carta1_ctx_destroy(carta1_ctx *ctx) {
 
 const char *carta1_last_error(const carta1_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 int carta1_ctx_sync(carta1_ctx *ctx) {
+  CtxLock ctx_lock(ctx);
   if (!ctx) return CARTA1_ERR_ARG;
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -663,12 +676,14 @@ int carta1_kernel_count(void) { return K_COUNT; }
 const char *carta1_kernel_name(int id) { return kernel_name(id); }
 
 int carta1_ctx_profile(carta1_ctx *ctx, int enable) {
+  CtxLock ctx_lock(ctx);
   if (!ctx) return CARTA1_ERR_ARG;
   ctx->prof.on = enable != 0;
   return CARTA1_OK;
 }
 
 int carta1_ctx_profile_read(carta1_ctx *ctx, double *ms_out, uint64_t *count_out, int n) {
+  CtxLock ctx_lock(ctx);
   if (!ctx) return CARTA1_ERR_ARG;
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -701,6 +716,7 @@ int carta1_host_alloc(size_t bytes, void **out) {
 void carta1_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 int carta1_ctx_set_max_units_per_pass(carta1_ctx *ctx, size_t units) {
+  CtxLock ctx_lock(ctx);
   if (!ctx) return CARTA1_ERR_ARG;
   ctx->max_units_per_pass = units ? units : (size_t)1 << 16;
   return CARTA1_OK;
@@ -776,6 +792,7 @@ int carta1_encode_device(carta1_ctx *ctx, const float *d_pcm, size_t row_stride,
                          size_t valid_samples, size_t halo_frames, size_t n_frames,
                          const carta1_enc_opts *opts, uint8_t *d_su, size_t su_frame_stride,
                          size_t su_stream_stride, int sync) {
+  CtxLock ctx_lock(ctx);
   if (!ctx) return CARTA1_ERR_ARG;
   if (!d_pcm || !d_su || n_streams <= 0) return fail(ctx, CARTA1_ERR_ARG, "carta1_encode_device: bad argument");
   if (halo_frames == 1) return fail(ctx, CARTA1_ERR_ARG, "carta1_encode_device: halo_frames must be 0 or >= 2");
@@ -794,6 +811,7 @@ int carta1_encode_device(carta1_ctx *ctx, const float *d_pcm, size_t row_stride,
 int carta1_decode_device(carta1_ctx *ctx, const uint8_t *d_su, size_t su_frame_stride,
                          size_t su_stream_stride, size_t n_su_valid, int n_streams, size_t halo_frames,
                          size_t n_frames, float *d_pcm, size_t row_stride, int sync) {
+  CtxLock ctx_lock(ctx);
   if (!ctx) return CARTA1_ERR_ARG;
   if (!d_su || !d_pcm || n_streams <= 0) return fail(ctx, CARTA1_ERR_ARG, "carta1_decode_device: bad argument");
   CU(ctx, cudaSetDevice(ctx->device));
@@ -1041,18 +1059,21 @@ static int encode_host_impl(carta1_ctx *ctx, const float *const *channels, const
 int carta1_encode_pcm(carta1_ctx *ctx, const float *const *channels, int n_ch, size_t n_samples,
                       const carta1_enc_opts *opts, uint8_t *su_out, size_t su_capacity_bytes,
                       size_t *n_su_out) {
+  CtxLock ctx_lock(ctx);
   return encode_host_impl(ctx, channels, nullptr, n_ch, n_samples, opts, su_out, su_capacity_bytes, n_su_out);
 }
 
 int carta1_encode_pcm_s16(carta1_ctx *ctx, const int16_t *interleaved, int n_ch, size_t n_samples,
                           const carta1_enc_opts *opts, uint8_t *su_out, size_t su_capacity_bytes,
                           size_t *n_su_out) {
+  CtxLock ctx_lock(ctx);
   return encode_host_impl(ctx, nullptr, interleaved, n_ch, n_samples, opts, su_out, su_capacity_bytes, n_su_out);
 }
 
 int carta1_encode_pcm_shard(carta1_ctx *ctx, const float *const *channels, int n_ch, size_t n_samples,
                             size_t halo_frames, const carta1_enc_opts *opts, uint8_t *su_out,
                             size_t su_capacity_bytes, size_t *n_su_out) {
+  CtxLock ctx_lock(ctx);
   return encode_host_impl(ctx, channels, nullptr, n_ch, n_samples, opts, su_out, su_capacity_bytes, n_su_out, halo_frames);
 }
 
@@ -1182,21 +1203,25 @@ static int decode_host_impl(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int
 }
 
 int carta1_decode_su(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch, float *const *channels_out) {
+  CtxLock ctx_lock(ctx);
   if (ctx && !channels_out) return fail(ctx, CARTA1_ERR_ARG, "carta1_decode_su: channels_out is NULL");
   return decode_host_impl(ctx, su, n_su, n_ch, channels_out, nullptr);
 }
 int carta1_decode_su_shard(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch, size_t halo_frames,
                            float *const *channels_out) {
+  CtxLock ctx_lock(ctx);
   if (ctx && !channels_out) return fail(ctx, CARTA1_ERR_ARG, "carta1_decode_su_shard: channels_out is NULL");
   return decode_host_impl(ctx, su, n_su, n_ch, channels_out, nullptr, halo_frames);
 }
 int carta1_decode_su_s16(carta1_ctx *ctx, const uint8_t *su, size_t n_su, int n_ch, int16_t *interleaved_out) {
+  CtxLock ctx_lock(ctx);
   if (ctx && !interleaved_out) return fail(ctx, CARTA1_ERR_ARG, "carta1_decode_su_s16: output is NULL");
   return decode_host_impl(ctx, su, n_su, n_ch, nullptr, interleaved_out);
 }
 
 // ------------------------------------------------------------------ stateful closures
 int carta1_enc_create(carta1_ctx *ctx, const carta1_enc_opts *opts, int n_streams, carta1_encoder **out) {
+  CtxLock ctx_lock(ctx);
   if (!ctx) return CARTA1_ERR_ARG;
   if (!out || n_streams <= 0) return fail(ctx, CARTA1_ERR_ARG, "carta1_enc_create: bad argument");
   CU(ctx, cudaSetDevice(ctx->device));
@@ -1219,6 +1244,7 @@ int carta1_enc_create(carta1_ctx *ctx, const carta1_enc_opts *opts, int n_stream
 }
 
 void carta1_enc_destroy(carta1_encoder *e) {
+  CtxLock ctx_lock(e ? e->ctx : nullptr);
   if (!e) return;
   cudaSetDevice(e->ctx->device);
   cudaStreamSynchronize(e->ctx->stream);
@@ -1230,6 +1256,7 @@ void carta1_enc_destroy(carta1_encoder *e) {
 }
 
 int carta1_enc_reset(carta1_encoder *e) {
+  CtxLock ctx_lock(e ? e->ctx : nullptr);
   if (!e) return CARTA1_ERR_ARG;
   carta1_ctx *ctx = e->ctx;
   CU(ctx, cudaSetDevice(ctx->device));
@@ -1241,6 +1268,7 @@ int carta1_enc_reset(carta1_encoder *e) {
 // spectra) is a function of the last 650 PCM samples, so the handle
 // keeps the last two frames of PCM per stream and re-derives it.
 int carta1_enc_frames(carta1_encoder *e, const float *pcm, int n_frames, uint8_t *su_out) {
+  CtxLock ctx_lock(e ? e->ctx : nullptr);
   if (!e) return CARTA1_ERR_ARG;
   carta1_ctx *ctx = e->ctx;
   if (n_frames < 0 || (n_frames && (!pcm || !su_out))) return fail(ctx, CARTA1_ERR_ARG, "carta1_enc_frames: bad argument");
@@ -1276,6 +1304,7 @@ int carta1_enc_frames(carta1_encoder *e, const float *pcm, int n_frames, uint8_t
 }
 
 int carta1_dec_create(carta1_ctx *ctx, int n_streams, carta1_decoder **out) {
+  CtxLock ctx_lock(ctx);
   if (!ctx) return CARTA1_ERR_ARG;
   if (!out || n_streams <= 0) return fail(ctx, CARTA1_ERR_ARG, "carta1_dec_create: bad argument");
   CU(ctx, cudaSetDevice(ctx->device));
@@ -1289,6 +1318,7 @@ int carta1_dec_create(carta1_ctx *ctx, int n_streams, carta1_decoder **out) {
 }
 
 void carta1_dec_destroy(carta1_decoder *d) {
+  CtxLock ctx_lock(d ? d->ctx : nullptr);
   if (!d) return;
   cudaSetDevice(d->ctx->device);
   cudaStreamSynchronize(d->ctx->stream);
@@ -1299,6 +1329,7 @@ void carta1_dec_destroy(carta1_decoder *d) {
 }
 
 int carta1_dec_reset(carta1_decoder *d) {
+  CtxLock ctx_lock(d ? d->ctx : nullptr);
   if (!d) return CARTA1_ERR_ARG;
   d->has_prev = false;
   return CARTA1_OK;
@@ -1351,6 +1382,7 @@ static int dec_frames_impl(carta1_decoder *d, const uint8_t *su, const int32_t *
 }
 
 int carta1_dec_frames(carta1_decoder *d, const uint8_t *su, int n_frames, float *pcm_out) {
+  CtxLock ctx_lock(d ? d->ctx : nullptr);
   if (!d) return CARTA1_ERR_ARG;
   if (n_frames < 0 || (n_frames && (!su || !pcm_out)))
     return fail(d->ctx, CARTA1_ERR_ARG, "carta1_dec_frames: bad argument");
@@ -1360,6 +1392,7 @@ int carta1_dec_frames(carta1_decoder *d, const uint8_t *su, int n_frames, float 
 
 int carta1_dec_frames_expanded(carta1_decoder *d, const int32_t *q, const uint8_t *sfi, const uint8_t *bits,
                                const int32_t *modes, int n_frames, float *pcm_out) {
+  CtxLock ctx_lock(d ? d->ctx : nullptr);
   if (!d) return CARTA1_ERR_ARG;
   if (n_frames < 0 || (n_frames && (!q || !sfi || !bits || !modes || !pcm_out)))
     return fail(d->ctx, CARTA1_ERR_ARG, "carta1_dec_frames_expanded: bad argument");
@@ -1374,6 +1407,7 @@ int carta1_dec_frames_expanded(carta1_decoder *d, const int32_t *q, const uint8_
 // ------------------------------------------------------------------ frame dump
 int carta1_deserialize_units(carta1_ctx *ctx, const uint8_t *su, size_t n_su, uint8_t *n_bfu, int8_t *block_modes,
                              uint8_t *wl, uint8_t *sfi, int32_t *q) {
+  CtxLock ctx_lock(ctx);
   if (!ctx) return CARTA1_ERR_ARG;
   if (n_su == 0) return CARTA1_OK;
   if (!su || !n_bfu || !block_modes || !wl || !sfi || !q) return fail(ctx, CARTA1_ERR_ARG, "carta1_deserialize_units: NULL argument");
@@ -1403,6 +1437,7 @@ int carta1_deserialize_units(carta1_ctx *ctx, const uint8_t *su, size_t n_su, ui
 // ------------------------------------------------------------------ stage taps
 int carta1_debug_encode_stages(carta1_ctx *ctx, const float *pcm, size_t n_samples, const carta1_enc_opts *opts,
                                float *bands, float *mags, int32_t *modes, float *coefs, uint8_t *su) {
+  CtxLock ctx_lock(ctx);
   if (!ctx) return CARTA1_ERR_ARG;
   const size_t frames = carta1_frame_count(n_samples);
   if (frames == 0) return CARTA1_OK;
@@ -1438,6 +1473,7 @@ int carta1_debug_encode_stages(carta1_ctx *ctx, const float *pcm, size_t n_sampl
 
 int carta1_debug_decode_stages(carta1_ctx *ctx, const uint8_t *su, size_t n_su, float *coefs, float *bands,
                                float *pcm) {
+  CtxLock ctx_lock(ctx);
   if (!ctx) return CARTA1_ERR_ARG;
   if (n_su == 0) return CARTA1_OK;
   CU(ctx, cudaSetDevice(ctx->device));
@@ -1458,6 +1494,7 @@ int carta1_debug_decode_stages(carta1_ctx *ctx, const uint8_t *su, size_t n_su, 
 
 int carta1_debug_transient_scores(carta1_ctx *ctx, const float *pcm, size_t n_samples, const carta1_enc_opts *opts,
                                   double *scores) {
+  CtxLock ctx_lock(ctx);
   if (!ctx) return CARTA1_ERR_ARG;
   const size_t frames = carta1_frame_count(n_samples);
   if (frames == 0) return CARTA1_OK;
@@ -1482,6 +1519,7 @@ int carta1_debug_transient_scores(carta1_ctx *ctx, const float *pcm, size_t n_sa
 }
 
 int carta1_ctx_near_threshold(carta1_ctx *ctx, uint64_t counts[3], int reset) {
+  CtxLock ctx_lock(ctx);
   if (!ctx || !counts) return CARTA1_ERR_ARG;
   CU(ctx, cudaSetDevice(ctx->device));
   unsigned long long near[2] = {0, 0};
@@ -1496,6 +1534,7 @@ int carta1_ctx_near_threshold(carta1_ctx *ctx, uint64_t counts[3], int reset) {
 }
 
 int carta1_debug_selftest(carta1_ctx *ctx, uint64_t *mismatches) {
+  CtxLock ctx_lock(ctx);
   if (!ctx || !mismatches) return CARTA1_ERR_ARG;
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, ctx->dbg.ensure(64));

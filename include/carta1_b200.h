@@ -11,9 +11,10 @@
  *   - plain pointers and sizes only; all functions return 0 on success, non-zero on error
  *     (carta1_last_error() gives the message; messages mirror the reference's throws).
  *   - "sound unit" (SU) = 212 bytes = one mono frame of 512 samples (codec/core/constants.js:7,19).
- *   - a handle is used by one thread at a time; different handles may be used from different
- *     threads at the same time (an encode and a decode call then overlap on the PCIe link).
- *     Calls are blocking.
+ *   - calls are blocking and thread-safe.  A context owns one stream, its scratch buffers and the
+ *     state of the handles created from it: calls on one context, or on encoders / decoders created
+ *     from it, are serialised by the library (any thread may make them).  Concurrency is one context
+ *     per thread: an encode call and a decode call on two contexts overlap on the PCIe link.
  *   - there is NO CPU fallback: every compute entry point fails if no sm_100 device /
  *     kernel image is available.
  */

@@ -143,3 +143,61 @@ def test_contexts_on_threads_from_cold(oracle):
         assert np.array_equal(got[i][0], want[i])
         for a, b in zip(got[i][1], want_pcm[i]):
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_one_context_from_several_threads(oracle):
+    """One context, used from three threads at once: an encoder handle fed frame by frame, a decoder handle fed
+    unit by unit, and whole-buffer calls on the context itself.  They share the context's stream and scratch buffers
+    (the encode and the decode path both write `coefs` and `modes`), so the library runs the calls one after the other
+    (include/carta1_b200.h conventions); every result has to be the oracle's."""
+    import carta1_b200
+
+    O = oracle
+    x = np.ascontiguousarray(S.cfg3_transients(0.6, seed=31, n_ch=1)[0])
+    frames = O.frame_count(len(x))
+    padded = np.zeros(frames * 512, np.float32)
+    padded[:len(x)] = x
+    want = O.encode_pcm([x])                      # [frames][212]
+    want_pcm = O.decode_su(want, 1)[0]
+    y = list(S.cfg1_stereo(0.25, seed=32))
+    want_y = O.encode_pcm(y)
+    ctx = carta1_b200.Context(0)
+    errs, out = [], {}
+
+    def enc_thread():
+        try:
+            enc = carta1_b200.StreamEncoder(ctx, None, 1)
+            got = [enc.frames(padded[512 * f:512 * (f + 1)].reshape(1, 1, 512)).reshape(212).copy() for f in range(frames)]
+            enc.close()
+            out["su"] = np.stack(got)
+        except Exception as ex:
+            errs.append(ex)
+
+    def dec_thread():
+        try:
+            dec = carta1_b200.StreamDecoder(ctx, 1)
+            got = [dec.frames(np.ascontiguousarray(want[f]).reshape(1, 1, 212)).reshape(512).copy() for f in range(frames)]
+            dec.close()
+            out["pcm"] = np.concatenate(got)
+        except Exception as ex:
+            errs.append(ex)
+
+    def whole_thread():
+        try:
+            out["y"] = [ctx.encode_pcm(y) for _ in range(6)]
+        except Exception as ex:
+            errs.append(ex)
+
+    th = [threading.Thread(target=f) for f in (enc_thread, dec_thread, whole_thread)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    try:
+        assert not errs, errs
+        assert np.array_equal(out["su"], want)
+        assert np.array_equal(out["pcm"].view(np.uint32), want_pcm[:frames * 512].view(np.uint32))
+        for g in out["y"]:
+            assert np.array_equal(g, want_y)
+    finally:
+        ctx.close()
