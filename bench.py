@@ -712,8 +712,8 @@ def run_ours(args, rank, local_rank, world):
             h.encode(ctx)
             h.decode(ctx)
 
-    # The same calls, in flight together: an encoder thread and a decoder thread, each on its own context (a handle is
-    # used by one thread at a time, include/carta1_b200.h).  carta1_encode_pcm is H2D-heavy and carta1_decode_su
+    # The same calls, in flight together: an encoder thread and a decoder thread, each on its own context (calls on one
+    # context are serialised by the library, include/carta1_b200.h).  carta1_encode_pcm is H2D-heavy and carta1_decode_su
     # D2H-heavy, so together they use both directions of the PCIe link.  Work per step is unchanged.
     def e2e_duplex_step():
         def dec():
