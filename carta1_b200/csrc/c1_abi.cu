@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -483,17 +484,28 @@ static int run_graphed(carta1_ctx *ctx, GraphCache &g, int shape, Body body) {
   }
   if (plan == 2) {
     const unsigned long long before = ctx->prof.launches;
+    static const bool trace = getenv("CARTA1_TRACE_GRAPH") != nullptr;  // development aid: where the capturing call spends its time
+    const auto t0 = std::chrono::steady_clock::now();
     if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
       const int rc = body();
       cudaGraph_t graph = nullptr;
       const cudaError_t ee = cudaStreamEndCapture(ctx->stream, &graph);
+      const auto t1 = std::chrono::steady_clock::now();
       cudaGraphExec_t exec = nullptr;
       if (rc == CARTA1_OK && ee == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        const auto t2 = std::chrono::steady_clock::now();
         cudaGraphDestroy(graph);
         g.exec = exec;
         g.generation = g_alloc_generation;
         g.kernels = ctx->prof.launches - before;
         CU(ctx, cudaGraphLaunch(g.exec, ctx->stream));
+        if (trace) {
+          cudaStreamSynchronize(ctx->stream);
+          const auto t3 = std::chrono::steady_clock::now();
+          auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+          fprintf(stderr, "[carta1] graph of shape %d: capture %.3f ms, instantiate %.3f ms, first launch + sync %.3f ms\n", shape,
+                  ms(t0, t1), ms(t1, t2), ms(t2, t3));
+        }
         return CARTA1_OK;
       }
       if (graph) cudaGraphDestroy(graph);
@@ -616,6 +628,24 @@ int carta1_ctx_create(int device, const carta1_tables *tables, carta1_ctx **out)
     cuda_fail(nullptr, e, "carta1_ctx_create");
     carta1_ctx_destroy(ctx);
     return CARTA1_ERR_CUDA;
+  }
+  {
+    // The first cudaGraphInstantiate of a process initialises the driver's graph machinery and takes 0.4 - 20 ms
+    // (measured, CARTA1_TRACE_GRAPH); later ones take 0.08 ms.  Pay it here, not in the second frame call of the first
+    // stateful handle.  Failures are ignored: graphs are an optimisation (GraphCache falls back to plain launches).
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      cudaMemsetAsync(ctx->d_near, 0, 2 * sizeof(unsigned long long), ctx->stream);
+      if (cudaStreamEndCapture(ctx->stream, &graph) == cudaSuccess && graph &&
+          cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        cudaGraphLaunch(exec, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+      }
+    }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
   }
   *out = ctx;
   return CARTA1_OK;
