@@ -1425,11 +1425,12 @@ __device__ __forceinline__ void put_bits(uint32_t *words, int pos, uint32_t valu
 }
 
 constexpr int kQpWarps = 8;
-struct QpBfu {          // per BFU of the unit being packed
+struct QpBfu {          // per BFU of the unit being packed: one 16-byte load per coefficient
   double norm;          // quantRange / scaleFactor, 0 when the BFU carries no bits or sfi == 0
-  uint32_t base_bits;   // bit offset | width << 11 | quantRange << 16
-  uint32_t pad;
+  uint32_t base_range;  // bit offset | quantRange << 16
+  uint32_t bits;        // width of a code, 0 when nothing of the BFU goes into the image
 };
+static_assert(sizeof(QpBfu) == 16, "QpBfu is one 16-byte record");
 struct QpWarpSmem {
   QpBfu bfu[52];
   uint32_t words[56];
@@ -1442,18 +1443,26 @@ template <bool kWrap>
 __device__ __forceinline__ void qp_coefs(QpWarpSmem &S, const float (&c)[16], const uint16_t *bj0, const uint16_t *bj1,
                                          const uint16_t *bj2) {
   uint32_t *words = S.words;
+  double half = 0.0;  // +-0.5 with the sign of x: only the high word is rewritten per coefficient (the low word stays 0)
 #pragma unroll
   for (int k = 0; k < 16; k++) {
     const uint32_t bj = (k < 4 ? bj0 : (k < 8 ? bj1 : bj2))[32 * k];
-    const QpBfu rec = S.bfu[bj >> 5];
-    const int bits = (rec.base_bits >> 11) & 31;
+    const uint4 rw = *reinterpret_cast<const uint4 *>(&S.bfu[bj >> 5]);  // norm (lo, hi), base_range, bits
+    const int bits = (int)rw.w;
     if (bits) {
-      const int range = (int)(rec.base_bits >> 16);
+      const int range = (int)(rw.z >> 16);
       // x = c * normFactor; y = (x + (x >= 0 ? 0.5 : -0.5)) | 0; clamp to +-range (norm > 0: uncoded BFUs were skipped)
-      const double x = (double)c[k] * rec.norm;
-      const int y = kWrap ? js_to_int32(x + (x >= 0.0 ? 0.5 : -0.5)) : __double2int_rz(x + copysign(0.5, x));
+      const double x = (double)c[k] * __hiloint2double((int)rw.y, (int)rw.x);
+      int y;
+      if (kWrap) {
+        y = js_to_int32(x + (x >= 0.0 ? 0.5 : -0.5));
+      } else {  // x + copysign(0.5, x): x >= 0 is true for -0 and so is a clear sign bit; x is never NaN here (finite c, norm)
+        const int hs = (__double2hiint(x) & (int)0x80000000) | 0x3FE00000;
+        asm("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tmov.b64 %0, {lo, %1};\n\t}" : "+d"(half) : "r"(hs));
+        y = __double2int_rz(x + half);
+      }
       const int q = min(max(y, -range), range);
-      put_bits(words, (int)(rec.base_bits & 2047u) + (int)(bj & 31u) * bits, (uint32_t)q, bits);
+      put_bits(words, (int)(rw.z & 0xFFFFu) + (int)(bj & 31u) * bits, (uint32_t)q, bits);
     }
   }
 }
@@ -1508,7 +1517,8 @@ __device__ __forceinline__ void qp_unit(QpWarpSmem &S, const uint16_t (*s_bj)[51
       S.bfu[b].norm = coded ? __ldg(&T->norm[wl][sfi]) : 0.0;
       // a BFU that carries bits but has scale-factor index 0 quantises to zeros (quantization.js:37-40):
       // nothing to merge into the image, so its width field is 0 and the coefficient loop skips it
-      S.bfu[b].base_bits = (uint32_t)base | ((uint32_t)(coded ? bits : 0) << 11) | ((uint32_t)((1 << wl) - 1) << 16);
+      S.bfu[b].base_range = (uint32_t)base | ((uint32_t)((1 << wl) - 1) << 16);
+      S.bfu[b].bits = (uint32_t)(coded ? bits : 0);
       wrap |= coded && sfi == 63;
       if (b < n) {
         put_bits(words, 16 + 4 * b, (uint32_t)wl, 4);
