@@ -140,15 +140,19 @@ __device__ __noinline__ void imdct_band_exact(int band, bool is_long, const floa
 // K5: unpack + dequantise, one warp per sound unit -> 512 coefficients + block modes.
 // ------------------------------------------------------------------------------------
 constexpr int kUnpackWarps = 8;
-struct UpBfu {          // per BFU of the unit being unpacked
+struct UpBfu {          // per BFU of the unit being unpacked: what every coefficient reads (one 8-byte load)
+  uint32_t base_bits;   // bit offset (malformed units: up to 16 + 520 + 16 * 512) | width << 16
+  int32_t tab;          // first entry of (wl, sfi) in DevTables::deq_tab, or -1: width above 7 bits, or a unit that claims
+                        // more bits than it has (then every BFU takes the general path, see `overrun`)
+};
+struct UpBfuWide {      // the same BFU for codes of 8 bits and more (the division path)
   double sf;            // SCALE_FACTORS[sfi]; 0 when sfi == 0 (dequantize returns zeros)
   double rcp;           // 1 / quantRange
   double range;         // quantRange = 2^(bits-1) - 1
-  uint32_t base_bits;   // bit offset (malformed units: up to 16 + 520 + 16 * 512) | width << 16
-  int32_t tab;          // first entry of (wl, sfi) in DevTables::deq_tab, or -1 (width above 7 bits)
 };
 struct UnpackWarpSmem {
   UpBfu bfu[52];
+  UpBfuWide wide[52];
   uint32_t words[56];
 };
 
@@ -233,10 +237,11 @@ unpack_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_
         }
         if (b < 52) {
           UpBfu &r = S.bfu[b];
+          UpBfuWide &rw = S.wide[b];
           const int range = (1 << wl) - 1;  // 2^(bits-1) - 1
-          r.sf = sfi ? __ldg(&T->sf[sfi]) : 0.0;
-          r.rcp = __ldg(&T->rcp_range[wl]);
-          r.range = (double)range;
+          rw.sf = sfi ? __ldg(&T->sf[sfi]) : 0.0;
+          rw.rcp = __ldg(&T->rcp_range[wl]);
+          rw.range = (double)range;
           r.base_bits = (uint32_t)(run + incl - cost) | ((uint32_t)bits << 16);
           r.tab = wl >= 1 && wl <= kDeqMaxWl ? deq_off(wl) + (sfi << bits) : -1;
         }
@@ -247,6 +252,10 @@ unpack_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_
       // `run` is the end of the coefficient bits: a unit that claims more than the 1696 it has
       // (malformed input) needs unpackBits' behaviour at the end of the buffer (bitstream.js:55-68)
       const bool overrun = run > kFrameBits;
+      if (overrun) {  // rare: no table look-ups for this unit, the coefficient loop then tests one field only
+        if (lane < 26) { S.bfu[lane].tab = -1; S.bfu[lane + 26].tab = -1; }
+        __syncwarp();
+      }
       const uint16_t *bj0 = s_bj[m0 != 0] + lane, *bj1 = s_bj[m1 != 0] + lane, *bj2 = s_bj[m2 != 0] + lane;
 #pragma unroll
       for (int k = 0; k < 16; k++) {  // serialization.js:153-166 + decoder.js:65-94
@@ -256,7 +265,7 @@ unpack_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_
         float val = 0.0f;
         if (bits > 0) {
           const int pos = (int)(r.base_bits & 0xFFFFu) + (int)(bj & 31u) * bits;
-          if (!overrun && r.tab >= 0) {
+          if (r.tab >= 0) {
             // short codes (2..7 bits): f32((q * SF) / R) was tabulated on the host for every bit pattern
             const int w = pos >> 5, off = pos & 31;
             const uint32_t top = __funnelshift_l(words[w + 1], words[w], off);  // bits pos.. at the top
@@ -271,7 +280,8 @@ unpack_kernel(const uint8_t *__restrict__ su, size_t su_frame_stride, size_t su_
               const int v = (int)get_bits(words, pos, bits);
               q = v >= (1 << (bits - 1)) ? v - (1 << bits) : v;
             }
-            if (r.sf != 0.0) val = (float)div_by_range(int_to_double(q) * r.sf, r.range, r.rcp);
+            const UpBfuWide rw = S.wide[bj >> 5];
+            if (rw.sf != 0.0) val = (float)div_by_range(int_to_double(q) * rw.sf, rw.range, rw.rcp);
           }
         }
         dst[lane + 32 * k] = val;
