@@ -539,12 +539,26 @@ def run_configs(torch, np, carta1_b200, ctx, dev, args):
         out_t = torch.empty((ns, nf, 512), dtype=torch.float32).pin_memory()
         pcm_t.copy_(torch.from_numpy(pcm_all[:, :nf]))
         calls = max(4, 128 // nf)
-        ms_e = wall_ms(lambda: enc.frames(pcm_t.numpy(), su_t.numpy()), calls)
-        ms_d = wall_ms(lambda: dec.frames(su_t.numpy(), out_t.numpy()), calls)
+
+        def per_call_ms(fn):
+            for _ in range(3):  # past the capture of the handle's graph for this call shape
+                fn()
+            ts = []
+            for _ in range(calls):
+                t0 = time.perf_counter()
+                fn()  # blocking: the result is in host memory when it returns
+                ts.append((time.perf_counter() - t0) * 1e3)
+            ts.sort()
+            return sum(ts) / len(ts), ts[len(ts) // 2], ts[min(len(ts) - 1, (9 * len(ts)) // 10)], ts[-1]
+
+        ms_e, med_e, p90_e, max_e = per_call_ms(lambda: enc.frames(pcm_t.numpy(), su_t.numpy()))
+        ms_d, med_d, p90_d, max_d = per_call_ms(lambda: dec.frames(su_t.numpy(), out_t.numpy()))
         audio = ns * nf * 512 / SR
         cfg4["frames_per_call"][str(nf)] = {
             "value": audio / ((ms_e + ms_d) / 1e3), "encode_only": audio / (ms_e / 1e3), "decode_only": audio / (ms_d / 1e3),
             "ms_per_encode_call": ms_e, "ms_per_decode_call": ms_d,
+            "per_call_ms": {"encode": {"mean": ms_e, "median": med_e, "p90": p90_e, "max": max_e},
+                            "decode": {"mean": ms_d, "median": med_d, "p90": p90_d, "max": max_d}},
             "e2e": {"value": audio / ((ms_e + ms_d) / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(ns * nf * (2048 + 212)),
                     "d2h_bytes_per_step": int(ns * nf * (2048 + 212)),
                     "note": "the stateful API takes host buffers: value and e2e are the same measurement"}}
